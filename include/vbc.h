@@ -1,0 +1,130 @@
+/* include/vbc.h -- C ABI of libvbc.so: B200 (sm_100a) device implementation of the blocked
+ * sparse multiply path of SparseMatrixVBCs.jl.
+ *
+ * This header is the drop-in boundary.  Each entry point names the reference interface it
+ * replaces (paths relative to the reference checkout).  All arguments are plain pointers and
+ * integers; no C++/torch types.  Index arrays crossing the boundary are 1-BASED and Ti-typed,
+ * exactly as the reference's Julia structs store them, so "bit-exact packed arrays" is a
+ * memcmp after vbc_download.
+ *
+ * Conventions
+ *   - every function returns a vbc_status (0 = VBC_OK); vbc_last_error() gives the message of
+ *     the calling thread's last failure.  The library never aborts or exits.
+ *   - `vt` is a vbc_dtype (Tv, and also the element type of x and y), `it` a vbc_itype (Ti).
+ *   - `on_device` = 0: x / y are host pointers, the call copies in/out and is synchronous on
+ *     return.  `on_device` = 1: x / y are device pointers on the matrix' device, the call only
+ *     enqueues work on the matrix' stream (vbc_set_stream, default: the legacy default
+ *     stream) -- use vbc_sync() or your own events to wait.
+ *   - a handle may be used from any thread, one call at a time; different handles are
+ *     independent.
+ */
+#ifndef VBC_H
+#define VBC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vbc_mat vbc_mat; /* device-resident 1D-VBC or 2D-VBC matrix ("CuVBC")            */
+typedef struct vbc_csc vbc_csc; /* device-resident CSC matrix (comparator for TrSpMV!)           */
+
+enum vbc_dtype { VBC_F32 = 0, VBC_F64 = 1 };
+enum vbc_itype { VBC_I32 = 0, VBC_I64 = 1 };
+
+enum vbc_status {
+    VBC_OK = 0,
+    VBC_EDIM = 1,   /* DimensionMismatch: multiply_1DVBC.jl:44-45,:139-140; multiply_VBC.jl:51-52,:152-153; TrSpMV.jl:3-4 */
+    VBC_EARG = 2,   /* ArgumentError: SparseMatrixVBCs.jl:45-50, :72-79 (m,n >= 0; U,W > 0) + malformed inputs   */
+    VBC_ELIMIT = 3, /* AssertionError `w <= W` constructors_1DVBC.jl:46 / constructors_VBC.jl:65, `u <= U` :58-60;
+                       also: sizes beyond the device layout's 32-bit fields                                        */
+    VBC_ECUDA = 4,  /* a CUDA runtime call failed (message has the CUDA error string)                            */
+    VBC_ENCCL = 5,  /* reserved for the multi-GPU layer                                                          */
+    VBC_ENOMEM = 6  /* host or device allocation failed                                                          */
+};
+
+/* options for vbc_set_option */
+enum vbc_option {
+    VBC_OPT_ADJ_GROUP = 1,  /* lanes cooperating on one stripe in the adjoint kernel: 0 = auto, else 4|8|16|32 */
+    VBC_OPT_FWD_GROUP = 2,  /* same for the forward (scatter) kernel                                         */
+    VBC_OPT_GRID_MULT = 3,  /* CTAs per SM for the persistent grid-stride launch: 0 = auto                   */
+    VBC_OPT_PARITY_MODE = 4 /* 1: multiply straight from the canonical Ti arrays (pos/idx/ofs/spl) with the
+                                  generic kernel instead of the compact device layout                         */
+};
+
+const char *vbc_last_error(void);
+int vbc_version(void);
+int vbc_device_count(int *count);
+
+/* ---- constructors ------------------------------------------------------------------------
+ * vbc_pack_csc: host CSC + host partition(s) -> device pack kernels.
+ *   1D (pi_spl == NULL): replaces `SparseMatrix1DVBC{W}(A::SparseMatrixCSC, Φ::SplitPartition)`
+ *                        constructors_1DVBC.jl:9-92 (and the StrictChunker body :94-143, whose
+ *                        output is identical on a strict partition).  U is ignored.
+ *   2D:                  replaces `SparseMatrixVBC{U,W}(A, Π, Φ)` constructors_VBC.jl:15-133.
+ *   colptr[n+1], rowval[nnz], nzval[nnz]: SparseMatrixCSC fields (1-based, rows ascending in a
+ *   column, no duplicates).  pi_spl[K+1], phi_spl[L+1]: SplitPartition.spl (1-based, spl[0]=1,
+ *   spl[K]=m+1 resp. spl[L]=n+1).
+ * vbc_pack_csc_dev: same, but every array argument is already a device pointer on `device`. */
+int vbc_pack_csc(vbc_mat **out, int vt, int it, int64_t m, int64_t n, int U, int W,
+                 const void *colptr, const void *rowval, const void *nzval,
+                 const void *pi_spl, int64_t K, const void *phi_spl, int64_t L, int device);
+int vbc_pack_csc_dev(vbc_mat **out, int vt, int it, int64_t m, int64_t n, int U, int W,
+                     const void *colptr, const void *rowval, const void *nzval,
+                     const void *pi_spl, int64_t K, const void *phi_spl, int64_t L, int device);
+
+/* vbc_upload: adopt arrays already packed by the reference on the host -- the fields of a
+ * `SparseMatrix1DVBC` (SparseMatrixVBCs.jl:36-43; pi_spl == NULL) or `SparseMatrixVBC`
+ * (:62-70).  val needs only its first ofs[L]-1 entries (the SIMD tail pad is not read). */
+int vbc_upload(vbc_mat **out, int vt, int it, int64_t m, int64_t n, int U, int W,
+               const void *pi_spl, int64_t K, const void *phi_spl, int64_t L,
+               const void *pos, const void *idx, const void *ofs, const void *val, int device);
+
+void vbc_destroy(vbc_mat *A);
+
+/* ---- introspection (`Base.size`, SparseMatrixVBCs.jl:55/:84, and the struct fields) -------- */
+int vbc_shape(const vbc_mat *A, int64_t *m, int64_t *n, int64_t *K, int64_t *L, int *U, int *W,
+              int *ndim /* 1 or 2 */, int *vt, int *it);
+/* nidx = pos[L]-1 (stored rows / blocks), nval = ofs[L]-1 (stored values) */
+int vbc_sizes(const vbc_mat *A, int64_t *nidx, int64_t *nval);
+/* copies pos[L+1], idx[nidx], ofs[L+1], val[nval] (1-based, Ti / Tv typed) to host; any may be NULL */
+int vbc_download(const vbc_mat *A, void *pos, void *idx, void *ofs, void *val);
+/* bytes: [0] the reference's format accounting `sizeof(Φ)+sizeof(Π)+sizeof(pos)+sizeof(idx)+sizeof(ofs)+sizeof(val)`
+ *            (bin/test_table.jl:78, :120);
+ *        [1] bytes of the device layout that one adjoint multiply reads (matrix part only);
+ *        [2] same for one forward multiply. */
+int vbc_format_bytes(const vbc_mat *A, int64_t bytes[3]);
+/* per-stripe cost under the reference's memory model (costs.jl:10 1D, :140 2D), computed on the
+ * device from the packed arrays: cost[L] (host pointer); *row_term = K*sizeof(Ti) for 2D, else 0. */
+int vbc_memory_cost(const vbc_mat *A, int64_t *cost, int64_t *row_term);
+
+/* ---- multiply ------------------------------------------------------------------------------
+ * y <- alpha * op(A) * x + beta * y.
+ *   trans = 0: op(A) = A   replaces `mul!(y, A, x, α, β)`  multiply_1DVBC.jl:9 / multiply_VBC.jl:3
+ *   trans = 1: op(A) = A'  replaces `mul!(y, A', x, α, β)` multiply_1DVBC.jl:85 / multiply_VBC.jl:89
+ * (BLAS semantics; coincides with the reference wherever its tests pin it, α=1, β=0.  The
+ * reference ignores α and, in the adjoint, β -- documented in DESIGN.md, not reproduced.)
+ * xlen / ylen are checked against the matrix shape -> VBC_EDIM. */
+int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, double beta,
+             void *y, int64_t ylen, int on_device);
+
+/* CSC comparator: `TrSpMV!(y, A::SparseMatrixCSC, x)` TrSpMV.jl:1-20, y = A' x. */
+int vbc_csc_upload(vbc_csc **out, int vt, int it, int64_t m, int64_t n, const void *colptr,
+                   const void *rowval, const void *nzval, int device);
+int vbc_csc_trspmv(vbc_csc *A, const void *x, int64_t xlen, void *y, int64_t ylen, int on_device);
+void vbc_csc_destroy(vbc_csc *A);
+
+/* ---- execution control ---------------------------------------------------------------------*/
+int vbc_set_stream(vbc_mat *A, void *cuda_stream); /* a cudaStream_t; NULL = legacy default stream */
+int vbc_csc_set_stream(vbc_csc *A, void *cuda_stream);
+int vbc_sync(vbc_mat *A);
+int vbc_set_option(vbc_mat *A, int option, int64_t value);
+int vbc_get_option(const vbc_mat *A, int option, int64_t *value);
+/* number of kernel launches this handle has made since creation (bench.py's gpu_launches) */
+int vbc_launch_count(const vbc_mat *A, int64_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBC_H */

@@ -1,0 +1,24 @@
+"""sparsematrixvbcs.jl_b200 -- B200-native blocked sparse multiply behind the API of SparseMatrixVBCs.jl.
+
+Import as `vbc_b200` (the directory name contains a dot, so the repo root ships `vbc_b200.py`,
+a two-line importlib shim that loads this package under that name).
+
+Only the hot path lives here: csrc/ (CUDA kernels + the C ABI of include/vbc.h -> libvbc.so), the
+host mirror of the reference's operator interface (matrix.py), the host-side inputs of the pack
+kernel (partition.py), synthetic workloads (synth.py) and the row-partitioned multi-GPU driver
+(dist.py).
+"""
+from ._lib import ArgumentError, DimensionMismatch, VBCError, LIB_PATH  # noqa: F401
+from .partition import (AlternatingPacker, EquiChunker, RandomChunker, SparseMatrixCSC,  # noqa: F401
+                        SplitPartition, StrictChunker, pack_plaid, pack_stripe)
+from .matrix import (Adjoint, CuSparseMatrixCSC, CuVBC1D, CuVBC2D, SparseMatrix1DVBC,  # noqa: F401
+                     SparseMatrixVBC, TrSpMV_, adjoint, mul_, size)
+from . import synth  # noqa: F401
+
+__all__ = [
+    "SparseMatrix1DVBC", "SparseMatrixVBC", "CuVBC1D", "CuVBC2D", "CuSparseMatrixCSC", "Adjoint",
+    "mul_", "TrSpMV_", "adjoint", "size",
+    "SparseMatrixCSC", "SplitPartition", "EquiChunker", "StrictChunker", "RandomChunker",
+    "AlternatingPacker", "pack_stripe", "pack_plaid",
+    "DimensionMismatch", "ArgumentError", "VBCError", "synth",
+]

@@ -1,0 +1,112 @@
+"""ctypes binding of libvbc.so (include/vbc.h).  There is no CPU fallback: if the CUDA library
+is missing or fails to load, importing the device types raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libvbc.so")
+
+VBC_F32, VBC_F64 = 0, 1
+VBC_I32, VBC_I64 = 0, 1
+VBC_OK, VBC_EDIM, VBC_EARG, VBC_ELIMIT, VBC_ECUDA, VBC_ENCCL, VBC_ENOMEM = range(7)
+OPT_ADJ_GROUP, OPT_FWD_GROUP, OPT_GRID_MULT, OPT_PARITY_MODE = 1, 2, 3, 4
+
+# every symbol include/vbc.h declares (tests/test_abi_symbols.py checks header <-> this list <-> .so)
+SYMBOLS = [
+    "vbc_last_error", "vbc_version", "vbc_device_count",
+    "vbc_pack_csc", "vbc_pack_csc_dev", "vbc_upload", "vbc_destroy",
+    "vbc_shape", "vbc_sizes", "vbc_download", "vbc_format_bytes", "vbc_memory_cost",
+    "vbc_spmv",
+    "vbc_csc_upload", "vbc_csc_trspmv", "vbc_csc_destroy",
+    "vbc_set_stream", "vbc_csc_set_stream", "vbc_sync", "vbc_set_option", "vbc_get_option",
+    "vbc_launch_count",
+]
+
+
+class VBCError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libvbc error {code}: {msg}")
+        self.code = code
+
+
+class DimensionMismatch(ValueError):
+    """Julia's `DimensionMismatch` (multiply_1DVBC.jl:44-45 etc.)."""
+
+
+class ArgumentError(ValueError):
+    """Julia's `ArgumentError` (SparseMatrixVBCs.jl:45-50, :72-79)."""
+
+
+_lib = None
+
+
+def build_hint():
+    return ("libvbc.so not found/loadable at %s -- build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C sparsematrixvbcs.jl_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(build_hint())
+    try:
+        L = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise ImportError(build_hint() + f" ({e})")
+    c_i64, c_int, c_vp, c_dbl = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_double
+    pp = ctypes.POINTER(c_vp)
+    L.vbc_last_error.restype = ctypes.c_char_p
+    L.vbc_last_error.argtypes = []
+    L.vbc_version.restype = c_int
+    L.vbc_device_count.argtypes = [ctypes.POINTER(c_int)]
+    pack_args = [pp, c_int, c_int, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int]
+    L.vbc_pack_csc.argtypes = pack_args
+    L.vbc_pack_csc_dev.argtypes = pack_args
+    L.vbc_upload.argtypes = [pp, c_int, c_int, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_i64,
+                             c_vp, c_vp, c_vp, c_vp, c_int]
+    L.vbc_destroy.argtypes = [c_vp]
+    L.vbc_destroy.restype = None
+    pi64, pint = ctypes.POINTER(c_i64), ctypes.POINTER(c_int)
+    L.vbc_shape.argtypes = [c_vp, pi64, pi64, pi64, pi64, pint, pint, pint, pint, pint]
+    L.vbc_sizes.argtypes = [c_vp, pi64, pi64]
+    L.vbc_download.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp]
+    L.vbc_format_bytes.argtypes = [c_vp, pi64]
+    L.vbc_memory_cost.argtypes = [c_vp, c_vp, pi64]
+    L.vbc_spmv.argtypes = [c_vp, c_int, c_dbl, c_vp, c_i64, c_dbl, c_vp, c_i64, c_int]
+    L.vbc_csc_upload.argtypes = [pp, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_int]
+    L.vbc_csc_trspmv.argtypes = [c_vp, c_vp, c_i64, c_vp, c_i64, c_int]
+    L.vbc_csc_destroy.argtypes = [c_vp]
+    L.vbc_csc_destroy.restype = None
+    L.vbc_set_stream.argtypes = [c_vp, c_vp]
+    L.vbc_csc_set_stream.argtypes = [c_vp, c_vp]
+    L.vbc_sync.argtypes = [c_vp]
+    L.vbc_set_option.argtypes = [c_vp, c_int, c_i64]
+    L.vbc_get_option.argtypes = [c_vp, c_int, pi64]
+    L.vbc_launch_count.argtypes = [c_vp, pi64]
+    for name in SYMBOLS:
+        f = getattr(L, name)
+        if name not in ("vbc_last_error", "vbc_destroy", "vbc_csc_destroy"):
+            f.restype = c_int
+    _lib = L
+    return L
+
+
+def check(rc):
+    """Map a vbc_status to the exception the reference would raise."""
+    if rc == VBC_OK:
+        return
+    msg = lib().vbc_last_error().decode("utf-8", "replace")
+    if rc == VBC_EDIM:
+        raise DimensionMismatch(msg)
+    if rc == VBC_EARG:
+        raise ArgumentError(msg)
+    if rc == VBC_ELIMIT and msg.startswith("AssertionError"):
+        raise AssertionError(msg)
+    if rc == VBC_ENOMEM:
+        raise MemoryError(msg)
+    raise VBCError(rc, msg)

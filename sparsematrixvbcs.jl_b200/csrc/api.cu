@@ -1,0 +1,396 @@
+// api.cu -- the extern "C" surface declared in include/vbc.h.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <new>
+
+#include "common.cuh"
+
+namespace vbc {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char *get_error() { return g_err; }
+
+static int check_types(int vt, int it)
+{
+    if (vt != VBC_F32 && vt != VBC_F64) VBC_FAIL(VBC_EARG, "vt must be VBC_F32 or VBC_F64, got %d", vt);
+    if (it != VBC_I32 && it != VBC_I64) VBC_FAIL(VBC_EARG, "it must be VBC_I32 or VBC_I64, got %d", it);
+    return VBC_OK;
+}
+
+// ArgumentError checks of the struct constructors, SparseMatrixVBCs.jl:45-50 and :72-79
+static int check_shape(int64_t m, int64_t n, int U, int W, bool d2, int64_t K, int64_t L)
+{
+    if (m < 0) VBC_FAIL(VBC_EARG, "ArgumentError: number of rows (m) must be >= 0, got %lld", (long long)m);
+    if (n < 0) VBC_FAIL(VBC_EARG, "ArgumentError: number of columns (n) must be >= 0, got %lld", (long long)n);
+    if (W <= 0) VBC_FAIL(VBC_EARG, "ArgumentError: W must be > 0");
+    if (d2 && U <= 0) VBC_FAIL(VBC_EARG, "ArgumentError: U must be > 0");
+    if (L < 0 || (d2 && K < 0)) VBC_FAIL(VBC_EARG, "partition lengths must be >= 0");
+    return VBC_OK;
+}
+
+static int64_t rd(const void *a, int it, int64_t i) { return it == VBC_I64 ? ((const int64_t *)a)[i] : (int64_t)((const int32_t *)a)[i]; }
+
+static int check_spl_host(const void *spl, int it, int64_t P, int64_t dim, int64_t limit, const char *what, int over_code, const char *over_msg)
+{
+    if (rd(spl, it, 0) != 1 || rd(spl, it, P) != dim + 1) VBC_FAIL(VBC_EARG, "%s is not a SplitPartition of 1:%lld (spl[1]=%lld, spl[end]=%lld)", what, (long long)dim, (long long)rd(spl, it, 0), (long long)rd(spl, it, P));
+    for (int64_t k = 0; k < P; k++) {
+        const int64_t d = rd(spl, it, k + 1) - rd(spl, it, k);
+        if (d < 0) VBC_FAIL(VBC_EARG, "%s.spl is decreasing at %lld", what, (long long)k);
+        if (d > limit) VBC_FAIL(over_code, "%s", over_msg);
+    }
+    return VBC_OK;
+}
+
+static vbc_mat *new_mat(int vt, int it, int64_t m, int64_t n, int U, int W, bool d2, int64_t K, int64_t L, int device)
+{
+    vbc_mat *A = new (std::nothrow) vbc_mat();
+    if (!A) return nullptr;
+    A->vt = vt; A->it = it; A->m = m; A->n = n; A->U = d2 ? U : 0; A->W = W; A->ndim = d2 ? 2 : 1;
+    A->K = d2 ? K : 0; A->L = L; A->device = device;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) A->sm_count = sms;
+    return A;
+}
+
+static int copy_in(void **dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st)
+{
+    VBC_CUDA(cudaMalloc(dst, bytes > 0 ? bytes : 1));
+    if (bytes > 0) VBC_CUDA(cudaMemcpyAsync(*dst, src, bytes, kind, st));
+    return VBC_OK;
+}
+
+static int pack_common(vbc_mat **out, int vt, int it, int64_t m, int64_t n, int U, int W, const void *colptr, const void *rowval,
+                       const void *nzval, const void *pi_spl, int64_t K, const void *phi_spl, int64_t L, int device, bool on_dev)
+{
+    if (!out) VBC_FAIL(VBC_EARG, "out is NULL");
+    *out = nullptr;
+    VBC_TRY(check_types(vt, it));
+    const bool d2 = pi_spl != nullptr;
+    VBC_TRY(check_shape(m, n, U, W, d2, K, L));
+    if (!colptr || !phi_spl || (!rowval && !on_dev)) VBC_FAIL(VBC_EARG, "NULL array argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", device);
+    const size_t ti = it_size(it), tv = vt_size(vt);
+    const cudaMemcpyKind kind = on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+
+    int64_t nnz = 0;
+    if (on_dev) {
+        char tmp[8] = {0};
+        VBC_CUDA(cudaMemcpy(tmp, (const char *)colptr + ti * (size_t)n, ti, cudaMemcpyDeviceToHost));
+        nnz = rd(tmp, it, 0) - 1;
+    } else {
+        if (rd(colptr, it, 0) != 1) VBC_FAIL(VBC_EARG, "colptr[1] must be 1");
+        for (int64_t j = 0; j < n; j++)
+            if (rd(colptr, it, j + 1) < rd(colptr, it, j)) VBC_FAIL(VBC_EARG, "colptr is decreasing at column %lld", (long long)(j + 1));
+        nnz = rd(colptr, it, n) - 1;
+    }
+    if (nnz < 0) VBC_FAIL(VBC_EARG, "colptr[end] < 1");
+
+    vbc_mat *A = new_mat(vt, it, m, n, U, W, d2, K, L, device);
+    if (!A) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
+    int rc = VBC_OK;
+    void *d_colptr = nullptr, *d_rowval = nullptr, *d_nzval = nullptr;
+    do {
+        if ((rc = copy_in(&A->d_phi_spl, phi_spl, ti * (size_t)(L + 1), kind, A->stream)) != VBC_OK) break;
+        if (d2 && (rc = copy_in(&A->d_pi_spl, pi_spl, ti * (size_t)(K + 1), kind, A->stream)) != VBC_OK) break;
+        if (on_dev) {
+            d_colptr = const_cast<void *>(colptr); d_rowval = const_cast<void *>(rowval); d_nzval = const_cast<void *>(nzval);
+        } else {
+            if ((rc = copy_in(&d_colptr, colptr, ti * (size_t)(n + 1), kind, A->stream)) != VBC_OK) break;
+            if ((rc = copy_in(&d_rowval, rowval, ti * (size_t)nnz, kind, A->stream)) != VBC_OK) break;
+            if ((rc = copy_in(&d_nzval, nzval, tv * (size_t)nnz, kind, A->stream)) != VBC_OK) break;
+        }
+        rc = pack_from_device_csc(A, d_colptr, d_rowval, d_nzval);
+    } while (0);
+    if (!on_dev) { cudaFree(d_colptr); cudaFree(d_rowval); cudaFree(d_nzval); }
+    if (rc != VBC_OK) { vbc_destroy(A); return rc; }
+    *out = A;
+    return VBC_OK;
+}
+
+static int ensure_vec(void **buf, int64_t *cap, int64_t len, size_t esz)
+{
+    if (*cap >= len && *buf) return VBC_OK;
+    if (*buf) { cudaFree(*buf); *buf = nullptr; *cap = 0; }
+    VBC_CUDA(cudaMalloc(buf, esz * (size_t)(len > 0 ? len : 1)));
+    *cap = len;
+    return VBC_OK;
+}
+
+} // namespace vbc
+
+using namespace vbc;
+
+extern "C" {
+
+const char *vbc_last_error(void) { return get_error(); }
+int vbc_version(void) { return 100; }
+
+int vbc_device_count(int *count)
+{
+    if (!count) VBC_FAIL(VBC_EARG, "count is NULL");
+    VBC_CUDA(cudaGetDeviceCount(count));
+    return VBC_OK;
+}
+
+int vbc_pack_csc(vbc_mat **out, int vt, int it, int64_t m, int64_t n, int U, int W, const void *colptr, const void *rowval,
+                 const void *nzval, const void *pi_spl, int64_t K, const void *phi_spl, int64_t L, int device)
+{
+    return pack_common(out, vt, it, m, n, U, W, colptr, rowval, nzval, pi_spl, K, phi_spl, L, device, false);
+}
+
+int vbc_pack_csc_dev(vbc_mat **out, int vt, int it, int64_t m, int64_t n, int U, int W, const void *colptr, const void *rowval,
+                     const void *nzval, const void *pi_spl, int64_t K, const void *phi_spl, int64_t L, int device)
+{
+    return pack_common(out, vt, it, m, n, U, W, colptr, rowval, nzval, pi_spl, K, phi_spl, L, device, true);
+}
+
+int vbc_upload(vbc_mat **out, int vt, int it, int64_t m, int64_t n, int U, int W, const void *pi_spl, int64_t K, const void *phi_spl,
+               int64_t L, const void *pos, const void *idx, const void *ofs, const void *val, int device)
+{
+    if (!out) VBC_FAIL(VBC_EARG, "out is NULL");
+    *out = nullptr;
+    VBC_TRY(check_types(vt, it));
+    const bool d2 = pi_spl != nullptr;
+    VBC_TRY(check_shape(m, n, U, W, d2, K, L));
+    if (!phi_spl || !pos || !ofs) VBC_FAIL(VBC_EARG, "NULL array argument");
+    VBC_TRY(check_spl_host(phi_spl, it, L, n, W, "Φ", VBC_ELIMIT, "AssertionError: w <= W"));
+    if (d2) VBC_TRY(check_spl_host(pi_spl, it, K, m, U, "Π", VBC_ELIMIT, "AssertionError: u <= U"));
+    if (rd(pos, it, 0) != 1 || rd(ofs, it, 0) != 1) VBC_FAIL(VBC_EARG, "pos[1] and ofs[1] must be 1");
+    for (int64_t l = 0; l < L; l++)
+        if (rd(pos, it, l + 1) < rd(pos, it, l) || rd(ofs, it, l + 1) < rd(ofs, it, l)) VBC_FAIL(VBC_EARG, "pos/ofs decreasing at stripe %lld", (long long)(l + 1));
+    const int64_t nidx = rd(pos, it, L) - 1, nval = rd(ofs, it, L) - 1;
+    if ((nidx > 0 && !idx) || (nval > 0 && !val)) VBC_FAIL(VBC_EARG, "NULL idx/val");
+    // idx range check: a malformed idx would make the kernels gather out of bounds
+    const int64_t idx_hi = d2 ? K : m;
+    for (int64_t t = 0; t < nidx; t++)
+        if (rd(idx, it, t) < 1 || rd(idx, it, t) > idx_hi) VBC_FAIL(VBC_EARG, "idx[%lld]=%lld out of 1:%lld", (long long)(t + 1), (long long)rd(idx, it, t), (long long)idx_hi);
+    DeviceGuard guard(device);
+    if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", device);
+    vbc_mat *A = new_mat(vt, it, m, n, U, W, d2, K, L, device);
+    if (!A) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
+    A->nidx = nidx; A->nval = nval;
+    const size_t ti = it_size(it), tv = vt_size(vt);
+    int rc = VBC_OK;
+    do {
+        if ((rc = copy_in(&A->d_phi_spl, phi_spl, ti * (size_t)(L + 1), cudaMemcpyHostToDevice, A->stream)) != VBC_OK) break;
+        if (d2 && (rc = copy_in(&A->d_pi_spl, pi_spl, ti * (size_t)(K + 1), cudaMemcpyHostToDevice, A->stream)) != VBC_OK) break;
+        if ((rc = copy_in(&A->d_pos, pos, ti * (size_t)(L + 1), cudaMemcpyHostToDevice, A->stream)) != VBC_OK) break;
+        if ((rc = copy_in(&A->d_ofs, ofs, ti * (size_t)(L + 1), cudaMemcpyHostToDevice, A->stream)) != VBC_OK) break;
+        if ((rc = copy_in(&A->d_idx, idx, ti * (size_t)nidx, cudaMemcpyHostToDevice, A->stream)) != VBC_OK) break;
+        const size_t pad = 64;
+        if (cudaMalloc(&A->d_val, tv * ((size_t)nval + pad)) != cudaSuccess) { set_error("cudaMalloc(val)"); rc = VBC_ENOMEM; break; }
+        if (cudaMemsetAsync((char *)A->d_val + tv * (size_t)nval, 0, tv * pad, A->stream) != cudaSuccess) { set_error("memset"); rc = VBC_ECUDA; break; }
+        if (nval > 0 && cudaMemcpyAsync(A->d_val, val, tv * (size_t)nval, cudaMemcpyHostToDevice, A->stream) != cudaSuccess) { set_error("memcpy(val)"); rc = VBC_ECUDA; break; }
+        rc = finalize_layout(A, pi_spl);
+        if (rc == VBC_OK && cudaStreamSynchronize(A->stream) != cudaSuccess) { set_error("upload: sync failed: %s", cudaGetErrorString(cudaGetLastError())); rc = VBC_ECUDA; }
+    } while (0);
+    if (rc != VBC_OK) { vbc_destroy(A); return rc; }
+    *out = A;
+    return VBC_OK;
+}
+
+void vbc_destroy(vbc_mat *A)
+{
+    if (!A) return;
+    DeviceGuard guard(A->device);
+    cudaFree(A->d_pi_spl); cudaFree(A->d_phi_spl); cudaFree(A->d_pos); cudaFree(A->d_idx); cudaFree(A->d_ofs); cudaFree(A->d_val);
+    cudaFree(A->d_meta); cudaFree(A->d_desc); cudaFree(A->d_brow); cudaFree(A->d_x); cudaFree(A->d_y);
+    delete A;
+}
+
+int vbc_shape(const vbc_mat *A, int64_t *m, int64_t *n, int64_t *K, int64_t *L, int *U, int *W, int *ndim, int *vt, int *it)
+{
+    if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
+    if (m) *m = A->m; if (n) *n = A->n; if (K) *K = A->K; if (L) *L = A->L;
+    if (U) *U = A->U; if (W) *W = A->W; if (ndim) *ndim = A->ndim; if (vt) *vt = A->vt; if (it) *it = A->it;
+    return VBC_OK;
+}
+
+int vbc_sizes(const vbc_mat *A, int64_t *nidx, int64_t *nval)
+{
+    if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
+    if (nidx) *nidx = A->nidx;
+    if (nval) *nval = A->nval;
+    return VBC_OK;
+}
+
+int vbc_download(const vbc_mat *A, void *pos, void *idx, void *ofs, void *val)
+{
+    if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
+    DeviceGuard guard(A->device);
+    const size_t ti = it_size(A->it), tv = vt_size(A->vt);
+    VBC_CUDA(cudaStreamSynchronize(A->stream));
+    if (pos) VBC_CUDA(cudaMemcpy(pos, A->d_pos, ti * (size_t)(A->L + 1), cudaMemcpyDeviceToHost));
+    if (ofs) VBC_CUDA(cudaMemcpy(ofs, A->d_ofs, ti * (size_t)(A->L + 1), cudaMemcpyDeviceToHost));
+    if (idx && A->nidx > 0) VBC_CUDA(cudaMemcpy(idx, A->d_idx, ti * (size_t)A->nidx, cudaMemcpyDeviceToHost));
+    if (val && A->nval > 0) VBC_CUDA(cudaMemcpy(val, A->d_val, tv * (size_t)A->nval, cudaMemcpyDeviceToHost));
+    return VBC_OK;
+}
+
+int vbc_format_bytes(const vbc_mat *A, int64_t bytes[3])
+{
+    if (!A || !bytes) VBC_FAIL(VBC_EARG, "NULL argument");
+    const int64_t ti = (int64_t)it_size(A->it), tv = (int64_t)vt_size(A->vt);
+    bytes[0] = ti * (A->L + 1) * 3 + (A->ndim == 2 ? ti * (A->K + 1) : 0) + ti * A->nidx + tv * A->nval;
+    if (A->opt_parity) { bytes[1] = bytes[0]; bytes[2] = bytes[0]; return VBC_OK; }
+    bytes[1] = (int64_t)sizeof(StripeMeta) * (A->L + 1) + 4 * A->ndesc + tv * A->nval;
+    bytes[2] = bytes[1];
+    return VBC_OK;
+}
+
+int vbc_memory_cost(const vbc_mat *A, int64_t *cost, int64_t *row_term)
+{
+    if (!A || (!cost && A->L > 0)) VBC_FAIL(VBC_EARG, "NULL argument");
+    DeviceGuard guard(A->device);
+    return memory_cost_device(A, cost, row_term);
+}
+
+int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, double beta, void *y, int64_t ylen, int on_device)
+{
+    if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
+    const int64_t need_x = trans ? A->m : A->n, need_y = trans ? A->n : A->m;
+    if (xlen != need_x || ylen != need_y)
+        VBC_FAIL(VBC_EDIM, "DimensionMismatch: op(A) is %lld x %lld, x has %lld, y has %lld", (long long)need_y, (long long)need_x, (long long)xlen, (long long)ylen);
+    if ((!x && xlen > 0) || (!y && ylen > 0)) VBC_FAIL(VBC_EARG, "NULL vector");
+    DeviceGuard guard(A->device);
+    if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", A->device);
+    if (on_device) return launch_spmv(A, trans, alpha, x, beta, y);
+    const size_t tv = vt_size(A->vt);
+    VBC_TRY(ensure_vec(&A->d_x, &A->x_cap, xlen, tv));
+    VBC_TRY(ensure_vec(&A->d_y, &A->y_cap, ylen, tv));
+    if (xlen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_x, x, tv * (size_t)xlen, cudaMemcpyHostToDevice, A->stream));
+    if (beta != 0.0 && ylen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_y, y, tv * (size_t)ylen, cudaMemcpyHostToDevice, A->stream));
+    VBC_TRY(launch_spmv(A, trans, alpha, A->d_x, beta, A->d_y));
+    if (ylen > 0) VBC_CUDA(cudaMemcpyAsync(y, A->d_y, tv * (size_t)ylen, cudaMemcpyDeviceToHost, A->stream));
+    VBC_CUDA(cudaStreamSynchronize(A->stream));
+    return VBC_OK;
+}
+
+int vbc_csc_upload(vbc_csc **out, int vt, int it, int64_t m, int64_t n, const void *colptr, const void *rowval, const void *nzval, int device)
+{
+    if (!out) VBC_FAIL(VBC_EARG, "out is NULL");
+    *out = nullptr;
+    VBC_TRY(check_types(vt, it));
+    if (m < 0 || n < 0) VBC_FAIL(VBC_EARG, "ArgumentError: m, n must be >= 0");
+    if (!colptr) VBC_FAIL(VBC_EARG, "colptr is NULL");
+    if (rd(colptr, it, 0) != 1) VBC_FAIL(VBC_EARG, "colptr[1] must be 1");
+    for (int64_t j = 0; j < n; j++)
+        if (rd(colptr, it, j + 1) < rd(colptr, it, j)) VBC_FAIL(VBC_EARG, "colptr is decreasing at column %lld", (long long)(j + 1));
+    const int64_t nnz = rd(colptr, it, n) - 1;
+    for (int64_t t = 0; t < nnz; t++)
+        if (rd(rowval, it, t) < 1 || rd(rowval, it, t) > m) VBC_FAIL(VBC_EARG, "rowval[%lld] out of 1:%lld", (long long)(t + 1), (long long)m);
+    DeviceGuard guard(device);
+    if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", device);
+    vbc_csc *A = new (std::nothrow) vbc_csc();
+    if (!A) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
+    A->vt = vt; A->it = it; A->m = m; A->n = n; A->nnz = nnz; A->device = device;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) A->sm_count = sms;
+    const size_t ti = it_size(it), tv = vt_size(vt);
+    int rc = VBC_OK;
+    do {
+        if ((rc = copy_in(&A->d_colptr, colptr, ti * (size_t)(n + 1), cudaMemcpyHostToDevice, A->stream)) != VBC_OK) break;
+        if ((rc = copy_in(&A->d_rowval, rowval, ti * (size_t)nnz, cudaMemcpyHostToDevice, A->stream)) != VBC_OK) break;
+        if ((rc = copy_in(&A->d_nzval, nzval, tv * (size_t)nnz, cudaMemcpyHostToDevice, A->stream)) != VBC_OK) break;
+        if (cudaMalloc(&A->d_x, tv * (size_t)(m > 0 ? m : 1)) != cudaSuccess || cudaMalloc(&A->d_y, tv * (size_t)(n > 0 ? n : 1)) != cudaSuccess) { set_error("cudaMalloc(x,y)"); rc = VBC_ENOMEM; break; }
+        if (cudaStreamSynchronize(A->stream) != cudaSuccess) { set_error("csc upload sync failed"); rc = VBC_ECUDA; }
+    } while (0);
+    if (rc != VBC_OK) { vbc_csc_destroy(A); return rc; }
+    *out = A;
+    return VBC_OK;
+}
+
+int vbc_csc_trspmv(vbc_csc *A, const void *x, int64_t xlen, void *y, int64_t ylen, int on_device)
+{
+    if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
+    if (A->n != ylen || A->m != xlen) VBC_FAIL(VBC_EDIM, "DimensionMismatch: A' is %lld x %lld, x has %lld, y has %lld", (long long)A->n, (long long)A->m, (long long)xlen, (long long)ylen);
+    DeviceGuard guard(A->device);
+    if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", A->device);
+    if (on_device) return launch_csc_trspmv(A, x, y);
+    const size_t tv = vt_size(A->vt);
+    if (xlen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_x, x, tv * (size_t)xlen, cudaMemcpyHostToDevice, A->stream));
+    VBC_TRY(launch_csc_trspmv(A, A->d_x, A->d_y));
+    if (ylen > 0) VBC_CUDA(cudaMemcpyAsync(y, A->d_y, tv * (size_t)ylen, cudaMemcpyDeviceToHost, A->stream));
+    VBC_CUDA(cudaStreamSynchronize(A->stream));
+    return VBC_OK;
+}
+
+void vbc_csc_destroy(vbc_csc *A)
+{
+    if (!A) return;
+    DeviceGuard guard(A->device);
+    cudaFree(A->d_colptr); cudaFree(A->d_rowval); cudaFree(A->d_nzval); cudaFree(A->d_x); cudaFree(A->d_y);
+    delete A;
+}
+
+int vbc_set_stream(vbc_mat *A, void *s)
+{
+    if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
+    A->stream = (cudaStream_t)s;
+    return VBC_OK;
+}
+
+int vbc_csc_set_stream(vbc_csc *A, void *s)
+{
+    if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
+    A->stream = (cudaStream_t)s;
+    return VBC_OK;
+}
+
+int vbc_sync(vbc_mat *A)
+{
+    if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
+    DeviceGuard guard(A->device);
+    VBC_CUDA(cudaStreamSynchronize(A->stream));
+    return VBC_OK;
+}
+
+int vbc_set_option(vbc_mat *A, int option, int64_t value)
+{
+    if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
+    switch (option) {
+    case VBC_OPT_ADJ_GROUP:
+    case VBC_OPT_FWD_GROUP:
+        if (value != 0 && value != 8 && value != 32) VBC_FAIL(VBC_EARG, "group must be 0 (auto), 8 or 32");
+        (option == VBC_OPT_ADJ_GROUP ? A->opt_adj_group : A->opt_fwd_group) = (int)value;
+        return VBC_OK;
+    case VBC_OPT_GRID_MULT:
+        if (value < 0 || value > 32) VBC_FAIL(VBC_EARG, "grid multiplier must be in 0..32");
+        A->opt_grid_mult = (int)value;
+        return VBC_OK;
+    case VBC_OPT_PARITY_MODE:
+        A->opt_parity = value ? 1 : 0;
+        return VBC_OK;
+    }
+    VBC_FAIL(VBC_EARG, "unknown option %d", option);
+}
+
+int vbc_get_option(const vbc_mat *A, int option, int64_t *value)
+{
+    if (!A || !value) VBC_FAIL(VBC_EARG, "NULL argument");
+    switch (option) {
+    case VBC_OPT_ADJ_GROUP: *value = A->opt_adj_group; return VBC_OK;
+    case VBC_OPT_FWD_GROUP: *value = A->opt_fwd_group; return VBC_OK;
+    case VBC_OPT_GRID_MULT: *value = A->opt_grid_mult; return VBC_OK;
+    case VBC_OPT_PARITY_MODE: *value = A->opt_parity; return VBC_OK;
+    }
+    VBC_FAIL(VBC_EARG, "unknown option %d", option);
+}
+
+int vbc_launch_count(const vbc_mat *A, int64_t *count)
+{
+    if (!A || !count) VBC_FAIL(VBC_EARG, "NULL argument");
+    *count = A->launches;
+    return VBC_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,114 @@
+// common.cuh -- shared declarations of libvbc.so (device VBC matrix, error plumbing).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vbc.h"
+
+namespace vbc {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+const char *get_error();
+
+#define VBC_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            vbc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return (e__ == cudaErrorMemoryAllocation) ? VBC_ENOMEM : VBC_ECUDA;                 \
+        }                                                                                       \
+    } while (0)
+
+#define VBC_TRY(expr)                                                                           \
+    do {                                                                                        \
+        int rc__ = (expr);                                                                      \
+        if (rc__ != VBC_OK) return rc__;                                                        \
+    } while (0)
+
+#define VBC_FAIL(code, ...)                                                                     \
+    do {                                                                                        \
+        vbc::set_error(__VA_ARGS__);                                                            \
+        return (code);                                                                          \
+    } while (0)
+
+static inline size_t vt_size(int vt) { return vt == VBC_F64 ? 8 : 4; }
+static inline size_t it_size(int it) { return it == VBC_I64 ? 8 : 4; }
+
+// ---- device layout --------------------------------------------------------------------------
+// One entry per stripe boundary (L+1 entries), 0-based.  16 bytes so one 128-bit load fetches it.
+struct __align__(16) StripeMeta {
+    long long ofs; // element offset of the stripe's first value in `val`
+    int pos;       // first descriptor of the stripe in `desc`
+    int col;       // first column of the stripe (Φ.spl[l] - 1)
+};
+
+enum DescMode {
+    DESC_ROWS = 0,   // desc[t] = 0-based x index of stored row t (1D; 2D with non-uniform part heights, expanded)
+    DESC_BLOCKS = 1  // desc[Q] = 0-based first x index of block Q; every part has height u0 (the last may be shorter)
+};
+
+} // namespace vbc
+
+struct vbc_mat {
+    int vt = VBC_F64, it = VBC_I64, ndim = 1, device = 0;
+    int64_t m = 0, n = 0, K = 0, L = 0;
+    int U = 0, W = 0;
+    int64_t nidx = 0, nval = 0;
+    // canonical arrays, device copies of the reference struct fields (1-based, Ti typed)
+    void *d_pi_spl = nullptr, *d_phi_spl = nullptr, *d_pos = nullptr, *d_idx = nullptr, *d_ofs = nullptr;
+    void *d_val = nullptr; // nval values + zero pad
+    // compact layout read by the multiply kernels
+    vbc::StripeMeta *d_meta = nullptr; // L+1
+    int *d_desc = nullptr;             // ndesc
+    int *d_brow = nullptr;             // 2D only: first (stripe-relative) expanded row of each block
+    int64_t ndesc = 0;
+    int desc_mode = vbc::DESC_ROWS;
+    int u0 = 1; // DESC_BLOCKS: uniform part height
+    int w_uniform = 0; // >0 when every stripe has this width
+    // staging vectors for host-pointer multiplies
+    void *d_x = nullptr, *d_y = nullptr;
+    int64_t x_cap = 0, y_cap = 0;
+    cudaStream_t stream = nullptr;
+    // options
+    int opt_adj_group = 0, opt_fwd_group = 0, opt_grid_mult = 0, opt_parity = 0;
+    int sm_count = 148;
+    int64_t launches = 0;
+};
+
+struct vbc_csc {
+    int vt = VBC_F64, it = VBC_I64, device = 0;
+    int64_t m = 0, n = 0, nnz = 0;
+    void *d_colptr = nullptr, *d_rowval = nullptr, *d_nzval = nullptr;
+    void *d_x = nullptr, *d_y = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int64_t launches = 0;
+};
+
+namespace vbc {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; prev = -1; }
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// pack.cu
+int pack_from_device_csc(vbc_mat *A, const void *d_colptr, const void *d_rowval, const void *d_nzval);
+int finalize_layout(vbc_mat *A, const void *h_pi_spl /* host copy, may be null for 1D */);
+int memory_cost_device(const vbc_mat *A, int64_t *h_cost, int64_t *row_term);
+// spmv.cu
+int launch_spmv(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y);
+// csc.cu
+int launch_csc_trspmv(vbc_csc *A, const void *d_x, void *d_y);
+
+} // namespace vbc

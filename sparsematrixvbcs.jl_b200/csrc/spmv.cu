@@ -1,0 +1,464 @@
+// spmv.cu -- VBC sparse matrix-vector multiply kernels for sm_100a.
+//
+//   adjoint  y <- alpha * A' x + beta * y   replaces  mul!(y, B', x, α, β)
+//            /root/reference/src/multiply_1DVBC.jl:85-180 (_1DVBR_mul! :90-134)
+//            /root/reference/src/multiply_VBC.jl:89-192   (_VBR_mul!   :93-147)
+//   forward  y <- alpha * A x + beta * y    replaces  mul!(y, B, x, α, β)
+//            /root/reference/src/multiply_1DVBC.jl:9-83, multiply_VBC.jl:3-87
+//
+// HBM-bound streaming kernels.  A stripe l is a dense R_l x w_l row-major slab of `val`
+// (1D: R_l stored rows; 2D: the rows of its blocks, block after block), and all slabs are
+// contiguous.  G lanes (a "group", G in {8,32}) cooperate on one stripe: consecutive lanes read
+// consecutive 16-byte vectors of the slab (fully coalesced), so lane v always holds the same
+// column-vector c = v mod cpr and rows r0, r0+rps, ...  Adjoint: per-lane FMAs into EPV
+// accumulators, then a shuffle reduction over the lanes that share c -- the owner-computes
+// "row block" kernel.  Forward: per-row shuffle reduction over the cpr lanes of a row, then
+// one fp atomic add per stored row (the scatter orientation, y[idx[Q]] += ...).
+//
+// Where the reference unrolls one body per width class (le_nest over ws, util.jl:28-38), the
+// kernels here instantiate one body per (elements-per-load EPV, vectors-per-row CPR) class
+// and select it per stripe.
+#include "common.cuh"
+
+namespace vbc {
+
+// ---- vector loads ---------------------------------------------------------------------------
+template <typename Tv, int EPV> struct Ld;
+template <> struct Ld<double, 1> { static __device__ __forceinline__ void s(const double *p, double (&v)[1]) { v[0] = __ldcs(p); } };
+template <> struct Ld<double, 2> { static __device__ __forceinline__ void s(const double *p, double (&v)[2]) { const double2 t = __ldcs(reinterpret_cast<const double2 *>(p)); v[0] = t.x; v[1] = t.y; } };
+template <> struct Ld<float, 1> { static __device__ __forceinline__ void s(const float *p, float (&v)[1]) { v[0] = __ldcs(p); } };
+template <> struct Ld<float, 2> { static __device__ __forceinline__ void s(const float *p, float (&v)[2]) { const float2 t = __ldcs(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; } };
+template <> struct Ld<float, 4> { static __device__ __forceinline__ void s(const float *p, float (&v)[4]) { const float4 t = __ldcs(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
+
+__device__ __forceinline__ StripeMeta ld_meta(const StripeMeta *p)
+{
+    const int4 t = __ldg(reinterpret_cast<const int4 *>(p));
+    StripeMeta s;
+    s.ofs = (long long)(((unsigned long long)(unsigned)t.y << 32) | (unsigned)t.x);
+    s.pos = t.z;
+    s.col = t.w;
+    return s;
+}
+
+template <int G> __device__ __forceinline__ unsigned group_mask()
+{
+    if constexpr (G == 32) return 0xffffffffu;
+    else return ((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G);
+}
+
+// x-index stream of a stripe for one lane: row r0, then r0+rps, ...
+template <int MODE> struct RowWalk;
+template <> struct RowWalk<DESC_ROWS> {
+    const int *dp; int step;
+    __device__ __forceinline__ void init(const int *desc, int pos0, int r0, int rps, int, int) { dp = desc + pos0 + r0; step = rps; }
+    __device__ __forceinline__ int next() { const int xi = __ldcs(dp); dp += step; return xi; }
+};
+template <> struct RowWalk<DESC_BLOCKS> {
+    const int *bp; int di, qb, rb, u0;
+    __device__ __forceinline__ void init(const int *desc, int pos0, int r0, int rps, int u0_, int log2u)
+    {
+        u0 = u0_;
+        if (log2u >= 0) { bp = desc + pos0 + (r0 >> log2u); di = r0 & (u0 - 1); qb = rps >> log2u; rb = rps & (u0 - 1); }
+        else { bp = desc + pos0 + r0 / u0; di = r0 % u0; qb = rps / u0; rb = rps % u0; }
+    }
+    __device__ __forceinline__ int next()
+    {
+        const int xi = __ldg(bp) + di;
+        bp += qb; di += rb;
+        if (di >= u0) { di -= u0; ++bp; }
+        return xi;
+    }
+};
+
+// ---- adjoint ----------------------------------------------------------------------------------
+// CPR > 0: compile-time vectors per row (power of two, <= G).  CPR == 0: runtime cpr <= G.
+template <typename Tv, int G, int MODE, int EPV, int CPR>
+__device__ __forceinline__ void adj_stripe(const StripeMeta a, const StripeMeta b, const int w, const int lane, const unsigned gmask,
+                                           const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
+                                           Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta)
+{
+    int cpr, rps, c, r0;
+    if constexpr (CPR > 0) { cpr = CPR; rps = G / CPR; c = lane % CPR; r0 = lane / CPR; }
+    else { cpr = w / EPV; rps = G / cpr; c = lane % cpr; r0 = lane / cpr; }
+    int R;
+    if (MODE == DESC_ROWS) R = b.pos - a.pos;
+    else { const int nv = (int)(b.ofs - a.ofs); if constexpr (CPR > 0) R = nv / (CPR * EPV); else R = nv / w; }
+    const bool active = (CPR > 0) || (lane < rps * cpr);
+    Tv acc[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; e++) acc[e] = (Tv)0;
+    int r = active ? r0 : R;
+    const Tv *vp = val + a.ofs + (long long)r0 * w + c * EPV;
+    const int vstride = rps * w;
+    RowWalk<MODE> walk;
+    walk.init(desc, a.pos, r0, rps, u0, log2u);
+    constexpr int UNR = 4;
+    for (; r + (UNR - 1) * rps < R; r += UNR * rps) {
+        Tv v[UNR][EPV];
+        int xi[UNR];
+        Tv xv[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; k++) { Ld<Tv, EPV>::s(vp, v[k]); vp += vstride; }
+#pragma unroll
+        for (int k = 0; k < UNR; k++) xi[k] = walk.next();
+#pragma unroll
+        for (int k = 0; k < UNR; k++) xv[k] = __ldg(x + xi[k]);
+#pragma unroll
+        for (int k = 0; k < UNR; k++)
+#pragma unroll
+            for (int e = 0; e < EPV; e++) acc[e] = fma(v[k][e], xv[k], acc[e]);
+    }
+    for (; r < R; r += rps) {
+        Tv v[EPV];
+        Ld<Tv, EPV>::s(vp, v); vp += vstride;
+        const Tv xv = __ldg(x + walk.next());
+#pragma unroll
+        for (int e = 0; e < EPV; e++) acc[e] = fma(v[e], xv, acc[e]);
+    }
+    // sum the lanes that hold the same column-vector c
+    if constexpr (CPR > 0) {
+#pragma unroll
+        for (int d = CPR; d < G; d <<= 1)
+#pragma unroll
+            for (int e = 0; e < EPV; e++) acc[e] += __shfl_xor_sync(gmask, acc[e], d, G);
+    } else {
+        for (int d = cpr; d < G; d <<= 1)
+#pragma unroll
+            for (int e = 0; e < EPV; e++) {
+                const Tv t = __shfl_down_sync(gmask, acc[e], d, G);
+                if (lane + d < G) acc[e] += t;
+            }
+    }
+    if (lane < cpr) { // y[j + Δj] = tmp[Δj]  (multiply_1DVBC.jl:114-116), with BLAS alpha/beta
+        Tv *yp = y + a.col + lane * EPV;
+#pragma unroll
+        for (int e = 0; e < EPV; e++) yp[e] = (beta == (Tv)0) ? alpha * acc[e] : alpha * acc[e] + beta * yp[e];
+    }
+}
+
+// wide stripes (more vectors per row than lanes): one lane per column, serial over rows
+template <typename Tv, int G, int MODE>
+__device__ __noinline__ void adj_stripe_wide(const StripeMeta a, const StripeMeta b, const int w, const int lane,
+                                             const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
+                                             Tv *__restrict__ y, const int u0, const Tv alpha, const Tv beta)
+{
+    const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
+    for (int col = lane; col < w; col += G) {
+        Tv acc = (Tv)0;
+        RowWalk<MODE> walk;
+        walk.init(desc, a.pos, 0, 1, u0, -1);
+        const Tv *vp = val + a.ofs + col;
+        for (int r = 0; r < R; r++) { acc = fma(__ldcs(vp), __ldg(x + walk.next()), acc); vp += w; }
+        Tv *yp = y + a.col + col;
+        *yp = (beta == (Tv)0) ? alpha * acc : alpha * acc + beta * *yp;
+    }
+}
+
+template <typename Tv, int G, int MODE, int EPV>
+__device__ __forceinline__ void adj_dispatch_cpr(const StripeMeta a, const StripeMeta b, const int w, const int lane, const unsigned gmask,
+                                                 const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
+                                                 Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta)
+{
+    const int cpr = w / EPV;
+    if (cpr == 1) adj_stripe<Tv, G, MODE, EPV, 1>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    else if (cpr == 2) adj_stripe<Tv, G, MODE, EPV, 2>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    else if (cpr == 4) adj_stripe<Tv, G, MODE, EPV, 4>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    else if (cpr <= G) adj_stripe<Tv, G, MODE, EPV, 0>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    else adj_stripe_wide<Tv, G, MODE>(a, b, w, lane, desc, val, x, y, u0, alpha, beta);
+}
+
+template <typename Tv, int G, int MODE>
+__global__ void __launch_bounds__(256) k_spmv_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+                                                   const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ y,
+                                                   const int L, const int u0, const int log2u, const Tv alpha, const Tv beta)
+{
+    constexpr int VE = 16 / (int)sizeof(Tv);
+    const int lane = threadIdx.x % G;
+    const unsigned gmask = group_mask<G>();
+    const int ngroups = (int)((gridDim.x * blockDim.x) / G);
+    for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G); l < L; l += ngroups) {
+        const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
+        const int w = b.col - a.col;
+        if (w <= 0) continue;
+        if ((w % VE) == 0 && (a.ofs % VE) == 0)
+            adj_dispatch_cpr<Tv, G, MODE, VE>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+        else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0)
+            adj_dispatch_cpr<Tv, G, MODE, (VE == 4 ? 2 : 1)>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+        else
+            adj_dispatch_cpr<Tv, G, MODE, 1>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    }
+}
+
+// ---- forward (scatter) ------------------------------------------------------------------------
+template <typename Tv, int G, int MODE, int EPV, int CPR>
+__device__ __forceinline__ void fwd_stripe(const StripeMeta a, const StripeMeta b, const int w, const int lane, const unsigned gmask,
+                                           const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
+                                           Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha)
+{
+    int cpr, rps, c, r0;
+    if constexpr (CPR > 0) { cpr = CPR; rps = G / CPR; c = lane % CPR; r0 = lane / CPR; }
+    else { cpr = w / EPV; rps = G / cpr; c = lane % cpr; r0 = lane / cpr; }
+    int R;
+    if (MODE == DESC_ROWS) R = b.pos - a.pos;
+    else { const int nv = (int)(b.ofs - a.ofs); if constexpr (CPR > 0) R = nv / (CPR * EPV); else R = nv / w; }
+    const bool active = (CPR > 0) || (lane < rps * cpr);
+    // tmp = x[j : j+w)  (multiply_1DVBC.jl:27)
+    Tv xs[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; e++) xs[e] = active ? __ldg(x + a.col + c * EPV + e) : (Tv)0;
+    const Tv *vp = val + a.ofs + (long long)r0 * w + c * EPV;
+    const int vstride = rps * w;
+    RowWalk<MODE> walk;
+    walk.init(desc, a.pos, r0, rps, u0, log2u);
+    for (int rb = 0; rb < R; rb += rps) { // group-uniform trip count: every lane joins the shuffles
+        const bool ok = active && (rb + r0 < R);
+        Tv p = (Tv)0;
+        int xi = 0;
+        if (ok) {
+            Tv v[EPV];
+            Ld<Tv, EPV>::s(vp, v);
+            xi = walk.next();
+#pragma unroll
+            for (int e = 0; e < EPV; e++) p = fma(v[e], xs[e], p);
+        }
+        vp += vstride;
+        if constexpr (CPR > 0) {
+#pragma unroll
+            for (int d = 1; d < CPR; d <<= 1) p += __shfl_xor_sync(gmask, p, d, G);
+        } else {
+            for (int d = 1; d < cpr; d <<= 1) {
+                const Tv t = __shfl_down_sync(gmask, p, d, G);
+                if (c + d < cpr) p += t;
+            }
+        }
+        if (ok && c == 0) atomicAdd(y + xi, alpha * p); // y[idx[Q]] += ...  (multiply_1DVBC.jl:34)
+    }
+}
+
+template <typename Tv, int G, int MODE>
+__device__ __noinline__ void fwd_stripe_wide(const StripeMeta a, const StripeMeta b, const int w, const int lane, const unsigned gmask,
+                                             const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
+                                             Tv *__restrict__ y, const int u0, const Tv alpha)
+{
+    const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
+    RowWalk<MODE> walk;
+    walk.init(desc, a.pos, 0, 1, u0, -1);
+    for (int r = 0; r < R; r++) {
+        const int xi = walk.next();
+        Tv p = (Tv)0;
+        for (int col = lane; col < w; col += G) p = fma(__ldcs(val + a.ofs + (long long)r * w + col), __ldg(x + a.col + col), p);
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) p += __shfl_xor_sync(gmask, p, d, G);
+        if (lane == 0) atomicAdd(y + xi, alpha * p);
+    }
+}
+
+template <typename Tv, int G, int MODE, int EPV>
+__device__ __forceinline__ void fwd_dispatch_cpr(const StripeMeta a, const StripeMeta b, const int w, const int lane, const unsigned gmask,
+                                                 const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
+                                                 Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha)
+{
+    const int cpr = w / EPV;
+    if (cpr == 1) fwd_stripe<Tv, G, MODE, EPV, 1>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha);
+    else if (cpr == 2) fwd_stripe<Tv, G, MODE, EPV, 2>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha);
+    else if (cpr == 4) fwd_stripe<Tv, G, MODE, EPV, 4>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha);
+    else if (cpr <= G) fwd_stripe<Tv, G, MODE, EPV, 0>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha);
+    else fwd_stripe_wide<Tv, G, MODE>(a, b, w, lane, gmask, desc, val, x, y, u0, alpha);
+}
+
+template <typename Tv, int G, int MODE>
+__global__ void __launch_bounds__(256) k_spmv_fwd(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+                                                   const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ y,
+                                                   const int L, const int u0, const int log2u, const Tv alpha)
+{
+    constexpr int VE = 16 / (int)sizeof(Tv);
+    const int lane = threadIdx.x % G;
+    const unsigned gmask = group_mask<G>();
+    const int ngroups = (int)((gridDim.x * blockDim.x) / G);
+    for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G); l < L; l += ngroups) {
+        const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
+        const int w = b.col - a.col;
+        if (w <= 0 || b.ofs == a.ofs) continue;
+        if ((w % VE) == 0 && (a.ofs % VE) == 0)
+            fwd_dispatch_cpr<Tv, G, MODE, VE>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha);
+        else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0)
+            fwd_dispatch_cpr<Tv, G, MODE, (VE == 4 ? 2 : 1)>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha);
+        else
+            fwd_dispatch_cpr<Tv, G, MODE, 1>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha);
+    }
+}
+
+// y <- beta * y (beta == 0 stores zeros without reading y)   multiply_1DVBC.jl:50-52
+template <typename Tv>
+__global__ void __launch_bounds__(256) k_scale(Tv *__restrict__ y, const int64_t len, const Tv beta)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = (beta == (Tv)0) ? (Tv)0 : beta * y[i];
+}
+
+// ---- parity mode: multiply straight from the canonical Ti arrays, the reference's loops verbatim
+// (one thread per (stripe, column) for the adjoint; one thread per stripe for the forward).
+template <typename Tv, typename Ti>
+__global__ void __launch_bounds__(128) k_parity_adj(const Ti *__restrict__ phi, const Ti *__restrict__ pi, const Ti *__restrict__ pos,
+                                                     const Ti *__restrict__ idx, const Ti *__restrict__ ofs, const Tv *__restrict__ val,
+                                                     const Tv *__restrict__ x, Tv *__restrict__ y, const int64_t n, const int64_t L,
+                                                     const int *__restrict__ c2s_unused, const int ndim, const Tv alpha, const Tv beta)
+{
+    (void)c2s_unused;
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const int64_t j = (int64_t)phi[l] - 1, w = (int64_t)phi[l + 1] - 1 - j;
+    for (int64_t dj = 0; dj < w; dj++) {
+        Tv tmp = (Tv)0;
+        int64_t q = (int64_t)ofs[l] - 1;
+        for (int64_t Q = (int64_t)pos[l] - 1; Q < (int64_t)pos[l + 1] - 1; Q++) {
+            if (ndim == 1) { tmp = fma(val[q + dj], x[(int64_t)idx[Q] - 1], tmp); q += w; }
+            else {
+                const int64_t k = (int64_t)idx[Q] - 1, i = (int64_t)pi[k] - 1, u = (int64_t)pi[k + 1] - 1 - i;
+                for (int64_t di = 0; di < u; di++) tmp = fma(val[q + w * di + dj], x[i + di], tmp);
+                q += u * w;
+            }
+        }
+        y[j + dj] = (beta == (Tv)0) ? alpha * tmp : alpha * tmp + beta * y[j + dj];
+    }
+    (void)n;
+}
+
+template <typename Tv, typename Ti>
+__global__ void __launch_bounds__(128) k_parity_fwd(const Ti *__restrict__ phi, const Ti *__restrict__ pi, const Ti *__restrict__ pos,
+                                                     const Ti *__restrict__ idx, const Ti *__restrict__ ofs, const Tv *__restrict__ val,
+                                                     const Tv *__restrict__ x, Tv *__restrict__ y, const int64_t L, const int ndim, const Tv alpha)
+{
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const int64_t j = (int64_t)phi[l] - 1, w = (int64_t)phi[l + 1] - 1 - j;
+    int64_t q = (int64_t)ofs[l] - 1;
+    for (int64_t Q = (int64_t)pos[l] - 1; Q < (int64_t)pos[l + 1] - 1; Q++) {
+        int64_t i, u;
+        if (ndim == 1) { i = (int64_t)idx[Q] - 1; u = 1; }
+        else { const int64_t k = (int64_t)idx[Q] - 1; i = (int64_t)pi[k] - 1; u = (int64_t)pi[k + 1] - 1 - i; }
+        for (int64_t di = 0; di < u; di++) {
+            Tv s = (Tv)0;
+            for (int64_t dj = 0; dj < w; dj++) s = fma(val[q + w * di + dj], x[j + dj], s);
+            atomicAdd(y + i + di, alpha * s);
+        }
+        q += u * w;
+    }
+}
+
+// ---- launchers ------------------------------------------------------------------------------
+static int ilog2_exact(int v)
+{
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int l = 0;
+    while ((1 << l) < v) l++;
+    return l;
+}
+
+static int auto_group(const vbc_mat *A)
+{
+    // ~ (bytes of an average stripe) / 16 B vectors; aim for >= 4 vectors per lane
+    if (A->L == 0) return 8;
+    const double vec_per_stripe = (double)A->nval * (double)vt_size(A->vt) / 16.0 / (double)A->L;
+    return vec_per_stripe >= 160.0 ? 32 : 8;
+}
+
+template <typename Tv, int G, int MODE>
+static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
+{
+    int occ = 0;
+    VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_adj<Tv, G, MODE>, 256, 0));
+    if (occ < 1) occ = 1;
+    if (A->opt_grid_mult > 0) occ = A->opt_grid_mult;
+    int64_t grid = (int64_t)A->sm_count * occ;
+    const int64_t need = (A->L * G + 255) / 256;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    k_spmv_adj<Tv, G, MODE><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, y, (int)A->L, A->u0, ilog2_exact(A->u0), alpha, beta);
+    A->launches++;
+    VBC_CUDA(cudaGetLastError());
+    return VBC_OK;
+}
+
+template <typename Tv, int G, int MODE>
+static int launch_fwd_t(vbc_mat *A, Tv alpha, const Tv *x, Tv *y)
+{
+    int occ = 0;
+    VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_fwd<Tv, G, MODE>, 256, 0));
+    if (occ < 1) occ = 1;
+    if (A->opt_grid_mult > 0) occ = A->opt_grid_mult;
+    int64_t grid = (int64_t)A->sm_count * occ;
+    const int64_t need = (A->L * G + 255) / 256;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    k_spmv_fwd<Tv, G, MODE><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, y, (int)A->L, A->u0, ilog2_exact(A->u0), alpha);
+    A->launches++;
+    VBC_CUDA(cudaGetLastError());
+    return VBC_OK;
+}
+
+template <typename Tv>
+static int scale_y(vbc_mat *A, Tv *y, int64_t len, Tv beta)
+{
+    if (len == 0 || beta == (Tv)1) return VBC_OK;
+    if (beta == (Tv)0) { VBC_CUDA(cudaMemsetAsync(y, 0, sizeof(Tv) * (size_t)len, A->stream)); return VBC_OK; }
+    int64_t g = (len + 255) / 256;
+    if (g > (int64_t)A->sm_count * 8) g = (int64_t)A->sm_count * 8;
+    k_scale<Tv><<<(unsigned)g, 256, 0, A->stream>>>(y, len, beta);
+    A->launches++;
+    VBC_CUDA(cudaGetLastError());
+    return VBC_OK;
+}
+
+template <typename Tv, typename Ti>
+static int launch_parity(vbc_mat *A, int trans, Tv alpha, const Tv *x, Tv beta, Tv *y)
+{
+    const unsigned g = (unsigned)((A->L + 127) / 128 > 0 ? (A->L + 127) / 128 : 1);
+    if (trans) {
+        if (A->L > 0) {
+            k_parity_adj<Tv, Ti><<<g, 128, 0, A->stream>>>((const Ti *)A->d_phi_spl, (const Ti *)A->d_pi_spl, (const Ti *)A->d_pos, (const Ti *)A->d_idx,
+                                                           (const Ti *)A->d_ofs, (const Tv *)A->d_val, x, y, A->n, A->L, nullptr, A->ndim, alpha, beta);
+            A->launches++;
+        }
+    } else {
+        VBC_TRY(scale_y<Tv>(A, y, A->m, beta));
+        if (A->L > 0) {
+            k_parity_fwd<Tv, Ti><<<g, 128, 0, A->stream>>>((const Ti *)A->d_phi_spl, (const Ti *)A->d_pi_spl, (const Ti *)A->d_pos, (const Ti *)A->d_idx,
+                                                           (const Ti *)A->d_ofs, (const Tv *)A->d_val, x, y, A->L, A->ndim, alpha);
+            A->launches++;
+        }
+    }
+    VBC_CUDA(cudaGetLastError());
+    return VBC_OK;
+}
+
+template <typename Tv>
+static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, double beta_d, void *yv)
+{
+    const Tv alpha = (Tv)alpha_d, beta = (Tv)beta_d;
+    const Tv *x = (const Tv *)xv;
+    Tv *y = (Tv *)yv;
+    if (A->opt_parity) {
+        if (A->it == VBC_I64) return launch_parity<Tv, int64_t>(A, trans, alpha, x, beta, y);
+        return launch_parity<Tv, int32_t>(A, trans, alpha, x, beta, y);
+    }
+    const bool rows = A->desc_mode == DESC_ROWS;
+    if (trans) {
+        if (A->L == 0) return VBC_OK; // n == 0: nothing to write
+        int G = A->opt_adj_group ? A->opt_adj_group : auto_group(A);
+        if (G >= 32) return rows ? launch_adj_t<Tv, 32, DESC_ROWS>(A, alpha, x, beta, y) : launch_adj_t<Tv, 32, DESC_BLOCKS>(A, alpha, x, beta, y);
+        return rows ? launch_adj_t<Tv, 8, DESC_ROWS>(A, alpha, x, beta, y) : launch_adj_t<Tv, 8, DESC_BLOCKS>(A, alpha, x, beta, y);
+    }
+    VBC_TRY(scale_y<Tv>(A, y, A->m, beta));
+    if (A->L == 0 || A->nval == 0) return VBC_OK;
+    int G = A->opt_fwd_group ? A->opt_fwd_group : auto_group(A);
+    if (G >= 32) return rows ? launch_fwd_t<Tv, 32, DESC_ROWS>(A, alpha, x, y) : launch_fwd_t<Tv, 32, DESC_BLOCKS>(A, alpha, x, y);
+    return rows ? launch_fwd_t<Tv, 8, DESC_ROWS>(A, alpha, x, y) : launch_fwd_t<Tv, 8, DESC_BLOCKS>(A, alpha, x, y);
+}
+
+int launch_spmv(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y)
+{
+    return A->vt == VBC_F64 ? launch_spmv_t<double>(A, trans, alpha, d_x, beta, d_y) : launch_spmv_t<float>(A, trans, alpha, d_x, beta, d_y);
+}
+
+} // namespace vbc

@@ -1,0 +1,125 @@
+"""Synthetic block-structured matrices for the benchmark configs (host side, numpy).
+
+Modelled on the reference's own generators for its time-model experiments
+(/root/reference/src/costs.jl:63-85 1D, :200-222 2D): dense w-wide row segments / u x w blocks at
+distinct (row part, stripe) positions, values `rand(Tv)` in [0, 1), partition `EquiChunker`.
+Values come from a counter-based hash (splitmix64 of seed and the entry's (row, col)), so any
+slab of the matrix can be regenerated independently (by another rank, or on the device) and
+always gives the same numbers.  Seed default 0xDEADBEEF = the reference's test seed
+(test/runtests.jl:11).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .partition import SparseMatrixCSC, SplitPartition
+
+SEED = 0xDEADBEEF
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(z):
+    """Vectorised splitmix64 finaliser on uint64 arrays."""
+    with np.errstate(over="ignore"):
+        z = (z + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return z ^ (z >> np.uint64(31))
+
+
+def entry_values(rows0, cols0, n, seed=SEED, dtype=np.float64):
+    """Value of entry (row, col) (0-based): uniform in [0, 1) with 24 (f32) / 53 (f64) random bits."""
+    with np.errstate(over="ignore"):
+        key = rows0.astype(np.uint64) * np.uint64(n) + cols0.astype(np.uint64)
+        h = splitmix64(key ^ np.uint64(seed))
+    if np.dtype(dtype) == np.float32:
+        return ((h >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+    return (h >> np.uint64(11)).astype(np.float64) * (2.0 ** -53)
+
+
+def vector(n, seed=1, dtype=np.float64):
+    """Deterministic dense vector in [0, 1)."""
+    return entry_values(np.arange(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64), 1, seed=seed ^ 0x5851F42D, dtype=dtype)
+
+
+def _csc_from_stripe_blocks(K, L, u, w, blk_stripe_counts, blk_parts, seed, dtype, ti):
+    """Uniform u x w blocks; stripe l owns blk_parts[bpos[l]:bpos[l+1]] (ascending part ids)."""
+    m, n = K * u, L * w
+    nb = blk_stripe_counts.astype(np.int64)
+    bpos = np.concatenate([[0], np.cumsum(nb)])
+    # rows of a stripe, stripe-major: every block contributes u consecutive rows
+    rows_stripe = (blk_parts.astype(np.int64)[:, None] * u + np.arange(u, dtype=np.int64)[None, :]).reshape(-1)
+    col_stripe = np.repeat(np.arange(L, dtype=np.int64), w)          # stripe of each column
+    col_len = (nb * u)[col_stripe]                                     # nnz per column
+    colptr0 = np.concatenate([[0], np.cumsum(col_len)])
+    nnz = int(colptr0[-1])
+    seg_start = (bpos[:-1] * u)[col_stripe]                            # start of the stripe's row list
+    gather = np.repeat(seg_start - colptr0[:-1], col_len) + np.arange(nnz, dtype=np.int64)
+    rowval0 = rows_stripe[gather]
+    del gather
+    cols0 = np.repeat(np.arange(n, dtype=np.int64), col_len)
+    nzval = entry_values(rowval0, cols0, n, seed=seed, dtype=dtype)
+    del cols0
+    A = SparseMatrixCSC(m, n, (colptr0 + 1).astype(ti), (rowval0 + 1).astype(ti), nzval)
+    Pi = SplitPartition(np.arange(1, m + 2, u, dtype=ti))
+    Phi = SplitPartition(np.arange(1, n + 2, w, dtype=ti))
+    return A, Pi, Phi
+
+
+def fem_stencil_offsets(S=63):
+    """13-offset block stencil {0, ±1, ±2, ±S, ±(S±1), ±S²} of SURVEY.md 8(d) config C2 (a 3-D
+    grid numbering with S³ ≈ K)."""
+    offs = [0, 1, -1, 2, -2, S, -S, S + 1, -(S + 1), S - 1, -(S - 1), S * S, -(S * S)]
+    return np.array(sorted(offs), dtype=np.int64)
+
+
+def banded_blocks(K, L, u, w, offsets, seed=SEED, dtype=np.float64, ti=np.int64):
+    """Block-banded matrix: stripe l has a dense u x w block at every row part l*K//L + δ,
+    δ in `offsets`, clipped to [0, K).  Returns (A::SparseMatrixCSC, Π, Φ) with Π = Equi(u),
+    Φ = Equi(w)."""
+    offsets = np.array(sorted(set(int(o) for o in offsets)), dtype=np.int64)
+    center = (np.arange(L, dtype=np.int64) * K) // L
+    kk = center[:, None] + offsets[None, :]
+    ok = (kk >= 0) & (kk < K)
+    counts = ok.sum(axis=1)
+    parts = kk[ok]  # row-major flatten keeps each stripe's part ids ascending
+    return _csc_from_stripe_blocks(K, L, u, w, counts, parts, seed, dtype, ti)
+
+
+def random_blocks(K, L, u, w, per_stripe, seed=SEED, dtype=np.float64, ti=np.int64):
+    """The reference's autotuner generator (costs.jl:63-85 / :200-222): `per_stripe` distinct
+    random row parts in every stripe, dense u x w blocks.  u = 1 gives the 1D generator."""
+    rng = np.random.default_rng(seed)
+    per_stripe = min(per_stripe, K)
+    if per_stripe * 4 <= K:
+        # rejection-free for sparse stripes: sample, sort, fix duplicates by re-drawing whole rows
+        parts = np.sort(rng.integers(0, K, size=(L, per_stripe), dtype=np.int64), axis=1)
+        bad = np.flatnonzero((np.diff(parts, axis=1) == 0).any(axis=1))
+        while len(bad):
+            parts[bad] = np.sort(rng.integers(0, K, size=(len(bad), per_stripe), dtype=np.int64), axis=1)
+            bad = bad[(np.diff(parts[bad], axis=1) == 0).any(axis=1)]
+    else:
+        parts = np.stack([np.sort(rng.choice(K, size=per_stripe, replace=False)) for _ in range(L)]).astype(np.int64)
+    counts = np.full(L, per_stripe, dtype=np.int64)
+    return _csc_from_stripe_blocks(K, L, u, w, counts, parts.reshape(-1), seed, dtype, ti)
+
+
+def config_c1(dtype=np.float64, ti=np.int64):
+    """C1: 1D-VBC, m = n = 10 000, W = 8, 100 distinct random rows per stripe => nnz = 1 000 000."""
+    A, _, Phi = random_blocks(10_000, 1_250, 1, 8, 100, dtype=dtype, ti=ti)
+    return A, Phi
+
+
+def config_c2(n=1_000_000, u=4, w=4, S=63, dtype=np.float64, ti=np.int64, seed=SEED):
+    """C2: 2D-VBC, m = n (default 1 000 000), U = W = 4, 13-block FEM-like stencil => nnz ≈ 52 M."""
+    K, L = n // u, n // w
+    return banded_blocks(K, L, u, w, fem_stencil_offsets(S), seed=seed, dtype=dtype, ti=ti)
+
+
+def variable_partition(n, w_max, seed, ti=np.int64, w_min=2):
+    """iid widths in [w_min, w_max] (config C2v: variable blocks)."""
+    rng = np.random.default_rng(seed)
+    widths = rng.integers(w_min, w_max + 1, size=n // w_min + 2)
+    spl = np.concatenate([[1], 1 + np.cumsum(widths)])
+    spl = spl[spl <= n]
+    return SplitPartition(np.append(spl, n + 1).astype(ti) if spl[-1] != n + 1 else spl.astype(ti))
