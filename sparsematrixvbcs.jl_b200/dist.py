@@ -1,0 +1,126 @@
+"""Row-block partitioning of the adjoint multiply across the GPUs of one box (north_star (e)).
+
+In the adjoint ("row block") orientation stripe l exclusively owns y[Φ.spl[l] : Φ.spl[l+1]) and
+reads all of x (multiply_1DVBC.jl:172-175, :114-116), so stripes shard with no data-path
+collective inside one multiply.  An iterated square operator x_{t+1} <- A' x_t needs one exchange
+per iteration: every rank's y slice must reach every rank's x -- an all-gather over NVLink.
+
+  * stripes are split into P contiguous ranges at the P-quantiles of the prefix sum of the
+    reference's own memory cost model (costs.jl:10 1D, :140 2D) -- bytes streamed per rank;
+  * slices have unequal lengths, so x lives in PADDED coordinates: rank r's slice occupies
+    [r*S, r*S + len_r) with S = max_r len_r.  The row indices of each rank's slab are remapped
+    to these coordinates on the host before the pack kernel runs (they are only gather
+    indices), which makes the exchange a plain equal-size NCCL all-gather
+    (torch.distributed.all_gather_into_tensor) straight from the kernel's y into everyone's x,
+    with no staging copy.
+
+One process per GPU (torchrun); torch.distributed is plumbing only -- the multiply is libvbc's.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .partition import SparseMatrixCSC, SplitPartition
+
+
+def stripe_costs(phi_widths, units_per_stripe, vals_per_stripe, tv_size, ti_size):
+    """Reference memory model per stripe: 3|Ti| + units*|Ti| + values*|Tv| (costs.jl:10 with
+    units = rows; costs.jl:140 with units = blocks, values = sum u*w)."""
+    del phi_widths
+    return 3 * ti_size + np.asarray(units_per_stripe, dtype=np.int64) * ti_size + np.asarray(vals_per_stripe, dtype=np.int64) * tv_size
+
+
+def split_by_cost(cost, P):
+    """Boundaries b[0..P] of P contiguous stripe ranges with (nearly) equal total cost."""
+    cost = np.asarray(cost, dtype=np.int64)
+    L = len(cost)
+    pre = np.concatenate([[0], np.cumsum(cost)])
+    total = pre[-1]
+    b = [0]
+    for r in range(1, P):
+        target = total * r / P
+        k = int(np.searchsorted(pre, target, side="left"))
+        # pick the boundary closest to the target, keep ranges monotone
+        if k > 0 and abs(pre[k - 1] - target) <= abs(pre[min(k, L)] - target):
+            k -= 1
+        b.append(min(max(k, b[-1]), L))
+    b.append(L)
+    return np.array(b, dtype=np.int64)
+
+
+class PaddedLayout:
+    """Map between global vector indices and the padded, per-rank-slice coordinates."""
+
+    def __init__(self, col_bounds):
+        self.col_bounds = np.asarray(col_bounds, dtype=np.int64)  # P+1 global element boundaries (0-based)
+        self.P = len(self.col_bounds) - 1
+        self.lens = np.diff(self.col_bounds)
+        self.S = int(self.lens.max()) if self.P else 0
+        self.padded_len = self.S * self.P
+
+    def to_padded(self, i0):
+        """global 0-based index array -> padded index array"""
+        r = np.searchsorted(self.col_bounds, i0, side="right") - 1
+        return r * self.S + (i0 - self.col_bounds[r])
+
+    def scatter(self, x_global):
+        xp = np.zeros(self.padded_len, dtype=x_global.dtype)
+        for r in range(self.P):
+            xp[r * self.S: r * self.S + self.lens[r]] = x_global[self.col_bounds[r]:self.col_bounds[r + 1]]
+        return xp
+
+    def gather(self, x_padded):
+        return np.concatenate([x_padded[r * self.S: r * self.S + self.lens[r]] for r in range(self.P)])
+
+
+def remap_rows_to_padded(A: SparseMatrixCSC, layout: PaddedLayout, u=1):
+    """Slab CSC (global rows) -> slab CSC whose rows live in padded coordinates.  Row parts of
+    height u stay contiguous because slice boundaries are multiples of the part height."""
+    rows0 = A.rowval.astype(np.int64) - 1
+    new_rows = layout.to_padded(rows0) + 1
+    return SparseMatrixCSC(layout.padded_len, A.n, A.colptr, new_rows.astype(A.colptr.dtype), A.nzval)
+
+
+def padded_row_partition(layout: PaddedLayout, u, ti):
+    """Π over the padded row space: Equi(u) inside every rank slice (slice starts are part-aligned)."""
+    assert layout.S % u == 0 and np.all(layout.col_bounds[:-1] % u == 0)
+    return SplitPartition(np.arange(1, layout.padded_len + 2, u, dtype=ti))
+
+
+class RowPartitionedOperator:
+    """One rank's share of the iterated adjoint multiply x <- A' x.
+
+    local   : this rank's device matrix (rows in padded coordinates, columns = its stripes)
+    layout  : PaddedLayout of the global vector
+    Buffers : x (padded_len) and y_pad (S) are torch CUDA tensors; step() runs the local SpMV
+              into y_pad and all-gathers y_pad from every rank into x.
+    """
+
+    def __init__(self, local, layout: PaddedLayout, rank, world, dtype):
+        import torch
+        self.local, self.layout, self.rank, self.world = local, layout, rank, world
+        self.x = torch.zeros(layout.padded_len, dtype=dtype, device="cuda")
+        self.y_pad = torch.zeros(layout.S, dtype=dtype, device="cuda")
+        self.n_local = int(layout.lens[rank])
+
+    def set_x(self, x_global_np):
+        import torch
+        self.x.copy_(torch.from_numpy(self.layout.scatter(x_global_np)))
+
+    def local_multiply(self):
+        from .matrix import mul_
+        mul_(self.y_pad[: self.n_local], self.local.T, self.x)
+
+    def exchange(self):
+        import torch.distributed as dist
+        if self.world == 1:
+            self.x[: self.layout.S].copy_(self.y_pad)
+        else:
+            dist.all_gather_into_tensor(self.x, self.y_pad)
+
+    def step(self):
+        self.local_multiply()
+        self.exchange()
+
+    def x_global(self):
+        return self.layout.gather(self.x.cpu().numpy())

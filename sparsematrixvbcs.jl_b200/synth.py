@@ -42,9 +42,12 @@ def vector(n, seed=1, dtype=np.float64):
     return entry_values(np.arange(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64), 1, seed=seed ^ 0x5851F42D, dtype=dtype)
 
 
-def _csc_from_stripe_blocks(K, L, u, w, blk_stripe_counts, blk_parts, seed, dtype, ti):
-    """Uniform u x w blocks; stripe l owns blk_parts[bpos[l]:bpos[l+1]] (ascending part ids)."""
+def _csc_from_stripe_blocks(K, L, u, w, blk_stripe_counts, blk_parts, seed, dtype, ti, col0=0, n_global=None):
+    """Uniform u x w blocks; stripe l owns blk_parts[bpos[l]:bpos[l+1]] (ascending part ids).
+    col0 / n_global: the L stripes are a slab starting at global column col0 of an n_global-column
+    matrix (values are hashed with GLOBAL coordinates, so slabs agree with the full matrix)."""
     m, n = K * u, L * w
+    n_global = n if n_global is None else n_global
     nb = blk_stripe_counts.astype(np.int64)
     bpos = np.concatenate([[0], np.cumsum(nb)])
     # rows of a stripe, stripe-major: every block contributes u consecutive rows
@@ -58,7 +61,7 @@ def _csc_from_stripe_blocks(K, L, u, w, blk_stripe_counts, blk_parts, seed, dtyp
     rowval0 = rows_stripe[gather]
     del gather
     cols0 = np.repeat(np.arange(n, dtype=np.int64), col_len)
-    nzval = entry_values(rowval0, cols0, n, seed=seed, dtype=dtype)
+    nzval = entry_values(rowval0, cols0 + col0, n_global, seed=seed, dtype=dtype)
     del cols0
     A = SparseMatrixCSC(m, n, (colptr0 + 1).astype(ti), (rowval0 + 1).astype(ti), nzval)
     Pi = SplitPartition(np.arange(1, m + 2, u, dtype=ti))
@@ -73,17 +76,19 @@ def fem_stencil_offsets(S=63):
     return np.array(sorted(offs), dtype=np.int64)
 
 
-def banded_blocks(K, L, u, w, offsets, seed=SEED, dtype=np.float64, ti=np.int64):
+def banded_blocks(K, L, u, w, offsets, seed=SEED, dtype=np.float64, ti=np.int64, stripes=None):
     """Block-banded matrix: stripe l has a dense u x w block at every row part l*K//L + δ,
     δ in `offsets`, clipped to [0, K).  Returns (A::SparseMatrixCSC, Π, Φ) with Π = Equi(u),
-    Φ = Equi(w)."""
+    Φ = Equi(w).  stripes=(l0, l1): only the column slab of stripes l0 <= l < l1 (A then has
+    (l1-l0)*w columns and all K*u rows) -- what one rank of the row-partitioned multiply owns."""
     offsets = np.array(sorted(set(int(o) for o in offsets)), dtype=np.int64)
-    center = (np.arange(L, dtype=np.int64) * K) // L
+    l0, l1 = (0, L) if stripes is None else stripes
+    center = (np.arange(l0, l1, dtype=np.int64) * K) // L
     kk = center[:, None] + offsets[None, :]
     ok = (kk >= 0) & (kk < K)
     counts = ok.sum(axis=1)
     parts = kk[ok]  # row-major flatten keeps each stripe's part ids ascending
-    return _csc_from_stripe_blocks(K, L, u, w, counts, parts, seed, dtype, ti)
+    return _csc_from_stripe_blocks(K, l1 - l0, u, w, counts, parts, seed, dtype, ti, col0=l0 * w, n_global=L * w)
 
 
 def random_blocks(K, L, u, w, per_stripe, seed=SEED, dtype=np.float64, ti=np.int64):
@@ -110,10 +115,10 @@ def config_c1(dtype=np.float64, ti=np.int64):
     return A, Phi
 
 
-def config_c2(n=1_000_000, u=4, w=4, S=63, dtype=np.float64, ti=np.int64, seed=SEED):
+def config_c2(n=1_000_000, u=4, w=4, S=63, dtype=np.float64, ti=np.int64, seed=SEED, stripes=None):
     """C2: 2D-VBC, m = n (default 1 000 000), U = W = 4, 13-block FEM-like stencil => nnz ≈ 52 M."""
     K, L = n // u, n // w
-    return banded_blocks(K, L, u, w, fem_stencil_offsets(S), seed=seed, dtype=dtype, ti=ti)
+    return banded_blocks(K, L, u, w, fem_stencil_offsets(S), seed=seed, dtype=dtype, ti=ti, stripes=stripes)
 
 
 def variable_partition(n, w_max, seed, ti=np.int64, w_min=2):

@@ -1,0 +1,81 @@
+"""CPU-only: libvbc.so loads and exports exactly the symbols include/vbc.h declares; the host
+layer fails loudly (no CPU fallback) when the CUDA library is missing."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import vbc_b200 as vb
+from conftest import ROOT
+from vbc_b200 import _lib
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "vbc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vbc_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_matches_binding_list():
+    assert header_functions() == sorted(_lib.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(vb.LIB_PATH), _lib.build_hint()
+    out = subprocess.run(["nm", "-D", "--defined-only", vb.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (vbc_[a-z_0-9]+)$", out, flags=re.M))
+    assert exported == set(header_functions())
+    L = _lib.lib()
+    for name in _lib.SYMBOLS:
+        assert hasattr(L, name)
+    assert L.vbc_version() >= 100
+    assert isinstance(L.vbc_last_error(), bytes)
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "--list-elf", vb.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on a CPU-only box."""
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    import numpy as np
+    one = np.array([1], dtype=np.int64)
+    p = ctypes.c_void_p(one.ctypes.data)
+    # ArgumentError: m must be >= 0  (SparseMatrixVBCs.jl:47)
+    rc = L.vbc_pack_csc(ctypes.byref(h), _lib.VBC_F64, _lib.VBC_I64, -1, 0, 0, 4, p, p, p, None, 0, p, 0, 0)
+    assert rc == _lib.VBC_EARG and b"rows" in L.vbc_last_error()
+    # ArgumentError: W must be > 0  (SparseMatrixVBCs.jl:50)
+    rc = L.vbc_pack_csc(ctypes.byref(h), _lib.VBC_F64, _lib.VBC_I64, 0, 0, 0, 0, p, p, p, None, 0, p, 0, 0)
+    assert rc == _lib.VBC_EARG and b"W must be > 0" in L.vbc_last_error()
+    # ArgumentError: U must be > 0  (SparseMatrixVBCs.jl:78) -- 2D because pi_spl != NULL
+    rc = L.vbc_pack_csc(ctypes.byref(h), _lib.VBC_F64, _lib.VBC_I64, 0, 0, 0, 4, p, p, p, p, 0, p, 0, 0)
+    assert rc == _lib.VBC_EARG and b"U must be > 0" in L.vbc_last_error()
+    with pytest.raises(vb.ArgumentError):
+        _lib.check(rc)
+    assert L.vbc_spmv(None, 0, 1.0, None, 0, 0.0, None, 0, 0) == _lib.VBC_EARG
+    with pytest.raises(vb.ArgumentError):
+        vb.SparseMatrix1DVBC[4.0]  # "W must be an Int"  SparseMatrixVBCs.jl:49
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(ROOT, "does_not_exist", "libvbc.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under the product package may reference it."""
+    pkg = os.path.join(ROOT, "sparsematrixvbcs.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text, f

@@ -1,0 +1,296 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libvbc.so) against the CPU oracle.
+
+Bar (BASELINE.json north_star): packed index arrays bit-exact; y within 1e-12 relative (Float64) /
+1e-5 (Float32), measured componentwise against |A||x| because summation order differs.
+"""
+import numpy as np
+import pytest
+
+import oracle
+import vbc_b200 as vb
+from conftest import SIZES, sprand
+from vbc_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}
+
+
+def parts_1d(A):
+    return [("strict4", vb.pack_stripe(A, vb.StrictChunker(4))), ("equi4", vb.pack_stripe(A, vb.EquiChunker(4))),
+            ("rand4", vb.pack_stripe(A, vb.RandomChunker(4, seed=A.nnz)))]
+
+
+def parts_2d(A):
+    out = []
+    for name, ch in (("strict4", vb.StrictChunker(4)), ("equi4", vb.EquiChunker(4)), ("rand4", vb.RandomChunker(4, seed=A.nnz + 1))):
+        pi, phi = vb.pack_plaid(A, vb.AlternatingPacker(ch, ch))
+        out.append((name, pi, phi))
+    return out
+
+
+def assert_packed_equal(B, H):
+    d = B.download()
+    for f in ("pos", "idx", "ofs"):
+        assert d[f].dtype == getattr(H, f).dtype
+        assert np.array_equal(d[f], getattr(H, f)), f
+    assert d["val"].dtype == H.val.dtype
+    assert d["val"].tobytes() == H.val.tobytes(), "val (bitwise)"
+
+
+def onehot_check(A, B, H):
+    """test/runtests.jl:29-53 / :63-87 with the device matrix in place of B; also == the oracle."""
+    m, n = A.shape
+    tv = A.nzval.dtype
+    x = np.zeros(n, dtype=tv)
+    y = np.empty(m, dtype=tv)
+    for j in range(n):
+        x[j] = 1
+        y.fill(7)
+        vb.mul_(y, B, x, True, False)
+        assert np.array_equal(y, oracle.csc_spmv(m, n, A.colptr, A.rowval, A.nzval, x)), f"forward col {j + 1}"
+        x[j] = 0
+    x = np.zeros(m, dtype=tv)
+    y = np.empty(n, dtype=tv)
+    for i in range(m):
+        x[i] = 1
+        y.fill(7)
+        vb.mul_(y, B.T, x, True, False)
+        assert np.array_equal(y, oracle.csc_trspmv(m, n, A.colptr, A.rowval, A.nzval, x)), f"adjoint row {i + 1}"
+        assert np.array_equal(y, oracle.mul(H, x, trans=True)), f"adjoint row {i + 1} vs oracle"
+        x[i] = 0
+
+
+def randx_check(A, B, H, rng):
+    tv = A.nzval.dtype
+    tol = TOL[np.dtype(tv)]
+    S = A.to_scipy().astype(np.float64)
+    absS = abs(S)
+    for trans in (False, True):
+        xlen, ylen = (A.m, A.n) if trans else (A.n, A.m)
+        x = rng.random(xlen).astype(tv)
+        y = vb.mul_(np.empty(ylen, dtype=tv), B.T if trans else B, x)
+        yo = oracle.mul(H, x, trans=trans)
+        Sx = (S.T if trans else S) @ x.astype(np.float64)
+        bound = (absS.T if trans else absS) @ np.abs(x.astype(np.float64))
+        assert np.all(np.abs(y - Sx) <= 4 * tol * bound + 1e-300), "vs exact product"
+        assert np.all(np.abs(y - yo) <= 8 * tol * bound + 1e-300), "vs oracle"
+
+
+@pytest.mark.parametrize("ti", [np.int64, np.int32])
+@pytest.mark.parametrize("tv", [np.float64, np.float32])
+def test_fixtures_pack_bitexact_and_multiply(fixtures, tv, ti):
+    rng = np.random.default_rng(11)
+    for name, A64 in fixtures.items():
+        A = A64.astype(tv, ti)
+        for pname, phi in parts_1d(A):
+            H = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 4)
+            B = vb.SparseMatrix1DVBC[4](A, phi)
+            assert B.shape == A.shape and B.L == H.L
+            assert_packed_equal(B, H)
+            randx_check(A, B, H, rng)
+        for pname, pi, phi in parts_2d(A):
+            H = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, 4, 4)
+            B = vb.SparseMatrixVBC[4, 4](A, pi, phi)
+            assert_packed_equal(B, H)
+            randx_check(A, B, H, rng)
+
+
+@pytest.mark.parametrize("name", ["LPnetlib__lpi_itest6", "HB__west0132", "LPnetlib__lp_blend", "Pajek__GD99_c"])
+def test_fixtures_onehot_exact(fixtures, name):
+    A = fixtures[name]
+    for pname, phi in parts_1d(A):
+        H = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 4)
+        onehot_check(A, vb.SparseMatrix1DVBC[4](A, phi), H)
+    for pname, pi, phi in parts_2d(A):
+        H = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, 4, 4)
+        onehot_check(A, vb.SparseMatrixVBC[4, 4](A, pi, phi), H)
+
+
+@pytest.mark.parametrize("kind", ["f64", "bool", "int32"])
+def test_size_grid(kind):
+    """runtests.jl:14-16 size grid (incl. 1x1, single rows/columns, empty columns)."""
+    rng = np.random.default_rng(0xDEADBEEF)
+    for m in SIZES:
+        for n in SIZES:
+            A = sprand(m, n, 0.2, rng, kind)
+            phi = vb.pack_stripe(A, vb.RandomChunker(4, seed=m * 31 + n))
+            H = oracle.pack_1d(m, n, A.colptr, A.rowval, A.nzval, phi.spl, 4)
+            B = vb.SparseMatrix1DVBC[4](A, phi)
+            assert_packed_equal(B, H)
+            pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(vb.RandomChunker(4, seed=m), vb.RandomChunker(4, seed=n)))
+            H2 = oracle.pack_2d(m, n, A.colptr, A.rowval, A.nzval, pi.spl, phi2.spl, 4, 4)
+            B2 = vb.SparseMatrixVBC[4, 4](A, pi, phi2)
+            assert_packed_equal(B2, H2)
+            if m <= 9 and n <= 9:
+                onehot_check(A, B, H)
+                onehot_check(A, B2, H2)
+            else:
+                randx_check(A, B, H, rng)
+                randx_check(A, B2, H2, rng)
+
+
+def test_empty_and_degenerate():
+    i64 = np.int64
+    # all-zero matrix: every stripe empty; the adjoint must still store zeros
+    A = vb.SparseMatrixCSC(5, 6, np.ones(7, dtype=i64), np.array([], dtype=i64), np.array([], dtype=np.float64))
+    B = vb.SparseMatrix1DVBC[4](A, vb.EquiChunker(4))
+    assert B.nidx == 0 and B.nval == 0
+    y = vb.mul_(np.full(6, 3.0), B.T, np.ones(5))
+    assert np.array_equal(y, np.zeros(6))
+    y = vb.mul_(np.full(5, 3.0), B, np.ones(6))
+    assert np.array_equal(y, np.zeros(5))
+    B2 = vb.SparseMatrixVBC[4, 4](A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(4)))
+    assert np.array_equal(vb.mul_(np.full(6, 3.0), B2.T, np.ones(5)), np.zeros(6))
+    # zero-sized dimensions
+    E = vb.SparseMatrixCSC(4, 0, np.ones(1, dtype=i64), np.array([], dtype=i64), np.array([], dtype=np.float64))
+    Be = vb.SparseMatrix1DVBC[4](E, vb.EquiChunker(4))
+    assert Be.shape == (4, 0)
+    assert np.array_equal(vb.mul_(np.full(4, 2.0), Be, np.zeros(0)), np.zeros(4))
+    assert vb.mul_(np.zeros(0), Be.T, np.ones(4)).shape == (0,)
+
+
+def test_wide_and_odd_widths_all_paths():
+    """Widths 1..12 in f64 and f32 hit every EPV/CPR class incl. the generic and 'wide' bodies."""
+    rng = np.random.default_rng(5)
+    for tv in (np.float64, np.float32):
+        for w in (1, 2, 3, 4, 5, 6, 7, 8, 12, 16, 24):
+            A = sprand(40, 3 * w + 1, 0.3, rng).astype(tv)
+            phi = vb.pack_stripe(A, vb.EquiChunker(w))
+            H = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, w)
+            B = vb.SparseMatrix1DVBC[w](A, phi)
+            assert_packed_equal(B, H)
+            for g in (8, 32):
+                B.set_option(_lib.OPT_ADJ_GROUP, g)
+                B.set_option(_lib.OPT_FWD_GROUP, g)
+                randx_check(A, B, H, rng)
+            for u in (1, 2, 3, 4, 8):
+                pi = vb.pack_stripe(A.transpose(), vb.EquiChunker(u))
+                H2 = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, u, w)
+                B2 = vb.SparseMatrixVBC[u, w](A, pi, phi)
+                assert_packed_equal(B2, H2)
+                for g in (8, 32):
+                    B2.set_option(_lib.OPT_ADJ_GROUP, g)
+                    B2.set_option(_lib.OPT_FWD_GROUP, g)
+                    randx_check(A, B2, H2, rng)
+
+
+def test_alpha_beta_blas_semantics():
+    rng = np.random.default_rng(9)
+    A = sprand(33, 29, 0.3, rng)
+    S = A.to_scipy()
+    B = vb.SparseMatrixVBC[4, 4](A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(4)))
+    B1 = vb.SparseMatrix1DVBC[4](A, vb.EquiChunker(4))
+    for M in (B, B1):
+        x, y0 = rng.random(29), rng.random(33)
+        y = vb.mul_(y0.copy(), M, x, 2.5, -0.5)
+        assert np.allclose(y, 2.5 * (S @ x) - 0.5 * y0, rtol=1e-13, atol=1e-13)
+        xt, yt0 = rng.random(33), rng.random(29)
+        yt = vb.mul_(yt0.copy(), M.T, xt, 2.5, -0.5)
+        assert np.allclose(yt, 2.5 * (S.T @ xt) - 0.5 * yt0, rtol=1e-13, atol=1e-13)
+        # beta == 0 must not propagate NaNs from y (BLAS convention; `fill!` in multiply_1DVBC.jl:51)
+        assert np.all(np.isfinite(vb.mul_(np.full(33, np.nan), M, x, True, False)))
+        assert np.all(np.isfinite(vb.mul_(np.full(29, np.nan), M.T, xt, True, False)))
+        assert np.allclose(M @ x, S @ x) and np.allclose(M.T @ xt, S.T @ xt)
+
+
+def test_upload_host_packed_and_parity_mode(fixtures):
+    rng = np.random.default_rng(3)
+    A = fixtures["LPnetlib__lp_blend"]
+    phi = vb.pack_stripe(A, vb.RandomChunker(4, 1))
+    H = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 4)
+    B = vb.SparseMatrix1DVBC.from_packed(4, A.m, A.n, H.spl, H.pos, H.idx, H.ofs, H.val)
+    assert_packed_equal(B, H)
+    randx_check(A, B, H, rng)
+    B.set_option(_lib.OPT_PARITY_MODE, 1)
+    randx_check(A, B, H, rng)
+    pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(vb.RandomChunker(4, 2), vb.RandomChunker(4, 3)))
+    H2 = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi2.spl, 4, 4)
+    B2 = vb.SparseMatrixVBC.from_packed(4, 4, A.m, A.n, H2.pi_spl, H2.spl, H2.pos, H2.idx, H2.ofs, H2.val)
+    assert_packed_equal(B2, H2)
+    randx_check(A, B2, H2, rng)
+    B2.set_option(_lib.OPT_PARITY_MODE, 1)
+    randx_check(A, B2, H2, rng)
+
+
+def test_errors_map_to_reference_exceptions():
+    A = sprand(8, 8, 0.3, np.random.default_rng(2))
+    phi = vb.pack_stripe(A, vb.EquiChunker(4))
+    with pytest.raises(AssertionError, match="w <= W"):  # constructors_1DVBC.jl:46
+        vb.SparseMatrix1DVBC[3](A, phi)
+    with pytest.raises(AssertionError, match="u <= U"):  # constructors_VBC.jl:58-60
+        vb.SparseMatrixVBC[2, 4](A, phi, phi)
+    with pytest.raises(vb.ArgumentError):
+        vb.SparseMatrix1DVBC[4](A, vb.SplitPartition(np.array([1, 5, 8], dtype=np.int64)))  # does not cover 1:n
+    B = vb.SparseMatrix1DVBC[4](A, phi)
+    with pytest.raises(vb.DimensionMismatch):  # multiply_1DVBC.jl:44-45
+        vb.mul_(np.zeros(8), B, np.zeros(7))
+    with pytest.raises(vb.DimensionMismatch):  # multiply_1DVBC.jl:139-140
+        vb.mul_(np.zeros(7), B.T, np.zeros(8))
+    with pytest.raises(vb.DimensionMismatch):  # TrSpMV.jl:3-4
+        vb.TrSpMV_(np.zeros(8), A, np.zeros(5))
+
+
+def test_csc_trspmv(fixtures):
+    rng = np.random.default_rng(4)
+    for tv, ti in ((np.float64, np.int64), (np.float32, np.int32)):
+        for name, A64 in fixtures.items():
+            A = A64.astype(tv, ti)
+            x = rng.random(A.m).astype(tv)
+            y = vb.TrSpMV_(np.empty(A.n, dtype=tv), A, x)
+            yo = oracle.csc_trspmv(A.m, A.n, A.colptr, A.rowval, A.nzval, x)
+            bound = abs(A64.to_scipy()).T @ np.abs(x.astype(np.float64))
+            assert np.all(np.abs(y - yo) <= 8 * TOL[np.dtype(tv)] * bound + 1e-300)
+
+
+def test_device_tensor_path_and_memory_cost(fixtures):
+    import torch
+    A = fixtures["HB__can_292"]
+    pi, phi = vb.pack_plaid(A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(4)))
+    B = vb.SparseMatrixVBC[4, 4](A, pi, phi)
+    H = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, 4, 4)
+    x = torch.rand(A.m, dtype=torch.float64, device="cuda")
+    y = torch.empty(A.n, dtype=torch.float64, device="cuda")
+    before = B.launch_count()
+    vb.mul_(y, B.T, x)
+    torch.cuda.synchronize()
+    assert B.launch_count() == before + 1
+    yo = oracle.mul(H, x.cpu().numpy(), trans=True)
+    assert np.allclose(y.cpu().numpy(), yo, rtol=1e-12, atol=1e-12)
+    cost, row_term = B.memory_cost()
+    co, ro = oracle.memory_cost(H)
+    assert np.array_equal(cost, co) and row_term == ro
+    ref_bytes, adj_bytes, _ = B.format_bytes()
+    assert ref_bytes == 8 * (3 * (H.L + 1) + (H.K + 1) + len(H.idx)) + 8 * len(H.val)
+    assert adj_bytes < ref_bytes
+
+
+def test_config_c1_1d_vbc():
+    """BASELINE configs[0]: 1D-VBC F64, n = 10k, nnz = 1M, W = 8 -- bit-exact pack, y within 1e-12."""
+    A, phi = synth.config_c1()
+    H = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 8)
+    B = vb.SparseMatrix1DVBC[8](A, phi)
+    assert B.nval == 1_000_000 and B.nidx == 125_000
+    assert_packed_equal(B, H)
+    randx_check(A, B, H, np.random.default_rng(1))
+
+
+def test_reduced_c2_and_variable_blocks():
+    """configs[1] shape at n = 40k (oracle finishes in seconds) + the C2v variable-block variant."""
+    A, pi, phi = synth.config_c2(n=40_000, S=21)
+    H = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, 4, 4)
+    B = vb.SparseMatrixVBC[4, 4](A, pi, phi)
+    assert_packed_equal(B, H)
+    rng = np.random.default_rng(2)
+    randx_check(A, B, H, rng)
+    pv = synth.variable_partition(A.m, 8, seed=1)
+    fv = synth.variable_partition(A.n, 8, seed=2)
+    Hv = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pv.spl, fv.spl, 8, 8)
+    Bv = vb.SparseMatrixVBC[8, 8](A, pv, fv)
+    assert_packed_equal(Bv, Hv)
+    randx_check(A, Bv, Hv, rng)
+    A32 = A.astype(np.float32, np.int32)
+    H32 = oracle.pack_2d(A.m, A.n, A32.colptr, A32.rowval, A32.nzval, pi.spl.astype(np.int32), phi.spl.astype(np.int32), 4, 4)
+    B32 = vb.SparseMatrixVBC[4, 4](A32, pi, phi)
+    assert_packed_equal(B32, H32)
+    randx_check(A32, B32, H32, rng)

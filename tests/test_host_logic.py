@@ -1,0 +1,82 @@
+"""CPU-only tests of the host-side logic: partition stand-ins and synthetic generators."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import vbc_b200 as vb
+from vbc_b200 import synth
+
+
+def test_equi_chunker():
+    A = vb.SparseMatrixCSC.from_scipy(sp.random(5, 10, 0.3, random_state=0, format="csc"))
+    assert vb.pack_stripe(A, vb.EquiChunker(4)).spl.tolist() == [1, 5, 9, 11]
+    assert vb.pack_stripe(A, vb.EquiChunker(5)).spl.tolist() == [1, 6, 11]
+    E = vb.SparseMatrixCSC(3, 0, np.array([1], dtype=np.int64), np.array([], dtype=np.int64), np.array([]))
+    assert vb.pack_stripe(E, vb.EquiChunker(4)).spl.tolist() == [1]
+
+
+def test_strict_chunker_groups_identical_patterns():
+    # columns: [a a a a a b b c]; w_max = 2 -> (a a)(a a)(a)(b b)(c)
+    pat = {"a": [0, 2], "b": [1], "c": []}
+    cols = "aaaaabbc"
+    rows, cc = [], []
+    for j, ch in enumerate(cols):
+        for r in pat[ch]:
+            rows.append(r); cc.append(j)
+    M = sp.csc_matrix((np.ones(len(rows)), (rows, cc)), shape=(3, len(cols)))
+    A = vb.SparseMatrixCSC.from_scipy(M)
+    assert vb.pack_stripe(A, vb.StrictChunker(2)).spl.tolist() == [1, 3, 5, 6, 8, 9]
+    assert vb.pack_stripe(A, vb.StrictChunker(8)).spl.tolist() == [1, 6, 8, 9]
+    # same count but different rows must not merge
+    M2 = sp.csc_matrix(np.array([[1, 0], [0, 1.0]]))
+    assert vb.pack_stripe(vb.SparseMatrixCSC.from_scipy(M2), vb.StrictChunker(4)).spl.tolist() == [1, 2, 3]
+
+
+@pytest.mark.parametrize("n,w", [(1, 4), (17, 4), (100, 8), (5, 1)])
+def test_random_chunker_is_a_valid_split(n, w):
+    A = vb.SparseMatrixCSC.from_scipy(sp.random(3, n, 0.5, random_state=1, format="csc"))
+    spl = vb.pack_stripe(A, vb.RandomChunker(w, seed=n)).spl
+    assert spl[0] == 1 and spl[-1] == n + 1
+    d = np.diff(spl)
+    assert d.min() >= 1 and d.max() <= w
+
+
+def test_alternating_packer_partitions_rows_and_columns():
+    A = vb.SparseMatrixCSC.from_scipy(sp.random(9, 13, 0.3, random_state=2, format="csc"))
+    pi, phi = vb.pack_plaid(A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(3)))
+    assert pi.spl.tolist() == [1, 5, 9, 10] and phi.spl.tolist() == [1, 4, 7, 10, 13, 14]
+
+
+def test_synth_banded_blocks_structure():
+    A, Pi, Phi = synth.banded_blocks(K=50, L=50, u=2, w=3, offsets=[0, 1, -1, 7, -7])
+    assert A.shape == (100, 150) and len(Pi) == 50 and len(Phi) == 50
+    S = A.to_scipy().tocoo()
+    kb, lb = S.row // 2, S.col // 3
+    assert set(np.unique(kb - lb)) == {-7, -1, 0, 1, 7}
+    # every block is dense: nnz = (#blocks) * u * w
+    nblocks = len(set(zip(kb.tolist(), lb.tolist())))
+    assert A.nnz == nblocks * 6
+    assert A.nzval.min() >= 0.0 and A.nzval.max() < 1.0
+    # regenerating any entry from its coordinates gives the stored value (slab independence)
+    v = synth.entry_values(S.row.astype(np.uint64), S.col.astype(np.uint64), 150)
+    assert np.array_equal(v, S.data)
+    # rows ascending inside every column (CSC invariant the pack kernel relies on)
+    for j in range(A.n):
+        seg = A.rowval[A.colptr[j] - 1:A.colptr[j + 1] - 1]
+        assert np.all(np.diff(seg) > 0)
+
+
+def test_synth_random_blocks_counts():
+    A, Pi, Phi = synth.random_blocks(K=200, L=25, u=1, w=8, per_stripe=10, seed=3)
+    assert A.shape == (200, 200) and A.nnz == 25 * 10 * 8
+    A2, _, _ = synth.random_blocks(K=6, L=4, u=2, w=2, per_stripe=5, seed=3)
+    assert A2.nnz == 4 * 5 * 4
+
+
+def test_config_c1_shape():
+    A, Phi = synth.config_c1()
+    assert A.shape == (10_000, 10_000) and A.nnz == 1_000_000 and len(Phi) == 1_250
+
+
+def test_fem_stencil_has_13_offsets():
+    assert len(synth.fem_stencil_offsets(63)) == 13

@@ -1,0 +1,187 @@
+"""Pins the oracle (oracle/vbc_oracle.c) against everything the reference's own tests hold for
+this path -- CPU only.
+
+  * test/matrices.jl:4-9       six literal matrices (tests/golden/fixtures.npz)
+  * test/runtests.jl:29-53     1D one-hot invariants, exact ==, both orientations
+  * test/runtests.jl:63-87     2D one-hot invariants
+  * test/runtests.jl:14-16     the 11x11 size grid of random matrices (f64 / Bool / Int32 values)
+  * bin/test_table.jl:42,:84   random-x isapprox against the CSC product
+  * SURVEY.md Appendix A / B   structural known answers (independent restatement)
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import vbc_b200 as vb
+from conftest import ROOT, SIZES, sprand
+
+KA = json.load(open(os.path.join(ROOT, "tests", "golden", "known_answers.json")))
+FIXTURE_NAMES = [k for k in KA if not k.startswith("_") and k != "appendix_a"]
+
+
+def partitions_1d(A):
+    yield "strict4", vb.pack_stripe(A, vb.StrictChunker(4)), True
+    yield "equi4", vb.pack_stripe(A, vb.EquiChunker(4)), False
+    yield "rand4", vb.pack_stripe(A, vb.RandomChunker(4, seed=A.nnz)), False
+
+
+def partitions_2d(A):
+    for name, ch in (("strict4", vb.StrictChunker(4)), ("equi4", vb.EquiChunker(4)),
+                     ("rand4", vb.RandomChunker(4, seed=A.nnz + 1))):
+        pi, phi = vb.pack_plaid(A, vb.AlternatingPacker(ch, ch))
+        yield name, pi, phi
+
+
+def onehot_check(A, B):
+    """runtests.jl:29-53: for every unit vector, mul!(y, B, e) == mul!(y, A, e), exactly, and the
+    same for the adjoint."""
+    m, n = A.shape
+    tv = A.nzval.dtype
+    x = np.zeros(n, dtype=tv)
+    for j in range(n):
+        x[j] = 1
+        y_ref = oracle.csc_spmv(m, n, A.colptr, A.rowval, A.nzval, x)
+        y_test = oracle.mul(B, x, trans=False, alpha=True, beta=False, y=np.full(m, 7, dtype=tv))
+        assert np.array_equal(y_ref, y_test), f"forward, column {j + 1}"
+        x[j] = 0
+    x = np.zeros(m, dtype=tv)
+    for i in range(m):
+        x[i] = 1
+        y_ref = oracle.csc_trspmv(m, n, A.colptr, A.rowval, A.nzval, x)
+        y_test = oracle.mul(B, x, trans=True, alpha=True, beta=False, y=np.full(n, 7, dtype=tv), nthreads=2)
+        assert np.array_equal(y_ref, y_test), f"adjoint, row {i + 1}"
+        x[i] = 0
+
+
+@pytest.mark.parametrize("name", FIXTURE_NAMES)
+def test_fixture_known_answers(fixtures, name):
+    A = fixtures[name]
+    ka = KA[name]
+    for key, ch in (("equi", vb.EquiChunker(4)), ("strict", vb.StrictChunker(4))):
+        phi = vb.pack_stripe(A, ch)
+        B = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 4)
+        assert [B.L, len(B.idx), len(B.val)] == ka[f"{key}1d"]
+        pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(ch, ch))
+        C = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi2.spl, 4, 4)
+        assert [C.K, C.L, len(C.idx), len(C.val)] == ka[f"{key}2d"]
+
+
+def test_appendix_a_worked_example():
+    a = KA["appendix_a"]
+    i64, f64 = np.int64, np.float64
+    colptr, rowval = np.array(a["colptr"], i64), np.array(a["rowval"], i64)
+    nzval = np.array(a["nzval"], f64)
+    B = oracle.pack_1d(a["m"], a["n"], colptr, rowval, nzval, np.array(a["phi_spl"], i64), 4)
+    for f in ("pos", "idx", "ofs", "val"):
+        assert np.array_equal(getattr(B, f), np.array(a["d1"][f])), f
+    C = oracle.pack_2d(a["m"], a["n"], colptr, rowval, nzval, np.array(a["pi_spl"], i64),
+                       np.array(a["phi_spl"], i64), 4, 4)
+    for f in ("pos", "idx", "ofs", "val"):
+        assert np.array_equal(getattr(C, f), np.array(a["d2"][f])), f
+    # empty stripes still store zeros into their y slice in the adjoint (Appendix A note)
+    y = oracle.mul(B, np.ones(6), trans=True, y=np.full(7, 5.0))
+    assert np.array_equal(y, np.array([4, 6, 0, 0, 19, 7, 9], dtype=f64))
+
+
+@pytest.mark.parametrize("name", FIXTURE_NAMES)
+def test_fixture_onehot_1d(fixtures, name):
+    A = fixtures[name]
+    for pname, phi, strict in partitions_1d(A):
+        B = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 4)
+        if strict:  # the StrictChunker constructor (constructors_1DVBC.jl:94-143) must agree
+            B2 = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 4, strict=True)
+            for f in ("pos", "idx", "ofs", "val"):
+                assert np.array_equal(getattr(B, f), getattr(B2, f)), (pname, f)
+        onehot_check(A, B)
+
+
+@pytest.mark.parametrize("name", FIXTURE_NAMES)
+def test_fixture_onehot_2d(fixtures, name):
+    A = fixtures[name]
+    for pname, pi, phi in partitions_2d(A):
+        B = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, 4, 4)
+        onehot_check(A, B)
+
+
+@pytest.mark.parametrize("kind", ["f64", "bool", "int32"])
+def test_size_grid_onehot(kind):
+    """runtests.jl:14-16: m, n in SIZES, density 0.2 (one trial per cell here; four in the reference)."""
+    rng = np.random.default_rng(0xDEADBEEF)
+    for m in SIZES:
+        for n in SIZES:
+            A = sprand(m, n, 0.2, rng, kind)
+            for _, phi, _s in partitions_1d(A):
+                onehot_check(A, oracle.pack_1d(m, n, A.colptr, A.rowval, A.nzval, phi.spl, 4))
+            for _, pi, phi in partitions_2d(A):
+                onehot_check(A, oracle.pack_2d(m, n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, 4, 4))
+
+
+@pytest.mark.parametrize("tv,ti,tol", [(np.float64, np.int64, 1e-12), (np.float64, np.int32, 1e-12),
+                                        (np.float32, np.int64, 1e-5), (np.float32, np.int32, 1e-5)])
+def test_random_x_isapprox_all_types(fixtures, tv, ti, tol):
+    """bin/test_table.jl:42/:84/:126 `@assert y ≈ z`, for every (Tv, Ti) instantiation."""
+    rng = np.random.default_rng(7)
+    for name, A64 in fixtures.items():
+        A = A64.astype(tv, ti)
+        S = A64.to_scipy()
+        absS = abs(S)
+        x, xt = rng.random(A.n), rng.random(A.m)
+        phi = vb.pack_stripe(A, vb.RandomChunker(4, 3))
+        pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(vb.RandomChunker(4, 5), vb.RandomChunker(4, 6)))
+        for B in (oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 4),
+                  oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi2.spl, 4, 4)):
+            assert B.pos.dtype == ti and B.val.dtype == tv
+            y = oracle.mul(B, x.astype(tv))
+            assert np.all(np.abs(y - S @ x) <= 4 * tol * (absS @ x) + 1e-300)
+            yt = oracle.mul(B, xt.astype(tv), trans=True, nthreads=3)
+            assert np.all(np.abs(yt - S.T @ xt) <= 4 * tol * (absS.T @ xt) + 1e-300)
+
+
+def test_reference_quirks_alpha_beta():
+    """forward computes y <- A x + beta y (alpha ignored); adjoint overwrites y."""
+    A = sprand(9, 7, 0.4, np.random.default_rng(1))
+    phi = vb.pack_stripe(A, vb.EquiChunker(3))
+    B = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 3)
+    S = A.to_scipy()
+    x, y0 = np.arange(1.0, 8.0), np.arange(1.0, 10.0)
+    y = oracle.mul(B, x, alpha=5.0, beta=2.0, y=y0.copy())
+    assert np.allclose(y, S @ x + 2.0 * y0)
+    xt, yt0 = np.arange(1.0, 10.0), np.arange(1.0, 8.0)
+    yt = oracle.mul(B, xt, trans=True, alpha=5.0, beta=2.0, y=yt0.copy())
+    assert np.allclose(yt, S.T @ xt)
+
+
+def test_errors():
+    A = sprand(8, 8, 0.3, np.random.default_rng(2))
+    phi = vb.pack_stripe(A, vb.EquiChunker(4))
+    with pytest.raises(oracle.OracleError) as e:  # @assert w <= W  constructors_1DVBC.jl:46
+        oracle.pack_1d(8, 8, A.colptr, A.rowval, A.nzval, phi.spl, 3)
+    assert e.value.code == 1
+    with pytest.raises(oracle.OracleError) as e:  # @assert u <= U  constructors_VBC.jl:58-60
+        oracle.pack_2d(8, 8, A.colptr, A.rowval, A.nzval, phi.spl, phi.spl, 2, 4)
+    assert e.value.code == 2
+    B = oracle.pack_1d(8, 8, A.colptr, A.rowval, A.nzval, phi.spl, 4)
+    with pytest.raises(oracle.OracleError) as e:  # DimensionMismatch multiply_1DVBC.jl:44-45
+        oracle.mul(B, np.zeros(7))
+    assert e.value.code == 3
+    with pytest.raises(oracle.OracleError):  # TrSpMV.jl:3-4
+        oracle.csc_trspmv(8, 8, A.colptr, A.rowval, A.nzval, np.zeros(5))
+
+
+def test_memory_cost_models(fixtures):
+    """costs.jl:10 / :140 on packed fixtures == the reference's format accounting minus the
+    per-array +1 entries (test_table.jl:78: sizeof(Φ)+sizeof(pos)+sizeof(idx)+sizeof(ofs)+sizeof(val))."""
+    A = fixtures["HB__west0132"]
+    phi = vb.pack_stripe(A, vb.EquiChunker(4))
+    B = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 4)
+    cost, extra = oracle.memory_cost(B)
+    assert extra == 0
+    assert cost.sum() == 3 * 8 * B.L + 8 * len(B.idx) + 8 * len(B.val)
+    pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(4)))
+    C = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi2.spl, 4, 4)
+    cost, extra = oracle.memory_cost(C)
+    assert extra == 8 * C.K
+    assert cost.sum() == 3 * 8 * C.L + 8 * len(C.idx) + 8 * len(C.val)
