@@ -1,0 +1,173 @@
+# CuVBC.jl -- the reference-side binding: a device matrix type for SparseMatrixVBCs.jl whose
+# constructors and `mul!` methods `ccall` libvbc.so (include/vbc.h).  Drop this file into the
+# reference's src/ and `include("CuVBC.jl")` after constructors_VBC.jl (SparseMatrixVBCs.jl:90).
+#
+# NOT EXECUTED IN THIS REPO: the build image has no Julia toolchain.  The same C entry points are
+# exercised by the Python ctypes mirror (sparsematrixvbcs.jl_b200/matrix.py) in tests/ and bench.py.
+#
+# Surface kept (reference file:line -> method here)
+#   SparseMatrix1DVBC{W}(A, Φ)            constructors_1DVBC.jl:9   -> CuVBC{W}(A, Φ)        (device pack kernel)
+#   SparseMatrixVBC{U,W}(A, Π, Φ)         constructors_VBC.jl:15    -> CuVBC{U,W}(A, Π, Φ)
+#   SparseMatrix1DVBC{W}(A, method)       constructors_1DVBC.jl:4   -> CuVBC{W}(A, method)   (partitioner stays host-side)
+#   SparseMatrixVBC{U,W}(A, method)       constructors_VBC.jl:10    -> CuVBC{U,W}(A, method)
+#   (host-packed struct)                                             -> CuVBC(B::SparseMatrix1DVBC / SparseMatrixVBC)
+#   Base.size                             SparseMatrixVBCs.jl:55,:84
+#   LinearAlgebra.mul!(y, B, x, α, β)     multiply_1DVBC.jl:9, multiply_VBC.jl:3
+#   LinearAlgebra.mul!(y, B', x, α, β)    multiply_1DVBC.jl:85, multiply_VBC.jl:89
+#   Base.:*                               multiply_1DVBC.jl:182-183, multiply_VBC.jl:194-195
+#   TrSpMV!(y, A, x)                      TrSpMV.jl:1 -> TrSpMV!(y, ::CuCSC, x)
+
+using LinearAlgebra
+using SparseArrays
+using ChainPartitioners
+
+const libvbc = get(ENV, "LIBVBC", "libvbc.so")
+
+const VBC_F32, VBC_F64 = Cint(0), Cint(1)
+const VBC_I32, VBC_I64 = Cint(0), Cint(1)
+vbc_vt(::Type{Float32}) = VBC_F32
+vbc_vt(::Type{Float64}) = VBC_F64
+vbc_it(::Type{Int32}) = VBC_I32
+vbc_it(::Type{Int64}) = VBC_I64
+
+struct VBCError <: Exception
+    code::Int
+    msg::String
+end
+
+# vbc_status -> the exception the reference throws at the same place
+function vbc_check(rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:vbc_last_error, libvbc), Cstring, ()))
+    rc == 1 && throw(DimensionMismatch(msg))                      # multiply_1DVBC.jl:44-45 ...
+    rc == 2 && throw(ArgumentError(msg))                          # SparseMatrixVBCs.jl:45-50
+    rc == 3 && startswith(msg, "AssertionError") && throw(AssertionError(msg))  # constructors_1DVBC.jl:46
+    rc == 6 && throw(OutOfMemoryError())
+    throw(VBCError(rc, msg))
+end
+
+"""
+    CuVBC{U, W, Tv, Ti} <: AbstractSparseMatrix{Tv, Ti}
+
+Device-resident VBC matrix.  `U == 0` marks the 1D format (`SparseMatrix1DVBC{W}`).
+"""
+mutable struct CuVBC{U, W, Tv, Ti<:Integer} <: AbstractSparseMatrix{Tv, Ti}
+    handle::Ptr{Cvoid}
+    m::Int
+    n::Int
+    Π::Union{Nothing, SplitPartition{Ti}}
+    Φ::SplitPartition{Ti}
+    function CuVBC{U, W, Tv, Ti}(handle, m, n, Π, Φ) where {U, W, Tv, Ti}
+        A = new{U, W, Tv, Ti}(handle, m, n, Π, Φ)
+        finalizer(a -> (ccall((:vbc_destroy, libvbc), Cvoid, (Ptr{Cvoid},), a.handle); a.handle = C_NULL), A)
+        return A
+    end
+end
+
+Base.size(A::CuVBC) = (A.m, A.n)
+
+# ---- constructors: host CSC + host partition -> device pack kernels -------------------------------
+function CuVBC{W}(A::SparseMatrixCSC{Tv, Ti}, Φ::SplitPartition{Ti}; device::Integer = 0) where {W, Tv, Ti}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    (m, n) = size(A)
+    GC.@preserve A Φ begin
+        vbc_check(ccall((:vbc_pack_csc, libvbc), Cint,
+            (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint),
+            h, vbc_vt(Tv), vbc_it(Ti), m, n, 0, W, A.colptr, A.rowval, A.nzval, C_NULL, 0, Φ.spl, length(Φ), device))
+    end
+    return CuVBC{0, W, Tv, Ti}(h[], m, n, nothing, Φ)
+end
+
+function CuVBC{U, W}(A::SparseMatrixCSC{Tv, Ti}, Π::SplitPartition{Ti}, Φ::SplitPartition{Ti}; device::Integer = 0) where {U, W, Tv, Ti}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    (m, n) = size(A)
+    GC.@preserve A Π Φ begin
+        vbc_check(ccall((:vbc_pack_csc, libvbc), Cint,
+            (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint),
+            h, vbc_vt(Tv), vbc_it(Ti), m, n, U, W, A.colptr, A.rowval, A.nzval, Π.spl, length(Π), Φ.spl, length(Φ), device))
+    end
+    return CuVBC{U, W, Tv, Ti}(h[], m, n, Π, Φ)
+end
+
+# partitioner front doors: the partition is computed on the host exactly as in the reference
+CuVBC{W}(A::SparseMatrixCSC, method; kw...) where {W} = CuVBC{W}(A, pack_stripe(A, method); kw...)
+function CuVBC{U, W}(A::SparseMatrixCSC, method; kw...) where {U, W}
+    Π, Φ = pack_plaid(A, method)
+    return CuVBC{U, W}(A, convert(SplitPartition, Π), convert(SplitPartition, Φ); kw...)
+end
+
+# adopt a matrix already packed on the host by the reference
+function CuVBC(B::SparseMatrix1DVBC{W, Tv, Ti}; device::Integer = 0) where {W, Tv, Ti}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve B begin
+        vbc_check(ccall((:vbc_upload, libvbc), Cint,
+            (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Cint, Cint, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+            h, vbc_vt(Tv), vbc_it(Ti), B.m, B.n, 0, W, C_NULL, 0, B.Φ.spl, length(B.Φ), B.pos, B.idx, B.ofs, B.val, device))
+    end
+    return CuVBC{0, W, Tv, Ti}(h[], B.m, B.n, nothing, B.Φ)
+end
+
+function CuVBC(B::SparseMatrixVBC{U, W, Tv, Ti}; device::Integer = 0) where {U, W, Tv, Ti}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve B begin
+        vbc_check(ccall((:vbc_upload, libvbc), Cint,
+            (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Cint, Cint, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+            h, vbc_vt(Tv), vbc_it(Ti), B.m, B.n, U, W, B.Π.spl, length(B.Π), B.Φ.spl, length(B.Φ), B.pos, B.idx, B.ofs, B.val, device))
+    end
+    return CuVBC{U, W, Tv, Ti}(h[], B.m, B.n, B.Π, B.Φ)
+end
+
+# download the packed arrays (bit-exact check against the host constructors)
+function Base.collect(A::CuVBC{U, W, Tv, Ti}) where {U, W, Tv, Ti}
+    nidx, nval = Ref{Int64}(0), Ref{Int64}(0)
+    vbc_check(ccall((:vbc_sizes, libvbc), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), A.handle, nidx, nval))
+    L = length(A.Φ)
+    pos, ofs = Vector{Ti}(undef, L + 1), Vector{Ti}(undef, L + 1)
+    idx, val = Vector{Ti}(undef, nidx[]), Vector{Tv}(undef, nval[])
+    vbc_check(ccall((:vbc_download, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), A.handle, pos, idx, ofs, val))
+    return (pos = pos, idx = idx, ofs = ofs, val = val)
+end
+
+# ---- multiply ----------------------------------------------------------------------------------------
+function _cuvbc_mul!(y::StridedVector{Tv}, A::CuVBC{U, W, Tv}, x::StridedVector{Tv}, α::Number, β::Number, trans::Bool) where {U, W, Tv}
+    GC.@preserve x y begin
+        vbc_check(ccall((:vbc_spmv, libvbc), Cint,
+            (Ptr{Cvoid}, Cint, Cdouble, Ptr{Cvoid}, Int64, Cdouble, Ptr{Cvoid}, Int64, Cint),
+            A.handle, trans, Float64(α), x, length(x), Float64(β), y, length(y), 0))
+    end
+    return y
+end
+
+LinearAlgebra.mul!(y::StridedVector, A::CuVBC, x::StridedVector, α::Number, β::Number) =
+    _cuvbc_mul!(y, A, x, α, β, false)
+LinearAlgebra.mul!(y::StridedVector, adjA::Union{Adjoint{<:Any, <:CuVBC}, Transpose{<:Any, <:CuVBC}}, x::StridedVector, α::Number, β::Number) =
+    _cuvbc_mul!(y, adjA.parent, x, α, β, true)
+
+Base.:*(A::Union{CuVBC, Adjoint{<:Any, <:CuVBC}, Transpose{<:Any, <:CuVBC}}, x::StridedVector{Tx}) where {Tx} =
+    (T = Base.promote_op(LinearAlgebra.matprod, eltype(A), Tx); mul!(similar(x, T, size(A, 1)), A, x, true, false))
+
+# ---- CSC comparator ----------------------------------------------------------------------------------
+mutable struct CuCSC{Tv, Ti}
+    handle::Ptr{Cvoid}
+    m::Int
+    n::Int
+    function CuCSC(A::SparseMatrixCSC{Tv, Ti}; device::Integer = 0) where {Tv, Ti}
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve A begin
+            vbc_check(ccall((:vbc_csc_upload, libvbc), Cint,
+                (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                h, vbc_vt(Tv), vbc_it(Ti), size(A, 1), size(A, 2), A.colptr, A.rowval, A.nzval, device))
+        end
+        C = new{Tv, Ti}(h[], size(A, 1), size(A, 2))
+        finalizer(c -> (ccall((:vbc_csc_destroy, libvbc), Cvoid, (Ptr{Cvoid},), c.handle); c.handle = C_NULL), C)
+        return C
+    end
+end
+
+function TrSpMV!(y::Vector{Tv}, A::CuCSC{Tv}, x::Vector{Tv}) where {Tv}
+    GC.@preserve x y begin
+        vbc_check(ccall((:vbc_csc_trspmv, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint),
+            A.handle, x, length(x), y, length(y), 0))
+    end
+    return y
+end
