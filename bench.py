@@ -142,7 +142,7 @@ def workload_config(world, nnz_local):
             "n_global": N_LOCAL * world, "partition": "EquiChunker(4) rows and columns",
             "index_types": "Ti=Int64 canonical arrays; kernel reads 16-B stripe meta + Int32 block descriptors",
             "l2": "inputs (431 MB/GPU) larger than L2 (126 MB); no explicit flush",
-            "parallelism": f"row-block partition over {world} GPU(s)" + (", x all-gather (NCCL) per step" if world > 1 else "")}
+            "parallelism": f"row-block partition over {world} GPU(s)" + (", x all-gather per step" if world > 1 else "")}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -181,15 +181,22 @@ def run_ours(args, rank, world, local_rank):
     else:
         imbalance = 1.0
 
-    op = vdist.RowPartitionedOperator(B, layout, rank, world, torch.float64)
+    # x_{t+1} <- alpha * A' x_t : alpha ~ 1 / (row sum) keeps the iterates in range at N > 1
+    alpha_step = 1.0 if world == 1 else 1.0 / 26.0
+    op = vdist.RowPartitionedOperator(lambda y, x: vb.mul_(y, B.T, x, alpha_step, False), layout, rank, world, torch.float64)
     xg = synth.vector(n_glob, 1)
     op.set_x(xg)
-    alpha_step = 1.0  # single multiply per step; x is re-fed through the gather only at N > 1
-    launches0 = B.launch_count()
+    peer = None
+    if world > 1 and args.exchange == "peer":
+        peer = vdist.PeerExchangeOperator(B, layout, rank, world, dev, alpha=alpha_step)
+        peer.set_x(xg)
+        dist.barrier()
 
     def step():
-        if world > 1:
-            op.step()
+        if peer is not None:
+            peer.step()          # multiply with the all-gather fused into its epilogue + flag kernel
+        elif world > 1:
+            op.step()            # multiply, then NCCL all-gather
         else:
             op.local_multiply()
 
@@ -197,7 +204,6 @@ def run_ours(args, rank, world, local_rank):
         step()
     torch.cuda.synchronize()
     if world > 1:
-        op.set_x(xg)  # keep magnitudes bounded: restart the iteration from the same x
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -211,7 +217,14 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     ms_total = ev0.elapsed_time(ev1)
-    gpu_launches = B.launch_count() - launches_before
+    gpu_launches = B.launch_count() - launches_before + (args.steps if peer is not None else 0)  # + flag kernel per step
+    if peer is not None and peer.timed_out():
+        raise RuntimeError("peer flag wait timed out")
+    # parity of the distributed iteration: after `warmup + steps` iterations both exchange paths hold the same x
+    x_check = None
+    if world > 1:
+        xs = peer.x_global() if peer is not None else op.x_global()
+        x_check = float(np.abs(xs).sum())
     # kernel-only time of the dominant kernel (no collective), for the roofline
     for _ in range(3):
         op.local_multiply()
@@ -279,6 +292,7 @@ def run_ours(args, rank, world, local_rank):
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "result_checksum": result_checksum},
             "gpu_launches": int(gpu_launches), "clocks": clk.summary(),
             "pack_seconds": pack_s, "cost_imbalance": imbalance, "alpha": alpha_step,
+            "exchange": (args.exchange if world > 1 else None), "x_abs_sum_after_run": x_check,
         }
         if world == 1 and not args.no_cpu_baseline:
             oracle, H = cpu_reference_setup(A, pi, phi)
@@ -304,6 +318,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = all-gather fused into the multiply through NVLink peer stores (default); "
+                         "'nccl' = multiply, then torch.distributed all_gather_into_tensor")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -318,7 +335,7 @@ def main():
         import subprocess
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__),
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--exchange", args.exchange]
         sys.exit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

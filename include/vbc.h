@@ -124,6 +124,42 @@ int vbc_get_option(const vbc_mat *A, int option, int64_t *value);
 /* number of kernel launches this handle has made since creation (bench.py's gpu_launches) */
 int vbc_launch_count(const vbc_mat *A, int64_t *count);
 
+/* ---- multi-GPU: row-block partition with x replicated through peer memory ---------------------
+ * north_star (e): stripes (the row blocks of A') are split across the GPUs of one box; every rank
+ * needs the whole x for its gathers, so each iteration x_{t+1} <- alpha * A' x_t ends with an
+ * all-gather of the y slices.  Here that all-gather is FUSED into the multiply: the adjoint kernel
+ * stores each finished y segment straight into the next-x buffer of every rank (its own and, over
+ * NVLink peer mappings, the others'), and a one-CTA flag kernel is the only cross-rank step.
+ * One process per GPU; the handles are exchanged by the host (torch.distributed / MPI / files).
+ * No reference counterpart: the reference is single-process. */
+typedef struct vbc_peer vbc_peer;
+#define VBC_IPC_HANDLE_BYTES 64
+#define VBC_PEER_HANDLES 3 /* x buffer 0, x buffer 1, flag block */
+#define VBC_MAX_PEERS 8
+
+/* Allocates this rank's two x buffers (xlen elements of vt each, zero-filled) and flag block on
+ * `device`, and writes VBC_PEER_HANDLES CUDA IPC handles to handles_out (3 * 64 bytes). */
+int vbc_peer_create(vbc_peer **out, int vt, int64_t xlen, int rank, int nranks, int device, void *handles_out);
+/* all_handles: nranks * 3 * 64 bytes, rank-major, as gathered from every rank.  Maps the peers. */
+int vbc_peer_connect(vbc_peer *P, const void *all_handles);
+/* Same-process variant (tests, one process driving several "ranks"): raw device pointers,
+ * ptrs[r * 3 + k] = buffer k of rank r. */
+int vbc_peer_connect_local(vbc_peer *P, void *const *ptrs);
+/* raw device pointers of this rank's buffers (k = 0, 1: x buffers; 2: flags) and the current x index */
+int vbc_peer_buffer(vbc_peer *P, int k, void **ptr);
+int vbc_peer_current(const vbc_peer *P, int *cur);
+/* One iteration: y = alpha * A' * x_cur on this rank's stripes, stored at element offset y_offset of
+ * x_{1-cur} on EVERY rank; then signal + wait for all ranks (flags), then cur flips.  A->n columns
+ * are written; A->m must equal xlen.  Enqueued on A's stream.  `barrier`: 3 = signal and wait
+ * (normal), 1 = signal only, 2 = wait only, 0 = neither (same-process tests must not wait inside
+ * one stream for a signal that a later launch of the same stream produces). */
+int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, int barrier);
+/* the flag kernel alone (barrier = 1 | 2 | 3 as above); does not flip cur */
+int vbc_peer_barrier(vbc_peer *P, void *cuda_stream, int barrier);
+/* 0 if no flag wait has timed out since creation (checked after a stream sync by the caller) */
+int vbc_peer_status(vbc_peer *P, int *timed_out);
+void vbc_peer_destroy(vbc_peer *P);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,11 @@ SYMBOLS = [
     "vbc_csc_upload", "vbc_csc_trspmv", "vbc_csc_destroy",
     "vbc_set_stream", "vbc_csc_set_stream", "vbc_sync", "vbc_set_option", "vbc_get_option",
     "vbc_launch_count",
+    "vbc_peer_create", "vbc_peer_connect", "vbc_peer_connect_local", "vbc_peer_buffer", "vbc_peer_current",
+    "vbc_peer_spmv_step", "vbc_peer_barrier", "vbc_peer_status", "vbc_peer_destroy",
 ]
+
+IPC_HANDLE_BYTES, PEER_HANDLES, MAX_PEERS = 64, 3, 8
 
 
 class VBCError(RuntimeError):
@@ -88,9 +92,19 @@ def lib():
     L.vbc_set_option.argtypes = [c_vp, c_int, c_i64]
     L.vbc_get_option.argtypes = [c_vp, c_int, pi64]
     L.vbc_launch_count.argtypes = [c_vp, pi64]
+    L.vbc_peer_create.argtypes = [pp, c_int, c_i64, c_int, c_int, c_int, c_vp]
+    L.vbc_peer_connect.argtypes = [c_vp, c_vp]
+    L.vbc_peer_connect_local.argtypes = [c_vp, ctypes.POINTER(c_vp)]
+    L.vbc_peer_buffer.argtypes = [c_vp, c_int, pp]
+    L.vbc_peer_current.argtypes = [c_vp, pint]
+    L.vbc_peer_spmv_step.argtypes = [c_vp, c_vp, c_dbl, c_i64, c_int]
+    L.vbc_peer_barrier.argtypes = [c_vp, c_vp, c_int]
+    L.vbc_peer_status.argtypes = [c_vp, pint]
+    L.vbc_peer_destroy.argtypes = [c_vp]
+    L.vbc_peer_destroy.restype = None
     for name in SYMBOLS:
         f = getattr(L, name)
-        if name not in ("vbc_last_error", "vbc_destroy", "vbc_csc_destroy"):
+        if name not in ("vbc_last_error", "vbc_destroy", "vbc_csc_destroy", "vbc_peer_destroy"):
             f.restype = c_int
     _lib = L
     return L

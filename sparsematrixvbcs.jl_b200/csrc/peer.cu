@@ -1,0 +1,229 @@
+// peer.cu -- row-partitioned multiply across the GPUs of one box: x replicated through peer
+// memory (CUDA IPC over NVLink / NVSwitch), the all-gather fused into the adjoint kernel's
+// epilogue (spmv.cu, PeerDst), and a flag kernel as the only cross-rank step.
+#include <new>
+
+#include "common.cuh"
+
+struct vbc_peer {
+    int vt = VBC_F64, rank = 0, nranks = 1, device = 0;
+    int64_t xlen = 0;
+    void *own[VBC_PEER_HANDLES] = {nullptr, nullptr, nullptr};               // x0, x1, flags (this rank)
+    void *bufs[VBC_MAX_PEERS][VBC_PEER_HANDLES] = {};                        // every rank's buffers as mapped here
+    bool ipc_opened[VBC_MAX_PEERS][VBC_PEER_HANDLES] = {};
+    bool connected = false;
+    int cur = 0;
+    unsigned long long epoch = 0;
+    int *d_timeout = nullptr;
+    int64_t launches = 0;
+};
+
+namespace vbc {
+
+struct FlagPtrs {
+    unsigned long long *p[VBC_MAX_PEERS]; // flag block of every rank (p[me] is local)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One CTA of 32 threads; thread r talks to rank r.
+//   signal: flags_r[me] = epoch  (release, system scope: this rank's earlier stores -- the y
+//           segments written by the preceding multiply on this stream -- are visible first)
+//   wait  : spin until flags_me[r] >= epoch for every r (acquire), with a wall-clock bound so a
+//           dead peer cannot hang the GPU.
+__global__ void k_peer_flags(const __grid_constant__ FlagPtrs f, const int me, const int nranks, const unsigned long long epoch,
+                             const int do_signal, const int do_wait, int *__restrict__ timed_out)
+{
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    if (do_signal) {
+        __threadfence_system();
+        st_release_sys(f.p[r] + me, epoch);
+    }
+    if (do_wait) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys(f.p[me] + r) < epoch) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ull) { // 4 s
+                atomicExch(timed_out, 1);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+}
+
+static int flags_launch(vbc_peer *P, cudaStream_t st, int barrier)
+{
+    if (!(barrier & 3)) return VBC_OK;
+    FlagPtrs f;
+    for (int r = 0; r < VBC_MAX_PEERS; r++) f.p[r] = r < P->nranks ? (unsigned long long *)P->bufs[r][2] : nullptr;
+    k_peer_flags<<<1, 32, 0, st>>>(f, P->rank, P->nranks, P->epoch, barrier & 1, (barrier & 2) ? 1 : 0, P->d_timeout);
+    P->launches++;
+    VBC_CUDA(cudaGetLastError());
+    return VBC_OK;
+}
+
+} // namespace vbc
+
+using namespace vbc;
+
+extern "C" {
+
+int vbc_peer_create(vbc_peer **out, int vt, int64_t xlen, int rank, int nranks, int device, void *handles_out)
+{
+    if (!out) VBC_FAIL(VBC_EARG, "out is NULL");
+    *out = nullptr;
+    if (vt != VBC_F32 && vt != VBC_F64) VBC_FAIL(VBC_EARG, "vt must be VBC_F32 or VBC_F64");
+    if (nranks < 1 || nranks > VBC_MAX_PEERS || rank < 0 || rank >= nranks) VBC_FAIL(VBC_EARG, "rank %d / nranks %d out of range (max %d)", rank, nranks, VBC_MAX_PEERS);
+    if (xlen < 0) VBC_FAIL(VBC_EARG, "xlen must be >= 0");
+    DeviceGuard guard(device);
+    if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", device);
+    vbc_peer *P = new (std::nothrow) vbc_peer();
+    if (!P) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
+    P->vt = vt; P->rank = rank; P->nranks = nranks; P->device = device; P->xlen = xlen;
+    const size_t xb = vt_size(vt) * (size_t)(xlen > 0 ? xlen : 1);
+    const size_t sizes[VBC_PEER_HANDLES] = {xb, xb, sizeof(unsigned long long) * VBC_MAX_PEERS};
+    int rc = VBC_OK;
+    for (int k = 0; k < VBC_PEER_HANDLES && rc == VBC_OK; k++) {
+        if (cudaMalloc(&P->own[k], sizes[k]) != cudaSuccess || cudaMemset(P->own[k], 0, sizes[k]) != cudaSuccess) {
+            set_error("vbc_peer_create: allocation of %zu bytes failed: %s", sizes[k], cudaGetErrorString(cudaGetLastError()));
+            rc = VBC_ENOMEM;
+        }
+    }
+    if (rc == VBC_OK && (cudaMalloc(&P->d_timeout, sizeof(int)) != cudaSuccess || cudaMemset(P->d_timeout, 0, sizeof(int)) != cudaSuccess)) {
+        set_error("vbc_peer_create: flag allocation failed");
+        rc = VBC_ENOMEM;
+    }
+    if (rc == VBC_OK && handles_out) {
+        for (int k = 0; k < VBC_PEER_HANDLES; k++) {
+            cudaIpcMemHandle_t h;
+            static_assert(sizeof(cudaIpcMemHandle_t) == VBC_IPC_HANDLE_BYTES, "IPC handle size");
+            if (cudaIpcGetMemHandle(&h, P->own[k]) != cudaSuccess) {
+                set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = VBC_ECUDA;
+                break;
+            }
+            memcpy((char *)handles_out + (size_t)k * VBC_IPC_HANDLE_BYTES, &h, VBC_IPC_HANDLE_BYTES);
+        }
+    }
+    if (rc != VBC_OK) { vbc_peer_destroy(P); return rc; }
+    for (int k = 0; k < VBC_PEER_HANDLES; k++) P->bufs[rank][k] = P->own[k];
+    if (nranks == 1) P->connected = true;
+    *out = P;
+    return VBC_OK;
+}
+
+int vbc_peer_connect(vbc_peer *P, const void *all_handles)
+{
+    if (!P || !all_handles) VBC_FAIL(VBC_EARG, "NULL argument");
+    DeviceGuard guard(P->device);
+    if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", P->device);
+    for (int r = 0; r < P->nranks; r++) {
+        if (r == P->rank) continue;
+        for (int k = 0; k < VBC_PEER_HANDLES; k++) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char *)all_handles + ((size_t)r * VBC_PEER_HANDLES + k) * VBC_IPC_HANDLE_BYTES, VBC_IPC_HANDLE_BYTES);
+            void *ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) VBC_FAIL(VBC_ECUDA, "cudaIpcOpenMemHandle(rank %d, buffer %d) failed: %s", r, k, cudaGetErrorString(e));
+            P->bufs[r][k] = ptr;
+            P->ipc_opened[r][k] = true;
+        }
+    }
+    P->connected = true;
+    return VBC_OK;
+}
+
+int vbc_peer_connect_local(vbc_peer *P, void *const *ptrs)
+{
+    if (!P || !ptrs) VBC_FAIL(VBC_EARG, "NULL argument");
+    for (int r = 0; r < P->nranks; r++)
+        for (int k = 0; k < VBC_PEER_HANDLES; k++)
+            if (r != P->rank) P->bufs[r][k] = ptrs[r * VBC_PEER_HANDLES + k];
+    P->connected = true;
+    return VBC_OK;
+}
+
+int vbc_peer_buffer(vbc_peer *P, int k, void **ptr)
+{
+    if (!P || !ptr || k < 0 || k >= VBC_PEER_HANDLES) VBC_FAIL(VBC_EARG, "bad argument");
+    *ptr = P->own[k];
+    return VBC_OK;
+}
+
+int vbc_peer_current(const vbc_peer *P, int *cur)
+{
+    if (!P || !cur) VBC_FAIL(VBC_EARG, "NULL argument");
+    *cur = P->cur;
+    return VBC_OK;
+}
+
+int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, int barrier)
+{
+    if (!P || !A) VBC_FAIL(VBC_EARG, "NULL argument");
+    if (!P->connected) VBC_FAIL(VBC_EARG, "vbc_peer_connect has not been called");
+    if (A->vt != P->vt) VBC_FAIL(VBC_EARG, "matrix and exchange buffers have different element types");
+    if (A->m != P->xlen) VBC_FAIL(VBC_EDIM, "DimensionMismatch: A' needs x of length %lld, exchange buffers hold %lld", (long long)A->m, (long long)P->xlen);
+    if (y_offset < 0 || y_offset + A->n > P->xlen) VBC_FAIL(VBC_EDIM, "DimensionMismatch: y slice [%lld, %lld) outside x of length %lld", (long long)y_offset, (long long)(y_offset + A->n), (long long)P->xlen);
+    DeviceGuard guard(P->device);
+    if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", P->device);
+    const size_t tv = vt_size(P->vt);
+    void *dst[VBC_MAX_PEERS];
+    const int nxt = 1 - P->cur;
+    // own buffer first: its stores are local; then the peers, starting after this rank so the
+    // ranks do not all hit the same destination at the same moment
+    int n = 0;
+    for (int i = 0; i < P->nranks; i++) {
+        const int r = (P->rank + i) % P->nranks;
+        dst[n++] = (char *)P->bufs[r][nxt] + tv * (size_t)y_offset;
+    }
+    VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst));
+    if (barrier & 1) P->epoch++;
+    VBC_TRY(flags_launch(P, A->stream, barrier));
+    P->cur = nxt;
+    return VBC_OK;
+}
+
+int vbc_peer_barrier(vbc_peer *P, void *cuda_stream, int barrier)
+{
+    if (!P) VBC_FAIL(VBC_EARG, "NULL argument");
+    if (!P->connected) VBC_FAIL(VBC_EARG, "vbc_peer_connect has not been called");
+    DeviceGuard guard(P->device);
+    if (barrier & 1) P->epoch++;
+    return flags_launch(P, (cudaStream_t)cuda_stream, barrier);
+}
+
+int vbc_peer_status(vbc_peer *P, int *timed_out)
+{
+    if (!P || !timed_out) VBC_FAIL(VBC_EARG, "NULL argument");
+    DeviceGuard guard(P->device);
+    VBC_CUDA(cudaMemcpy(timed_out, P->d_timeout, sizeof(int), cudaMemcpyDeviceToHost));
+    return VBC_OK;
+}
+
+void vbc_peer_destroy(vbc_peer *P)
+{
+    if (!P) return;
+    DeviceGuard guard(P->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < VBC_MAX_PEERS; r++)
+        for (int k = 0; k < VBC_PEER_HANDLES; k++)
+            if (P->ipc_opened[r][k]) cudaIpcCloseMemHandle(P->bufs[r][k]);
+    for (int k = 0; k < VBC_PEER_HANDLES; k++) cudaFree(P->own[k]);
+    cudaFree(P->d_timeout);
+    delete P;
+}
+
+} // extern "C"

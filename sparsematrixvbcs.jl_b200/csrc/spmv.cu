@@ -46,6 +46,33 @@ template <int G> __device__ __forceinline__ unsigned group_mask()
     else return ((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G);
 }
 
+// Destinations of the adjoint result.  n == 0: the caller's y (alpha/beta applied).  n > 0: the
+// fused all-gather of the row-partitioned multiply -- every finished y segment is stored into the
+// next-x buffer of each of the n ranks (own HBM and NVLink peer mappings); beta is not applied.
+struct PeerDst {
+    int n;
+    void *p[VBC_MAX_PEERS];
+};
+
+template <typename Tv, int EPV, bool PEER>
+__device__ __forceinline__ void store_y(Tv *__restrict__ y, const PeerDst &dst, const int col, const Tv (&acc)[EPV], const Tv alpha, const Tv beta)
+{
+    if constexpr (PEER) {
+        Tv v[EPV];
+#pragma unroll
+        for (int e = 0; e < EPV; e++) v[e] = alpha * acc[e];
+        for (int i = 0; i < dst.n; i++) {
+            Tv *yp = reinterpret_cast<Tv *>(dst.p[i]) + col;
+#pragma unroll
+            for (int e = 0; e < EPV; e++) yp[e] = v[e];
+        }
+    } else {
+        Tv *yp = y + col;
+#pragma unroll
+        for (int e = 0; e < EPV; e++) yp[e] = (beta == (Tv)0) ? alpha * acc[e] : alpha * acc[e] + beta * yp[e];
+    }
+}
+
 // x-index stream of a stripe for one lane: row r0, then r0+rps, ...
 template <int MODE> struct RowWalk;
 template <> struct RowWalk<DESC_ROWS> {
@@ -72,10 +99,10 @@ template <> struct RowWalk<DESC_BLOCKS> {
 
 // ---- adjoint ----------------------------------------------------------------------------------
 // CPR > 0: compile-time vectors per row (power of two, <= G).  CPR == 0: runtime cpr <= G.
-template <typename Tv, int G, int MODE, int EPV, int CPR>
+template <typename Tv, int G, int MODE, int EPV, int CPR, bool PEER>
 __device__ __forceinline__ void adj_stripe(const StripeMeta a, const StripeMeta b, const int w, const int lane, const unsigned gmask,
                                            const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
-                                           Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta)
+                                           Tv *__restrict__ y, const PeerDst &dst, const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
     int cpr, rps, c, r0;
     if constexpr (CPR > 0) { cpr = CPR; rps = G / CPR; c = lane % CPR; r0 = lane / CPR; }
@@ -129,18 +156,15 @@ __device__ __forceinline__ void adj_stripe(const StripeMeta a, const StripeMeta 
                 if (lane + d < G) acc[e] += t;
             }
     }
-    if (lane < cpr) { // y[j + Δj] = tmp[Δj]  (multiply_1DVBC.jl:114-116), with BLAS alpha/beta
-        Tv *yp = y + a.col + lane * EPV;
-#pragma unroll
-        for (int e = 0; e < EPV; e++) yp[e] = (beta == (Tv)0) ? alpha * acc[e] : alpha * acc[e] + beta * yp[e];
-    }
+    // y[j + Δj] = tmp[Δj]  (multiply_1DVBC.jl:114-116), with BLAS alpha/beta
+    if (lane < cpr) store_y<Tv, EPV, PEER>(y, dst, a.col + lane * EPV, acc, alpha, beta);
 }
 
 // wide stripes (more vectors per row than lanes): one lane per column, serial over rows
-template <typename Tv, int G, int MODE>
+template <typename Tv, int G, int MODE, bool PEER>
 __device__ __noinline__ void adj_stripe_wide(const StripeMeta a, const StripeMeta b, const int w, const int lane,
                                              const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
-                                             Tv *__restrict__ y, const int u0, const Tv alpha, const Tv beta)
+                                             Tv *__restrict__ y, const PeerDst &dst, const int u0, const Tv alpha, const Tv beta)
 {
     const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
     for (int col = lane; col < w; col += G) {
@@ -149,27 +173,28 @@ __device__ __noinline__ void adj_stripe_wide(const StripeMeta a, const StripeMet
         walk.init(desc, a.pos, 0, 1, u0, -1);
         const Tv *vp = val + a.ofs + col;
         for (int r = 0; r < R; r++) { acc = fma(__ldcs(vp), __ldg(x + walk.next()), acc); vp += w; }
-        Tv *yp = y + a.col + col;
-        *yp = (beta == (Tv)0) ? alpha * acc : alpha * acc + beta * *yp;
+        const Tv accv[1] = {acc};
+        store_y<Tv, 1, PEER>(y, dst, a.col + col, accv, alpha, beta);
     }
 }
 
-template <typename Tv, int G, int MODE, int EPV>
+template <typename Tv, int G, int MODE, int EPV, bool PEER>
 __device__ __forceinline__ void adj_dispatch_cpr(const StripeMeta a, const StripeMeta b, const int w, const int lane, const unsigned gmask,
                                                  const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
-                                                 Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta)
+                                                 Tv *__restrict__ y, const PeerDst &dst, const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
     const int cpr = w / EPV;
-    if (cpr == 1) adj_stripe<Tv, G, MODE, EPV, 1>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
-    else if (cpr == 2) adj_stripe<Tv, G, MODE, EPV, 2>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
-    else if (cpr == 4) adj_stripe<Tv, G, MODE, EPV, 4>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
-    else if (cpr <= G) adj_stripe<Tv, G, MODE, EPV, 0>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
-    else adj_stripe_wide<Tv, G, MODE>(a, b, w, lane, desc, val, x, y, u0, alpha, beta);
+    if (cpr == 1) adj_stripe<Tv, G, MODE, EPV, 1, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
+    else if (cpr == 2) adj_stripe<Tv, G, MODE, EPV, 2, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
+    else if (cpr == 4) adj_stripe<Tv, G, MODE, EPV, 4, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
+    else if (cpr <= G) adj_stripe<Tv, G, MODE, EPV, 0, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
+    else adj_stripe_wide<Tv, G, MODE, PEER>(a, b, w, lane, desc, val, x, y, dst, u0, alpha, beta);
 }
 
-template <typename Tv, int G, int MODE>
+template <typename Tv, int G, int MODE, bool PEER>
 __global__ void __launch_bounds__(256) k_spmv_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                    const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ y,
+                                                   const __grid_constant__ PeerDst dst,
                                                    const int L, const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
     constexpr int VE = 16 / (int)sizeof(Tv);
@@ -181,11 +206,11 @@ __global__ void __launch_bounds__(256) k_spmv_adj(const StripeMeta *__restrict__
         const int w = b.col - a.col;
         if (w <= 0) continue;
         if ((w % VE) == 0 && (a.ofs % VE) == 0)
-            adj_dispatch_cpr<Tv, G, MODE, VE>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+            adj_dispatch_cpr<Tv, G, MODE, VE, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
         else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0)
-            adj_dispatch_cpr<Tv, G, MODE, (VE == 4 ? 2 : 1)>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+            adj_dispatch_cpr<Tv, G, MODE, (VE == 4 ? 2 : 1), PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
         else
-            adj_dispatch_cpr<Tv, G, MODE, 1>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+            adj_dispatch_cpr<Tv, G, MODE, 1, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
     }
 }
 
@@ -363,18 +388,18 @@ static int auto_group(const vbc_mat *A)
     return vec_per_stripe >= 160.0 ? 32 : 8;
 }
 
-template <typename Tv, int G, int MODE>
-static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
+template <typename Tv, int G, int MODE, bool PEER>
+static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y, const PeerDst &dst)
 {
     int occ = 0;
-    VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_adj<Tv, G, MODE>, 256, 0));
+    VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_adj<Tv, G, MODE, PEER>, 256, 0));
     if (occ < 1) occ = 1;
     if (A->opt_grid_mult > 0) occ = A->opt_grid_mult;
     int64_t grid = (int64_t)A->sm_count * occ;
     const int64_t need = (A->L * G + 255) / 256;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    k_spmv_adj<Tv, G, MODE><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, y, (int)A->L, A->u0, ilog2_exact(A->u0), alpha, beta);
+    k_spmv_adj<Tv, G, MODE, PEER><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, y, dst, (int)A->L, A->u0, ilog2_exact(A->u0), alpha, beta);
     A->launches++;
     VBC_CUDA(cudaGetLastError());
     return VBC_OK;
@@ -395,6 +420,15 @@ static int launch_fwd_t(vbc_mat *A, Tv alpha, const Tv *x, Tv *y)
     A->launches++;
     VBC_CUDA(cudaGetLastError());
     return VBC_OK;
+}
+
+template <typename Tv, bool PEER>
+static int launch_adj_any(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y, const PeerDst &dst)
+{
+    const bool rows = A->desc_mode == DESC_ROWS;
+    const int G = A->opt_adj_group ? A->opt_adj_group : auto_group(A);
+    if (G >= 32) return rows ? launch_adj_t<Tv, 32, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 32, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
+    return rows ? launch_adj_t<Tv, 8, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 8, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
 }
 
 template <typename Tv>
@@ -445,15 +479,27 @@ static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, 
     const bool rows = A->desc_mode == DESC_ROWS;
     if (trans) {
         if (A->L == 0) return VBC_OK; // n == 0: nothing to write
-        int G = A->opt_adj_group ? A->opt_adj_group : auto_group(A);
-        if (G >= 32) return rows ? launch_adj_t<Tv, 32, DESC_ROWS>(A, alpha, x, beta, y) : launch_adj_t<Tv, 32, DESC_BLOCKS>(A, alpha, x, beta, y);
-        return rows ? launch_adj_t<Tv, 8, DESC_ROWS>(A, alpha, x, beta, y) : launch_adj_t<Tv, 8, DESC_BLOCKS>(A, alpha, x, beta, y);
+        return launch_adj_any<Tv, false>(A, alpha, x, beta, y, PeerDst{0, {nullptr}});
     }
     VBC_TRY(scale_y<Tv>(A, y, A->m, beta));
     if (A->L == 0 || A->nval == 0) return VBC_OK;
     int G = A->opt_fwd_group ? A->opt_fwd_group : auto_group(A);
     if (G >= 32) return rows ? launch_fwd_t<Tv, 32, DESC_ROWS>(A, alpha, x, y) : launch_fwd_t<Tv, 32, DESC_BLOCKS>(A, alpha, x, y);
     return rows ? launch_fwd_t<Tv, 8, DESC_ROWS>(A, alpha, x, y) : launch_fwd_t<Tv, 8, DESC_BLOCKS>(A, alpha, x, y);
+}
+
+// adjoint multiply whose result goes to `n` destination buffers (each already offset to this
+// rank's first column): the compute half of vbc_peer_spmv_step.
+int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs)
+{
+    if (A->opt_parity) VBC_FAIL(VBC_EARG, "peer multiply needs the compact layout (parity mode is on)");
+    if (n < 1 || n > VBC_MAX_PEERS) VBC_FAIL(VBC_EARG, "peer count %d out of 1..%d", n, VBC_MAX_PEERS);
+    if (A->L == 0) return VBC_OK;
+    PeerDst dst;
+    dst.n = n;
+    for (int i = 0; i < VBC_MAX_PEERS; i++) dst.p[i] = i < n ? dst_ptrs[i] : nullptr;
+    if (A->vt == VBC_F64) return launch_adj_any<double, true>(A, alpha, (const double *)d_x, 0.0, nullptr, dst);
+    return launch_adj_any<float, true>(A, (float)alpha, (const float *)d_x, 0.0f, nullptr, dst);
 }
 
 int launch_spmv(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y)

@@ -88,19 +88,19 @@ def padded_row_partition(layout: PaddedLayout, u, ti):
 
 
 class RowPartitionedOperator:
-    """One rank's share of the iterated adjoint multiply x <- A' x.
+    """One rank's share of the iterated adjoint multiply x <- alpha * A' x with the x exchange done by
+    a torch.distributed all-gather (NCCL on GPUs; gloo in the CPU tests).
 
-    local   : this rank's device matrix (rows in padded coordinates, columns = its stripes)
-    layout  : PaddedLayout of the global vector
-    Buffers : x (padded_len) and y_pad (S) are torch CUDA tensors; step() runs the local SpMV
-              into y_pad and all-gathers y_pad from every rank into x.
+    local_mul(y_slice, x) : fills this rank's y slice from the full (padded) x -- on a GPU
+                            `lambda y, x: mul_(y, B.T, x, alpha)`, in CPU tests the oracle
+    layout                : PaddedLayout of the global vector
     """
 
-    def __init__(self, local, layout: PaddedLayout, rank, world, dtype):
+    def __init__(self, local_mul, layout: PaddedLayout, rank, world, dtype, device="cuda"):
         import torch
-        self.local, self.layout, self.rank, self.world = local, layout, rank, world
-        self.x = torch.zeros(layout.padded_len, dtype=dtype, device="cuda")
-        self.y_pad = torch.zeros(layout.S, dtype=dtype, device="cuda")
+        self.local_mul, self.layout, self.rank, self.world = local_mul, layout, rank, world
+        self.x = torch.zeros(layout.padded_len, dtype=dtype, device=device)
+        self.y_pad = torch.zeros(layout.S, dtype=dtype, device=device)
         self.n_local = int(layout.lens[rank])
 
     def set_x(self, x_global_np):
@@ -108,15 +108,17 @@ class RowPartitionedOperator:
         self.x.copy_(torch.from_numpy(self.layout.scatter(x_global_np)))
 
     def local_multiply(self):
-        from .matrix import mul_
-        mul_(self.y_pad[: self.n_local], self.local.T, self.x)
+        self.local_mul(self.y_pad[: self.n_local], self.x)
 
     def exchange(self):
         import torch.distributed as dist
         if self.world == 1:
             self.x[: self.layout.S].copy_(self.y_pad)
-        else:
+            return
+        try:
             dist.all_gather_into_tensor(self.x, self.y_pad)
+        except (RuntimeError, NotImplementedError):  # backends without the flat variant
+            dist.all_gather(list(self.x.view(self.world, self.layout.S).unbind(0)), self.y_pad)
 
     def step(self):
         self.local_multiply()
@@ -124,3 +126,90 @@ class RowPartitionedOperator:
 
     def x_global(self):
         return self.layout.gather(self.x.cpu().numpy())
+
+
+class PeerExchangeOperator:
+    """Same iteration with the all-gather FUSED into the multiply (libvbc `vbc_peer_*`): the adjoint
+    kernel stores every finished y segment into the next-x buffer of all ranks through CUDA-IPC
+    peer mappings (NVLink), and a one-CTA flag kernel is the only cross-rank step.  x is double
+    buffered inside libvbc; handles are exchanged once with torch.distributed (any backend)."""
+
+    def __init__(self, B, layout: PaddedLayout, rank, world, device, alpha=1.0):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        self.B, self.layout, self.rank, self.world, self.alpha = B, layout, rank, world, float(alpha)
+        self._h = ctypes.c_void_p()
+        L = _lib.lib()
+        vt = _lib.VBC_F64 if B.Tv == np.dtype(np.float64) else _lib.VBC_F32
+        mine = (ctypes.c_char * (_lib.PEER_HANDLES * _lib.IPC_HANDLE_BYTES))()
+        _lib.check(L.vbc_peer_create(ctypes.byref(self._h), vt, layout.padded_len, rank, world, int(device), mine))
+        if world > 1:
+            t = torch.tensor(list(bytes(mine)), dtype=torch.uint8)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            allh = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allh, t)
+            blob = b"".join(bytes(h.cpu().tolist()) for h in allh)
+            _lib.check(L.vbc_peer_connect(self._h, blob))
+        self.y_offset = rank * layout.S
+        self.Tv = B.Tv
+        self._lib = _lib
+
+    def _buf_ptr(self, k):
+        import ctypes
+        p = ctypes.c_void_p()
+        self._lib.check(self._lib.lib().vbc_peer_buffer(self._h, k, ctypes.byref(p)))
+        return p.value
+
+    def current(self):
+        import ctypes
+        c = ctypes.c_int()
+        self._lib.check(self._lib.lib().vbc_peer_current(self._h, ctypes.byref(c)))
+        return c.value
+
+    def _as_tensor(self, k):
+        """torch view of x buffer k (memory owned by libvbc)."""
+        import torch
+
+        class _Wrap:
+            pass
+        w = _Wrap()
+        w.__cuda_array_interface__ = {"shape": (self.layout.padded_len,), "typestr": "<f8" if self.Tv == np.dtype(np.float64) else "<f4",
+                                      "data": (self._buf_ptr(k), False), "version": 2}
+        return torch.as_tensor(w, device="cuda")
+
+    def set_x(self, x_global_np):
+        import torch
+        self._as_tensor(self.current()).copy_(torch.from_numpy(self.layout.scatter(x_global_np)))
+        torch.cuda.synchronize()
+
+    def step(self, barrier=3):
+        self.B._use_torch_stream()
+        self._lib.check(self._lib.lib().vbc_peer_spmv_step(self._h, self.B._h, self.alpha, self.y_offset, barrier))
+
+    def timed_out(self):
+        import ctypes
+        c = ctypes.c_int()
+        self._lib.check(self._lib.lib().vbc_peer_status(self._h, ctypes.byref(c)))
+        return bool(c.value)
+
+    def x_global(self):
+        import torch
+        torch.cuda.synchronize()
+        return self.layout.gather(self._as_tensor(self.current()).cpu().numpy())
+
+    def close(self):
+        if self._h.value:
+            self._lib.lib().vbc_peer_destroy(self._h)
+            import ctypes
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,87 @@
+"""CPU-only, world_size 2 over gloo: the host-side logic of the row-partitioned multiply --
+cost-balanced stripe split, padded layout, row remapping, and the all-gather iteration -- with the
+oracle standing in for the per-rank device multiply."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_split_by_cost_balances_and_is_monotone():
+    from vbc_b200 import dist as vdist
+    rng = np.random.default_rng(0)
+    cost = rng.integers(1, 1000, size=1000)
+    for P in (1, 2, 4, 8):
+        b = vdist.split_by_cost(cost, P)
+        assert b[0] == 0 and b[-1] == 1000 and np.all(np.diff(b) >= 0)
+        sums = np.array([cost[b[r]:b[r + 1]].sum() for r in range(P)])
+        assert sums.max() <= cost.sum() / P + cost.max()
+    assert vdist.split_by_cost(np.array([5, 0, 0, 5]), 2).tolist() in ([0, 1, 4], [0, 2, 4], [0, 3, 4])
+    assert vdist.split_by_cost(np.array([], dtype=np.int64), 2).tolist() == [0, 0, 0]
+
+
+def test_padded_layout_roundtrip():
+    from vbc_b200 import dist as vdist
+    lay = vdist.PaddedLayout(np.array([0, 12, 20, 40]))
+    assert lay.S == 20 and lay.padded_len == 60
+    x = np.arange(40.0)
+    assert np.array_equal(lay.gather(lay.scatter(x)), x)
+    assert lay.to_padded(np.array([0, 11, 12, 19, 20, 39])).tolist() == [0, 11, 20, 27, 40, 59]
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from vbc_b200 import dist as vdist
+    from vbc_b200 import synth
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, u, w = 4_000, 4, 4
+    L = n // w
+    A, pi, phi = synth.config_c2(n=n, S=7)  # every rank can build the global matrix at this size
+    H = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, u, w)
+    cost, _ = oracle.memory_cost(H)
+    b = vdist.split_by_cost(cost, world)
+    b[1:-1] += 5  # unequal slices
+    layout = vdist.PaddedLayout(b * w)
+    Ar, _, phir = synth.config_c2(n=n, S=7, stripes=(int(b[rank]), int(b[rank + 1])))
+    Ar = vdist.remap_rows_to_padded(Ar, layout, u)
+    pir = vdist.padded_row_partition(layout, u, np.int64)
+    Hr = oracle.pack_2d(Ar.m, Ar.n, Ar.colptr, Ar.rowval, Ar.nzval, pir.spl, phir.spl, u, w)
+
+    def local_mul(y, x):
+        y.copy_(torch.from_numpy(0.04 * oracle.mul(Hr, x.numpy(), trans=True)))
+
+    op = vdist.RowPartitionedOperator(local_mul, layout, rank, world, torch.float64, device="cpu")
+    x0 = synth.vector(n, 2)
+    op.set_x(x0)
+    ref = x0.copy()
+    S = A.to_scipy()
+    for _ in range(3):
+        op.step()
+        ref = 0.04 * (S.T @ ref)
+    ok = bool(np.allclose(op.x_global(), ref, rtol=1e-12, atol=0))
+    q.put((rank, ok, b.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_partitioned_iteration_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    assert res[0][2] == res[1][2]  # every rank computed the same split

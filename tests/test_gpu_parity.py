@@ -294,3 +294,64 @@ def test_reduced_c2_and_variable_blocks():
     B32 = vb.SparseMatrixVBC[4, 4](A32, pi, phi)
     assert_packed_equal(B32, H32)
     randx_check(A32, B32, H32, rng)
+
+
+def test_peer_exchange_two_ranks_on_one_gpu():
+    """The fused multiply + all-gather (vbc_peer_*) with two "ranks" driven by one process on one GPU:
+    signal and wait are issued separately so no launch waits for a later launch of the same stream."""
+    import ctypes
+    import torch
+    from vbc_b200 import dist as vdist
+    n, u, w, P = 8_000, 4, 4, 2
+    A, pi, phi = synth.config_c2(n=n, S=9)
+    S = A.to_scipy()
+    L = n // w
+    cost = np.asarray([3 * 8 + (A.colptr[(l + 1) * w] - A.colptr[l * w]) // w * (8 // u) + (A.colptr[(l + 1) * w] - A.colptr[l * w]) * 8 for l in range(L)])
+    b = vdist.split_by_cost(cost, P)
+    b[1] += 37  # force unequal slices so the padded layout is exercised
+    layout = vdist.PaddedLayout(b * w)
+    mats, peers = [], []
+    Lh = _lib.lib()
+    for r in range(P):
+        Ar, pir, phir = synth.config_c2(n=n, S=9, stripes=(int(b[r]), int(b[r + 1])))
+        Ar = vdist.remap_rows_to_padded(Ar, layout, u)
+        mats.append(vb.SparseMatrixVBC[u, w](Ar, vdist.padded_row_partition(layout, u, np.int64), phir))
+        h = ctypes.c_void_p()
+        _lib.check(Lh.vbc_peer_create(ctypes.byref(h), _lib.VBC_F64, layout.padded_len, r, P, 0, None))
+        peers.append(h)
+    ptrs = (ctypes.c_void_p * (P * 3))()
+    for r in range(P):
+        for k in range(3):
+            p = ctypes.c_void_p()
+            _lib.check(Lh.vbc_peer_buffer(peers[r], k, ctypes.byref(p)))
+            ptrs[r * 3 + k] = p.value
+    for r in range(P):
+        _lib.check(Lh.vbc_peer_connect_local(peers[r], ptrs))
+    x0 = synth.vector(n, 3)
+    xp = layout.scatter(x0)
+    for r in range(P):  # load x into buffer 0 of every rank
+        _lib.check(Lh.vbc_peer_buffer(peers[r], 0, ctypes.byref(p)))
+        assert torch.cuda.current_device() == 0
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(p.value), ctypes.c_void_p(xp.ctypes.data), ctypes.c_size_t(xp.nbytes), 1)
+    x_ref = x0.copy()
+    for it in range(3):
+        for r in range(P):
+            _lib.check(Lh.vbc_peer_spmv_step(peers[r], mats[r]._h, 0.05, r * layout.S, 0))
+        for r in range(P):
+            _lib.check(Lh.vbc_peer_barrier(peers[r], None, 1))
+        for r in range(P):
+            _lib.check(Lh.vbc_peer_barrier(peers[r], None, 2))
+        x_ref = 0.05 * (S.T @ x_ref)
+    torch.cuda.synchronize()
+    out = np.empty(layout.padded_len)
+    for r in range(P):
+        cur, to = ctypes.c_int(), ctypes.c_int()
+        _lib.check(Lh.vbc_peer_current(peers[r], ctypes.byref(cur)))
+        assert cur.value == 1  # three flips from 0
+        _lib.check(Lh.vbc_peer_status(peers[r], ctypes.byref(to)))
+        assert to.value == 0
+        _lib.check(Lh.vbc_peer_buffer(peers[r], cur.value, ctypes.byref(p)))
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(p.value), ctypes.c_size_t(out.nbytes), 2)
+        assert np.allclose(layout.gather(out), x_ref, rtol=1e-12, atol=0), f"rank {r}"
+    for h in peers:
+        Lh.vbc_peer_destroy(h)
