@@ -13,7 +13,8 @@ struct vbc_peer {
     bool ipc_opened[VBC_MAX_PEERS][VBC_PEER_HANDLES] = {};
     bool connected = false;
     int cur = 0;
-    unsigned long long epoch = 0;
+    unsigned long long *d_epoch = nullptr; // device-side epoch counter: the flag kernel advances it itself, so a
+                                           // captured CUDA graph of steps stays correct when replayed
     int *d_timeout = nullptr;
     int64_t launches = 0;
 };
@@ -40,10 +41,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 //           segments written by the preceding multiply on this stream -- are visible first)
 //   wait  : spin until flags_me[r] >= epoch for every r (acquire), with a wall-clock bound so a
 //           dead peer cannot hang the GPU.
-__global__ void k_peer_flags(const __grid_constant__ FlagPtrs f, const int me, const int nranks, const unsigned long long epoch,
+__global__ void k_peer_flags(const __grid_constant__ FlagPtrs f, const int me, const int nranks, unsigned long long *__restrict__ d_epoch,
                              const int do_signal, const int do_wait, int *__restrict__ timed_out)
 {
     const int r = threadIdx.x;
+    // epoch of this barrier: a signal opens a new epoch, a wait-only launch waits for the open one
+    const unsigned long long epoch = *d_epoch + (do_signal ? 1ull : 0ull);
+    __syncwarp();
+    if (r == 0 && do_signal) *d_epoch = epoch;
     if (r >= nranks) return;
     if (do_signal) {
         __threadfence_system();
@@ -69,7 +74,7 @@ static int flags_launch(vbc_peer *P, cudaStream_t st, int barrier)
     if (!(barrier & 3)) return VBC_OK;
     FlagPtrs f;
     for (int r = 0; r < VBC_MAX_PEERS; r++) f.p[r] = r < P->nranks ? (unsigned long long *)P->bufs[r][2] : nullptr;
-    k_peer_flags<<<1, 32, 0, st>>>(f, P->rank, P->nranks, P->epoch, barrier & 1, (barrier & 2) ? 1 : 0, P->d_timeout);
+    k_peer_flags<<<1, 32, 0, st>>>(f, P->rank, P->nranks, P->d_epoch, barrier & 1, (barrier & 2) ? 1 : 0, P->d_timeout);
     P->launches++;
     VBC_CUDA(cudaGetLastError());
     return VBC_OK;
@@ -101,6 +106,10 @@ int vbc_peer_create(vbc_peer **out, int vt, int64_t xlen, int rank, int nranks, 
             set_error("vbc_peer_create: allocation of %zu bytes failed: %s", sizes[k], cudaGetErrorString(cudaGetLastError()));
             rc = VBC_ENOMEM;
         }
+    }
+    if (rc == VBC_OK && (cudaMalloc(&P->d_epoch, sizeof(unsigned long long)) != cudaSuccess || cudaMemset(P->d_epoch, 0, sizeof(unsigned long long)) != cudaSuccess)) {
+        set_error("vbc_peer_create: epoch allocation failed");
+        rc = VBC_ENOMEM;
     }
     if (rc == VBC_OK && (cudaMalloc(&P->d_timeout, sizeof(int)) != cudaSuccess || cudaMemset(P->d_timeout, 0, sizeof(int)) != cudaSuccess)) {
         set_error("vbc_peer_create: flag allocation failed");
@@ -190,7 +199,6 @@ int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, 
         dst[n++] = (char *)P->bufs[r][nxt] + tv * (size_t)y_offset;
     }
     VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst));
-    if (barrier & 1) P->epoch++;
     VBC_TRY(flags_launch(P, A->stream, barrier));
     P->cur = nxt;
     return VBC_OK;
@@ -201,7 +209,6 @@ int vbc_peer_barrier(vbc_peer *P, void *cuda_stream, int barrier)
     if (!P) VBC_FAIL(VBC_EARG, "NULL argument");
     if (!P->connected) VBC_FAIL(VBC_EARG, "vbc_peer_connect has not been called");
     DeviceGuard guard(P->device);
-    if (barrier & 1) P->epoch++;
     return flags_launch(P, (cudaStream_t)cuda_stream, barrier);
 }
 
@@ -223,6 +230,7 @@ void vbc_peer_destroy(vbc_peer *P)
             if (P->ipc_opened[r][k]) cudaIpcCloseMemHandle(P->bufs[r][k]);
     for (int k = 0; k < VBC_PEER_HANDLES; k++) cudaFree(P->own[k]);
     cudaFree(P->d_timeout);
+    cudaFree(P->d_epoch);
     delete P;
 }
 

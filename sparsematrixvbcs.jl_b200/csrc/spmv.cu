@@ -22,13 +22,56 @@
 
 namespace vbc {
 
+// ---- compile-time tuning knobs (tools/build_variants.sh builds one library per setting) -------
+#ifndef VBC_ADJ_UNR
+#define VBC_ADJ_UNR 4      // independent row-steps in flight per lane in the adjoint main loop
+#endif
+#ifndef VBC_ADJ_MINB
+#define VBC_ADJ_MINB 0     // __launch_bounds__ min CTAs/SM for the adjoint kernel (caps registers); 0 = compiler default
+#endif
+#if VBC_ADJ_MINB > 0
+#define VBC_ADJ_BOUNDS __launch_bounds__(256, VBC_ADJ_MINB)
+#else
+#define VBC_ADJ_BOUNDS __launch_bounds__(256)
+#endif
+#ifndef VBC_LD_MODE
+#define VBC_LD_MODE 0      // val loads: 0 = ld.global.cs (streaming), 1 = ld.global.nc, 2 = ld.global.nc.L1::no_allocate
+#endif
+#ifndef VBC_WIDE_LD
+#define VBC_WIDE_LD 0      // 1: 256-bit loads (sm_100+ LDG.256) for Float64 stripes whose width is a multiple of 4
+#endif
+
 // ---- vector loads ---------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T ld_val(const T *p)
+{
+#if VBC_LD_MODE == 0
+    return __ldcs(p);
+#else
+    return __ldg(p);
+#endif
+}
+#if VBC_LD_MODE == 2
+template <> __device__ __forceinline__ double2 ld_val<double2>(const double2 *p)
+{
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+template <> __device__ __forceinline__ float4 ld_val<float4>(const float4 *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+#endif
 template <typename Tv, int EPV> struct Ld;
-template <> struct Ld<double, 1> { static __device__ __forceinline__ void s(const double *p, double (&v)[1]) { v[0] = __ldcs(p); } };
-template <> struct Ld<double, 2> { static __device__ __forceinline__ void s(const double *p, double (&v)[2]) { const double2 t = __ldcs(reinterpret_cast<const double2 *>(p)); v[0] = t.x; v[1] = t.y; } };
-template <> struct Ld<float, 1> { static __device__ __forceinline__ void s(const float *p, float (&v)[1]) { v[0] = __ldcs(p); } };
-template <> struct Ld<float, 2> { static __device__ __forceinline__ void s(const float *p, float (&v)[2]) { const float2 t = __ldcs(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; } };
-template <> struct Ld<float, 4> { static __device__ __forceinline__ void s(const float *p, float (&v)[4]) { const float4 t = __ldcs(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
+template <> struct Ld<double, 1> { static __device__ __forceinline__ void s(const double *p, double (&v)[1]) { v[0] = ld_val(p); } };
+template <> struct Ld<double, 2> { static __device__ __forceinline__ void s(const double *p, double (&v)[2]) { const double2 t = ld_val(reinterpret_cast<const double2 *>(p)); v[0] = t.x; v[1] = t.y; } };
+template <> struct Ld<double, 4> { static __device__ __forceinline__ void s(const double *p, double (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p)); } };
+template <> struct Ld<float, 1> { static __device__ __forceinline__ void s(const float *p, float (&v)[1]) { v[0] = ld_val(p); } };
+template <> struct Ld<float, 2> { static __device__ __forceinline__ void s(const float *p, float (&v)[2]) { const float2 t = ld_val(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; } };
+template <> struct Ld<float, 4> { static __device__ __forceinline__ void s(const float *p, float (&v)[4]) { const float4 t = ld_val(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
 
 __device__ __forceinline__ StripeMeta ld_meta(const StripeMeta *p)
 {
@@ -119,7 +162,7 @@ __device__ __forceinline__ void adj_stripe(const StripeMeta a, const StripeMeta 
     const int vstride = rps * w;
     RowWalk<MODE> walk;
     walk.init(desc, a.pos, r0, rps, u0, log2u);
-    constexpr int UNR = 4;
+    constexpr int UNR = VBC_ADJ_UNR;
     for (; r + (UNR - 1) * rps < R; r += UNR * rps) {
         Tv v[UNR][EPV];
         int xi[UNR];
@@ -192,7 +235,7 @@ __device__ __forceinline__ void adj_dispatch_cpr(const StripeMeta a, const Strip
 }
 
 template <typename Tv, int G, int MODE, bool PEER>
-__global__ void __launch_bounds__(256) k_spmv_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+__global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                    const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ y,
                                                    const __grid_constant__ PeerDst dst,
                                                    const int L, const int u0, const int log2u, const Tv alpha, const Tv beta)
@@ -205,6 +248,11 @@ __global__ void __launch_bounds__(256) k_spmv_adj(const StripeMeta *__restrict__
         const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
         const int w = b.col - a.col;
         if (w <= 0) continue;
+#if VBC_WIDE_LD
+        if (sizeof(Tv) == 8 && (w % 4) == 0 && (a.ofs % 4) == 0)
+            adj_dispatch_cpr<Tv, G, MODE, (sizeof(Tv) == 8 ? 4 : VE), PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
+        else
+#endif
         if ((w % VE) == 0 && (a.ofs % VE) == 0)
             adj_dispatch_cpr<Tv, G, MODE, VE, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
         else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0)
