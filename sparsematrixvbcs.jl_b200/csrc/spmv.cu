@@ -27,7 +27,8 @@ namespace vbc {
 #define VBC_ADJ_UNR 4      // independent row-steps in flight per lane in the adjoint main loop
 #endif
 #ifndef VBC_ADJ_MINB
-#define VBC_ADJ_MINB 0     // __launch_bounds__ min CTAs/SM for the adjoint kernel (caps registers); 0 = compiler default
+#define VBC_ADJ_MINB 4     // __launch_bounds__ min CTAs/SM for the adjoint kernel (caps registers at 64); 0 = compiler default
+                           // (tools/tune.py sweep, profiles/r01_tuning.md: 4 CTAs x 64 regs beats 5 x 48 and 3 x 80)
 #endif
 #if VBC_ADJ_MINB > 0
 #define VBC_ADJ_BOUNDS __launch_bounds__(256, VBC_ADJ_MINB)
@@ -122,6 +123,7 @@ template <> struct RowWalk<DESC_ROWS> {
     const int *dp; int step;
     __device__ __forceinline__ void init(const int *desc, int pos0, int r0, int rps, int, int) { dp = desc + pos0 + r0; step = rps; }
     __device__ __forceinline__ int next() { const int xi = __ldcs(dp); dp += step; return xi; }
+    __device__ __forceinline__ int next_if(bool ok) { const int xi = ok ? __ldcs(dp) : 0; dp += step; return xi; }
 };
 template <> struct RowWalk<DESC_BLOCKS> {
     const int *bp; int di, qb, rb, u0;
@@ -134,6 +136,13 @@ template <> struct RowWalk<DESC_BLOCKS> {
     __device__ __forceinline__ int next()
     {
         const int xi = __ldg(bp) + di;
+        bp += qb; di += rb;
+        if (di >= u0) { di -= u0; ++bp; }
+        return xi;
+    }
+    __device__ __forceinline__ int next_if(bool ok)
+    {
+        const int xi = ok ? __ldg(bp) + di : 0;
         bp += qb; di += rb;
         if (di >= u0) { di -= u0; ++bp; }
         return xi;
@@ -162,28 +171,32 @@ __device__ __forceinline__ void adj_stripe(const StripeMeta a, const StripeMeta 
     const int vstride = rps * w;
     RowWalk<MODE> walk;
     walk.init(desc, a.pos, r0, rps, u0, log2u);
+    // Batches of UNR independent row-steps: all loads of a batch are issued before the first FMA;
+    // the last batch is predicated instead of falling into a serial remainder loop.
     constexpr int UNR = VBC_ADJ_UNR;
-    for (; r + (UNR - 1) * rps < R; r += UNR * rps) {
+    for (; r < R; r += UNR * rps) {
         Tv v[UNR][EPV];
         int xi[UNR];
         Tv xv[UNR];
+        bool ok[UNR];
 #pragma unroll
-        for (int k = 0; k < UNR; k++) { Ld<Tv, EPV>::s(vp, v[k]); vp += vstride; }
+        for (int k = 0; k < UNR; k++) {
+            ok[k] = r + k * rps < R;
+            if (ok[k]) Ld<Tv, EPV>::s(vp, v[k]);
+            else {
 #pragma unroll
-        for (int k = 0; k < UNR; k++) xi[k] = walk.next();
+                for (int e = 0; e < EPV; e++) v[k][e] = (Tv)0;
+            }
+            vp += vstride;
+        }
 #pragma unroll
-        for (int k = 0; k < UNR; k++) xv[k] = __ldg(x + xi[k]);
+        for (int k = 0; k < UNR; k++) xi[k] = walk.next_if(ok[k]);
+#pragma unroll
+        for (int k = 0; k < UNR; k++) xv[k] = ok[k] ? __ldg(x + xi[k]) : (Tv)0;
 #pragma unroll
         for (int k = 0; k < UNR; k++)
 #pragma unroll
             for (int e = 0; e < EPV; e++) acc[e] = fma(v[k][e], xv[k], acc[e]);
-    }
-    for (; r < R; r += rps) {
-        Tv v[EPV];
-        Ld<Tv, EPV>::s(vp, v); vp += vstride;
-        const Tv xv = __ldg(x + walk.next());
-#pragma unroll
-        for (int e = 0; e < EPV; e++) acc[e] = fma(v[e], xv, acc[e]);
     }
     // sum the lanes that hold the same column-vector c
     if constexpr (CPR > 0) {
@@ -244,8 +257,12 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
     const int lane = threadIdx.x % G;
     const unsigned gmask = group_mask<G>();
     const int ngroups = (int)((gridDim.x * blockDim.x) / G);
-    for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G); l < L; l += ngroups) {
-        const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
+    int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G);
+    if (l >= L) return;
+    StripeMeta na = ld_meta(meta + l), nb = ld_meta(meta + l + 1);
+    for (; l < L; l += ngroups) {
+        const StripeMeta a = na, b = nb;
+        if (l + ngroups < L) { na = ld_meta(meta + l + ngroups); nb = ld_meta(meta + l + ngroups + 1); } // next stripe's meta rides along
         const int w = b.col - a.col;
         if (w <= 0) continue;
 #if VBC_WIDE_LD
@@ -476,6 +493,7 @@ static int launch_adj_any(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y, con
     const bool rows = A->desc_mode == DESC_ROWS;
     const int G = A->opt_adj_group ? A->opt_adj_group : auto_group(A);
     if (G >= 32) return rows ? launch_adj_t<Tv, 32, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 32, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
+    if (G >= 16) return rows ? launch_adj_t<Tv, 16, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 16, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
     return rows ? launch_adj_t<Tv, 8, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 8, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
 }
 

@@ -14,20 +14,17 @@ build() { # tag, defines...
 }
 make -j4 >/dev/null
 build base
-build unr2 -DVBC_ADJ_UNR=2
-build unr8 -DVBC_ADJ_UNR=8
-build minb1 -DVBC_ADJ_MINB=1
-build minb4 -DVBC_ADJ_MINB=4
-build minb6 -DVBC_ADJ_MINB=6
+build m4u4 -DVBC_ADJ_MINB=4 -DVBC_ADJ_UNR=4
+build m4u8 -DVBC_ADJ_MINB=4 -DVBC_ADJ_UNR=8
+build m4u2 -DVBC_ADJ_MINB=4 -DVBC_ADJ_UNR=2
+build m3u4 -DVBC_ADJ_MINB=3 -DVBC_ADJ_UNR=4
+build m3u8 -DVBC_ADJ_MINB=3 -DVBC_ADJ_UNR=8
 wait
-build minb8_unr2 -DVBC_ADJ_MINB=8 -DVBC_ADJ_UNR=2
-build ldg -DVBC_LD_MODE=1
-build ldna -DVBC_LD_MODE=2
-build wide -DVBC_WIDE_LD=1
-build wide_minb4 -DVBC_WIDE_LD=1 -DVBC_ADJ_MINB=4
-build wide_unr2 -DVBC_WIDE_LD=1 -DVBC_ADJ_UNR=2
-wait
-build minb6_unr2 -DVBC_ADJ_MINB=6 -DVBC_ADJ_UNR=2
-build wide_unr2_minb5 -DVBC_WIDE_LD=1 -DVBC_ADJ_UNR=2 -DVBC_ADJ_MINB=5
+build m5u4 -DVBC_ADJ_MINB=5 -DVBC_ADJ_UNR=4
+build m5u2 -DVBC_ADJ_MINB=5 -DVBC_ADJ_UNR=2
+build m6u2 -DVBC_ADJ_MINB=6 -DVBC_ADJ_UNR=2
+build wm4u4 -DVBC_WIDE_LD=1 -DVBC_ADJ_MINB=4 -DVBC_ADJ_UNR=4
+build wm4u2 -DVBC_WIDE_LD=1 -DVBC_ADJ_MINB=4 -DVBC_ADJ_UNR=2
+build wm3u4 -DVBC_WIDE_LD=1 -DVBC_ADJ_MINB=3 -DVBC_ADJ_UNR=4
 wait
 ls -la $OUT/*.so | wc -l

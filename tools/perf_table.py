@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Per-kernel throughput table over the workloads of BASELINE.json (run on a B200 via gpurun).
+Every row: kernel time from one CUDA-event pair per launch (median of 30), algorithmic bytes of the
+device layout + vectors, achieved GB/s and useful GFLOP/s.  Written to gpurun_out/perf_table.json."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import vbc_b200 as vb  # noqa: E402
+from vbc_b200 import _lib, synth  # noqa: E402
+
+
+def tk(fn, reps=30):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in pairs:
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) for a, b in pairs)
+    return t[len(t) // 2] * 1e-3, t[0] * 1e-3
+
+
+rows = []
+
+
+def report(name, B, A, groups=(0,)):
+    tdt = torch.float64 if B.Tv == np.float64 else torch.float32
+    es = 8 if B.Tv == np.float64 else 4
+    ref_b, adj_b, fwd_b = B.format_bytes()
+    xm = torch.rand(A.m, dtype=tdt, device="cuda"); yn = torch.empty(A.n, dtype=tdt, device="cuda")
+    xn = torch.rand(A.n, dtype=tdt, device="cuda"); ym = torch.empty(A.m, dtype=tdt, device="cuda")
+    for g in groups:
+        B.set_option(_lib.OPT_ADJ_GROUP, g); B.set_option(_lib.OPT_FWD_GROUP, g if g != 16 else 0)
+        for kind, fn, nb in (("adjoint", lambda: vb.mul_(yn, B.T, xm), adj_b + es * (A.m + A.n)),
+                             ("forward", lambda: vb.mul_(ym, B, xn), fwd_b + es * (A.n + 2 * A.m))):
+            if kind == "forward" and g == 16:
+                continue
+            med, mn = tk(fn)
+            r = dict(workload=name, kernel=kind, group=g, us_med=med * 1e6, us_min=mn * 1e6, bytes=nb, gbs=nb / med / 1e9,
+                     gflops=2.0 * A.nnz / med / 1e9, nnz=A.nnz, nval=B.nval, ref_format_bytes=ref_b)
+            rows.append(r)
+            print(f"{name:34s} {kind:8s} G={g:2d} {med * 1e6:8.1f} us  {r['gbs']:7.0f} GB/s  {r['gflops']:8.1f} GFLOP/s", flush=True)
+
+
+def csc_row(name, A):
+    tdt = torch.float64 if A.nzval.dtype == np.float64 else torch.float32
+    es = A.nzval.dtype.itemsize
+    C = vb.CuSparseMatrixCSC(A)
+    xm = torch.rand(A.m, dtype=tdt, device="cuda"); yn = torch.empty(A.n, dtype=tdt, device="cuda")
+    med, mn = tk(lambda: vb.TrSpMV_(yn, C, xm))
+    nb = A.colptr.nbytes + A.rowval.nbytes + A.nzval.nbytes + es * (A.m + A.n)
+    rows.append(dict(workload=name, kernel="csc_trspmv", group=0, us_med=med * 1e6, us_min=mn * 1e6, bytes=nb, gbs=nb / med / 1e9,
+                     gflops=2.0 * A.nnz / med / 1e9, nnz=A.nnz))
+    print(f"{name:34s} {'csc':8s}      {med * 1e6:8.1f} us  {nb / med / 1e9:7.0f} GB/s  {2.0 * A.nnz / med / 1e9:8.1f} GFLOP/s", flush=True)
+
+
+def pack_time(name, ctor):
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); B = ctor(); torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+        if _ < 2:
+            B.close()
+    print(f"{name:34s} pack (H2D + kernels, wall)  {min(ts) * 1e3:8.1f} ms", flush=True)
+    rows.append(dict(workload=name, kernel="pack_wall", us_med=min(ts) * 1e6))
+    return B
+
+
+def main():
+    which = os.environ.get("PERF_ONLY", "").split(",") if os.environ.get("PERF_ONLY") else None
+
+    def want(k):
+        return which is None or k in which
+    if want("c2"):
+        A, pi, phi = synth.config_c2()
+        B = pack_time("C2 2D f64 4x4 n=1M", lambda: vb.SparseMatrixVBC[4, 4](A, pi, phi))
+        report("C2 2D f64 4x4 n=1M", B, A, groups=(8, 16, 32))
+        csc_row("C2 matrix as CSC f64/i64", A)
+        B.close()
+        A32 = A.astype(np.float32, np.int32)
+        B = pack_time("C2 2D f32/i32 4x4 n=1M", lambda: vb.SparseMatrixVBC[4, 4](A32, pi, phi))
+        report("C2 2D f32/i32 4x4 n=1M", B, A32, groups=(8, 16, 32))
+        csc_row("C2 matrix as CSC f32/i32", A32)
+        B.close()
+        del A, A32
+    if want("c3"):
+        # C3's matrix: 1D-VBC, n = 1M, W = 8, 50 rows per stripe, banded
+        K, L = 1_000_000, 125_000
+        offs = np.arange(-25, 25) * 37
+        A, _, phi = synth.banded_blocks(K, L, 1, 8, offs)
+        B = pack_time("C3 1D f64 w=8 n=1M 50 rows/stripe", lambda: vb.SparseMatrix1DVBC[8](A, phi))
+        report("C3 1D f64 w=8 n=1M 50 rows/stripe", B, A, groups=(8, 16, 32))
+        B.close()
+        del A
+    if want("c1"):
+        A, phi = synth.config_c1()
+        B = pack_time("C1 1D f64 w=8 n=10k (L2-resident)", lambda: vb.SparseMatrix1DVBC[8](A, phi))
+        report("C1 1D f64 w=8 n=10k (L2-resident)", B, A, groups=(8, 16, 32))
+        csc_row("C1 matrix as CSC", A)
+        B.close()
+    if want("c2v"):
+        A, pi, phi = synth.config_c2(n=400_000, S=41)
+        pv, fv = synth.variable_partition(A.m, 8, 1), synth.variable_partition(A.n, 8, 2)
+        B = pack_time("C2v 2D f64 variable 2..8 n=400k", lambda: vb.SparseMatrixVBC[8, 8](A, pv, fv))
+        report("C2v 2D f64 variable 2..8 n=400k", B, A, groups=(8, 16, 32))
+        B.close()
+    out = os.path.join(ROOT, "gpurun_out", "perf_table.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    json.dump(rows, open(out, "w"), indent=0)
+
+
+if __name__ == "__main__":
+    main()

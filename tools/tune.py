@@ -66,8 +66,8 @@ def main():
         fb = (i64 * 3)()
         L.vbc_format_bytes(h, fb)
         nbytes = fb[1] + x.element_size() * (A.m + A.n)
-        for G in (8, 32):
-            for mult in (0, 4, 6, 8):
+        for G in (8, 16, 32):
+            for mult in (0,):
                 L.vbc_set_option(h, 1, G)
                 L.vbc_set_option(h, 3, mult)
 
