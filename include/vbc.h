@@ -109,6 +109,26 @@ int vbc_memory_cost(const vbc_mat *A, int64_t *cost, int64_t *row_term);
 int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, double beta,
              void *y, int64_t ylen, int on_device);
 
+/* k right-hand sides: Y <- alpha * op(A) * X + beta * Y, X: cols(op(A)) x k, Y: rows(op(A)) x k.
+ * Stands in for `*(A, B::DenseMatrix)` (multiply_1DVBC.jl:184-185, multiply_VBC.jl:196-197), which the
+ * reference declares but cannot execute (no matrix `mul!` method) -- new functionality,
+ * oracle = k independent vbc_spmv.  layout 0: row-major panels, element (i, c) at X[i*ldx + c]
+ * (ldx >= k; the fast path); layout 1: column-major as Julia stores a Matrix, X[c*ldx + i]
+ * (ldx >= rows; transposed on the device into row-major staging buffers and back). */
+int vbc_spmm(vbc_mat *A, int trans, int64_t k, double alpha, const void *X, int64_t ldx, double beta,
+             void *Y, int64_t ldy, int layout, int on_device);
+
+/* Lower-triangular solve  tril(A') x = b  (A square).  EXTENSION: the reference has no triangular solve
+ * ("TrSpMV" there is the transposed multiply); BASELINE.json's north_star (d) asks for a
+ * blocked, level-scheduled one.  Row block l of A' is stripe l; entries above the diagonal of A' are
+ * ignored (BLAS trsv 'L'), the diagonal must be stored and nonzero.  vbc_trsv_analyse builds the level
+ * schedule (also done lazily by the first solve) and reports the number of levels; the solve is one
+ * cooperative persistent kernel that walks the row blocks in level order and waits on per-row-block
+ * flags.  Stripes may be at most 8 columns wide (VBC_ELIMIT).  b and x have n entries; x != b. */
+int vbc_trsv_analyse(vbc_mat *A, int *nlevels);
+int vbc_trsv_levels(const vbc_mat *A, int *nlevels);
+int vbc_trsv_lower(vbc_mat *A, const void *b, void *x, int64_t len, int on_device);
+
 /* CSC comparator: `TrSpMV!(y, A::SparseMatrixCSC, x)` TrSpMV.jl:1-20, y = A' x. */
 int vbc_csc_upload(vbc_csc **out, int vt, int it, int64_t m, int64_t n, const void *colptr,
                    const void *rowval, const void *nzval, int device);

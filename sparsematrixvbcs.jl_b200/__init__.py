@@ -12,12 +12,12 @@ from ._lib import ArgumentError, DimensionMismatch, VBCError, LIB_PATH  # noqa: 
 from .partition import (AlternatingPacker, EquiChunker, RandomChunker, SparseMatrixCSC,  # noqa: F401
                         SplitPartition, StrictChunker, pack_plaid, pack_stripe)
 from .matrix import (Adjoint, CuSparseMatrixCSC, CuVBC1D, CuVBC2D, SparseMatrix1DVBC,  # noqa: F401
-                     SparseMatrixVBC, TrSpMV_, adjoint, mul_, size)
+                     SparseMatrixVBC, TrSpMV_, adjoint, ldiv_lower_, mul_, size, trsv_analyse)
 from . import synth  # noqa: F401
 
 __all__ = [
     "SparseMatrix1DVBC", "SparseMatrixVBC", "CuVBC1D", "CuVBC2D", "CuSparseMatrixCSC", "Adjoint",
-    "mul_", "TrSpMV_", "adjoint", "size",
+    "mul_", "TrSpMV_", "adjoint", "size", "ldiv_lower_", "trsv_analyse",
     "SparseMatrixCSC", "SplitPartition", "EquiChunker", "StrictChunker", "RandomChunker",
     "AlternatingPacker", "pack_stripe", "pack_plaid",
     "DimensionMismatch", "ArgumentError", "VBCError", "synth",

@@ -204,6 +204,7 @@ void vbc_destroy(vbc_mat *A)
     DeviceGuard guard(A->device);
     cudaFree(A->d_pi_spl); cudaFree(A->d_phi_spl); cudaFree(A->d_pos); cudaFree(A->d_idx); cudaFree(A->d_ofs); cudaFree(A->d_val);
     cudaFree(A->d_meta); cudaFree(A->d_desc); cudaFree(A->d_brow); cudaFree(A->d_x); cudaFree(A->d_y);
+    destroy_trsv_plan(A->trsv);
     delete A;
 }
 
@@ -351,6 +352,9 @@ int vbc_sync(vbc_mat *A)
     if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
     DeviceGuard guard(A->device);
     VBC_CUDA(cudaStreamSynchronize(A->stream));
+    int flag = 0;
+    VBC_TRY(trsv_error_flag(A, &flag));
+    if (flag) VBC_FAIL(VBC_ECUDA, "a triangular-solve dependency wait timed out");
     return VBC_OK;
 }
 

@@ -52,6 +52,8 @@ enum DescMode {
 
 } // namespace vbc
 
+struct vbc_trsv_plan; // trsv.cu
+
 struct vbc_mat {
     int vt = VBC_F64, it = VBC_I64, ndim = 1, device = 0;
     int64_t m = 0, n = 0, K = 0, L = 0;
@@ -76,6 +78,7 @@ struct vbc_mat {
     int opt_adj_group = 0, opt_fwd_group = 0, opt_grid_mult = 0, opt_parity = 0;
     int sm_count = 148;
     int64_t launches = 0;
+    vbc_trsv_plan *trsv = nullptr; // level schedule of the triangular solve (vbc_trsv_analyse)
 };
 
 struct vbc_csc {
@@ -109,6 +112,9 @@ int memory_cost_device(const vbc_mat *A, int64_t *h_cost, int64_t *row_term);
 // spmv.cu
 int launch_spmv(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y);
 int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs);
+// trsv.cu
+void destroy_trsv_plan(vbc_trsv_plan *p);
+int trsv_error_flag(const vbc_mat *A, int *flag);
 // csc.cu
 int launch_csc_trspmv(vbc_csc *A, const void *d_x, void *d_y);
 

@@ -1,0 +1,274 @@
+// spmm.cu -- VBC sparse matrix x dense matrix (k right-hand sides), north_star item (c).
+//
+//   Y <- alpha * op(A) * X + beta * Y,   X: cols(op(A)) x k,  Y: rows(op(A)) x k
+//
+// The reference declares `*(A, B::DenseMatrix)` (multiply_1DVBC.jl:184-185, multiply_VBC.jl:196-197)
+// but none of its `mul!` methods accepts matrices, so the call is non-functional there:
+// this is new functionality whose oracle is k independent `mul!`s, column by column.
+//
+// Kernel shape (row-major panels, one row of X / Y = k contiguous values): one warp per stripe, lane t
+// owns right-hand sides t, t+32, ... (KT per lane).  Adjoint: a WB x KT register tile of the stripe's
+// w x k output accumulates  val[r, dj] * X[row_r, c]  over the stored rows -- the X row is one coalesced
+// load per warp, the val row is a warp-uniform (broadcast) load; the tile is stored once.  Forward:
+// the stripe's X[j:j+w, c] tile sits in registers and each stored row ends in one coalesced
+// red.global.add per right-hand side.  Every val byte is read once per 32*KT right-hand sides, so the
+// flop/byte ratio grows with k (k = 32, Float64: 3.3 flop/B) -- DFMA throughput and the L2 gathers of X
+// rows bound it, not HBM.  Column-major panels (Julia's layout) are transposed into row-major staging
+// buffers on the device and back.
+#include "common.cuh"
+#include "walk.cuh"
+
+namespace vbc {
+
+template <typename Tv, int MODE, int WB, int KT>
+__global__ void __launch_bounds__(256) k_spmm_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+                                                   const Tv *__restrict__ val, const Tv *__restrict__ X, const long long ldx,
+                                                   Tv *__restrict__ Y, const long long ldy, const int L, const int k,
+                                                   const int u0, const int log2u, const Tv alpha, const Tv beta)
+{
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); l < L; l += nwarps) {
+        const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
+        const int w = b.col - a.col;
+        if (w <= 0) continue;
+        const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
+        for (int kb = 0; kb < k; kb += 32 * KT) {
+            for (int wb = 0; wb < w; wb += WB) {
+                Tv acc[WB][KT];
+#pragma unroll
+                for (int dj = 0; dj < WB; dj++)
+#pragma unroll
+                    for (int t = 0; t < KT; t++) acc[dj][t] = (Tv)0;
+                RowWalk<MODE> walk;
+                walk.init(desc, a.pos, 0, 1, u0, log2u);
+                const Tv *vp = val + a.ofs + wb;
+                for (int r = 0; r < R; r += 2) {
+                    const bool ok1 = r + 1 < R;
+                    const int xi0 = walk.next_if(true), xi1 = walk.next_if(ok1);
+                    Tv x0[KT], x1[KT];
+#pragma unroll
+                    for (int t = 0; t < KT; t++) {
+                        const int c = kb + t * 32 + lane;
+                        x0[t] = c < k ? __ldg(X + (long long)xi0 * ldx + c) : (Tv)0;
+                        x1[t] = (ok1 && c < k) ? __ldg(X + (long long)xi1 * ldx + c) : (Tv)0;
+                    }
+#pragma unroll
+                    for (int dj = 0; dj < WB; dj++) {
+                        const bool in = wb + dj < w;
+                        const Tv v0 = in ? __ldg(vp + dj) : (Tv)0;             // warp-uniform address
+                        const Tv v1 = (in && ok1) ? __ldg(vp + w + dj) : (Tv)0;
+#pragma unroll
+                        for (int t = 0; t < KT; t++) acc[dj][t] = fma(v1, x1[t], fma(v0, x0[t], acc[dj][t]));
+                    }
+                    vp += 2 * w;
+                }
+#pragma unroll
+                for (int dj = 0; dj < WB; dj++) {
+                    if (wb + dj < w) {
+                        Tv *yp = Y + (long long)(a.col + wb + dj) * ldy;
+#pragma unroll
+                        for (int t = 0; t < KT; t++) {
+                            const int c = kb + t * 32 + lane;
+                            if (c < k) yp[c] = (beta == (Tv)0) ? alpha * acc[dj][t] : alpha * acc[dj][t] + beta * yp[c];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <typename Tv, int MODE, int WB, int KT>
+__global__ void __launch_bounds__(256) k_spmm_fwd(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+                                                   const Tv *__restrict__ val, const Tv *__restrict__ X, const long long ldx,
+                                                   Tv *__restrict__ Y, const long long ldy, const int L, const int k,
+                                                   const int u0, const int log2u, const Tv alpha)
+{
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); l < L; l += nwarps) {
+        const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
+        const int w = b.col - a.col;
+        if (w <= 0 || b.ofs == a.ofs) continue;
+        const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
+        for (int kb = 0; kb < k; kb += 32 * KT) {
+            for (int wb = 0; wb < w; wb += WB) {
+                Tv xs[WB][KT]; // X[j + wb + dj, c]
+#pragma unroll
+                for (int dj = 0; dj < WB; dj++)
+#pragma unroll
+                    for (int t = 0; t < KT; t++) {
+                        const int c = kb + t * 32 + lane;
+                        xs[dj][t] = (wb + dj < w && c < k) ? __ldg(X + (long long)(a.col + wb + dj) * ldx + c) : (Tv)0;
+                    }
+                RowWalk<MODE> walk;
+                walk.init(desc, a.pos, 0, 1, u0, log2u);
+                const Tv *vp = val + a.ofs + wb;
+                for (int r = 0; r < R; r++) {
+                    const int xi = walk.next();
+                    Tv p[KT];
+#pragma unroll
+                    for (int t = 0; t < KT; t++) p[t] = (Tv)0;
+#pragma unroll
+                    for (int dj = 0; dj < WB; dj++) {
+                        const Tv v = (wb + dj < w) ? __ldg(vp + dj) : (Tv)0;
+#pragma unroll
+                        for (int t = 0; t < KT; t++) p[t] = fma(v, xs[dj][t], p[t]);
+                    }
+                    vp += w;
+#pragma unroll
+                    for (int t = 0; t < KT; t++) {
+                        const int c = kb + t * 32 + lane;
+                        if (c < k) atomicAdd(Y + (long long)xi * ldy + c, alpha * p[t]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Y[r, 0:k) <- beta * Y[r, 0:k)
+template <typename Tv>
+__global__ void __launch_bounds__(256) k_scale_panel(Tv *__restrict__ Y, const long long ldy, const long long rows, const int k, const Tv beta)
+{
+    const long long total = rows * k;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        Tv *p = Y + (i / k) * ldy + (i % k);
+        *p = (beta == (Tv)0) ? (Tv)0 : beta * *p;
+    }
+}
+
+// out[c * ldo + r] = in[r * ldi + c]   (rows x cols input, tiled through shared memory)
+template <typename Tv>
+__global__ void __launch_bounds__(256) k_transpose(const Tv *__restrict__ in, const long long ldi, const long long rows, const long long cols,
+                                                    Tv *__restrict__ out, const long long ldo)
+{
+    __shared__ Tv tile[32][33];
+    const long long r0 = (long long)blockIdx.x * 32, c0 = (long long)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+    for (int i = ty; i < 32; i += 8)
+        if (r0 + i < rows && c0 + tx < cols) tile[i][tx] = in[(r0 + i) * ldi + c0 + tx];
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows) out[(c0 + i) * ldo + r0 + tx] = tile[tx][i];
+}
+
+template <typename Tv, int MODE>
+static int launch_spmm_mode(vbc_mat *A, int trans, int k, Tv alpha, const Tv *X, long long ldx, Tv beta, Tv *Y, long long ldy)
+{
+    const int L = (int)A->L;
+    int log2u = -1;
+    if (A->u0 > 0 && !(A->u0 & (A->u0 - 1))) { log2u = 0; while ((1 << log2u) < A->u0) log2u++; }
+    int64_t grid = (int64_t)A->sm_count * 6;
+    const int64_t need = ((int64_t)L * 32 + 255) / 256;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    const bool wide = A->W > 8;
+    const bool k2 = k > 32;
+#define SPMM_LAUNCH(KERNEL, WBv, KTv, ...) KERNEL<Tv, MODE, WBv, KTv><<<(unsigned)grid, 256, 0, A->stream>>>(__VA_ARGS__)
+    if (trans) {
+        if (L == 0) return VBC_OK;
+        if (wide) { if (k2) SPMM_LAUNCH(k_spmm_adj, 16, 2, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta);
+                    else    SPMM_LAUNCH(k_spmm_adj, 16, 1, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta); }
+        else      { if (k2) SPMM_LAUNCH(k_spmm_adj, 8, 2, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta);
+                    else    SPMM_LAUNCH(k_spmm_adj, 8, 1, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta); }
+        A->launches++;
+    } else {
+        if (A->m > 0 && beta != (Tv)1) {
+            int64_t g = (A->m * (int64_t)k + 255) / 256;
+            if (g > (int64_t)A->sm_count * 8) g = (int64_t)A->sm_count * 8;
+            k_scale_panel<Tv><<<(unsigned)g, 256, 0, A->stream>>>(Y, ldy, A->m, k, beta);
+            A->launches++;
+        }
+        if (L == 0 || A->nval == 0) return VBC_OK;
+        if (wide) { if (k2) SPMM_LAUNCH(k_spmm_fwd, 16, 2, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha);
+                    else    SPMM_LAUNCH(k_spmm_fwd, 16, 1, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha); }
+        else      { if (k2) SPMM_LAUNCH(k_spmm_fwd, 8, 2, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha);
+                    else    SPMM_LAUNCH(k_spmm_fwd, 8, 1, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha); }
+        A->launches++;
+    }
+#undef SPMM_LAUNCH
+    VBC_CUDA(cudaGetLastError());
+    return VBC_OK;
+}
+
+template <typename Tv>
+static int transpose_launch(vbc_mat *A, const Tv *in, long long ldi, long long rows, long long cols, Tv *out, long long ldo)
+{
+    if (rows == 0 || cols == 0) return VBC_OK;
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+    k_transpose<Tv><<<grid, 256, 0, A->stream>>>(in, ldi, rows, cols, out, ldo);
+    A->launches++;
+    VBC_CUDA(cudaGetLastError());
+    return VBC_OK;
+}
+
+// device pointers; layout 0 = row-major panels (X[i*ldx + c]), 1 = column-major (X[c*ldx + i])
+template <typename Tv>
+static int spmm_t(vbc_mat *A, int trans, int64_t k, double alpha_d, const Tv *X, int64_t ldx, double beta_d, Tv *Y, int64_t ldy, int layout)
+{
+    const Tv alpha = (Tv)alpha_d, beta = (Tv)beta_d;
+    const int64_t xr = trans ? A->m : A->n, yr = trans ? A->n : A->m;
+    if (layout == 0) {
+        return A->desc_mode == DESC_ROWS ? launch_spmm_mode<Tv, DESC_ROWS>(A, trans, (int)k, alpha, X, ldx, beta, Y, ldy)
+                                         : launch_spmm_mode<Tv, DESC_BLOCKS>(A, trans, (int)k, alpha, X, ldx, beta, Y, ldy);
+    }
+    // column-major: stage through row-major buffers
+    Tv *Xr = nullptr, *Yr = nullptr;
+    VBC_CUDA(cudaMalloc(&Xr, sizeof(Tv) * (size_t)(xr * k > 0 ? xr * k : 1)));
+    if (cudaMalloc(&Yr, sizeof(Tv) * (size_t)(yr * k > 0 ? yr * k : 1)) != cudaSuccess) { cudaFree(Xr); VBC_FAIL(VBC_ENOMEM, "spmm staging allocation failed"); }
+    int rc = transpose_launch<Tv>(A, X, ldx, k, xr, Xr, k); // input viewed as k rows (columns of X) of length xr
+    if (rc == VBC_OK && beta != (Tv)0) rc = transpose_launch<Tv>(A, Y, ldy, k, yr, Yr, k);
+    if (rc == VBC_OK)
+        rc = A->desc_mode == DESC_ROWS ? launch_spmm_mode<Tv, DESC_ROWS>(A, trans, (int)k, alpha, Xr, k, beta, Yr, k)
+                                       : launch_spmm_mode<Tv, DESC_BLOCKS>(A, trans, (int)k, alpha, Xr, k, beta, Yr, k);
+    if (rc == VBC_OK) rc = transpose_launch<Tv>(A, Yr, k, yr, k, Y, ldy);
+    cudaError_t e = cudaStreamSynchronize(A->stream); // staging buffers are freed below
+    cudaFree(Xr); cudaFree(Yr);
+    if (rc == VBC_OK && e != cudaSuccess) VBC_FAIL(VBC_ECUDA, "spmm: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+int launch_spmm(vbc_mat *A, int trans, int64_t k, double alpha, const void *X, int64_t ldx, double beta, void *Y, int64_t ldy, int layout)
+{
+    if (A->opt_parity) VBC_FAIL(VBC_EARG, "spmm needs the compact layout (parity mode is on)");
+    return A->vt == VBC_F64 ? spmm_t<double>(A, trans, k, alpha, (const double *)X, ldx, beta, (double *)Y, ldy, layout)
+                            : spmm_t<float>(A, trans, k, alpha, (const float *)X, ldx, beta, (float *)Y, ldy, layout);
+}
+
+} // namespace vbc
+
+using namespace vbc;
+
+extern "C" int vbc_spmm(vbc_mat *A, int trans, int64_t k, double alpha, const void *X, int64_t ldx, double beta, void *Y, int64_t ldy,
+                        int layout, int on_device)
+{
+    if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
+    if (k < 0 || k > (1 << 20)) VBC_FAIL(VBC_EARG, "k out of range");
+    if (layout != 0 && layout != 1) VBC_FAIL(VBC_EARG, "layout must be 0 (row-major panels) or 1 (column-major)");
+    const int64_t xr = trans ? A->m : A->n, yr = trans ? A->n : A->m;
+    const int64_t min_ldx = layout == 0 ? k : xr, min_ldy = layout == 0 ? k : yr;
+    if (ldx < min_ldx || ldy < min_ldy) VBC_FAIL(VBC_EDIM, "DimensionMismatch: leading dimensions (%lld, %lld) smaller than (%lld, %lld)", (long long)ldx, (long long)ldy, (long long)min_ldx, (long long)min_ldy);
+    if (k == 0) return VBC_OK;
+    if ((!X && xr > 0) || (!Y && yr > 0)) VBC_FAIL(VBC_EARG, "NULL panel");
+    DeviceGuard guard(A->device);
+    if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", A->device);
+    if (on_device) return launch_spmm(A, trans, k, alpha, X, ldx, beta, Y, ldy, layout);
+    // host panels: copy the ld-strided storage as is (outer x ld elements)
+    const size_t tv = vt_size(A->vt);
+    const int64_t xo = layout == 0 ? xr : k, yo = layout == 0 ? yr : k; // outer extents
+    void *dX = nullptr, *dY = nullptr;
+    VBC_CUDA(cudaMalloc(&dX, tv * (size_t)(xo * ldx > 0 ? xo * ldx : 1)));
+    if (cudaMalloc(&dY, tv * (size_t)(yo * ldy > 0 ? yo * ldy : 1)) != cudaSuccess) { cudaFree(dX); VBC_FAIL(VBC_ENOMEM, "spmm panel allocation failed"); }
+    int rc = VBC_OK;
+    cudaError_t e = cudaSuccess;
+    if (xo * ldx > 0) e = cudaMemcpyAsync(dX, X, tv * (size_t)(xo * ldx), cudaMemcpyHostToDevice, A->stream);
+    if (e == cudaSuccess && yo * ldy > 0) e = cudaMemcpyAsync(dY, Y, tv * (size_t)(yo * ldy), cudaMemcpyHostToDevice, A->stream); // keeps ld padding intact
+    if (e == cudaSuccess) rc = launch_spmm(A, trans, k, alpha, dX, ldx, beta, dY, ldy, layout);
+    if (e == cudaSuccess && rc == VBC_OK && yo * ldy > 0) e = cudaMemcpyAsync(Y, dY, tv * (size_t)(yo * ldy), cudaMemcpyDeviceToHost, A->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(A->stream);
+    cudaFree(dX); cudaFree(dY);
+    if (e != cudaSuccess) VBC_FAIL(VBC_ECUDA, "vbc_spmm: %s", cudaGetErrorString(e));
+    return rc;
+}

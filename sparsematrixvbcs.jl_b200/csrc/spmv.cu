@@ -19,6 +19,7 @@
 // kernels here instantiate one body per (elements-per-load EPV, vectors-per-row CPR) class
 // and select it per stripe.
 #include "common.cuh"
+#include "walk.cuh"
 
 namespace vbc {
 
@@ -74,22 +75,6 @@ template <> struct Ld<float, 1> { static __device__ __forceinline__ void s(const
 template <> struct Ld<float, 2> { static __device__ __forceinline__ void s(const float *p, float (&v)[2]) { const float2 t = ld_val(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; } };
 template <> struct Ld<float, 4> { static __device__ __forceinline__ void s(const float *p, float (&v)[4]) { const float4 t = ld_val(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
 
-__device__ __forceinline__ StripeMeta ld_meta(const StripeMeta *p)
-{
-    const int4 t = __ldg(reinterpret_cast<const int4 *>(p));
-    StripeMeta s;
-    s.ofs = (long long)(((unsigned long long)(unsigned)t.y << 32) | (unsigned)t.x);
-    s.pos = t.z;
-    s.col = t.w;
-    return s;
-}
-
-template <int G> __device__ __forceinline__ unsigned group_mask()
-{
-    if constexpr (G == 32) return 0xffffffffu;
-    else return ((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G);
-}
-
 // Destinations of the adjoint result.  n == 0: the caller's y (alpha/beta applied).  n > 0: the
 // fused all-gather of the row-partitioned multiply -- every finished y segment is stored into the
 // next-x buffer of each of the n ranks (own HBM and NVLink peer mappings); beta is not applied.
@@ -116,38 +101,6 @@ __device__ __forceinline__ void store_y(Tv *__restrict__ y, const PeerDst &dst, 
         for (int e = 0; e < EPV; e++) yp[e] = (beta == (Tv)0) ? alpha * acc[e] : alpha * acc[e] + beta * yp[e];
     }
 }
-
-// x-index stream of a stripe for one lane: row r0, then r0+rps, ...
-template <int MODE> struct RowWalk;
-template <> struct RowWalk<DESC_ROWS> {
-    const int *dp; int step;
-    __device__ __forceinline__ void init(const int *desc, int pos0, int r0, int rps, int, int) { dp = desc + pos0 + r0; step = rps; }
-    __device__ __forceinline__ int next() { const int xi = __ldcs(dp); dp += step; return xi; }
-    __device__ __forceinline__ int next_if(bool ok) { const int xi = ok ? __ldcs(dp) : 0; dp += step; return xi; }
-};
-template <> struct RowWalk<DESC_BLOCKS> {
-    const int *bp; int di, qb, rb, u0;
-    __device__ __forceinline__ void init(const int *desc, int pos0, int r0, int rps, int u0_, int log2u)
-    {
-        u0 = u0_;
-        if (log2u >= 0) { bp = desc + pos0 + (r0 >> log2u); di = r0 & (u0 - 1); qb = rps >> log2u; rb = rps & (u0 - 1); }
-        else { bp = desc + pos0 + r0 / u0; di = r0 % u0; qb = rps / u0; rb = rps % u0; }
-    }
-    __device__ __forceinline__ int next()
-    {
-        const int xi = __ldg(bp) + di;
-        bp += qb; di += rb;
-        if (di >= u0) { di -= u0; ++bp; }
-        return xi;
-    }
-    __device__ __forceinline__ int next_if(bool ok)
-    {
-        const int xi = ok ? __ldg(bp) + di : 0;
-        bp += qb; di += rb;
-        if (di >= u0) { di -= u0; ++bp; }
-        return xi;
-    }
-};
 
 // ---- adjoint ----------------------------------------------------------------------------------
 // CPR > 0: compile-time vectors per row (power of two, <= G).  CPR == 0: runtime cpr <= G.

@@ -286,8 +286,51 @@ def adjoint(B):
     return B.T
 
 
+def _panel_args(handle_dtype, v, name):
+    """2-D panel -> (pointer, rows, k, ld, layout, on_device, keepalive); layout 0 = row-major (C order),
+    1 = column-major (Fortran order, what a Julia Matrix is)."""
+    if _is_torch(v):
+        import torch
+        want = torch.float64 if handle_dtype == np.dtype(np.float64) else torch.float32
+        if v.dtype != want or v.dim() != 2 or not v.is_cuda:
+            raise TypeError(f"{name} must be a 2-D {want} CUDA tensor")
+        rows, k = v.shape
+        s0, s1 = v.stride()
+        if s1 == 1 and s0 >= max(k, 1):
+            return ctypes.c_void_p(v.data_ptr()), rows, k, s0, 0, 1, v
+        if s0 == 1 and s1 >= max(rows, 1):
+            return ctypes.c_void_p(v.data_ptr()), rows, k, s1, 1, 1, v
+        raise TypeError(f"{name} must be row- or column-contiguous")
+    a = np.asarray(v)
+    if a.dtype != handle_dtype or a.ndim != 2:
+        raise TypeError(f"{name} must be a 2-D {handle_dtype} array")
+    rows, k = a.shape
+    if a.flags.c_contiguous:
+        return _vp(a), rows, k, max(k, 1), 0, 0, a
+    if a.flags.f_contiguous:
+        return _vp(a), rows, k, max(rows, 1), 1, 0, a
+    raise TypeError(f"{name} must be C- or Fortran-contiguous")
+
+
+def _mul_panel(Y, B, trans, X, alpha, beta):
+    xp, xr, xk, ldx, xl, xdev, _kx = _panel_args(B.Tv, X, "X")
+    yp, yr, yk, ldy, yl, ydev, _ky = _panel_args(B.Tv, Y, "Y")
+    if xdev != ydev:
+        raise TypeError("X and Y must both be host arrays or both be device tensors")
+    if xl != yl:
+        raise TypeError("X and Y must have the same memory layout (both row-major or both column-major)")
+    need_x, need_y = (B.m, B.n) if trans else (B.n, B.m)
+    if xk != yk or xr != need_x or yr != need_y:
+        raise DimensionMismatch(f"op(A) is {need_y} x {need_x}, X is {xr} x {xk}, Y is {yr} x {yk}")
+    if xdev:
+        B._use_torch_stream()
+    check(_lib.lib().vbc_spmm(B._h, 1 if trans else 0, xk, float(alpha), xp, ldx, float(beta), yp, ldy, xl, xdev))
+    return Y
+
+
 def mul_(y, A, x, alpha=True, beta=False):
-    """`LinearAlgebra.mul!(y, A, x, α, β)`: y <- α op(A) x + β y, in place; returns y.
+    """`LinearAlgebra.mul!(y, A, x, α, β)`: y <- α op(A) x + β y, in place; returns y.  x and y are
+    vectors, or 2-D panels of k right-hand sides (SpMM).
 
     BLAS semantics.  (The reference ignores α everywhere and β in the adjoint -- SURVEY.md R6 --
     but its tests and benchmarks only ever pass (true, false), where both agree.)"""
@@ -295,6 +338,8 @@ def mul_(y, A, x, alpha=True, beta=False):
     B = A.parent if trans else A
     if not isinstance(B, _CuVBC):
         raise TypeError("mul_ expects a SparseMatrix1DVBC / SparseMatrixVBC or its adjoint")
+    if getattr(x, "ndim", 1) == 2:
+        return _mul_panel(y, B, trans, x, alpha, beta)
     xp, xlen, xdev, _kx = _vec_args(B.Tv, x, "x")
     yp, ylen, ydev, _ky = _vec_args(B.Tv, y, "y")
     if xdev != ydev:
@@ -310,11 +355,43 @@ def _matvec(A, x):
     rows = A.shape[0]
     if _is_torch(x):
         import torch
-        y = torch.empty(rows, dtype=x.dtype, device=x.device)
+        shape = (rows,) if x.dim() == 1 else (rows, x.shape[1])
+        y = torch.empty(shape, dtype=x.dtype, device=x.device)
+        if x.dim() == 2 and x.stride(0) == 1 and x.shape[1] > 1:  # column-major in, column-major out
+            y = torch.empty((x.shape[1], rows), dtype=x.dtype, device=x.device).t()
     else:
         x = np.asarray(x)
-        y = np.empty(rows, dtype=x.dtype)
+        shape = (rows,) if x.ndim == 1 else (rows, x.shape[1])
+        y = np.empty(shape, dtype=x.dtype, order="F" if (x.ndim == 2 and x.flags.f_contiguous and not x.flags.c_contiguous) else "C")
     return mul_(y, A, x, True, False)
+
+
+def trsv_analyse(A):
+    """Level schedule for `ldiv_lower_` on `A` (an Adjoint of a device VBC matrix); returns #levels."""
+    if not isinstance(A, Adjoint) or not isinstance(A.parent, _CuVBC):
+        raise TypeError("the triangular solve works on the adjoint orientation: pass B.T")
+    n = ctypes.c_int()
+    check(_lib.lib().vbc_trsv_analyse(A.parent._h, ctypes.byref(n)))
+    return n.value
+
+
+def ldiv_lower_(x, A, b):
+    """x <- LowerTriangular(B') \\ b  with A = B.T.  EXTENSION (no reference counterpart; the reference's
+    "TrSpMV" is the transposed multiply): blocked, level-scheduled forward substitution on the row
+    blocks of B'.  Entries of B' above its diagonal are ignored."""
+    if not isinstance(A, Adjoint) or not isinstance(A.parent, _CuVBC):
+        raise TypeError("the triangular solve works on the adjoint orientation: pass B.T")
+    B = A.parent
+    bp, blen, bdev, _kb = _vec_args(B.Tv, b, "b")
+    xp, xlen, xdev, _kx = _vec_args(B.Tv, x, "x")
+    if bdev != xdev:
+        raise TypeError("b and x must both be host arrays or both be device tensors")
+    if blen != xlen:
+        raise DimensionMismatch(f"b has {blen} entries, x has {xlen}")
+    if xdev:
+        B._use_torch_stream()
+    check(_lib.lib().vbc_trsv_lower(B._h, bp, xp, xlen, xdev))
+    return x
 
 
 class CuSparseMatrixCSC:

@@ -42,7 +42,7 @@ def vector(n, seed=1, dtype=np.float64):
     return entry_values(np.arange(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64), 1, seed=seed ^ 0x5851F42D, dtype=dtype)
 
 
-def _csc_from_stripe_blocks(K, L, u, w, blk_stripe_counts, blk_parts, seed, dtype, ti, col0=0, n_global=None):
+def _csc_from_stripe_blocks(K, L, u, w, blk_stripe_counts, blk_parts, seed, dtype, ti, col0=0, n_global=None, diag_boost=0.0):
     """Uniform u x w blocks; stripe l owns blk_parts[bpos[l]:bpos[l+1]] (ascending part ids).
     col0 / n_global: the L stripes are a slab starting at global column col0 of an n_global-column
     matrix (values are hashed with GLOBAL coordinates, so slabs agree with the full matrix)."""
@@ -62,6 +62,8 @@ def _csc_from_stripe_blocks(K, L, u, w, blk_stripe_counts, blk_parts, seed, dtyp
     del gather
     cols0 = np.repeat(np.arange(n, dtype=np.int64), col_len)
     nzval = entry_values(rowval0, cols0 + col0, n_global, seed=seed, dtype=dtype)
+    if diag_boost:
+        nzval[rowval0 == cols0 + col0] += np.dtype(dtype).type(diag_boost)
     del cols0
     A = SparseMatrixCSC(m, n, (colptr0 + 1).astype(ti), (rowval0 + 1).astype(ti), nzval)
     Pi = SplitPartition(np.arange(1, m + 2, u, dtype=ti))
@@ -76,7 +78,7 @@ def fem_stencil_offsets(S=63):
     return np.array(sorted(offs), dtype=np.int64)
 
 
-def banded_blocks(K, L, u, w, offsets, seed=SEED, dtype=np.float64, ti=np.int64, stripes=None):
+def banded_blocks(K, L, u, w, offsets, seed=SEED, dtype=np.float64, ti=np.int64, stripes=None, diag_boost=0.0):
     """Block-banded matrix: stripe l has a dense u x w block at every row part l*K//L + δ,
     δ in `offsets`, clipped to [0, K).  Returns (A::SparseMatrixCSC, Π, Φ) with Π = Equi(u),
     Φ = Equi(w).  stripes=(l0, l1): only the column slab of stripes l0 <= l < l1 (A then has
@@ -88,7 +90,7 @@ def banded_blocks(K, L, u, w, offsets, seed=SEED, dtype=np.float64, ti=np.int64,
     ok = (kk >= 0) & (kk < K)
     counts = ok.sum(axis=1)
     parts = kk[ok]  # row-major flatten keeps each stripe's part ids ascending
-    return _csc_from_stripe_blocks(K, l1 - l0, u, w, counts, parts, seed, dtype, ti, col0=l0 * w, n_global=L * w)
+    return _csc_from_stripe_blocks(K, l1 - l0, u, w, counts, parts, seed, dtype, ti, col0=l0 * w, n_global=L * w, diag_boost=diag_boost)
 
 
 def random_blocks(K, L, u, w, per_stripe, seed=SEED, dtype=np.float64, ti=np.int64):
@@ -128,3 +130,13 @@ def variable_partition(n, w_max, seed, ti=np.int64, w_min=2):
     spl = np.concatenate([[1], 1 + np.cumsum(widths)])
     spl = spl[spl <= n]
     return SplitPartition(np.append(spl, n + 1).astype(ti) if spl[-1] != n + 1 else spl.astype(ti))
+
+
+def config_c4_triangular(n=2_000_000, u=4, w=4, S=79, dtype=np.float64, ti=np.int64, seed=SEED):
+    """C4 (BASELINE wording): square block matrix A whose adjoint A' is block lower triangular -- blocks at
+    part offsets {0, -(S-1), -S, -(S+1), -S^2} (the lower half of the FEM stencil without the +-1, +-2
+    neighbours, so the dependency depth is ~K/(S-1) row blocks instead of K), diagonal boosted so the
+    solve tril(A') x = b is well conditioned."""
+    K, L = n // u, n // w
+    offs = [0, -(S - 1), -S, -(S + 1), -(S * S)]
+    return banded_blocks(K, L, u, w, offs, seed=seed, dtype=dtype, ti=ti, diag_boost=float(8 * len(offs) * u))

@@ -355,3 +355,81 @@ def test_peer_exchange_two_ranks_on_one_gpu():
         assert np.allclose(layout.gather(out), x_ref, rtol=1e-12, atol=0), f"rank {r}"
     for h in peers:
         Lh.vbc_peer_destroy(h)
+
+
+def test_spmm_matches_column_by_column_oracle(fixtures):
+    """north_star (c): k right-hand sides.  Oracle = k independent `mul!`s (the reference's matrix `*` is
+    non-functional)."""
+    rng = np.random.default_rng(21)
+    A = fixtures["LPnetlib__lp_blend"]
+    S = A.to_scipy()
+    absS = abs(S)
+    phi = vb.pack_stripe(A, vb.RandomChunker(8, 4))
+    pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(4)))
+    piv, phiv = vb.pack_plaid(A, vb.AlternatingPacker(vb.RandomChunker(4, 7), vb.RandomChunker(12, 8)))
+    mats = [(vb.SparseMatrix1DVBC[8](A, phi), oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 8)),
+            (vb.SparseMatrixVBC[4, 4](A, pi, phi2), oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi2.spl, 4, 4)),
+            (vb.SparseMatrixVBC[4, 12](A, piv, phiv), oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, piv.spl, phiv.spl, 4, 12))]
+    for B, H in mats:
+        for k in (1, 3, 32, 40, 70):
+            for order in ("C", "F"):
+                for trans in (False, True):
+                    xr, yr = (A.m, A.n) if trans else (A.n, A.m)
+                    X = np.asarray(rng.random((xr, k)), order=order)
+                    Y0 = np.asarray(rng.random((yr, k)), order=order)
+                    Y = vb.mul_(Y0.copy(order=order), B.T if trans else B, X, 1.5, -0.25)
+                    Sx = (S.T if trans else S) @ X
+                    bound = (absS.T if trans else absS) @ np.abs(X) + np.abs(Y0)
+                    assert np.all(np.abs(Y - (1.5 * Sx - 0.25 * Y0)) <= 1e-11 * bound), (k, order, trans)
+                    for c in (0, k - 1):
+                        yo = oracle.mul(H, np.ascontiguousarray(X[:, c]), trans=trans)
+                        Yb = vb.mul_(np.full((yr, k), np.nan, order=order), B.T if trans else B, X)
+                        assert np.all(np.abs(Yb[:, c] - yo) <= 8e-12 * ((absS.T if trans else absS) @ np.abs(X[:, c])) + 1e-300)
+    # device panels + `@` sugar
+    import torch
+    B, H = mats[1]
+    Xd = torch.rand(A.m, 32, dtype=torch.float64, device="cuda")
+    Yd = B.T @ Xd
+    assert np.allclose(Yd.cpu().numpy(), S.T @ Xd.cpu().numpy(), rtol=1e-11, atol=1e-12)
+    with pytest.raises(vb.DimensionMismatch):
+        vb.mul_(np.zeros((A.m, 3)), B, np.zeros((A.n + 1, 3)))
+
+
+def test_triangular_solve_extension():
+    """north_star (d): tril(A') x = b.  No reference counterpart (parity unpinned): oracle = scipy's
+    forward substitution on the CSC matrix."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import spsolve_triangular
+    rng = np.random.default_rng(31)
+    cases = []
+    A, pi, phi = synth.config_c4_triangular(n=12_000, S=13)
+    cases.append(("2D 4x4 f64", A, lambda: vb.SparseMatrixVBC[4, 4](A, pi, phi), 1e-11))
+    cases.append(("1D w=4 f64", A, lambda: vb.SparseMatrix1DVBC[4](A, phi), 1e-11))
+    pv, fv = synth.variable_partition(A.m, 8, 3), synth.variable_partition(A.n, 8, 4)
+    cases.append(("2D variable f64", A, lambda: vb.SparseMatrixVBC[8, 8](A, pv, fv), 1e-11))
+    A32 = A.astype(np.float32, np.int32)
+    cases.append(("2D 4x4 f32", A32, lambda: vb.SparseMatrixVBC[4, 4](A32, pi, phi), 2e-5))
+    Ar = sprand(300, 300, 0.05, rng)
+    Sr = sp.triu(Ar.to_scipy()) + sp.identity(300) * 10.0  # A upper triangular <=> A' lower triangular
+    Ar = vb.SparseMatrixCSC.from_scipy(sp.csc_matrix(Sr))
+    cases.append(("1D random w<=3", Ar, lambda: vb.SparseMatrix1DVBC[3](Ar, vb.RandomChunker(3, 9)), 1e-11))
+    for name, M, ctor, tol in cases:
+        B = ctor()
+        tv = M.nzval.dtype
+        T = sp.tril(M.to_scipy().T.astype(np.float64)).tocsr()
+        b = rng.random(M.n).astype(tv)
+        x = vb.ldiv_lower_(np.empty(M.n, dtype=tv), B.T, b)
+        xo = spsolve_triangular(T, b.astype(np.float64), lower=True)
+        assert np.all(np.isfinite(x)), name
+        assert np.max(np.abs(x - xo)) <= tol * max(1.0, np.max(np.abs(xo))), name
+        assert np.max(np.abs(T @ x.astype(np.float64) - b)) <= 50 * tol * np.max(np.abs(b)) * 40, name
+        assert vb.trsv_analyse(B.T) >= 1
+        # second solve on the same plan (epoch flags) and the device-vector path
+        import torch
+        bd = torch.from_numpy(b).cuda()
+        xd = torch.empty_like(bd)
+        vb.ldiv_lower_(xd, B.T, bd)
+        B.sync()
+        assert np.array_equal(xd.cpu().numpy(), x), name
+    with pytest.raises(vb.DimensionMismatch):
+        vb.ldiv_lower_(np.zeros(5), B.T, np.zeros(5))
