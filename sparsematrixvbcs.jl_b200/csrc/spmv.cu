@@ -210,6 +210,44 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
     const int lane = threadIdx.x % G;
     const unsigned gmask = group_mask<G>();
     const int ngroups = (int)((gridDim.x * blockDim.x) / G);
+    if constexpr (PEER) {
+        // Fused all-gather: the warp's groups own adjacent stripes, i.e. one contiguous run of columns.
+        // Their results are staged in shared memory and flushed to every destination (own next-x buffer
+        // and the peers' over NVLink) with full-warp coalesced stores -- 128-256 B per store instruction
+        // instead of one 16-32 B store per group, which is what NVLink write packets want.
+        constexpr int GPW = 32 / G;
+        __shared__ Tv stage_all[8][GPW * 32];
+        Tv *stage = stage_all[threadIdx.x >> 5];
+        const int lane32 = threadIdx.x & 31, gid = lane32 / G;
+        const int nwarps = ngroups / GPW;
+        const PeerDst none{0, {nullptr}};
+        for (int lbase = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW; lbase < L; lbase += nwarps * GPW) {
+            const int l = lbase + gid;
+            const int lend = min(lbase + GPW, L);
+            const int colbase = ld_meta(meta + lbase).col, colend = ld_meta(meta + lend).col;
+            if (l < L) {
+                const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
+                const int w = b.col - a.col;
+                Tv *ys = stage - colbase; // the stripe bodies store y[a.col + ...]: lands in the staging run
+                if (w > 0) {
+                    if ((w % VE) == 0 && (a.ofs % VE) == 0)
+                        adj_dispatch_cpr<Tv, G, MODE, VE, false>(a, b, w, lane, gmask, desc, val, x, ys, none, u0, log2u, alpha, (Tv)0);
+                    else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0)
+                        adj_dispatch_cpr<Tv, G, MODE, (VE == 4 ? 2 : 1), false>(a, b, w, lane, gmask, desc, val, x, ys, none, u0, log2u, alpha, (Tv)0);
+                    else
+                        adj_dispatch_cpr<Tv, G, MODE, 1, false>(a, b, w, lane, gmask, desc, val, x, ys, none, u0, log2u, alpha, (Tv)0);
+                }
+            }
+            __syncwarp();
+            const int ncols = colend - colbase;
+            for (int i = 0; i < dst.n; i++) {
+                Tv *d = reinterpret_cast<Tv *>(dst.p[i]) + colbase;
+                for (int c = lane32; c < ncols; c += 32) d[c] = stage[c];
+            }
+            __syncwarp();
+        }
+        return;
+    }
     int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G);
     if (l >= L) return;
     StripeMeta na = ld_meta(meta + l), nb = ld_meta(meta + l + 1);
@@ -220,15 +258,15 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
         if (w <= 0) continue;
 #if VBC_WIDE_LD
         if (sizeof(Tv) == 8 && (w % 4) == 0 && (a.ofs % 4) == 0)
-            adj_dispatch_cpr<Tv, G, MODE, (sizeof(Tv) == 8 ? 4 : VE), PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
+            adj_dispatch_cpr<Tv, G, MODE, (sizeof(Tv) == 8 ? 4 : VE), false>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
         else
 #endif
         if ((w % VE) == 0 && (a.ofs % VE) == 0)
-            adj_dispatch_cpr<Tv, G, MODE, VE, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
+            adj_dispatch_cpr<Tv, G, MODE, VE, false>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
         else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0)
-            adj_dispatch_cpr<Tv, G, MODE, (VE == 4 ? 2 : 1), PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
+            adj_dispatch_cpr<Tv, G, MODE, (VE == 4 ? 2 : 1), false>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
         else
-            adj_dispatch_cpr<Tv, G, MODE, 1, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
+            adj_dispatch_cpr<Tv, G, MODE, 1, false>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
     }
 }
 
