@@ -190,8 +190,9 @@ def run_ours(args, rank, world, local_rank):
     xg = synth.vector(n_glob, 1)
     op.set_x(xg)
     peer = None
-    if world > 1 and args.exchange == "peer":
-        peer = vdist.PeerExchangeOperator(B, layout, rank, world, dev, alpha=alpha_step)
+    if world > 1 and args.exchange in ("peer", "halo"):
+        rows_read = (A.rowval.astype(np.int64) - 1) if args.exchange == "halo" else None
+        peer = vdist.PeerExchangeOperator(B, layout, rank, world, dev, alpha=alpha_step, rows_read=rows_read)
         peer.set_x(xg)
         dist.barrier()
 
@@ -320,6 +321,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(gpu_launches), "clocks": clk.summary(),
             "pack_seconds": pack_s, "cost_imbalance": imbalance, "alpha": alpha_step,
             "exchange": (args.exchange if world > 1 else None), "x_abs_sum_after_run": x_check,
+            "exchange_sent_fraction": (peer.sent_fraction if peer is not None else None),
         }
         if world == 1 and not args.no_cpu_baseline:
             oracle, H = cpu_reference_setup(A, pi, phi)
@@ -345,8 +347,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: 'peer' = all-gather fused into the multiply through NVLink peer stores (default); "
+    ap.add_argument("--exchange", default="peer", choices=["peer", "halo", "nccl"],
+                    help="N > 1: 'peer' = all-gather fused into the multiply through NVLink peer stores, x fully replicated "
+                         "(default); 'halo' = same kernel, but a y segment is sent only to the ranks whose stripes read it; "
                          "'nccl' = multiply, then torch.distributed all_gather_into_tensor")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -174,6 +174,13 @@ int vbc_peer_current(const vbc_peer *P, int *cur);
  * (normal), 1 = signal only, 2 = wait only, 0 = neither (same-process tests must not wait inside
  * one stream for a signal that a later launch of the same stream produces). */
 int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, int barrier);
+/* Sparsity-aware replication (optional).  mask[c >> chunk_shift] (c = column inside this rank's slab,
+ * nchunks bytes) has bit i set when the i-th destination reads that chunk of columns; destination 0 is
+ * this rank itself, destination i is rank (rank + i) % nranks.  With a mask the fused epilogue sends a
+ * y segment only to the ranks whose stripes gather from it (for a banded operator: the neighbours'
+ * halos) -- x stays complete on every rank exactly where that rank reads it.  mask == NULL restores
+ * full replication. */
+int vbc_peer_set_mask(vbc_peer *P, const void *mask, int64_t nchunks, int chunk_shift);
 /* the flag kernel alone (barrier = 1 | 2 | 3 as above); does not flip cur */
 int vbc_peer_barrier(vbc_peer *P, void *cuda_stream, int barrier);
 /* 0 if no flag wait has timed out since creation (checked after a stream sync by the caller) */

@@ -16,6 +16,9 @@ struct vbc_peer {
     unsigned long long *d_epoch = nullptr; // device-side epoch counter: the flag kernel advances it itself, so a
                                            // captured CUDA graph of steps stays correct when replayed
     int *d_timeout = nullptr;
+    unsigned char *d_mask = nullptr; // per column chunk of this rank's slice: which destinations read it
+    int chunk_shift = 0;
+    int64_t mask_len = 0;
     int64_t launches = 0;
 };
 
@@ -198,9 +201,27 @@ int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, 
         const int r = (P->rank + i) % P->nranks;
         dst[n++] = (char *)P->bufs[r][nxt] + tv * (size_t)y_offset;
     }
-    VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst));
+    if (P->d_mask && A->n > 0 && ((A->n - 1) >> P->chunk_shift) >= P->mask_len)
+        VBC_FAIL(VBC_EDIM, "peer mask covers %lld chunks, the y slice needs %lld", (long long)P->mask_len, (long long)(((A->n - 1) >> P->chunk_shift) + 1));
+    // the mask is indexed by (column in the y slice) >> shift; the kernel indexes by slab column, so no offset is needed
+    VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift));
     VBC_TRY(flags_launch(P, A->stream, barrier));
     P->cur = nxt;
+    return VBC_OK;
+}
+
+int vbc_peer_set_mask(vbc_peer *P, const void *mask, int64_t nchunks, int chunk_shift)
+{
+    if (!P) VBC_FAIL(VBC_EARG, "NULL argument");
+    DeviceGuard guard(P->device);
+    cudaFree(P->d_mask);
+    P->d_mask = nullptr; P->mask_len = 0; P->chunk_shift = 0;
+    if (!mask) return VBC_OK; // back to full replication
+    if (nchunks < 1 || chunk_shift < 0 || chunk_shift > 30) VBC_FAIL(VBC_EARG, "bad mask geometry");
+    VBC_CUDA(cudaMalloc(&P->d_mask, (size_t)nchunks));
+    VBC_CUDA(cudaMemcpy(P->d_mask, mask, (size_t)nchunks, cudaMemcpyHostToDevice));
+    P->mask_len = nchunks;
+    P->chunk_shift = chunk_shift;
     return VBC_OK;
 }
 
@@ -231,6 +252,7 @@ void vbc_peer_destroy(vbc_peer *P)
     for (int k = 0; k < VBC_PEER_HANDLES; k++) cudaFree(P->own[k]);
     cudaFree(P->d_timeout);
     cudaFree(P->d_epoch);
+    cudaFree(P->d_mask);
     delete P;
 }
 

@@ -81,6 +81,8 @@ template <> struct Ld<float, 4> { static __device__ __forceinline__ void s(const
 struct PeerDst {
     int n;
     void *p[VBC_MAX_PEERS];
+    const unsigned char *mask; // optional: mask[(col >> chunk_shift)] bit i set <=> destination i reads that column chunk
+    int chunk_shift;
 };
 
 template <typename Tv, int EPV, bool PEER>
@@ -220,7 +222,7 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
         Tv *stage = stage_all[threadIdx.x >> 5];
         const int lane32 = threadIdx.x & 31, gid = lane32 / G;
         const int nwarps = ngroups / GPW;
-        const PeerDst none{0, {nullptr}};
+        const PeerDst none{0, {nullptr}, nullptr, 0};
         for (int lbase = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW; lbase < L; lbase += nwarps * GPW) {
             const int l = lbase + gid;
             const int lend = min(lbase + GPW, L);
@@ -240,9 +242,18 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
             }
             __syncwarp();
             const int ncols = colend - colbase;
-            for (int i = 0; i < dst.n; i++) {
-                Tv *d = reinterpret_cast<Tv *>(dst.p[i]) + colbase;
-                for (int c = lane32; c < ncols; c += 32) d[c] = stage[c];
+            if (dst.mask == nullptr) { // full replication
+                for (int i = 0; i < dst.n; i++) {
+                    Tv *d = reinterpret_cast<Tv *>(dst.p[i]) + colbase;
+                    for (int c = lane32; c < ncols; c += 32) d[c] = stage[c];
+                }
+            } else { // sparsity-aware replication: a destination gets only the column chunks it gathers from
+                for (int c = lane32; c < ncols; c += 32) {
+                    const unsigned mk = __ldg(dst.mask + ((colbase + c) >> dst.chunk_shift));
+                    const Tv v = stage[c];
+                    for (int i = 0; i < dst.n; i++)
+                        if ((mk >> i) & 1u) reinterpret_cast<Tv *>(dst.p[i])[colbase + c] = v;
+                }
             }
             __syncwarp();
         }
@@ -536,7 +547,7 @@ static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, 
     const bool rows = A->desc_mode == DESC_ROWS;
     if (trans) {
         if (A->L == 0) return VBC_OK; // n == 0: nothing to write
-        return launch_adj_any<Tv, false>(A, alpha, x, beta, y, PeerDst{0, {nullptr}});
+        return launch_adj_any<Tv, false>(A, alpha, x, beta, y, PeerDst{0, {nullptr}, nullptr, 0});
     }
     VBC_TRY(scale_y<Tv>(A, y, A->m, beta));
     if (A->L == 0 || A->nval == 0) return VBC_OK;
@@ -547,7 +558,7 @@ static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, 
 
 // adjoint multiply whose result goes to `n` destination buffers (each already offset to this
 // rank's first column): the compute half of vbc_peer_spmv_step.
-int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs)
+int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs, const unsigned char *d_mask, int chunk_shift)
 {
     if (A->opt_parity) VBC_FAIL(VBC_EARG, "peer multiply needs the compact layout (parity mode is on)");
     if (n < 1 || n > VBC_MAX_PEERS) VBC_FAIL(VBC_EARG, "peer count %d out of 1..%d", n, VBC_MAX_PEERS);
@@ -555,6 +566,8 @@ int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void 
     PeerDst dst;
     dst.n = n;
     for (int i = 0; i < VBC_MAX_PEERS; i++) dst.p[i] = i < n ? dst_ptrs[i] : nullptr;
+    dst.mask = d_mask;
+    dst.chunk_shift = chunk_shift;
     if (A->vt == VBC_F64) return launch_adj_any<double, true>(A, alpha, (const double *)d_x, 0.0, nullptr, dst);
     return launch_adj_any<float, true>(A, (float)alpha, (const float *)d_x, 0.0f, nullptr, dst);
 }

@@ -134,7 +134,10 @@ class PeerExchangeOperator:
     peer mappings (NVLink), and a one-CTA flag kernel is the only cross-rank step.  x is double
     buffered inside libvbc; handles are exchanged once with torch.distributed (any backend)."""
 
-    def __init__(self, B, layout: PaddedLayout, rank, world, device, alpha=1.0):
+    def __init__(self, B, layout: PaddedLayout, rank, world, device, alpha=1.0, rows_read=None, chunk_shift=7, row_pad=None):
+        """rows_read: optional 0-based (padded) x indices this rank's stripes gather from (e.g. the slab's
+        CSC rowval - 1).  When every rank passes it, replication becomes sparsity-aware: a y segment is
+        stored only into the ranks that read it (`vbc_peer_set_mask`); otherwise x is fully replicated."""
         import ctypes
 
         import torch
@@ -158,6 +161,37 @@ class PeerExchangeOperator:
         self.y_offset = rank * layout.S
         self.Tv = B.Tv
         self._lib = _lib
+        self.halo = False
+        self.sent_fraction = 1.0
+        if rows_read is not None and world > 1:
+            C = 1 << chunk_shift
+            ng = (layout.padded_len + C - 1) // C
+            need = np.zeros(ng, dtype=np.uint8)
+            rr = np.asarray(rows_read, dtype=np.int64)
+            # a 2D block reads all u rows of its row part, stored or zero-filled: widen by U-1 rows both ways
+            pad = (max(int(B.U), 1) - 1) if row_pad is None else int(row_pad)
+            need[rr >> chunk_shift] = 1
+            if pad:
+                need[np.maximum(rr - pad, 0) >> chunk_shift] = 1
+                need[np.minimum(rr + pad, layout.padded_len - 1) >> chunk_shift] = 1
+            t = torch.from_numpy(need)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            alln = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(alln, t)
+            need_all = np.stack([a.cpu().numpy() for a in alln])  # [rank, global chunk]
+            nl = (B.n + C - 1) // C
+            lo = (self.y_offset + np.arange(nl, dtype=np.int64) * C) >> chunk_shift
+            hi = np.minimum(self.y_offset + (np.arange(nl, dtype=np.int64) + 1) * C - 1, layout.padded_len - 1) >> chunk_shift
+            mask = np.ones(nl, dtype=np.uint8)  # bit 0: this rank always keeps its own slice
+            for i in range(1, world):
+                r = (rank + i) % world
+                needed = need_all[r][lo] | need_all[r][hi]
+                mask |= (needed.astype(np.uint8) << i).astype(np.uint8)
+            _lib.check(L.vbc_peer_set_mask(self._h, mask.ctypes.data_as(ctypes.c_void_p), nl, chunk_shift))
+            self.halo = True
+            bits = np.unpackbits(mask[:, None], axis=1).sum()
+            self.sent_fraction = float(bits) / float(nl * world)
 
     def _buf_ptr(self, k):
         import ctypes
@@ -198,9 +232,17 @@ class PeerExchangeOperator:
         return bool(c.value)
 
     def x_global(self):
+        """The full vector, assembled from every rank's OWN slice (always current, with or without a mask)."""
         import torch
+        import torch.distributed as dist
         torch.cuda.synchronize()
-        return self.layout.gather(self._as_tensor(self.current()).cpu().numpy())
+        cur = self._as_tensor(self.current())
+        mine = cur[self.y_offset: self.y_offset + self.layout.S].clone()
+        if self.world == 1:
+            return self.layout.gather(mine.cpu().numpy())
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine)
+        return self.layout.gather(torch.cat(parts).cpu().numpy())
 
     def close(self):
         if self._h.value:
