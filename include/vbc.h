@@ -181,6 +181,13 @@ int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, 
  * halos) -- x stays complete on every rank exactly where that rank reads it.  mask == NULL restores
  * full replication. */
 int vbc_peer_set_mask(vbc_peer *P, const void *mask, int64_t nchunks, int chunk_shift);
+/* Fused flag exchange (optional).  With enable = 1, vbc_peer_spmv_step(..., barrier = 3) launches ONE
+ * kernel per iteration: it first runs the stripes [i0, i1) -- which must gather only from this rank's
+ * own slice and (under the mask) feed only this rank -- then waits for the peers' flags of the
+ * previous iteration, runs the remaining stripes, and the last CTA to finish publishes this rank's
+ * flag.  The wait is hidden behind the work of [i0, i1), and ranks may drift by that much.  With full
+ * replication pass i0 == i1 (nothing can run before the wait). */
+int vbc_peer_set_fused_sync(vbc_peer *P, int enable, int64_t i0, int64_t i1);
 /* the flag kernel alone (barrier = 1 | 2 | 3 as above); does not flip cur */
 int vbc_peer_barrier(vbc_peer *P, void *cuda_stream, int barrier);
 /* 0 if no flag wait has timed out since creation (checked after a stream sync by the caller) */

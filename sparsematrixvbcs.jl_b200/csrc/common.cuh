@@ -111,7 +111,16 @@ int finalize_layout(vbc_mat *A, const void *h_pi_spl /* host copy, may be null f
 int memory_cost_device(const vbc_mat *A, int64_t *h_cost, int64_t *row_term);
 // spmv.cu
 int launch_spmv(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y);
-int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs, const unsigned char *d_mask, int chunk_shift);
+struct PeerSyncArgs { // in-kernel flag exchange of the fused multiply + all-gather (peer.cu -> spmv.cu)
+    int nranks, me;
+    unsigned long long *flags[VBC_MAX_PEERS];
+    unsigned long long *d_epoch;
+    unsigned *d_done;
+    int *timed_out;
+    int i0, i1;
+};
+int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs, const unsigned char *d_mask, int chunk_shift,
+                         const PeerSyncArgs *sync);
 // trsv.cu
 void destroy_trsv_plan(vbc_trsv_plan *p);
 int trsv_error_flag(const vbc_mat *A, int *flag);

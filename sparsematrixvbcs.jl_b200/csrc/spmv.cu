@@ -83,7 +83,25 @@ struct PeerDst {
     void *p[VBC_MAX_PEERS];
     const unsigned char *mask; // optional: mask[(col >> chunk_shift)] bit i set <=> destination i reads that column chunk
     int chunk_shift;
+    // in-kernel cross-rank synchronisation (fused flag exchange); sync_n == 0: none (the caller launches k_peer_flags)
+    int sync_n, me;                               // ranks, this rank
+    unsigned long long *flags[VBC_MAX_PEERS];     // flag block of every rank (flags[me] is local)
+    unsigned long long *d_epoch;                  // epoch signalled at the end of this rank's previous step
+    unsigned *d_done;                             // CTAs finished in this launch
+    int *timed_out;
+    int i0, i1;                                   // stripes [i0, i1) need nothing from other ranks and feed only this rank
 };
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <typename Tv, int EPV, bool PEER>
 __device__ __forceinline__ void store_y(Tv *__restrict__ y, const PeerDst &dst, const int col, const Tv (&acc)[EPV], const Tv alpha, const Tv beta)
@@ -222,12 +240,14 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
         Tv *stage = stage_all[threadIdx.x >> 5];
         const int lane32 = threadIdx.x & 31, gid = lane32 / G;
         const int nwarps = ngroups / GPW;
-        const PeerDst none{0, {nullptr}, nullptr, 0};
-        for (int lbase = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW; lbase < L; lbase += nwarps * GPW) {
+        const PeerDst none{};
+        const int warp0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+        auto run_range = [&](const int lo, const int hi) {
+        for (int lbase = lo + warp0 * GPW; lbase < hi; lbase += nwarps * GPW) {
             const int l = lbase + gid;
-            const int lend = min(lbase + GPW, L);
+            const int lend = min(lbase + GPW, hi);
             const int colbase = ld_meta(meta + lbase).col, colend = ld_meta(meta + lend).col;
-            if (l < L) {
+            if (l < hi) {
                 const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
                 const int w = b.col - a.col;
                 Tv *ys = stage - colbase; // the stripe bodies store y[a.col + ...]: lands in the staging run
@@ -256,6 +276,46 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
                 }
             }
             __syncwarp();
+        }
+        };
+        if (dst.sync_n == 0) {
+            run_range(0, L);
+        } else {
+            // (A) stripes that gather only from this rank's own slice and feed only this rank: no peer involved
+            run_range(dst.i0, dst.i1);
+            // (B) every other stripe reads x entries written by peers in their previous step: wait for their flags
+            if (lane32 == 0) {
+                const unsigned long long want = *dst.d_epoch;
+                for (int r = 0; r < dst.sync_n; r++) {
+                    if (r == dst.me) continue;
+                    if (ld_acquire_sys_u64(dst.flags[dst.me] + r) < want) {
+                        unsigned long long t0, t1;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                        while (ld_acquire_sys_u64(dst.flags[dst.me] + r) < want) {
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                            if (t1 - t0 > 4000000000ull) { atomicExch(dst.timed_out, 1); break; }
+                            __nanosleep(64);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // (C) the rest
+            run_range(0, dst.i0);
+            run_range(dst.i1, L);
+            // (D) the last CTA to finish publishes the new epoch to every rank
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                if (atomicAdd(dst.d_done, 1u) == gridDim.x - 1) {
+                    *dst.d_done = 0;
+                    const unsigned long long e = *dst.d_epoch + 1;
+                    *dst.d_epoch = e;
+                    __threadfence_system();
+                    for (int r = 0; r < dst.sync_n; r++)
+                        if (r != dst.me) st_release_sys_u64(dst.flags[r] + dst.me, e);
+                }
+            }
         }
         return;
     }
@@ -547,7 +607,7 @@ static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, 
     const bool rows = A->desc_mode == DESC_ROWS;
     if (trans) {
         if (A->L == 0) return VBC_OK; // n == 0: nothing to write
-        return launch_adj_any<Tv, false>(A, alpha, x, beta, y, PeerDst{0, {nullptr}, nullptr, 0});
+        return launch_adj_any<Tv, false>(A, alpha, x, beta, y, PeerDst{});
     }
     VBC_TRY(scale_y<Tv>(A, y, A->m, beta));
     if (A->L == 0 || A->nval == 0) return VBC_OK;
@@ -558,16 +618,25 @@ static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, 
 
 // adjoint multiply whose result goes to `n` destination buffers (each already offset to this
 // rank's first column): the compute half of vbc_peer_spmv_step.
-int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs, const unsigned char *d_mask, int chunk_shift)
+int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs, const unsigned char *d_mask, int chunk_shift,
+                         const PeerSyncArgs *sync)
 {
     if (A->opt_parity) VBC_FAIL(VBC_EARG, "peer multiply needs the compact layout (parity mode is on)");
     if (n < 1 || n > VBC_MAX_PEERS) VBC_FAIL(VBC_EARG, "peer count %d out of 1..%d", n, VBC_MAX_PEERS);
     if (A->L == 0) return VBC_OK;
-    PeerDst dst;
+    PeerDst dst{};
     dst.n = n;
     for (int i = 0; i < VBC_MAX_PEERS; i++) dst.p[i] = i < n ? dst_ptrs[i] : nullptr;
     dst.mask = d_mask;
     dst.chunk_shift = chunk_shift;
+    dst.sync_n = 0;
+    if (sync) {
+        dst.sync_n = sync->nranks; dst.me = sync->me;
+        for (int r = 0; r < VBC_MAX_PEERS; r++) dst.flags[r] = r < sync->nranks ? sync->flags[r] : nullptr;
+        dst.d_epoch = sync->d_epoch; dst.d_done = sync->d_done; dst.timed_out = sync->timed_out;
+        dst.i0 = sync->i0 < 0 ? 0 : (sync->i0 > (int)A->L ? (int)A->L : sync->i0);
+        dst.i1 = sync->i1 < dst.i0 ? dst.i0 : (sync->i1 > (int)A->L ? (int)A->L : sync->i1);
+    }
     if (A->vt == VBC_F64) return launch_adj_any<double, true>(A, alpha, (const double *)d_x, 0.0, nullptr, dst);
     return launch_adj_any<float, true>(A, (float)alpha, (const float *)d_x, 0.0f, nullptr, dst);
 }

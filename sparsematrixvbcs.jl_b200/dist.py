@@ -87,6 +87,44 @@ def padded_row_partition(layout: PaddedLayout, u, ti):
     return SplitPartition(np.arange(1, layout.padded_len + 2, u, dtype=ti))
 
 
+def stripe_read_ranges(A: SparseMatrixCSC, phi: SplitPartition, pad=0):
+    """Per stripe: smallest and largest 0-based row its columns store (-> x entries it gathers), widened by
+    `pad` rows (a 2D block reads its whole row part).  Empty stripes get (big, -1)."""
+    cp = A.colptr.astype(np.int64) - 1
+    n = A.n
+    big = np.int64(np.iinfo(np.int64).max // 4)
+    nonempty = cp[1:] > cp[:-1]
+    cmin = np.full(n, big, dtype=np.int64)
+    cmax = np.full(n, -1, dtype=np.int64)
+    cmin[nonempty] = A.rowval[cp[:-1][nonempty]].astype(np.int64) - 1
+    cmax[nonempty] = A.rowval[cp[1:][nonempty] - 1].astype(np.int64) - 1
+    spl = phi.spl.astype(np.int64) - 1
+    L = len(spl) - 1
+    rmin = np.full(L, big, dtype=np.int64)
+    rmax = np.full(L, -1, dtype=np.int64)
+    wide = spl[1:] > spl[:-1]
+    if n > 0 and wide.any():
+        starts = spl[:-1][wide]
+        rmin[wide] = np.minimum.reduceat(cmin, starts)[: wide.sum()]
+        rmax[wide] = np.maximum.reduceat(cmax, starts)[: wide.sum()]
+        # reduceat runs to the next start; stripes are contiguous and cover all columns, so that is exact
+    has = rmax >= 0
+    rmin[has] -= pad
+    rmax[has] += pad
+    return rmin, rmax
+
+
+def longest_true_run(flags):
+    """[i0, i1) of the longest run of True in a boolean array ((0, 0) if none)."""
+    f = np.concatenate([[False], np.asarray(flags, dtype=bool), [False]])
+    d = np.diff(f.astype(np.int8))
+    starts, ends = np.flatnonzero(d == 1), np.flatnonzero(d == -1)
+    if len(starts) == 0:
+        return 0, 0
+    k = int(np.argmax(ends - starts))
+    return int(starts[k]), int(ends[k])
+
+
 class RowPartitionedOperator:
     """One rank's share of the iterated adjoint multiply x <- alpha * A' x with the x exchange done by
     a torch.distributed all-gather (NCCL on GPUs; gloo in the CPU tests).
@@ -134,7 +172,8 @@ class PeerExchangeOperator:
     peer mappings (NVLink), and a one-CTA flag kernel is the only cross-rank step.  x is double
     buffered inside libvbc; handles are exchanged once with torch.distributed (any backend)."""
 
-    def __init__(self, B, layout: PaddedLayout, rank, world, device, alpha=1.0, rows_read=None, chunk_shift=7, row_pad=None):
+    def __init__(self, B, layout: PaddedLayout, rank, world, device, alpha=1.0, rows_read=None, chunk_shift=7, row_pad=None,
+                 fused_sync=False, stripe_ranges=None):
         """rows_read: optional 0-based (padded) x indices this rank's stripes gather from (e.g. the slab's
         CSC rowval - 1).  When every rank passes it, replication becomes sparsity-aware: a y segment is
         stored only into the ranks that read it (`vbc_peer_set_mask`); otherwise x is fully replicated."""
@@ -192,6 +231,21 @@ class PeerExchangeOperator:
             self.halo = True
             bits = np.unpackbits(mask[:, None], axis=1).sum()
             self.sent_fraction = float(bits) / float(nl * world)
+            self._mask, self._chunk_shift = mask, chunk_shift
+        self.interior = (0, 0)
+        if fused_sync:
+            i0 = i1 = 0
+            if self.halo and stripe_ranges is not None:
+                rmin, rmax = stripe_ranges
+                own_lo, own_hi = self.y_offset, self.y_offset + int(layout.lens[rank])
+                reads_own = (rmax < 0) | ((rmin >= own_lo) & (rmax < own_hi))
+                spl0 = B.Phi.spl.astype(np.int64) - 1
+                c_lo = spl0[:-1] >> self._chunk_shift
+                c_hi = np.maximum(spl0[1:] - 1, spl0[:-1]) >> self._chunk_shift
+                feeds_self = (self._mask[np.minimum(c_lo, len(self._mask) - 1)] == 1) & (self._mask[np.minimum(c_hi, len(self._mask) - 1)] == 1)
+                i0, i1 = longest_true_run(reads_own & feeds_self)
+            _lib.check(L.vbc_peer_set_fused_sync(self._h, 1, i0, i1))
+            self.interior = (i0, i1)
 
     def _buf_ptr(self, k):
         import ctypes

@@ -433,3 +433,39 @@ def test_triangular_solve_extension():
         assert np.array_equal(xd.cpu().numpy(), x), name
     with pytest.raises(vb.DimensionMismatch):
         vb.ldiv_lower_(np.zeros(5), B.T, np.zeros(5))
+
+
+def test_peer_fused_sync_single_rank():
+    """The one-kernel-per-step variant (in-kernel wait + last-CTA signal) with a single rank: phases A/C/D
+    and the mask path run, nothing to wait for."""
+    import ctypes
+    import torch
+    n, u, w = 12_000, 4, 4
+    A, pi, phi = synth.config_c2(n=n, S=11)
+    S = A.to_scipy()
+    B = vb.SparseMatrixVBC[u, w](A, pi, phi)
+    Lh = _lib.lib()
+    h = ctypes.c_void_p()
+    _lib.check(Lh.vbc_peer_create(ctypes.byref(h), _lib.VBC_F64, n, 0, 1, 0, None))
+    mask = np.ones((n + 127) // 128, dtype=np.uint8)
+    _lib.check(Lh.vbc_peer_set_mask(h, mask.ctypes.data_as(ctypes.c_void_p), len(mask), 7))
+    _lib.check(Lh.vbc_peer_set_fused_sync(h, 1, 1000, 2001))
+    p = ctypes.c_void_p()
+    _lib.check(Lh.vbc_peer_buffer(h, 0, ctypes.byref(p)))
+    x0 = synth.vector(n, 4)
+    rt = ctypes.CDLL("libcudart.so")
+    rt.cudaMemcpy(ctypes.c_void_p(p.value), ctypes.c_void_p(x0.ctypes.data), ctypes.c_size_t(x0.nbytes), 1)
+    ref = x0.copy()
+    for _ in range(3):
+        _lib.check(Lh.vbc_peer_spmv_step(h, B._h, 0.04, 0, 3))
+        ref = 0.04 * (S.T @ ref)
+    torch.cuda.synchronize()
+    cur, to = ctypes.c_int(), ctypes.c_int()
+    _lib.check(Lh.vbc_peer_current(h, ctypes.byref(cur)))
+    _lib.check(Lh.vbc_peer_status(h, ctypes.byref(to)))
+    assert cur.value == 1 and to.value == 0
+    _lib.check(Lh.vbc_peer_buffer(h, 1, ctypes.byref(p)))
+    out = np.empty(n)
+    rt.cudaMemcpy(ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(p.value), ctypes.c_size_t(out.nbytes), 2)
+    assert np.allclose(out, ref, rtol=1e-12, atol=0)
+    Lh.vbc_peer_destroy(h)
