@@ -194,7 +194,7 @@ def run_ours(args, rank, world, local_rank):
         rows_read = (A.rowval.astype(np.int64) - 1) if args.exchange == "halo" else None
         ranges = vdist.stripe_read_ranges(A, phi, pad=u - 1) if args.exchange == "halo" else None
         peer = vdist.PeerExchangeOperator(B, layout, rank, world, dev, alpha=alpha_step, rows_read=rows_read,
-                                          fused_sync=not args.flag_kernel, stripe_ranges=ranges)
+                                          fused_sync=args.sync_mode, stripe_ranges=ranges)
         peer.set_x(xg)
         dist.barrier()
 
@@ -223,7 +223,8 @@ def run_ours(args, rank, world, local_rank):
         with torch.cuda.graph(graph, stream=side):
             for _ in range(args.steps):
                 step()
-        gpu_launches = B.launch_count() - launches_before + (args.steps if (peer is not None and args.flag_kernel) else 0)  # + flag kernel per step
+        flag_launches = 0 if peer is None else {0: 1, 1: 0, 2: (2 if peer.interior[1] > peer.interior[0] else 1)}[args.sync_mode]
+        gpu_launches = B.launch_count() - launches_before + args.steps * flag_launches  # + flag kernel(s) per step
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -324,7 +325,8 @@ def run_ours(args, rank, world, local_rank):
             "pack_seconds": pack_s, "cost_imbalance": imbalance, "alpha": alpha_step,
             "exchange": (args.exchange if world > 1 else None), "x_abs_sum_after_run": x_check,
             "exchange_sent_fraction": (peer.sent_fraction if peer is not None else None),
-            "exchange_sync": (None if peer is None else ("flag kernel" if args.flag_kernel else f"in-kernel, stripes {list(peer.interior)} run before the wait")),
+            "exchange_sync": (None if peer is None else {0: "flag kernel after the multiply", 1: f"in-kernel, stripes {list(peer.interior)} run before the wait",
+                                                               2: f"split launches, stripes {list(peer.interior)} run before the wait"}[args.sync_mode]),
         }
         if world == 1 and not args.no_cpu_baseline:
             oracle, H = cpu_reference_setup(A, pi, phi)
@@ -350,8 +352,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--flag-kernel", action="store_true",
-                    help="peer/halo: exchange the flags with a separate one-CTA kernel per step instead of inside the multiply")
+    ap.add_argument("--sync-mode", type=int, default=0, choices=[0, 1, 2],
+                    help="peer/halo flag exchange: 0 = one flag kernel (signal+wait) after the multiply; 1 = inside the multiply "
+                         "kernel; 2 = split launches [interior stripes][wait][other stripes][signal] (halo only)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "halo", "nccl"],
                     help="N > 1: 'peer' = all-gather fused into the multiply through NVLink peer stores, x fully replicated "
                          "(default); 'halo' = same kernel, but a y segment is sent only to the ranks whose stripes read it; "

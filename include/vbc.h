@@ -181,7 +181,10 @@ int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, 
  * halos) -- x stays complete on every rank exactly where that rank reads it.  mask == NULL restores
  * full replication. */
 int vbc_peer_set_mask(vbc_peer *P, const void *mask, int64_t nchunks, int chunk_shift);
-/* Fused flag exchange (optional).  With enable = 1, vbc_peer_spmv_step(..., barrier = 3) launches ONE
+/* Overlapping the flag exchange with the multiply (optional).  enable = 2: barrier = 3 steps become four
+ * launches -- [stripes i0..i1) | wait for the peers' previous step | remaining stripes | signal -- so the
+ * wait (and the drift between ranks) hides behind the first launch; the default (enable = 0) is
+ * [all stripes | signal + wait].  enable = 1: vbc_peer_spmv_step(..., barrier = 3) launches ONE
  * kernel per iteration: it first runs the stripes [i0, i1) -- which must gather only from this rank's
  * own slice and (under the mask) feed only this rank -- then waits for the peers' flags of the
  * previous iteration, runs the remaining stripes, and the last CTA to finish publishes this rank's

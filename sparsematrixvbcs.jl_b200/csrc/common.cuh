@@ -120,7 +120,7 @@ struct PeerSyncArgs { // in-kernel flag exchange of the fused multiply + all-gat
     int i0, i1;
 };
 int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs, const unsigned char *d_mask, int chunk_shift,
-                         const PeerSyncArgs *sync);
+                         const PeerSyncArgs *sync, const int *ranges /* {a0,a1,b0,b1} or null = all */);
 // trsv.cu
 void destroy_trsv_plan(vbc_trsv_plan *p);
 int trsv_error_flag(const vbc_mat *A, int *flag);

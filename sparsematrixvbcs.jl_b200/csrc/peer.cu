@@ -19,7 +19,8 @@ struct vbc_peer {
     unsigned char *d_mask = nullptr; // per column chunk of this rank's slice: which destinations read it
     int chunk_shift = 0;
     int64_t mask_len = 0;
-    bool fused_sync = false; // flags exchanged inside the multiply kernel instead of by k_peer_flags
+    int fused_sync = 0;      // 0: multiply, then k_peer_flags; 1: flags inside the multiply kernel; 2: split launches
+                             // [stripes i0..i1] [wait] [the rest] [signal] so the wait hides behind the first launch
     int i0 = 0, i1 = 0;      // stripes [i0, i1): no peer involved (run before the in-kernel wait)
     unsigned *d_done = nullptr;
     int64_t launches = 0;
@@ -207,15 +208,22 @@ int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, 
     if (P->d_mask && A->n > 0 && ((A->n - 1) >> P->chunk_shift) >= P->mask_len)
         VBC_FAIL(VBC_EDIM, "peer mask covers %lld chunks, the y slice needs %lld", (long long)P->mask_len, (long long)(((A->n - 1) >> P->chunk_shift) + 1));
     // the mask is indexed by (column in the y slice) >> shift; the kernel indexes by slab column, so no offset is needed
-    if (P->fused_sync && barrier == 3) {
+    if (P->fused_sync == 1 && barrier == 3) {
         PeerSyncArgs sa;
         sa.nranks = P->nranks; sa.me = P->rank;
         for (int r = 0; r < VBC_MAX_PEERS; r++) sa.flags[r] = r < P->nranks ? (unsigned long long *)P->bufs[r][2] : nullptr;
         sa.d_epoch = P->d_epoch; sa.d_done = P->d_done; sa.timed_out = P->d_timeout;
         sa.i0 = P->i0; sa.i1 = P->i1;
-        VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, &sa));
+        VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, &sa, nullptr));
+    } else if (P->fused_sync == 2 && barrier == 3 && P->i1 > P->i0) {
+        const int L = (int)A->L;
+        const int ra[4] = {P->i0, P->i1, 0, 0}, rc[4] = {0, P->i0, P->i1, L};
+        VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, nullptr, ra));
+        VBC_TRY(flags_launch(P, A->stream, 2)); // wait for the peers' previous step
+        VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, nullptr, rc));
+        VBC_TRY(flags_launch(P, A->stream, 1)); // publish this step
     } else {
-        VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, nullptr));
+        VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, nullptr, nullptr));
         VBC_TRY(flags_launch(P, A->stream, barrier));
     }
     P->cur = nxt;
@@ -241,13 +249,13 @@ int vbc_peer_set_mask(vbc_peer *P, const void *mask, int64_t nchunks, int chunk_
 int vbc_peer_set_fused_sync(vbc_peer *P, int enable, int64_t i0, int64_t i1)
 {
     if (!P) VBC_FAIL(VBC_EARG, "NULL argument");
-    if (i0 < 0 || i1 < i0) VBC_FAIL(VBC_EARG, "bad interior range");
+    if (i0 < 0 || i1 < i0 || enable < 0 || enable > 2) VBC_FAIL(VBC_EARG, "bad interior range / mode");
     DeviceGuard guard(P->device);
     if (enable && !P->d_done) {
         VBC_CUDA(cudaMalloc(&P->d_done, sizeof(unsigned)));
         VBC_CUDA(cudaMemset(P->d_done, 0, sizeof(unsigned)));
     }
-    P->fused_sync = enable != 0;
+    P->fused_sync = enable;
     P->i0 = (int)i0;
     P->i1 = (int)i1;
     return VBC_OK;

@@ -90,6 +90,7 @@ struct PeerDst {
     unsigned *d_done;                             // CTAs finished in this launch
     int *timed_out;
     int i0, i1;                                   // stripes [i0, i1) need nothing from other ranks and feed only this rank
+    int ra0, ra1, rb0, rb1;                       // sync_n == 0: the stripe ranges this launch covers ([ra0,ra1) then [rb0,rb1))
 };
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
@@ -279,7 +280,8 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
         }
         };
         if (dst.sync_n == 0) {
-            run_range(0, L);
+            run_range(dst.ra0, min(dst.ra1, L));
+            run_range(dst.rb0, min(dst.rb1, L));
         } else {
             // (A) stripes that gather only from this rank's own slice and feed only this rank: no peer involved
             run_range(dst.i0, dst.i1);
@@ -619,7 +621,7 @@ static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, 
 // adjoint multiply whose result goes to `n` destination buffers (each already offset to this
 // rank's first column): the compute half of vbc_peer_spmv_step.
 int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs, const unsigned char *d_mask, int chunk_shift,
-                         const PeerSyncArgs *sync)
+                         const PeerSyncArgs *sync, const int *ranges)
 {
     if (A->opt_parity) VBC_FAIL(VBC_EARG, "peer multiply needs the compact layout (parity mode is on)");
     if (n < 1 || n > VBC_MAX_PEERS) VBC_FAIL(VBC_EARG, "peer count %d out of 1..%d", n, VBC_MAX_PEERS);
@@ -630,6 +632,8 @@ int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void 
     dst.mask = d_mask;
     dst.chunk_shift = chunk_shift;
     dst.sync_n = 0;
+    dst.ra0 = 0; dst.ra1 = (int)A->L; dst.rb0 = dst.rb1 = 0;
+    if (ranges) { dst.ra0 = ranges[0]; dst.ra1 = ranges[1]; dst.rb0 = ranges[2]; dst.rb1 = ranges[3]; }
     if (sync) {
         dst.sync_n = sync->nranks; dst.me = sync->me;
         for (int r = 0; r < VBC_MAX_PEERS; r++) dst.flags[r] = r < sync->nranks ? sync->flags[r] : nullptr;

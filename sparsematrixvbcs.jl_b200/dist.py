@@ -244,7 +244,7 @@ class PeerExchangeOperator:
                 c_hi = np.maximum(spl0[1:] - 1, spl0[:-1]) >> self._chunk_shift
                 feeds_self = (self._mask[np.minimum(c_lo, len(self._mask) - 1)] == 1) & (self._mask[np.minimum(c_hi, len(self._mask) - 1)] == 1)
                 i0, i1 = longest_true_run(reads_own & feeds_self)
-            _lib.check(L.vbc_peer_set_fused_sync(self._h, 1, i0, i1))
+            _lib.check(L.vbc_peer_set_fused_sync(self._h, int(fused_sync), i0, i1))
             self.interior = (i0, i1)
 
     def _buf_ptr(self, k):
