@@ -144,7 +144,7 @@ def workload_config(world, nnz_local):
             "l2": "inputs (431 MB/GPU) larger than L2 (126 MB); no explicit flush",
             "timing": "K steps captured in one CUDA graph, replayed once between two CUDA events; max over ranks "
                       "(--exchange nccl: plain launch loop between the events)",
-            "parallelism": f"row-block partition over {world} GPU(s)" + (", x all-gather per step" if world > 1 else "")}
+            "parallelism": f"row-block partition over {world} GPU(s)" + (", x exchange per step (see 'exchange')" if world > 1 else "")}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -323,7 +323,10 @@ def run_ours(args, rank, world, local_rank):
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "result_checksum": result_checksum},
             "gpu_launches": int(gpu_launches), "clocks": clk.summary(),
             "pack_seconds": pack_s, "cost_imbalance": imbalance, "alpha": alpha_step,
-            "exchange": (args.exchange if world > 1 else None), "x_abs_sum_after_run": x_check,
+            "exchange": (None if world == 1 else {"halo": "fused into the multiply kernel (NVLink peer stores); each y segment goes to the ranks whose stripes read it",
+                                                  "peer": "fused into the multiply kernel (NVLink peer stores); every y segment goes to every rank (all-gather)",
+                                                  "nccl": "torch.distributed all_gather_into_tensor after the multiply"}[args.exchange]),
+            "exchange_mode": (args.exchange if world > 1 else None), "x_abs_sum_after_run": x_check,
             "exchange_sent_fraction": (peer.sent_fraction if peer is not None else None),
             "exchange_sync": (None if peer is None else {0: "flag kernel after the multiply", 1: f"in-kernel, stripes {list(peer.interior)} run before the wait",
                                                                2: f"split launches, stripes {list(peer.interior)} run before the wait"}[args.sync_mode]),
@@ -355,10 +358,11 @@ def main():
     ap.add_argument("--sync-mode", type=int, default=0, choices=[0, 1, 2],
                     help="peer/halo flag exchange: 0 = one flag kernel (signal+wait) after the multiply; 1 = inside the multiply "
                          "kernel; 2 = split launches [interior stripes][wait][other stripes][signal] (halo only)")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "halo", "nccl"],
-                    help="N > 1: 'peer' = all-gather fused into the multiply through NVLink peer stores, x fully replicated "
-                         "(default); 'halo' = same kernel, but a y segment is sent only to the ranks whose stripes read it; "
-                         "'nccl' = multiply, then torch.distributed all_gather_into_tensor")
+    ap.add_argument("--exchange", default="halo", choices=["halo", "peer", "nccl"],
+                    help="N > 1, how x_{t+1} reaches the ranks: 'halo' (default) = exchange fused into the multiply kernel through "
+                         "NVLink peer stores, each y segment sent to exactly the ranks whose stripes read it; 'peer' = same kernel, "
+                         "every segment sent to every rank (full replication, a fused all-gather); 'nccl' = multiply, then "
+                         "torch.distributed all_gather_into_tensor")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
