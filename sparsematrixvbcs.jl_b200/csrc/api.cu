@@ -364,8 +364,8 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
     switch (option) {
     case VBC_OPT_ADJ_GROUP:
     case VBC_OPT_FWD_GROUP:
-        if (value != 0 && value != 8 && value != 16 && value != 32) VBC_FAIL(VBC_EARG, "group must be 0 (auto), 8, 16 or 32");
-        if (option == VBC_OPT_FWD_GROUP && value == 16) VBC_FAIL(VBC_EARG, "forward kernel groups: 0 (auto), 8 or 32");
+        if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32) VBC_FAIL(VBC_EARG, "group must be 0 (auto), 4, 8, 16 or 32");
+        if (option == VBC_OPT_FWD_GROUP && (value == 16 || value == 4)) VBC_FAIL(VBC_EARG, "forward kernel groups: 0 (auto), 8 or 32");
         (option == VBC_OPT_ADJ_GROUP ? A->opt_adj_group : A->opt_fwd_group) = (int)value;
         return VBC_OK;
     case VBC_OPT_GRID_MULT:

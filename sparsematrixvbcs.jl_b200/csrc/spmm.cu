@@ -20,12 +20,28 @@
 
 namespace vbc {
 
+// x index of stored row r of a stripe (any lane, no walk state)
+template <int MODE>
+__device__ __forceinline__ int row_xindex(const int *__restrict__ desc, const int pos0, const int r, const int u0, const int log2u)
+{
+    if (MODE == DESC_ROWS) return __ldg(desc + pos0 + r);
+    if (log2u >= 0) return __ldg(desc + pos0 + (r >> log2u)) + (r & (u0 - 1));
+    return __ldg(desc + pos0 + r / u0) + r % u0;
+}
+
+// Adjoint SpMM.  One warp per stripe; rows are taken RB = 8 at a time: the 8 x indices are loaded by 8 lanes
+// and broadcast, the 8 X rows are 8 independent coalesced loads in flight per lane, the 8 x w val slab is
+// loaded coalesced (each value once per warp) and staged in shared memory, from where the FMAs read it
+// with warp-uniform (broadcast) LDS -- 128-bit when w is even.
 template <typename Tv, int MODE, int WB, int KT>
 __global__ void __launch_bounds__(256) k_spmm_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                    const Tv *__restrict__ val, const Tv *__restrict__ X, const long long ldx,
                                                    Tv *__restrict__ Y, const long long ldy, const int L, const int k,
                                                    const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
+    constexpr int RB = 8;
+    __shared__ __align__(16) Tv vs_all[8][RB * WB];
+    Tv *vs = vs_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
     for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); l < L; l += nwarps) {
@@ -35,37 +51,57 @@ __global__ void __launch_bounds__(256) k_spmm_adj(const StripeMeta *__restrict__
         const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
         for (int kb = 0; kb < k; kb += 32 * KT) {
             for (int wb = 0; wb < w; wb += WB) {
+                const int wc = min(WB, w - wb); // columns of this chunk
                 Tv acc[WB][KT];
 #pragma unroll
                 for (int dj = 0; dj < WB; dj++)
 #pragma unroll
                     for (int t = 0; t < KT; t++) acc[dj][t] = (Tv)0;
-                RowWalk<MODE> walk;
-                walk.init(desc, a.pos, 0, 1, u0, log2u);
-                const Tv *vp = val + a.ofs + wb;
-                for (int r = 0; r < R; r += 2) {
-                    const bool ok1 = r + 1 < R;
-                    const int xi0 = walk.next_if(true), xi1 = walk.next_if(ok1);
-                    Tv x0[KT], x1[KT];
-#pragma unroll
-                    for (int t = 0; t < KT; t++) {
-                        const int c = kb + t * 32 + lane;
-                        x0[t] = c < k ? __ldg(X + (long long)xi0 * ldx + c) : (Tv)0;
-                        x1[t] = (ok1 && c < k) ? __ldg(X + (long long)xi1 * ldx + c) : (Tv)0;
+                for (int r = 0; r < R; r += RB) {
+                    const int nr = min(RB, R - r);
+                    // stage val[r .. r+nr) x [wb .. wb+wc) as vs[j * WB + dj], zero-padded to RB x WB
+                    __syncwarp();
+                    for (int i = lane; i < RB * WB; i += 32) {
+                        const int j = i / WB, dj = i % WB;
+                        vs[i] = (j < nr && dj < wc) ? __ldcs(val + a.ofs + (long long)(r + j) * w + wb + dj) : (Tv)0;
                     }
+                    const int myxi = lane < nr ? row_xindex<MODE>(desc, a.pos, r + lane, u0, log2u) : 0;
+                    Tv xv[RB][KT];
 #pragma unroll
-                    for (int dj = 0; dj < WB; dj++) {
-                        const bool in = wb + dj < w;
-                        const Tv v0 = in ? __ldg(vp + dj) : (Tv)0;             // warp-uniform address
-                        const Tv v1 = (in && ok1) ? __ldg(vp + w + dj) : (Tv)0;
+                    for (int j = 0; j < RB; j++) {
+                        const int xi = __shfl_sync(0xffffffffu, myxi, j);
 #pragma unroll
-                        for (int t = 0; t < KT; t++) acc[dj][t] = fma(v1, x1[t], fma(v0, x0[t], acc[dj][t]));
+                        for (int t = 0; t < KT; t++) {
+                            const int c = kb + t * 32 + lane;
+                            xv[j][t] = (j < nr && c < k) ? __ldg(X + (long long)xi * ldx + c) : (Tv)0;
+                        }
                     }
-                    vp += 2 * w;
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < RB; j++) {
+                        if constexpr (WB % 2 == 0 && sizeof(Tv) == 8) {
+#pragma unroll
+                            for (int dj = 0; dj < WB; dj += 2) {
+                                const double2 v2 = *reinterpret_cast<const double2 *>(vs + j * WB + dj); // warp-uniform LDS.128
+#pragma unroll
+                                for (int t = 0; t < KT; t++) {
+                                    acc[dj][t] = fma((Tv)v2.x, xv[j][t], acc[dj][t]);
+                                    acc[dj + 1][t] = fma((Tv)v2.y, xv[j][t], acc[dj + 1][t]);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int dj = 0; dj < WB; dj++) {
+                                const Tv v = vs[j * WB + dj];
+#pragma unroll
+                                for (int t = 0; t < KT; t++) acc[dj][t] = fma(v, xv[j][t], acc[dj][t]);
+                            }
+                        }
+                    }
                 }
 #pragma unroll
                 for (int dj = 0; dj < WB; dj++) {
-                    if (wb + dj < w) {
+                    if (dj < wc) {
                         Tv *yp = Y + (long long)(a.col + wb + dj) * ldy;
 #pragma unroll
                         for (int t = 0; t < KT; t++) {
@@ -166,11 +202,14 @@ static int launch_spmm_mode(vbc_mat *A, int trans, int k, Tv alpha, const Tv *X,
     if (grid < 1) grid = 1;
     const bool wide = A->W > 8;
     const bool k2 = k > 32;
+    const bool narrow = A->W <= 4;
 #define SPMM_LAUNCH(KERNEL, WBv, KTv, ...) KERNEL<Tv, MODE, WBv, KTv><<<(unsigned)grid, 256, 0, A->stream>>>(__VA_ARGS__)
     if (trans) {
         if (L == 0) return VBC_OK;
         if (wide) { if (k2) SPMM_LAUNCH(k_spmm_adj, 16, 2, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta);
                     else    SPMM_LAUNCH(k_spmm_adj, 16, 1, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta); }
+        else if (narrow) { if (k2) SPMM_LAUNCH(k_spmm_adj, 4, 2, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta);
+                    else    SPMM_LAUNCH(k_spmm_adj, 4, 1, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta); }
         else      { if (k2) SPMM_LAUNCH(k_spmm_adj, 8, 2, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta);
                     else    SPMM_LAUNCH(k_spmm_adj, 8, 1, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta); }
         A->launches++;

@@ -513,8 +513,10 @@ static int auto_group(const vbc_mat *A)
 {
     // ~ (bytes of an average stripe) / 16 B vectors; aim for >= 4 vectors per lane
     if (A->L == 0) return 8;
+    // tools/perf_table.py: 4 lanes win below ~80 16-byte vectors per stripe (52 -> 36.7 vs 38.5 us), 8 lanes from
+    // ~100 to a few hundred (104 -> 68.2 vs 69.7; 200 -> 71.5 vs 75.0 at 32 lanes)
     const double vec_per_stripe = (double)A->nval * (double)vt_size(A->vt) / 16.0 / (double)A->L;
-    return vec_per_stripe >= 160.0 ? 32 : 8;
+    return vec_per_stripe < 80.0 ? 4 : (vec_per_stripe < 512.0 ? 8 : 32);
 }
 
 template <typename Tv, int G, int MODE, bool PEER>
@@ -558,7 +560,8 @@ static int launch_adj_any(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y, con
     const int G = A->opt_adj_group ? A->opt_adj_group : auto_group(A);
     if (G >= 32) return rows ? launch_adj_t<Tv, 32, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 32, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
     if (G >= 16) return rows ? launch_adj_t<Tv, 16, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 16, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
-    return rows ? launch_adj_t<Tv, 8, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 8, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
+    if (G >= 8) return rows ? launch_adj_t<Tv, 8, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 8, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
+    return rows ? launch_adj_t<Tv, 4, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 4, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
 }
 
 template <typename Tv>
@@ -614,6 +617,7 @@ static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, 
     VBC_TRY(scale_y<Tv>(A, y, A->m, beta));
     if (A->L == 0 || A->nval == 0) return VBC_OK;
     int G = A->opt_fwd_group ? A->opt_fwd_group : auto_group(A);
+    if (G < 8) G = 8;
     if (G >= 32) return rows ? launch_fwd_t<Tv, 32, DESC_ROWS>(A, alpha, x, y) : launch_fwd_t<Tv, 32, DESC_BLOCKS>(A, alpha, x, y);
     return rows ? launch_fwd_t<Tv, 8, DESC_ROWS>(A, alpha, x, y) : launch_fwd_t<Tv, 8, DESC_BLOCKS>(A, alpha, x, y);
 }
