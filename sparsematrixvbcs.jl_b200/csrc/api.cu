@@ -203,7 +203,7 @@ void vbc_destroy(vbc_mat *A)
     if (!A) return;
     DeviceGuard guard(A->device);
     cudaFree(A->d_pi_spl); cudaFree(A->d_phi_spl); cudaFree(A->d_pos); cudaFree(A->d_idx); cudaFree(A->d_ofs); cudaFree(A->d_val);
-    cudaFree(A->d_meta); cudaFree(A->d_desc); cudaFree(A->d_brow); cudaFree(A->d_x); cudaFree(A->d_y);
+    cudaFree(A->d_meta); cudaFree(A->d_desc); cudaFree(A->d_brow); cudaFree(A->d_order); cudaFree(A->d_x); cudaFree(A->d_y);
     destroy_trsv_plan(A->trsv);
     delete A;
 }
@@ -243,7 +243,7 @@ int vbc_format_bytes(const vbc_mat *A, int64_t bytes[3])
     const int64_t ti = (int64_t)it_size(A->it), tv = (int64_t)vt_size(A->vt);
     bytes[0] = ti * (A->L + 1) * 3 + (A->ndim == 2 ? ti * (A->K + 1) : 0) + ti * A->nidx + tv * A->nval;
     if (A->opt_parity) { bytes[1] = bytes[0]; bytes[2] = bytes[0]; return VBC_OK; }
-    bytes[1] = (int64_t)sizeof(StripeMeta) * (A->L + 1) + 4 * A->ndesc + tv * A->nval;
+    bytes[1] = (int64_t)sizeof(StripeMeta) * (A->L + 1) + 4 * A->ndesc + tv * A->nval + (A->d_order ? 4 * A->L : 0);
     bytes[2] = bytes[1];
     return VBC_OK;
 }

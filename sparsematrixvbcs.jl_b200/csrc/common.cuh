@@ -66,6 +66,8 @@ struct vbc_mat {
     vbc::StripeMeta *d_meta = nullptr; // L+1
     int *d_desc = nullptr;             // ndesc
     int *d_brow = nullptr;             // 2D only: first (stripe-relative) expanded row of each block
+    int *d_order = nullptr;            // stripes grouped by kernel body class (null: all stripes share one class)
+    int nclasses = 1;
     int64_t ndesc = 0;
     int desc_mode = vbc::DESC_ROWS;
     int u0 = 1; // DESC_BLOCKS: uniform part height

@@ -235,6 +235,80 @@ __global__ void k_memory_cost(const Ti *__restrict__ spl, const Ti *__restrict__
     cost[l] = 3 * ti + units * ti + nv * (long long)tv_size;
 }
 
+static inline unsigned nblk(int64_t n, int t);
+
+// Kernel-body class of a stripe: must mirror the per-stripe dispatch of k_spmv_adj / k_spmv_fwd (spmv.cu):
+// elements per load (from width and slab alignment) and vectors per row.
+__device__ __forceinline__ int stripe_class(const StripeMeta a, const StripeMeta b, const int VE)
+{
+    const int w = b.col - a.col;
+    if (w <= 0) return 0;
+    int epv_code, cpr;
+    if ((w % VE) == 0 && (a.ofs % VE) == 0) { epv_code = 0; cpr = w / VE; }
+    else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0) { epv_code = 1; cpr = w / 2; }
+    else { epv_code = 2; cpr = w; }
+    return 1 + epv_code * 64 + (cpr > 63 ? 63 : cpr);
+}
+
+__global__ void k_class_hist(const StripeMeta *__restrict__ meta, int64_t L, int VE, unsigned *__restrict__ hist)
+{
+    __shared__ unsigned sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < L; l += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh[stripe_class(meta[l], meta[l + 1], VE) & 255], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// order[cursor[class]++] = l.  Stripes are visited in ascending blocks, so neighbours of one class stay close.
+__global__ void k_class_scatter(const StripeMeta *__restrict__ meta, int64_t L, int VE, unsigned *__restrict__ cursor, int *__restrict__ order)
+{
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const int c = stripe_class(meta[l], meta[l + 1], VE) & 255;
+    order[atomicAdd(&cursor[c], 1u)] = (int)l;
+}
+
+// Group the stripes by kernel-body class when the matrix mixes several (variable widths): a warp then runs
+// one body instead of serialising up to four.
+static int build_class_order(vbc_mat *A)
+{
+    const int64_t L = A->L;
+    A->nclasses = 1;
+    if (L < 2) return VBC_OK;
+    cudaStream_t st = A->stream;
+    const int VE = 16 / (int)vt_size(A->vt);
+    unsigned *d_hist = nullptr;
+    VBC_CUDA(cudaMalloc(&d_hist, 256 * sizeof(unsigned)));
+    unsigned h[256];
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned), st);
+    if (e == cudaSuccess) {
+        int64_t g = (L + 255) / 256;
+        if (g > 2048) g = 2048;
+        k_class_hist<<<(unsigned)g, 256, 0, st>>>(A->d_meta, L, VE, d_hist);
+        A->launches++;
+        e = cudaMemcpyAsync(h, d_hist, sizeof(h), cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(d_hist); VBC_FAIL(VBC_ECUDA, "class histogram: %s", cudaGetErrorString(e)); }
+    int ncls = 0;
+    unsigned run = 0, cur[256];
+    for (int c = 0; c < 256; c++) { cur[c] = run; run += h[c]; if (h[c]) ncls++; }
+    A->nclasses = ncls;
+    if (ncls <= 1) { cudaFree(d_hist); return VBC_OK; }
+    e = cudaMalloc(&A->d_order, sizeof(int) * (size_t)L);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_hist, cur, sizeof(cur), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        k_class_scatter<<<nblk(L, 256), 256, 0, st>>>(A->d_meta, L, VE, d_hist, A->d_order);
+        A->launches++;
+        e = cudaStreamSynchronize(st);
+    }
+    cudaFree(d_hist);
+    if (e != cudaSuccess) VBC_FAIL(VBC_ECUDA, "class order: %s", cudaGetErrorString(e));
+    return VBC_OK;
+}
+
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t > 0 ? (n + t - 1) / t : 1); }
 
 // ---------------------------------------------------------------------------------------------
@@ -306,7 +380,8 @@ static int finalize_t(vbc_mat *A, const void *h_pi_spl_v)
 
 int finalize_layout(vbc_mat *A, const void *h_pi_spl)
 {
-    return A->it == VBC_I64 ? finalize_t<int64_t>(A, h_pi_spl) : finalize_t<int32_t>(A, h_pi_spl);
+    VBC_TRY(A->it == VBC_I64 ? finalize_t<int64_t>(A, h_pi_spl) : finalize_t<int32_t>(A, h_pi_spl));
+    return build_class_order(A);
 }
 
 template <typename Ti, typename Tv>

@@ -34,7 +34,7 @@ __device__ __forceinline__ int row_xindex(const int *__restrict__ desc, const in
 // loaded coalesced (each value once per warp) and staged in shared memory, from where the FMAs read it
 // with warp-uniform (broadcast) LDS -- 128-bit when w is even.
 template <typename Tv, int MODE, int WB, int KT>
-__global__ void __launch_bounds__(256) k_spmm_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+__global__ void __launch_bounds__(256, (WB * KT <= 8 ? 3 : 2)) k_spmm_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                    const Tv *__restrict__ val, const Tv *__restrict__ X, const long long ldx,
                                                    Tv *__restrict__ Y, const long long ldy, const int L, const int k,
                                                    const int u0, const int log2u, const Tv alpha, const Tv beta)
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256) k_spmm_adj(const StripeMeta *__restrict__
                 for (int dj = 0; dj < WB; dj++)
 #pragma unroll
                     for (int t = 0; t < KT; t++) acc[dj][t] = (Tv)0;
+                int nxi = lane < min(RB, R) ? row_xindex<MODE>(desc, a.pos, lane, u0, log2u) : 0; // x indices one batch ahead
                 for (int r = 0; r < R; r += RB) {
                     const int nr = min(RB, R - r);
                     // stage val[r .. r+nr) x [wb .. wb+wc) as vs[j * WB + dj], zero-padded to RB x WB
@@ -65,7 +66,8 @@ __global__ void __launch_bounds__(256) k_spmm_adj(const StripeMeta *__restrict__
                         const int j = i / WB, dj = i % WB;
                         vs[i] = (j < nr && dj < wc) ? __ldcs(val + a.ofs + (long long)(r + j) * w + wb + dj) : (Tv)0;
                     }
-                    const int myxi = lane < nr ? row_xindex<MODE>(desc, a.pos, r + lane, u0, log2u) : 0;
+                    const int myxi = nxi;
+                    nxi = (lane < RB && r + RB + lane < R) ? row_xindex<MODE>(desc, a.pos, r + RB + lane, u0, log2u) : 0;
                     Tv xv[RB][KT];
 #pragma unroll
                     for (int j = 0; j < RB; j++) {

@@ -132,7 +132,7 @@ __device__ __forceinline__ void adj_stripe(const StripeMeta a, const StripeMeta 
 {
     int cpr, rps, c, r0;
     if constexpr (CPR > 0) { cpr = CPR; rps = G / CPR; c = lane % CPR; r0 = lane / CPR; }
-    else { cpr = w / EPV; rps = G / cpr; c = lane % cpr; r0 = lane / cpr; }
+    else { cpr = w / EPV; rps = small_div(G, cpr); r0 = small_div(lane, cpr); c = lane - r0 * cpr; }
     int R;
     if (MODE == DESC_ROWS) R = b.pos - a.pos;
     else { const int nv = (int)(b.ofs - a.ofs); if constexpr (CPR > 0) R = nv / (CPR * EPV); else R = nv / w; }
@@ -224,7 +224,7 @@ __device__ __forceinline__ void adj_dispatch_cpr(const StripeMeta a, const Strip
 template <typename Tv, int G, int MODE, bool PEER>
 __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                    const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ y,
-                                                   const __grid_constant__ PeerDst dst,
+                                                   const __grid_constant__ PeerDst dst, const int *__restrict__ order,
                                                    const int L, const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
     constexpr int VE = 16 / (int)sizeof(Tv);
@@ -323,10 +323,19 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
     }
     int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G);
     if (l >= L) return;
-    StripeMeta na = ld_meta(meta + l), nb = ld_meta(meta + l + 1);
+    // order == null: stripes in index order, next stripe's meta prefetched.  order != null (mixed widths):
+    // position l holds stripe order[l], stripes of one body class are adjacent, so a warp's groups agree.
+    StripeMeta na, nb;
+    if (order == nullptr) { na = ld_meta(meta + l); nb = ld_meta(meta + l + 1); }
     for (; l < L; l += ngroups) {
-        const StripeMeta a = na, b = nb;
-        if (l + ngroups < L) { na = ld_meta(meta + l + ngroups); nb = ld_meta(meta + l + ngroups + 1); } // next stripe's meta rides along
+        StripeMeta a, b;
+        if (order == nullptr) {
+            a = na; b = nb;
+            if (l + ngroups < L) { na = ld_meta(meta + l + ngroups); nb = ld_meta(meta + l + ngroups + 1); } // next stripe's meta rides along
+        } else {
+            const int ls = __ldg(order + l);
+            a = ld_meta(meta + ls); b = ld_meta(meta + ls + 1);
+        }
         const int w = b.col - a.col;
         if (w <= 0) continue;
 #if VBC_WIDE_LD
@@ -351,7 +360,7 @@ __device__ __forceinline__ void fwd_stripe(const StripeMeta a, const StripeMeta 
 {
     int cpr, rps, c, r0;
     if constexpr (CPR > 0) { cpr = CPR; rps = G / CPR; c = lane % CPR; r0 = lane / CPR; }
-    else { cpr = w / EPV; rps = G / cpr; c = lane % cpr; r0 = lane / cpr; }
+    else { cpr = w / EPV; rps = small_div(G, cpr); r0 = small_div(lane, cpr); c = lane - r0 * cpr; }
     int R;
     if (MODE == DESC_ROWS) R = b.pos - a.pos;
     else { const int nv = (int)(b.ofs - a.ofs); if constexpr (CPR > 0) R = nv / (CPR * EPV); else R = nv / w; }
@@ -423,14 +432,15 @@ __device__ __forceinline__ void fwd_dispatch_cpr(const StripeMeta a, const Strip
 template <typename Tv, int G, int MODE>
 __global__ void __launch_bounds__(256) k_spmv_fwd(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                    const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ y,
-                                                   const int L, const int u0, const int log2u, const Tv alpha)
+                                                   const int *__restrict__ order, const int L, const int u0, const int log2u, const Tv alpha)
 {
     constexpr int VE = 16 / (int)sizeof(Tv);
     const int lane = threadIdx.x % G;
     const unsigned gmask = group_mask<G>();
     const int ngroups = (int)((gridDim.x * blockDim.x) / G);
     for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G); l < L; l += ngroups) {
-        const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
+        const int ls = order ? __ldg(order + l) : l;
+        const StripeMeta a = ld_meta(meta + ls), b = ld_meta(meta + ls + 1);
         const int w = b.col - a.col;
         if (w <= 0 || b.ofs == a.ofs) continue;
         if ((w % VE) == 0 && (a.ofs % VE) == 0)
@@ -516,7 +526,11 @@ static int auto_group(const vbc_mat *A)
     // tools/perf_table.py: 4 lanes win below ~80 16-byte vectors per stripe (52 -> 36.7 vs 38.5 us), 8 lanes from
     // ~100 to a few hundred (104 -> 68.2 vs 69.7; 200 -> 71.5 vs 75.0 at 32 lanes)
     const double vec_per_stripe = (double)A->nval * (double)vt_size(A->vt) / 16.0 / (double)A->L;
-    return vec_per_stripe < 80.0 ? 4 : (vec_per_stripe < 512.0 ? 8 : 32);
+    int G = vec_per_stripe < 80.0 ? 4 : (vec_per_stripe < 512.0 ? 8 : 32);
+    // few stripes (C1: L = 1250): widen the groups until the grid has ~1 CTA of 256 threads per SM x 4, as long as
+    // a stripe still has >= 2 vectors per lane (4.0 vs 7.1 us on C1 at 32 vs 8 lanes)
+    while (G < 32 && (double)A->L * G < 148.0 * 4 * 256 && vec_per_stripe >= 4.0 * G) G *= 2;
+    return G;
 }
 
 template <typename Tv, int G, int MODE, bool PEER>
@@ -530,7 +544,7 @@ static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y, const
     const int64_t need = (A->L * G + 255) / 256;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    k_spmv_adj<Tv, G, MODE, PEER><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, y, dst, (int)A->L, A->u0, ilog2_exact(A->u0), alpha, beta);
+    k_spmv_adj<Tv, G, MODE, PEER><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, y, dst, PEER ? nullptr : A->d_order, (int)A->L, A->u0, ilog2_exact(A->u0), alpha, beta);
     A->launches++;
     VBC_CUDA(cudaGetLastError());
     return VBC_OK;
@@ -547,7 +561,7 @@ static int launch_fwd_t(vbc_mat *A, Tv alpha, const Tv *x, Tv *y)
     const int64_t need = (A->L * G + 255) / 256;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    k_spmv_fwd<Tv, G, MODE><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, y, (int)A->L, A->u0, ilog2_exact(A->u0), alpha);
+    k_spmv_fwd<Tv, G, MODE><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, y, A->d_order, (int)A->L, A->u0, ilog2_exact(A->u0), alpha);
     A->launches++;
     VBC_CUDA(cudaGetLastError());
     return VBC_OK;

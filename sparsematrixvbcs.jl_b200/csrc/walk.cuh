@@ -5,6 +5,17 @@
 
 namespace vbc {
 
+// floor(a / b) for 0 <= a < 2048, 1 <= b <= 32 without an integer division: (a * ceil(2^16 / b)) >> 16
+// (exact on that range; checked exhaustively).  The generic stripe bodies divide lane ids and group
+// sizes by the runtime vectors-per-row count once per stripe; a real division costs ~20 instructions.
+__constant__ unsigned short c_inv16[33] = {0, 0 /* b = 1 handled below */, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462,
+                                           5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428,
+                                           2341, 2260, 2185, 2115, 2048};
+__device__ __forceinline__ int small_div(const int a, const int b)
+{
+    return b == 1 ? a : (int)(((unsigned)a * (unsigned)c_inv16[b]) >> 16);
+}
+
 __device__ __forceinline__ StripeMeta ld_meta(const StripeMeta *p)
 {
     const int4 t = __ldg(reinterpret_cast<const int4 *>(p));

@@ -142,7 +142,7 @@ def main():
         A, pi, phi = synth.config_c2(n=400_000, S=41)
         pv, fv = synth.variable_partition(A.m, 8, 1), synth.variable_partition(A.n, 8, 2)
         B = pack_time("C2v 2D f64 variable 2..8 n=400k", lambda: vb.SparseMatrixVBC[8, 8](A, pv, fv))
-        report("C2v 2D f64 variable 2..8 n=400k", B, A, groups=(8, 16, 32))
+        report("C2v 2D f64 variable 2..8 n=400k", B, A, groups=(4, 8, 16, 32))
         B.close()
     if want("c4"):
         A, pi, phi = synth.config_c4_triangular()
