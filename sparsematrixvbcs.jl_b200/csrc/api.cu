@@ -203,7 +203,7 @@ void vbc_destroy(vbc_mat *A)
     if (!A) return;
     DeviceGuard guard(A->device);
     cudaFree(A->d_pi_spl); cudaFree(A->d_phi_spl); cudaFree(A->d_pos); cudaFree(A->d_idx); cudaFree(A->d_ofs); cudaFree(A->d_val);
-    cudaFree(A->d_meta); cudaFree(A->d_desc); cudaFree(A->d_brow); cudaFree(A->d_order); cudaFree(A->d_x); cudaFree(A->d_y);
+    cudaFree(A->d_meta); cudaFree(A->d_desc); cudaFree(A->d_brow); cudaFree(A->d_order); cudaFree(A->d_px); cudaFree(A->d_py); cudaFree(A->d_x); cudaFree(A->d_y);
     destroy_trsv_plan(A->trsv);
     delete A;
 }

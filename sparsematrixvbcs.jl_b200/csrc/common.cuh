@@ -75,6 +75,9 @@ struct vbc_mat {
     // staging vectors for host-pointer multiplies
     void *d_x = nullptr, *d_y = nullptr;
     int64_t x_cap = 0, y_cap = 0;
+    // row-major staging panels of the column-major SpMM path (grow-only, reused across calls)
+    void *d_px = nullptr, *d_py = nullptr;
+    int64_t px_cap = 0, py_cap = 0;
     cudaStream_t stream = nullptr;
     // options
     int opt_adj_group = 0, opt_fwd_group = 0, opt_grid_mult = 0, opt_parity = 0;

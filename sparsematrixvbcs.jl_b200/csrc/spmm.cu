@@ -255,20 +255,29 @@ static int spmm_t(vbc_mat *A, int trans, int64_t k, double alpha_d, const Tv *X,
         return A->desc_mode == DESC_ROWS ? launch_spmm_mode<Tv, DESC_ROWS>(A, trans, (int)k, alpha, X, ldx, beta, Y, ldy)
                                          : launch_spmm_mode<Tv, DESC_BLOCKS>(A, trans, (int)k, alpha, X, ldx, beta, Y, ldy);
     }
-    // column-major: stage through row-major buffers
-    Tv *Xr = nullptr, *Yr = nullptr;
-    VBC_CUDA(cudaMalloc(&Xr, sizeof(Tv) * (size_t)(xr * k > 0 ? xr * k : 1)));
-    if (cudaMalloc(&Yr, sizeof(Tv) * (size_t)(yr * k > 0 ? yr * k : 1)) != cudaSuccess) { cudaFree(Xr); VBC_FAIL(VBC_ENOMEM, "spmm staging allocation failed"); }
-    int rc = transpose_launch<Tv>(A, X, ldx, k, xr, Xr, k); // input viewed as k rows (columns of X) of length xr
-    if (rc == VBC_OK && beta != (Tv)0) rc = transpose_launch<Tv>(A, Y, ldy, k, yr, Yr, k);
-    if (rc == VBC_OK)
-        rc = A->desc_mode == DESC_ROWS ? launch_spmm_mode<Tv, DESC_ROWS>(A, trans, (int)k, alpha, Xr, k, beta, Yr, k)
-                                       : launch_spmm_mode<Tv, DESC_BLOCKS>(A, trans, (int)k, alpha, Xr, k, beta, Yr, k);
-    if (rc == VBC_OK) rc = transpose_launch<Tv>(A, Yr, k, yr, k, Y, ldy);
-    cudaError_t e = cudaStreamSynchronize(A->stream); // staging buffers are freed below
-    cudaFree(Xr); cudaFree(Yr);
-    if (rc == VBC_OK && e != cudaSuccess) VBC_FAIL(VBC_ECUDA, "spmm: %s", cudaGetErrorString(e));
-    return rc;
+    // column-major: stage through row-major buffers kept in the handle (grow-only), so repeated calls pay
+    // no allocation and stay stream-ordered
+    const int64_t nx = xr * k, ny = yr * k;
+    if (A->px_cap < nx * (int64_t)sizeof(Tv)) {
+        VBC_CUDA(cudaStreamSynchronize(A->stream));
+        cudaFree(A->d_px); A->d_px = nullptr; A->px_cap = 0;
+        VBC_CUDA(cudaMalloc(&A->d_px, sizeof(Tv) * (size_t)(nx > 0 ? nx : 1)));
+        A->px_cap = nx * (int64_t)sizeof(Tv);
+    }
+    if (A->py_cap < ny * (int64_t)sizeof(Tv)) {
+        VBC_CUDA(cudaStreamSynchronize(A->stream));
+        cudaFree(A->d_py); A->d_py = nullptr; A->py_cap = 0;
+        VBC_CUDA(cudaMalloc(&A->d_py, sizeof(Tv) * (size_t)(ny > 0 ? ny : 1)));
+        A->py_cap = ny * (int64_t)sizeof(Tv);
+    }
+    Tv *Xr = (Tv *)A->d_px, *Yr = (Tv *)A->d_py;
+    VBC_TRY(transpose_launch<Tv>(A, X, ldx, k, xr, Xr, k)); // input viewed as k rows (columns of X) of length xr
+    if (beta != (Tv)0) VBC_TRY(transpose_launch<Tv>(A, Y, ldy, k, yr, Yr, k));
+    int rc;
+    if (A->desc_mode == DESC_ROWS) rc = launch_spmm_mode<Tv, DESC_ROWS>(A, trans, (int)k, alpha, Xr, k, beta, Yr, k);
+    else rc = launch_spmm_mode<Tv, DESC_BLOCKS>(A, trans, (int)k, alpha, Xr, k, beta, Yr, k);
+    VBC_TRY(rc);
+    return transpose_launch<Tv>(A, Yr, k, yr, k, Y, ldy);
 }
 
 int launch_spmm(vbc_mat *A, int trans, int64_t k, double alpha, const void *X, int64_t ldx, double beta, void *Y, int64_t ldy, int layout)
