@@ -217,6 +217,12 @@ class SparseMatrix1DVBC(_CuVBC, metaclass=_ParamMeta):
         self._query()
 
     @classmethod
+    def from_device_csc(cls, W, m, n, colptr, rowval, nzval, phi_spl, device=0):
+        """Pack from a CSC matrix whose arrays (and Φ.spl) are torch CUDA tensors (vbc_pack_csc_dev): the
+        path for matrices generated on the device."""
+        return _from_device_csc(cls[W] if cls._params is None else cls, 0, W, m, n, colptr, rowval, nzval, None, phi_spl, device)
+
+    @classmethod
     def from_packed(cls, W, m, n, phi_spl, pos, idx, ofs, val, device=0):
         """Adopt the fields of a host `SparseMatrix1DVBC` packed by the reference (vbc_upload)."""
         self = object.__new__(cls[W] if cls._params is None else cls)
@@ -260,6 +266,11 @@ class SparseMatrixVBC(_CuVBC, metaclass=_ParamMeta):
         self._query()
 
     @classmethod
+    def from_device_csc(cls, U, W, m, n, colptr, rowval, nzval, pi_spl, phi_spl, device=0):
+        """2D pack from device-resident CSC arrays and partitions (vbc_pack_csc_dev)."""
+        return _from_device_csc(cls[U, W] if cls._params is None else cls, U, W, m, n, colptr, rowval, nzval, pi_spl, phi_spl, device)
+
+    @classmethod
     def from_packed(cls, U, W, m, n, pi_spl, phi_spl, pos, idx, ofs, val, device=0):
         self = object.__new__(cls[U, W] if cls._params is None else cls)
         _CuVBC.__init__(self)
@@ -272,6 +283,30 @@ class SparseMatrixVBC(_CuVBC, metaclass=_ParamMeta):
                                     int(device)))
         self._query()
         return self
+
+
+def _from_device_csc(cls, U, W, m, n, colptr, rowval, nzval, pi_spl, phi_spl, device):
+    import torch
+    it = {torch.int32: _lib.VBC_I32, torch.int64: _lib.VBC_I64}[colptr.dtype]
+    vt = {torch.float32: _lib.VBC_F32, torch.float64: _lib.VBC_F64}[nzval.dtype]
+    tens = [colptr, rowval, nzval, phi_spl] + ([pi_spl] if pi_spl is not None else [])
+    for t in tens:
+        if not (t.is_cuda and t.is_contiguous()):
+            raise TypeError("from_device_csc needs contiguous CUDA tensors")
+    if rowval.dtype != colptr.dtype or phi_spl.dtype != colptr.dtype or (pi_spl is not None and pi_spl.dtype != colptr.dtype):
+        raise TypeError("colptr, rowval and the partitions must share one index type Ti")
+    torch.cuda.synchronize()
+    self = object.__new__(cls)
+    _CuVBC.__init__(self)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    check(_lib.lib().vbc_pack_csc_dev(ctypes.byref(self._h), vt, it, int(m), int(n), int(U), int(W), p(colptr), p(rowval), p(nzval),
+                                      (p(pi_spl) if pi_spl is not None else None), (pi_spl.numel() - 1 if pi_spl is not None else 0),
+                                      p(phi_spl), phi_spl.numel() - 1, int(device)))
+    self.Phi = SplitPartition(phi_spl.cpu().numpy())
+    if pi_spl is not None:
+        self.Pi = SplitPartition(pi_spl.cpu().numpy())
+    self._query()
+    return self
 
 
 CuVBC1D = SparseMatrix1DVBC

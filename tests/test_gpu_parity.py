@@ -469,3 +469,20 @@ def test_peer_fused_sync_single_rank():
     rt.cudaMemcpy(ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(p.value), ctypes.c_size_t(out.nbytes), 2)
     assert np.allclose(out, ref, rtol=1e-12, atol=0)
     Lh.vbc_peer_destroy(h)
+
+
+def test_pack_from_device_resident_csc(fixtures):
+    """vbc_pack_csc_dev: CSC arrays and partitions already in HBM (matrices generated on the device)."""
+    import torch
+    for tv, ti in ((np.float64, np.int64), (np.float32, np.int32)):
+        A = fixtures["LPnetlib__lp_etamacro"].astype(tv, ti)
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        phi = vb.pack_stripe(A, vb.RandomChunker(4, 11))
+        H = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 4)
+        B = vb.SparseMatrix1DVBC.from_device_csc(4, A.m, A.n, d(A.colptr), d(A.rowval), d(A.nzval), d(phi.spl))
+        assert_packed_equal(B, H)
+        pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(vb.RandomChunker(4, 12), vb.RandomChunker(4, 13)))
+        H2 = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi2.spl, 4, 4)
+        B2 = vb.SparseMatrixVBC.from_device_csc(4, 4, A.m, A.n, d(A.colptr), d(A.rowval), d(A.nzval), d(pi.spl), d(phi2.spl))
+        assert_packed_equal(B2, H2)
+        randx_check(A, B2, H2, np.random.default_rng(5))
