@@ -49,8 +49,10 @@ enum vbc_option {
     VBC_OPT_ADJ_GROUP = 1,  /* lanes cooperating on one stripe in the adjoint kernel: 0 = auto, else 4|8|16|32 */
     VBC_OPT_FWD_GROUP = 2,  /* same for the forward (scatter) kernel                                         */
     VBC_OPT_GRID_MULT = 3,  /* CTAs per SM for the persistent grid-stride launch: 0 = auto                   */
-    VBC_OPT_PARITY_MODE = 4 /* 1: multiply straight from the canonical Ti arrays (pos/idx/ofs/spl) with the
+    VBC_OPT_PARITY_MODE = 4, /* 1: multiply straight from the canonical Ti arrays (pos/idx/ofs/spl) with the
                                   generic kernel instead of the compact device layout                         */
+    VBC_OPT_FWD_MODE = 5     /* forward multiply: 0 = owner-computes through a transposed unit index built at first
+                                  use (when the layout allows it), 1 = always the atomic scatter kernel             */
 };
 
 const char *vbc_last_error(void);

@@ -205,6 +205,7 @@ void vbc_destroy(vbc_mat *A)
     cudaFree(A->d_pi_spl); cudaFree(A->d_phi_spl); cudaFree(A->d_pos); cudaFree(A->d_idx); cudaFree(A->d_ofs); cudaFree(A->d_val);
     cudaFree(A->d_meta); cudaFree(A->d_desc); cudaFree(A->d_brow); cudaFree(A->d_order); cudaFree(A->d_px); cudaFree(A->d_py); cudaFree(A->d_x); cudaFree(A->d_y);
     destroy_trsv_plan(A->trsv);
+    destroy_tindex(A->tindex);
     delete A;
 }
 
@@ -244,7 +245,7 @@ int vbc_format_bytes(const vbc_mat *A, int64_t bytes[3])
     bytes[0] = ti * (A->L + 1) * 3 + (A->ndim == 2 ? ti * (A->K + 1) : 0) + ti * A->nidx + tv * A->nval;
     if (A->opt_parity) { bytes[1] = bytes[0]; bytes[2] = bytes[0]; return VBC_OK; }
     bytes[1] = (int64_t)sizeof(StripeMeta) * (A->L + 1) + 4 * A->ndesc + tv * A->nval + (A->d_order ? 4 * A->L : 0);
-    bytes[2] = bytes[1];
+    bytes[2] = (A->tindex && !A->opt_fwd_atomic) ? tv * A->nval + tindex_bytes(A) : bytes[1];
     return VBC_OK;
 }
 
@@ -375,6 +376,9 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
     case VBC_OPT_PARITY_MODE:
         A->opt_parity = value ? 1 : 0;
         return VBC_OK;
+    case VBC_OPT_FWD_MODE:
+        A->opt_fwd_atomic = value ? 1 : 0;
+        return VBC_OK;
     }
     VBC_FAIL(VBC_EARG, "unknown option %d", option);
 }
@@ -387,6 +391,7 @@ int vbc_get_option(const vbc_mat *A, int option, int64_t *value)
     case VBC_OPT_FWD_GROUP: *value = A->opt_fwd_group; return VBC_OK;
     case VBC_OPT_GRID_MULT: *value = A->opt_grid_mult; return VBC_OK;
     case VBC_OPT_PARITY_MODE: *value = A->opt_parity; return VBC_OK;
+    case VBC_OPT_FWD_MODE: *value = A->opt_fwd_atomic; return VBC_OK;
     }
     VBC_FAIL(VBC_EARG, "unknown option %d", option);
 }

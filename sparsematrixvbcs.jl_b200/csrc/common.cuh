@@ -53,6 +53,7 @@ enum DescMode {
 } // namespace vbc
 
 struct vbc_trsv_plan; // trsv.cu
+namespace vbc { struct TIndex; } // fwdt.cu
 
 struct vbc_mat {
     int vt = VBC_F64, it = VBC_I64, ndim = 1, device = 0;
@@ -84,6 +85,8 @@ struct vbc_mat {
     int sm_count = 148;
     int64_t launches = 0;
     vbc_trsv_plan *trsv = nullptr; // level schedule of the triangular solve (vbc_trsv_analyse)
+    vbc::TIndex *tindex = nullptr; // transposed unit index of the owner-computes forward multiply (built at first use)
+    int opt_fwd_atomic = 0;        // 1: always use the atomic scatter kernel for the forward multiply
 };
 
 struct vbc_csc {
@@ -126,6 +129,11 @@ struct PeerSyncArgs { // in-kernel flag exchange of the fused multiply + all-gat
 };
 int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs, const unsigned char *d_mask, int chunk_shift,
                          const PeerSyncArgs *sync, const int *ranges /* {a0,a1,b0,b1} or null = all */);
+// fwdt.cu
+int ensure_tindex(vbc_mat *A);
+int launch_fwdt(vbc_mat *A, double alpha, const void *x, double beta, void *y);
+void destroy_tindex(TIndex *t);
+int64_t tindex_bytes(const vbc_mat *A);
 // trsv.cu
 void destroy_trsv_plan(vbc_trsv_plan *p);
 int trsv_error_flag(const vbc_mat *A, int *flag);

@@ -1,0 +1,307 @@
+// fwdt.cu -- owner-computes forward multiply  y <- alpha * A x + beta * y  through a transposed unit index.
+//
+// The reference's forward `mul!` (multiply_1DVBC.jl:9-83, multiply_VBC.jl:3-87) is a serial scatter,
+// y[idx[Q]] += ...; the straightforward GPU version of it (k_spmv_fwd, spmv.cu) needs one fp atomic per
+// stored row and is bound by atomic throughput (3.3 TB/s on configs[1]).  Here the scatter is turned
+// around at first use: a device-built index lists, for every destination row (1D / expanded rows) or row
+// part (2D blocks), the units that write to it -- 16 B per unit {value offset, stripe column, stripe
+// width}.  A group of SG lanes then owns one destination: it streams its units' values with the same
+// 16-byte coalesced loads as the adjoint kernel, multiplies by the stripe's x segment, reduces with
+// shuffles and stores y once with alpha/beta -- no atomics, no separate y <- beta*y pass, deterministic
+// for a given handle.  Extra traffic: 16 B per unit (12.5 % for 4x4 Float64 blocks).
+//
+// Blocks mode keeps per-lane accumulators for a fixed (row-in-block, column-vector) and therefore needs
+// one stripe width for the whole matrix; rows mode takes any widths.  Everything else falls back to the
+// atomic kernel (VBC_OPT_FWD_MODE = 1 forces that).
+#include <new>
+
+#include "common.cuh"
+#include "scan.cuh"
+#include "walk.cuh"
+
+namespace vbc {
+
+struct __align__(16) TRec {
+    long long vofs; // element offset of the unit's first value in val
+    int col;        // first column of the unit's stripe
+    int w;          // width of that stripe
+};
+
+__device__ __forceinline__ TRec ld_rec(const TRec *p)
+{
+    const int4 t = __ldcs(reinterpret_cast<const int4 *>(p));
+    TRec r;
+    r.vofs = (long long)(((unsigned long long)(unsigned)t.y << 32) | (unsigned)t.x);
+    r.col = t.z;
+    r.w = t.w;
+    return r;
+}
+
+// destination key of unit t: rows mode -> the row; blocks mode -> the row part
+template <int MODE> __device__ __forceinline__ int unit_key(const int *__restrict__ desc, const int t, const int u0, const int log2u)
+{
+    const int i = __ldg(desc + t);
+    if (MODE == DESC_ROWS) return i;
+    return log2u >= 0 ? (i >> log2u) : i / u0;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_t_count(const StripeMeta *__restrict__ meta, const int *__restrict__ desc, const int L,
+                                                  const int u0, const int log2u, unsigned long long *__restrict__ cnt)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const StripeMeta a = meta[l], b = meta[l + 1];
+    if (b.col - a.col <= 0) return;
+    for (int t = a.pos; t < b.pos; t++) atomicAdd(&cnt[unit_key<MODE>(desc, t, u0, log2u)], 1ull);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_t_fill(const StripeMeta *__restrict__ meta, const int *__restrict__ desc, const int L,
+                                                 const int u0, const int log2u, const int *__restrict__ tptr,
+                                                 unsigned *__restrict__ cursor, TRec *__restrict__ rec)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const StripeMeta a = meta[l], b = meta[l + 1];
+    const int w = b.col - a.col;
+    if (w <= 0) return;
+    const long long unit_vals = (MODE == DESC_ROWS) ? w : (long long)u0 * w; // only a stripe's last block can be shorter
+    for (int t = a.pos; t < b.pos; t++) {
+        const int key = unit_key<MODE>(desc, t, u0, log2u);
+        TRec r;
+        r.vofs = a.ofs + (long long)(t - a.pos) * unit_vals;
+        r.col = a.col;
+        r.w = w;
+        rec[tptr[key] + atomicAdd(&cursor[key], 1u)] = r;
+    }
+}
+
+// ---- rows mode: SG lanes per destination row, units are w-wide row segments ---------------------
+template <typename Tv, int SG>
+__global__ void __launch_bounds__(256) k_fwdt_rows(const int *__restrict__ tptr, const TRec *__restrict__ rec, const Tv *__restrict__ val,
+                                                    const Tv *__restrict__ x, Tv *__restrict__ y, const int nkeys, const Tv alpha, const Tv beta)
+{
+    constexpr int VE = 16 / (int)sizeof(Tv);
+    const int lane = threadIdx.x % SG;
+    unsigned gmask = 0xffffffffu;
+    if constexpr (SG < 32) gmask = ((1u << SG) - 1u) << (((threadIdx.x & 31) / SG) * SG);
+    const int ngroups = (int)((gridDim.x * blockDim.x) / SG);
+    for (int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) / SG); i < nkeys; i += ngroups) {
+        const int t0 = __ldg(tptr + i), t1 = __ldg(tptr + i + 1);
+        Tv acc = (Tv)0;
+        constexpr int UNR = 4;
+        for (int t = t0; t < t1; t += UNR) {
+            TRec r[UNR];
+#pragma unroll
+            for (int k = 0; k < UNR; k++) {
+                r[k].w = 0;
+                if (t + k < t1) r[k] = ld_rec(rec + t + k);
+            }
+#pragma unroll
+            for (int k = 0; k < UNR; k++) {
+                const int w = r[k].w;
+                if (w == 0) continue;
+                const Tv *vp = val + r[k].vofs;
+                const Tv *xp = x + r[k].col;
+                if ((w % VE) == 0 && (r[k].vofs % VE) == 0) {
+                    for (int e = lane * VE; e < w; e += SG * VE) {
+                        Tv v[VE];
+                        if constexpr (VE == 2) { const double2 q = __ldcs(reinterpret_cast<const double2 *>(vp + e)); v[0] = (Tv)q.x; v[1] = (Tv)q.y; }
+                        else { const float4 q = __ldcs(reinterpret_cast<const float4 *>(vp + e)); v[0] = (Tv)q.x; v[1] = (Tv)q.y; v[2] = (Tv)q.z; v[3] = (Tv)q.w; }
+#pragma unroll
+                        for (int j = 0; j < VE; j++) acc = fma(v[j], __ldg(xp + e + j), acc);
+                    }
+                } else {
+                    for (int e = lane; e < w; e += SG) acc = fma(__ldcs(vp + e), __ldg(xp + e), acc);
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 1; d < SG; d <<= 1) acc += __shfl_xor_sync(gmask, acc, d, SG);
+        if (lane == 0) y[i] = (beta == (Tv)0) ? alpha * acc : alpha * acc + beta * y[i];
+    }
+}
+
+// ---- blocks mode: one stripe width w0 and part height u0 for the whole matrix; SG = lanes per part ---
+// lane v of the group holds vector v of every block (row-in-block v / cpr, column-vector v % cpr).
+template <typename Tv, int SG>
+__global__ void __launch_bounds__(256) k_fwdt_blocks(const int *__restrict__ tptr, const TRec *__restrict__ rec, const Tv *__restrict__ val,
+                                                      const Tv *__restrict__ x, Tv *__restrict__ y, const int nkeys, const int u0, const int w0,
+                                                      const long long m, const Tv alpha, const Tv beta)
+{
+    constexpr int VE = 16 / (int)sizeof(Tv);
+    const int lane = threadIdx.x % SG;
+    unsigned gmask = 0xffffffffu;
+    if constexpr (SG < 32) gmask = ((1u << SG) - 1u) << (((threadIdx.x & 31) / SG) * SG);
+    const int ngroups = (int)((gridDim.x * blockDim.x) / SG);
+    const int cpr = w0 / VE;          // vectors per block row
+    const int nvec = u0 * cpr;        // vectors per full block
+    for (int k = (int)((blockIdx.x * blockDim.x + threadIdx.x) / SG); k < nkeys; k += ngroups) {
+        const int t0 = __ldg(tptr + k), t1 = __ldg(tptr + k + 1);
+        const long long i0 = (long long)k * u0;
+        const int u = (int)((m - i0) < u0 ? (m - i0) : u0); // the last part may be shorter
+        for (int vb = 0; vb < nvec; vb += SG) { // SG >= nvec in the tuned cases: one pass
+            const int v = vb + lane;
+            const int di = small_div(v, cpr), cv = v - di * cpr;
+            const bool mine = v < u * cpr;
+            Tv acc[VE];
+#pragma unroll
+            for (int j = 0; j < VE; j++) acc[j] = (Tv)0;
+            constexpr int UNR = 4;
+            for (int t = t0; t < t1; t += UNR) {
+                TRec r[UNR];
+                Tv vv[UNR][VE], xx[UNR][VE];
+#pragma unroll
+                for (int q = 0; q < UNR; q++) {
+                    r[q].w = 0;
+                    if (t + q < t1) r[q] = ld_rec(rec + t + q);
+                }
+#pragma unroll
+                for (int q = 0; q < UNR; q++) {
+                    const bool ok = mine && r[q].w != 0;
+#pragma unroll
+                    for (int j = 0; j < VE; j++) { vv[q][j] = (Tv)0; xx[q][j] = (Tv)0; }
+                    if (ok) {
+                        const Tv *vp = val + r[q].vofs + (long long)v * VE;
+                        if constexpr (VE == 2) { const double2 a2 = __ldcs(reinterpret_cast<const double2 *>(vp)); vv[q][0] = (Tv)a2.x; vv[q][1] = (Tv)a2.y; }
+                        else { const float4 a4 = __ldcs(reinterpret_cast<const float4 *>(vp)); vv[q][0] = (Tv)a4.x; vv[q][1] = (Tv)a4.y; vv[q][2] = (Tv)a4.z; vv[q][3] = (Tv)a4.w; }
+#pragma unroll
+                        for (int j = 0; j < VE; j++) xx[q][j] = __ldg(x + r[q].col + cv * VE + j);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < UNR; q++)
+#pragma unroll
+                    for (int j = 0; j < VE; j++) acc[j] = fma(vv[q][j], xx[q][j], acc[j]);
+            }
+            Tv s = (Tv)0;
+#pragma unroll
+            for (int j = 0; j < VE; j++) s += acc[j];
+            // sum the cpr lanes of a block row (adjacent lanes)
+            for (int d = 1; d < cpr; d <<= 1) {
+                const Tv o = __shfl_down_sync(gmask, s, d, SG);
+                if (cv + d < cpr) s += o;
+            }
+            if (mine && cv == 0) {
+                Tv *yp = y + i0 + di;
+                *yp = (beta == (Tv)0) ? alpha * s : alpha * s + beta * *yp;
+            }
+        }
+    }
+}
+
+struct TIndex {
+    int *d_tptr = nullptr;
+    TRec *d_rec = nullptr;
+    int nkeys = 0;
+    int mode = 0; // DESC_ROWS / DESC_BLOCKS
+};
+
+void destroy_tindex(TIndex *t)
+{
+    if (!t) return;
+    cudaFree(t->d_tptr);
+    cudaFree(t->d_rec);
+    delete t;
+}
+
+static int ilog2x(int v)
+{
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int l = 0;
+    while ((1 << l) < v) l++;
+    return l;
+}
+
+template <int MODE>
+static int build_tindex_mode(vbc_mat *A, TIndex *T)
+{
+    const int L = (int)A->L;
+    const int64_t nkeys = MODE == DESC_ROWS ? A->m : (A->m + A->u0 - 1) / A->u0;
+    T->nkeys = (int)nkeys;
+    T->mode = MODE;
+    cudaStream_t st = A->stream;
+    unsigned long long *d_cnt = nullptr;
+    long long *d_tmp = nullptr;
+    unsigned *d_cur = nullptr;
+    const size_t nk = (size_t)(nkeys > 0 ? nkeys : 1);
+    VBC_CUDA(cudaMalloc(&d_cnt, sizeof(unsigned long long) * nk));
+    cudaError_t e = cudaMalloc(&d_tmp, sizeof(long long) * (size_t)scan_tmp_elems(nkeys));
+    if (e == cudaSuccess) e = cudaMalloc(&d_cur, sizeof(unsigned) * nk);
+    if (e == cudaSuccess) e = cudaMalloc(&T->d_tptr, sizeof(int) * (nk + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&T->d_rec, sizeof(TRec) * (size_t)(A->ndesc > 0 ? A->ndesc : 1));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * nk, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_cur, 0, sizeof(unsigned) * nk, st);
+    int rc = VBC_OK;
+    if (e != cudaSuccess) { set_error("transposed index allocation: %s", cudaGetErrorString(e)); rc = VBC_ENOMEM; }
+    const int log2u = ilog2x(A->u0);
+    const unsigned g = (unsigned)((L + 127) / 128 > 0 ? (L + 127) / 128 : 1);
+    if (rc == VBC_OK && L > 0) { k_t_count<MODE><<<g, 128, 0, st>>>(A->d_meta, A->d_desc, L, A->u0, log2u, d_cnt); A->launches++; }
+    long long total = 0;
+    if (rc == VBC_OK) rc = exclusive_scan<int>((const long long *)d_cnt, T->d_tptr, nkeys, 0, d_tmp, &total, st, &A->launches);
+    if (rc == VBC_OK && L > 0) { k_t_fill<MODE><<<g, 128, 0, st>>>(A->d_meta, A->d_desc, L, A->u0, log2u, T->d_tptr, d_cur, T->d_rec); A->launches++; }
+    if (rc == VBC_OK && (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)) { set_error("transposed index kernels failed"); rc = VBC_ECUDA; }
+    cudaFree(d_cnt); cudaFree(d_tmp); cudaFree(d_cur);
+    return rc;
+}
+
+// eligible: rows mode always; blocks mode when every stripe has one width that is a multiple of the 16-byte vector
+static bool tindex_eligible(const vbc_mat *A)
+{
+    if (A->L == 0 || A->m == 0) return false;
+    if (A->desc_mode == DESC_ROWS) return true;
+    const int VE = 16 / (int)vt_size(A->vt);
+    return A->w_uniform > 0 && (A->w_uniform % VE) == 0 && A->u0 * (A->w_uniform / VE) <= 32;
+}
+
+int ensure_tindex(vbc_mat *A)
+{
+    if (A->tindex || !tindex_eligible(A)) return VBC_OK;
+    TIndex *T = new (std::nothrow) TIndex();
+    if (!T) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
+    const int rc = A->desc_mode == DESC_ROWS ? build_tindex_mode<DESC_ROWS>(A, T) : build_tindex_mode<DESC_BLOCKS>(A, T);
+    if (rc != VBC_OK) { destroy_tindex(T); return rc; }
+    A->tindex = T;
+    return VBC_OK;
+}
+
+int64_t tindex_bytes(const vbc_mat *A)
+{
+    if (!A->tindex) return 0;
+    return (int64_t)sizeof(TRec) * A->ndesc + 4 * ((int64_t)A->tindex->nkeys + 1);
+}
+
+template <typename Tv>
+static int launch_fwdt_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
+{
+    const TIndex *T = A->tindex;
+    const int VE = 16 / (int)sizeof(Tv);
+    int64_t grid = (int64_t)A->sm_count * 6;
+    auto clamp = [&](int sg) { const int64_t need = ((int64_t)T->nkeys * sg + 255) / 256; return (unsigned)(grid > need ? (need > 0 ? need : 1) : grid); };
+    if (T->mode == DESC_ROWS) {
+        // lanes per destination row ~ vectors of a typical row segment
+        const double w_avg = A->ndesc > 0 ? (double)A->nval / (double)A->ndesc : 1.0;
+        const int cpr = (int)((w_avg + VE - 1) / VE);
+        if (cpr >= 4) k_fwdt_rows<Tv, 4><<<clamp(4), 256, 0, A->stream>>>(T->d_tptr, T->d_rec, (const Tv *)A->d_val, x, y, T->nkeys, alpha, beta);
+        else if (cpr >= 2) k_fwdt_rows<Tv, 2><<<clamp(2), 256, 0, A->stream>>>(T->d_tptr, T->d_rec, (const Tv *)A->d_val, x, y, T->nkeys, alpha, beta);
+        else k_fwdt_rows<Tv, 1><<<clamp(1), 256, 0, A->stream>>>(T->d_tptr, T->d_rec, (const Tv *)A->d_val, x, y, T->nkeys, alpha, beta);
+    } else {
+        const int nvec = A->u0 * (A->w_uniform / VE);
+        if (nvec > 16) k_fwdt_blocks<Tv, 32><<<clamp(32), 256, 0, A->stream>>>(T->d_tptr, T->d_rec, (const Tv *)A->d_val, x, y, T->nkeys, A->u0, A->w_uniform, A->m, alpha, beta);
+        else if (nvec > 8) k_fwdt_blocks<Tv, 16><<<clamp(16), 256, 0, A->stream>>>(T->d_tptr, T->d_rec, (const Tv *)A->d_val, x, y, T->nkeys, A->u0, A->w_uniform, A->m, alpha, beta);
+        else if (nvec > 4) k_fwdt_blocks<Tv, 8><<<clamp(8), 256, 0, A->stream>>>(T->d_tptr, T->d_rec, (const Tv *)A->d_val, x, y, T->nkeys, A->u0, A->w_uniform, A->m, alpha, beta);
+        else k_fwdt_blocks<Tv, 4><<<clamp(4), 256, 0, A->stream>>>(T->d_tptr, T->d_rec, (const Tv *)A->d_val, x, y, T->nkeys, A->u0, A->w_uniform, A->m, alpha, beta);
+    }
+    A->launches++;
+    VBC_CUDA(cudaGetLastError());
+    return VBC_OK;
+}
+
+int launch_fwdt(vbc_mat *A, double alpha, const void *x, double beta, void *y)
+{
+    return A->vt == VBC_F64 ? launch_fwdt_t<double>(A, alpha, (const double *)x, beta, (double *)y)
+                            : launch_fwdt_t<float>(A, (float)alpha, (const float *)x, (float)beta, (float *)y);
+}
+
+} // namespace vbc

@@ -250,13 +250,20 @@ __device__ __forceinline__ int stripe_class(const StripeMeta a, const StripeMeta
     return 1 + epv_code * 64 + (cpr > 63 ? 63 : cpr);
 }
 
+// hist[0..255]: stripes per class; hist[256], hist[257]: min and max stripe width
 __global__ void k_class_hist(const StripeMeta *__restrict__ meta, int64_t L, int VE, unsigned *__restrict__ hist)
 {
     __shared__ unsigned sh[256];
     sh[threadIdx.x] = 0;
     __syncthreads();
-    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < L; l += (int64_t)gridDim.x * blockDim.x)
+    unsigned wmin = 0xffffffffu, wmax = 0;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < L; l += (int64_t)gridDim.x * blockDim.x) {
         atomicAdd(&sh[stripe_class(meta[l], meta[l + 1], VE) & 255], 1u);
+        const unsigned w = (unsigned)(meta[l + 1].col - meta[l].col);
+        wmin = w < wmin ? w : wmin;
+        wmax = w > wmax ? w : wmax;
+    }
+    if (wmin != 0xffffffffu) { atomicMin(&hist[256], wmin); atomicMax(&hist[257], wmax); }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
@@ -276,13 +283,15 @@ static int build_class_order(vbc_mat *A)
 {
     const int64_t L = A->L;
     A->nclasses = 1;
-    if (L < 2) return VBC_OK;
+    A->w_uniform = 0;
+    if (L < 1) return VBC_OK;
     cudaStream_t st = A->stream;
     const int VE = 16 / (int)vt_size(A->vt);
     unsigned *d_hist = nullptr;
-    VBC_CUDA(cudaMalloc(&d_hist, 256 * sizeof(unsigned)));
-    unsigned h[256];
-    cudaError_t e = cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned), st);
+    VBC_CUDA(cudaMalloc(&d_hist, 258 * sizeof(unsigned)));
+    unsigned h[258];
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, 258 * sizeof(unsigned), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_hist + 256, 0xff, sizeof(unsigned), st); // running minimum
     if (e == cudaSuccess) {
         int64_t g = (L + 255) / 256;
         if (g > 2048) g = 2048;
@@ -292,6 +301,7 @@ static int build_class_order(vbc_mat *A)
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { cudaFree(d_hist); VBC_FAIL(VBC_ECUDA, "class histogram: %s", cudaGetErrorString(e)); }
+    if (h[256] == h[257] && h[257] > 0) A->w_uniform = (int)h[257];
     int ncls = 0;
     unsigned run = 0, cur[256];
     for (int c = 0; c < 256; c++) { cur[c] = run; run += h[c]; if (h[c]) ncls++; }

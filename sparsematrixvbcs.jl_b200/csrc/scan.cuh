@@ -39,7 +39,7 @@ __device__ __forceinline__ long long block_excl_scan(long long v, long long *tot
     return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const long long *__restrict__ in, long long *__restrict__ tile_sums, int64_t N)
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const long long *__restrict__ in, long long *__restrict__ tile_sums, int64_t N)
 {
     __shared__ long long smem[33];
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const long long *
 }
 
 // one block: exclusive scan of tile_sums[ntiles] in place; grand total to *total_out.
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_offsets(long long *__restrict__ tile_sums, int64_t ntiles, long long *__restrict__ total_out)
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_offsets(long long *__restrict__ tile_sums, int64_t ntiles, long long *__restrict__ total_out)
 {
     __shared__ long long smem[33];
     long long carry = 0;

@@ -628,6 +628,10 @@ static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, 
         if (A->L == 0) return VBC_OK; // n == 0: nothing to write
         return launch_adj_any<Tv, false>(A, alpha, x, beta, y, PeerDst{});
     }
+    if (!A->opt_fwd_atomic) { // owner-computes forward through the transposed unit index (fwdt.cu)
+        VBC_TRY(ensure_tindex(A));
+        if (A->tindex) return launch_fwdt(A, alpha_d, xv, beta_d, yv);
+    }
     VBC_TRY(scale_y<Tv>(A, y, A->m, beta));
     if (A->L == 0 || A->nval == 0) return VBC_OK;
     int G = A->opt_fwd_group ? A->opt_fwd_group : auto_group(A);

@@ -163,15 +163,17 @@ def test_wide_and_odd_widths_all_paths():
             for g in (8, 32):
                 B.set_option(_lib.OPT_ADJ_GROUP, g)
                 B.set_option(_lib.OPT_FWD_GROUP, g)
+                B.set_option(_lib.OPT_FWD_MODE, 1 if g == 8 else 0)  # atomic scatter kernel / transposed-index kernel
                 randx_check(A, B, H, rng)
             for u in (1, 2, 3, 4, 8):
                 pi = vb.pack_stripe(A.transpose(), vb.EquiChunker(u))
                 H2 = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, u, w)
                 B2 = vb.SparseMatrixVBC[u, w](A, pi, phi)
                 assert_packed_equal(B2, H2)
-                for g in (8, 32):
+                for g in (4, 8, 16, 32):
                     B2.set_option(_lib.OPT_ADJ_GROUP, g)
-                    B2.set_option(_lib.OPT_FWD_GROUP, g)
+                    B2.set_option(_lib.OPT_FWD_GROUP, g if g in (8, 32) else 0)
+                    B2.set_option(_lib.OPT_FWD_MODE, 1 if g in (4, 8) else 0)
                     randx_check(A, B2, H2, rng)
 
 
@@ -181,7 +183,9 @@ def test_alpha_beta_blas_semantics():
     S = A.to_scipy()
     B = vb.SparseMatrixVBC[4, 4](A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(4)))
     B1 = vb.SparseMatrix1DVBC[4](A, vb.EquiChunker(4))
-    for M in (B, B1):
+    Ba = vb.SparseMatrixVBC[4, 4](A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(4)))
+    Ba.set_option(_lib.OPT_FWD_MODE, 1)  # forward through the atomic scatter kernel
+    for M in (B, B1, Ba):
         x, y0 = rng.random(29), rng.random(33)
         y = vb.mul_(y0.copy(), M, x, 2.5, -0.5)
         assert np.allclose(y, 2.5 * (S @ x) - 0.5 * y0, rtol=1e-13, atol=1e-13)

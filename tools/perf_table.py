@@ -60,9 +60,18 @@ def report(name, B, A, groups=(0,)):
     for g in groups:
         B.set_option(_lib.OPT_ADJ_GROUP, g); B.set_option(_lib.OPT_FWD_GROUP, g if g not in (4, 16) else 0)
         for kind, fn, nb in (("adjoint", lambda: vb.mul_(yn, B.T, xm), adj_b + es * (A.m + A.n)),
-                             ("forward", lambda: vb.mul_(ym, B, xn), fwd_b + es * (A.n + 2 * A.m))):
+                             ("forward", lambda: vb.mul_(ym, B, xn), fwd_b + es * (A.n + 2 * A.m)),
+                             ("fwd_tindex", lambda: vb.mul_(ym, B, xn), None)):
             if kind == "forward" and g in (4, 16):
                 continue
+            if kind == "fwd_tindex":
+                if g != groups[0]:
+                    continue
+                B.set_option(_lib.OPT_FWD_MODE, 0)
+                vb.mul_(ym, B, xn)  # builds the index outside graph capture
+                nb = B.format_bytes()[2] + es * (A.n + A.m)
+            elif kind == "forward":
+                B.set_option(_lib.OPT_FWD_MODE, 1)
             med, mn = tk(fn)
             r = dict(workload=name, kernel=kind, group=g, us_med=med * 1e6, us_min=mn * 1e6, bytes=nb, gbs=nb / med / 1e9,
                      gflops=2.0 * A.nnz / med / 1e9, nnz=A.nnz, nval=B.nval, ref_format_bytes=ref_b)

@@ -20,7 +20,8 @@ for B in mats:
     assert np.allclose(vb.mul_(np.empty(A.n), B.T, xt), S.T @ xt)
     X = rng.random((A.m, 5))
     assert np.allclose(vb.mul_(np.empty((A.n, 5)), B.T, X), S.T @ X)
-    assert np.allclose(vb.mul_(np.empty((A.m, 5)), B, rng.random((A.n, 5)).copy()), S @ _ if False else vb.mul_(np.empty((A.m, 5)), B, X[:A.n] if A.n <= A.m else X), atol=np.inf)
+    Xn = rng.random((A.n, 5))
+    assert np.allclose(vb.mul_(np.empty((A.m, 5)), B, Xn), S @ Xn)
 assert np.allclose(vb.TrSpMV_(np.empty(A.n), A, xt), S.T @ xt)
 T, tpi, tphi = synth.config_c4_triangular(n=4000, S=7)
 Bt = vb.SparseMatrixVBC[4, 4](T, tpi, tphi)
