@@ -245,7 +245,7 @@ int vbc_format_bytes(const vbc_mat *A, int64_t bytes[3])
     bytes[0] = ti * (A->L + 1) * 3 + (A->ndim == 2 ? ti * (A->K + 1) : 0) + ti * A->nidx + tv * A->nval;
     if (A->opt_parity) { bytes[1] = bytes[0]; bytes[2] = bytes[0]; return VBC_OK; }
     bytes[1] = (int64_t)sizeof(StripeMeta) * (A->L + 1) + 4 * A->ndesc + tv * A->nval + (A->d_order ? 4 * A->L : 0);
-    bytes[2] = (A->tindex && !A->opt_fwd_atomic) ? tv * A->nval + tindex_bytes(A) : bytes[1];
+    bytes[2] = (A->tindex && A->opt_fwd_atomic != 1) ? tv * A->nval + tindex_bytes(A) : bytes[1];
     return VBC_OK;
 }
 
@@ -377,7 +377,8 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
         A->opt_parity = value ? 1 : 0;
         return VBC_OK;
     case VBC_OPT_FWD_MODE:
-        A->opt_fwd_atomic = value ? 1 : 0;
+        if (value < 0 || value > 2) VBC_FAIL(VBC_EARG, "forward mode must be 0 (auto), 1 (atomic scatter) or 2 (transposed index whenever possible)");
+        A->opt_fwd_atomic = (int)value;
         return VBC_OK;
     }
     VBC_FAIL(VBC_EARG, "unknown option %d", option);

@@ -247,10 +247,13 @@ static int build_tindex_mode(vbc_mat *A, TIndex *T)
 }
 
 // eligible: rows mode always; blocks mode when every stripe has one width that is a multiple of the 16-byte vector
+// (opt_fwd_atomic: 0 = auto, 1 = never, 2 = whenever possible).  Measured (profiles/r01_tuning.md): the index wins
+// for uniform 2D blocks (113 vs 127 us on configs[1]) and loses to 32-lane atomics in rows mode (116 vs 110 us
+// on the 1D w=8 matrix), so auto uses it for blocks mode only.
 static bool tindex_eligible(const vbc_mat *A)
 {
-    if (A->L == 0 || A->m == 0) return false;
-    if (A->desc_mode == DESC_ROWS) return true;
+    if (A->L == 0 || A->m == 0 || A->opt_fwd_atomic == 1) return false;
+    if (A->desc_mode == DESC_ROWS) return A->opt_fwd_atomic == 2;
     const int VE = 16 / (int)vt_size(A->vt);
     return A->w_uniform > 0 && (A->w_uniform % VE) == 0 && A->u0 * (A->w_uniform / VE) <= 32;
 }

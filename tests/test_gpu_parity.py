@@ -163,7 +163,7 @@ def test_wide_and_odd_widths_all_paths():
             for g in (8, 32):
                 B.set_option(_lib.OPT_ADJ_GROUP, g)
                 B.set_option(_lib.OPT_FWD_GROUP, g)
-                B.set_option(_lib.OPT_FWD_MODE, 1 if g == 8 else 0)  # atomic scatter kernel / transposed-index kernel
+                B.set_option(_lib.OPT_FWD_MODE, 1 if g == 8 else 2)  # atomic scatter kernel / transposed-index kernel
                 randx_check(A, B, H, rng)
             for u in (1, 2, 3, 4, 8):
                 pi = vb.pack_stripe(A.transpose(), vb.EquiChunker(u))
@@ -173,7 +173,7 @@ def test_wide_and_odd_widths_all_paths():
                 for g in (4, 8, 16, 32):
                     B2.set_option(_lib.OPT_ADJ_GROUP, g)
                     B2.set_option(_lib.OPT_FWD_GROUP, g if g in (8, 32) else 0)
-                    B2.set_option(_lib.OPT_FWD_MODE, 1 if g in (4, 8) else 0)
+                    B2.set_option(_lib.OPT_FWD_MODE, 1 if g in (4, 8) else 2)
                     randx_check(A, B2, H2, rng)
 
 

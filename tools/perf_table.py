@@ -67,7 +67,7 @@ def report(name, B, A, groups=(0,)):
             if kind == "fwd_tindex":
                 if g != groups[0]:
                     continue
-                B.set_option(_lib.OPT_FWD_MODE, 0)
+                B.set_option(_lib.OPT_FWD_MODE, 2)
                 vb.mul_(ym, B, xn)  # builds the index outside graph capture
                 nb = B.format_bytes()[2] + es * (A.n + A.m)
             elif kind == "forward":
