@@ -13,12 +13,17 @@ from .partition import (AlternatingPacker, EquiChunker, RandomChunker, SparseMat
                         SplitPartition, StrictChunker, pack_plaid, pack_stripe)
 from .matrix import (Adjoint, CuSparseMatrixCSC, CuVBC1D, CuVBC2D, SparseMatrix1DVBC,  # noqa: F401
                      SparseMatrixVBC, TrSpMV_, adjoint, ldiv_lower_, mul_, size, trsv_analyse)
-from . import synth  # noqa: F401
+from . import costs, synth  # noqa: F401
+from .costs import (model_SparseMatrix1DVBC_blocks, model_SparseMatrix1DVBC_memory,  # noqa: F401
+                    model_SparseMatrix1DVBC_TrSpMV_time, model_SparseMatrixVBC_blocks,
+                    model_SparseMatrixVBC_memory, model_SparseMatrixVBC_TrSpMV_time, total_value)
 
 __all__ = [
     "SparseMatrix1DVBC", "SparseMatrixVBC", "CuVBC1D", "CuVBC2D", "CuSparseMatrixCSC", "Adjoint",
     "mul_", "TrSpMV_", "adjoint", "size", "ldiv_lower_", "trsv_analyse",
     "SparseMatrixCSC", "SplitPartition", "EquiChunker", "StrictChunker", "RandomChunker",
     "AlternatingPacker", "pack_stripe", "pack_plaid",
-    "DimensionMismatch", "ArgumentError", "VBCError", "synth",
+    "DimensionMismatch", "ArgumentError", "VBCError", "synth", "costs",
+    "model_SparseMatrix1DVBC_blocks", "model_SparseMatrix1DVBC_memory", "model_SparseMatrix1DVBC_TrSpMV_time",
+    "model_SparseMatrixVBC_blocks", "model_SparseMatrixVBC_memory", "model_SparseMatrixVBC_TrSpMV_time", "total_value",
 ]

@@ -490,3 +490,23 @@ def test_pack_from_device_resident_csc(fixtures):
         B2 = vb.SparseMatrixVBC.from_device_csc(4, 4, A.m, A.n, d(A.colptr), d(A.rowval), d(A.nzval), d(pi.spl), d(phi2.spl))
         assert_packed_equal(B2, H2)
         randx_check(A, B2, H2, np.random.default_rng(5))
+
+
+def test_gpu_time_model_autotuner_small():
+    """the costs.jl time-model sweep + fit, on the device (small cache budget so it runs in seconds)."""
+    from vbc_b200 import costs
+    d = costs.model_SparseMatrix1DVBC_TrSpMV_time_data(4, np.float64, np.int64, np.float64, cache_bytes=4 << 20, use_cache=False)
+    assert len(d["T"]) == 16 and all(t > 0 for t in d["T"])
+    mdl = costs.model_SparseMatrix1DVBC_TrSpMV_time(4, np.float64, np.int64, np.float64, cache_bytes=4 << 20)
+    assert np.all(np.diff(np.asarray(mdl.alpha_col)) >= 0) and np.all(np.diff(np.asarray(mdl.beta_col)) >= 0)
+    m2 = costs.model_SparseMatrixVBC_TrSpMV_time(2, 2, 2, np.float64, np.int64, np.float64, cache_bytes=4 << 20, use_cache=False)
+    assert len(m2.beta_row) == 2 and len(m2.beta_col) == 2
+    # evaluate models on a packed matrix (`total_value`, bin/test_table.jl:82/:124)
+    A, pi, phi = synth.config_c2(n=4000, S=7)
+    B = vb.SparseMatrixVBC[4, 4](A, pi, phi)
+    ref_bytes = B.format_bytes()[0]
+    mem = costs.total_value(B, costs.model_SparseMatrixVBC_memory(np.float64, np.int64))
+    assert mem == ref_bytes - 8 * 4  # the model has no "+1" entries: Π, Φ, pos, ofs each one element longer
+    B1 = vb.SparseMatrix1DVBC[4](A, phi)
+    assert costs.total_value(B1, costs.model_SparseMatrix1DVBC_blocks()) == B1.nidx
+    assert costs.total_value(B1, costs.model_SparseMatrix1DVBC_memory(np.float64, np.int64)) == B1.format_bytes()[0] - 8 * 3

@@ -80,3 +80,52 @@ def test_config_c1_shape():
 
 def test_fem_stencil_has_13_offsets():
     assert len(synth.fem_stencil_offsets(63)) == 13
+
+
+def test_time_model_fit_recovers_coefficients_1d():
+    """costs.jl:112-131 restated in costs.fit_1d: relative LSQ on the one-hot design recovers a planted model."""
+    from vbc_b200 import costs
+    W = 4
+    rng = np.random.default_rng(0)
+    a_row, a_col, b_col = 2e-12, np.array([1e-9, 1.5e-9, 2e-9, 2.2e-9]), np.array([3e-10, 4e-10, 6e-10, 7e-10])
+    ms, Ls, ws, qs, T = [], [], [], [], []
+    for w in range(W, 0, -1):
+        L0 = 10_000 * w
+        for (m, L, q) in ((L0 * w, L0, 8 * L0), (L0 * w, L0 // 2, 8 * L0), (L0 * w // 2, L0, 8 * L0), (L0 * w, L0, 4 * L0)):
+            ms.append(m); Ls.append(L); ws.append(w); qs.append(q)
+            T.append(a_row * m + a_col[w - 1] * L + b_col[w - 1] * q)
+    ar, ac, bc = costs.fit_1d(W, ms, Ls, ws, qs, T)
+    assert np.allclose(ac, a_col, rtol=1e-6) and np.allclose(bc, b_col, rtol=1e-6) and np.isclose(ar, a_row, rtol=1e-6)
+    # monotonisation: a dip is lifted to its predecessor
+    T2 = list(T)
+    ar, ac, bc = costs.fit_1d(W, ms, Ls, ws, qs, [t * (0.5 if w == 3 else 1.0) for t, w in zip(T2, ws)])
+    assert np.all(np.diff(ac) >= 0) and np.all(np.diff(bc) >= 0)
+
+
+def test_time_model_fit_2d_rank_and_monotone():
+    from vbc_b200 import costs
+    U = W = 3
+    br, bcv = np.array([1.0, 1.6, 2.0]), np.array([2e-10, 3e-10, 3.5e-10])  # rank-1 planted beta
+    a_row, a_col = np.array([1e-10, 1e-10, 1e-10]), np.array([1e-9, 1.2e-9, 1.4e-9])
+    Ks, Ls, us, ws, qs, T = [], [], [], [], [], []
+    for u in range(U, 0, -1):
+        for w in range(W, 0, -1):
+            L0 = 5000
+            K0 = L0 * w // u
+            for (K, L, q) in ((K0, L0, 8 * L0), (K0, L0 // 2, 8 * L0), (K0 // 2, L0, 8 * L0), (K0, L0, 4 * L0)):
+                Ks.append(K); Ls.append(L); us.append(u); ws.append(w); qs.append(q)
+                T.append(a_row[u - 1] * K + a_col[w - 1] * L + br[u - 1] * bcv[w - 1] * q)
+    ar, ac, brow, bcol, beta = costs.fit_2d(1, U, W, Ks, Ls, us, ws, qs, T)
+    assert np.allclose(beta, np.outer(br, bcv), rtol=1e-6)
+    recon = np.outer(brow[0], bcol[0])
+    assert np.allclose(recon, beta, rtol=1e-6)
+    assert np.allclose(ar, a_row, rtol=1e-5) and np.allclose(ac, a_col, rtol=1e-5)
+
+
+def test_memory_models_match_reference_formulas():
+    from vbc_b200 import costs
+    m1 = costs.model_SparseMatrix1DVBC_memory(np.float64, np.int64)
+    assert m1.stripe_value(4, 10) == 3 * 8 + 10 * (8 + 4 * 8)  # costs.jl:10
+    m2 = costs.model_SparseMatrixVBC_memory(np.float32, np.int32)
+    assert m2.block_value(4, 4) == 4 + 4 * 4 * 4  # |Ti| + u*w*|Tv|  (costs.jl:140)
+    assert costs.model_SparseMatrix1DVBC_blocks().stripe_value(7, 13) == 13  # costs.jl:8
