@@ -146,6 +146,33 @@ LinearAlgebra.mul!(y::StridedVector, adjA::Union{Adjoint{<:Any, <:CuVBC}, Transp
 Base.:*(A::Union{CuVBC, Adjoint{<:Any, <:CuVBC}, Transpose{<:Any, <:CuVBC}}, x::StridedVector{Tx}) where {Tx} =
     (T = Base.promote_op(LinearAlgebra.matprod, eltype(A), Tx); mul!(similar(x, T, size(A, 1)), A, x, true, false))
 
+# ---- k right-hand sides: the `*(A, B::DenseMatrix)` of multiply_1DVBC.jl:184-185 / multiply_VBC.jl:196-197, which the
+# reference declares but cannot execute.  A Julia Matrix is column-major: layout = 1, ld = stride(X, 2).
+function _cuvbc_mul!(Y::StridedMatrix{Tv}, A::CuVBC{U, W, Tv}, X::StridedMatrix{Tv}, α::Number, β::Number, trans::Bool) where {U, W, Tv}
+    size(X, 2) == size(Y, 2) || throw(DimensionMismatch())
+    GC.@preserve X Y begin
+        vbc_check(ccall((:vbc_spmm, libvbc), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Cdouble, Ptr{Cvoid}, Int64, Cdouble, Ptr{Cvoid}, Int64, Cint, Cint),
+            A.handle, trans, size(X, 2), Float64(α), X, stride(X, 2), Float64(β), Y, stride(Y, 2), 1, 0))
+    end
+    return Y
+end
+LinearAlgebra.mul!(Y::StridedMatrix, A::CuVBC, X::StridedMatrix, α::Number, β::Number) = _cuvbc_mul!(Y, A, X, α, β, false)
+LinearAlgebra.mul!(Y::StridedMatrix, adjA::Union{Adjoint{<:Any, <:CuVBC}, Transpose{<:Any, <:CuVBC}}, X::StridedMatrix, α::Number, β::Number) =
+    _cuvbc_mul!(Y, adjA.parent, X, α, β, true)
+Base.:*(A::Union{CuVBC, Adjoint{<:Any, <:CuVBC}, Transpose{<:Any, <:CuVBC}}, X::StridedMatrix{Tx}) where {Tx} =
+    (T = Base.promote_op(LinearAlgebra.matprod, eltype(A), Tx); mul!(similar(X, T, (size(A, 1), size(X, 2))), A, X, true, false))
+
+# ---- extension: x = LowerTriangular(B') \ b (the reference has no solve; BASELINE.json north_star (d))
+function ldiv_lower!(x::StridedVector{Tv}, adjA::Union{Adjoint{<:Any, <:CuVBC{U, W, Tv}}, Transpose{<:Any, <:CuVBC{U, W, Tv}}}, b::StridedVector{Tv}) where {U, W, Tv}
+    length(x) == length(b) || throw(DimensionMismatch())
+    GC.@preserve x b begin
+        vbc_check(ccall((:vbc_trsv_lower, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint),
+            adjA.parent.handle, b, x, length(x), 0))
+    end
+    return x
+end
+
 # ---- CSC comparator ----------------------------------------------------------------------------------
 mutable struct CuCSC{Tv, Ti}
     handle::Ptr{Cvoid}
