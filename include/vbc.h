@@ -138,6 +138,14 @@ int vbc_csc_upload(vbc_csc **out, int vt, int it, int64_t m, int64_t n, const vo
 int vbc_csc_trspmv(vbc_csc *A, const void *x, int64_t xlen, void *y, int64_t ylen, int on_device);
 void vbc_csc_destroy(vbc_csc *A);
 
+/* ---- host-side helper of the partitioners (no device work) ---------------------------------
+ * Minimum-total-cost contiguous partition with stripes at most W wide: cost[b*W + (w-1)] is the cost of
+ * the stripe of columns [b-w, b) (0-based, b = 1..n).  Writes the 1-based SplitPartition.spl (at most n+1
+ * entries) and its length L.  The recurrence behind ChainPartitioners' DynamicTotalChunker
+ * (constructors_1DVBC.jl:1-2, test/runtests.jl:22-23); ChainPartitioners is not vendored, tie-breaking
+ * parity is unpinned. */
+int vbc_dp_chunk(int64_t n, int W, const double *cost, int64_t *spl, int64_t *L_out);
+
 /* ---- execution control ---------------------------------------------------------------------*/
 int vbc_set_stream(vbc_mat *A, void *cuda_stream); /* a cudaStream_t; NULL = legacy default stream */
 int vbc_csc_set_stream(vbc_csc *A, void *cuda_stream);

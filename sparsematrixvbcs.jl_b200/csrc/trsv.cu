@@ -75,28 +75,47 @@ __global__ void __launch_bounds__(256) k_trsv_lower(const StripeMeta *__restrict
         const bool active = lane < rps * w;
         Tv acc = (Tv)0;
         if (active) {
+            // Everything that does not depend on other row blocks is issued first (descriptors, values, the
+            // column->stripe lookups), in batches of TB rows per lane; only then does the lane wait on the
+            // flags of the row blocks it gathers from, and only then does it read x.
+            constexpr int TB = 4;
             RowWalk<MODE> walk;
             walk.init(desc, a.pos, r0, rps, u0, log2u);
             const Tv *vp = val + a.ofs + (long long)r0 * w + c;
-            for (int r = r0; r < R; r += rps) {
-                const int i = walk.next();
-                const Tv v = __ldcs(vp);
-                vp += (long long)rps * w;
-                if (i < j0) {
-                    const int dep = __ldg(c2s + i);
-                    if (ld_acquire_gpu_u32(flags + dep) != epoch) {
+            for (int r = r0; r < R; r += TB * rps) {
+                int xi[TB], dep[TB];
+                Tv v[TB];
+#pragma unroll
+                for (int k = 0; k < TB; k++) {
+                    const bool ok = r + k * rps < R;
+                    xi[k] = walk.next_if(ok);
+                    v[k] = ok ? __ldcs(vp) : (Tv)0;
+                    vp += (long long)rps * w;
+                    if (!ok) xi[k] = -1;
+                }
+#pragma unroll
+                for (int k = 0; k < TB; k++) {
+                    dep[k] = -1;
+                    if (xi[k] >= 0 && xi[k] < j0) dep[k] = __ldg(c2s + xi[k]);
+                    else if (xi[k] >= j0 && xi[k] < j0 + w) Dsm[wib][xi[k] - j0][c] = v[k]; // diagonal block row
+                }
+#pragma unroll
+                for (int k = 0; k < TB; k++) {
+                    if (dep[k] < 0) continue;
+                    if (ld_acquire_gpu_u32(flags + dep[k]) != epoch) {
                         unsigned long long t0, t1;
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                        while (ld_acquire_gpu_u32(flags + dep) != epoch) {
+                        while (ld_acquire_gpu_u32(flags + dep[k]) != epoch) {
                             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                             if (t1 - t0 > 3000000000ull) { atomicExch(err, 1); break; }
-                            __nanosleep(32);
                         }
                     }
-                    acc = fma(v, __ldcg(x + i), acc); // .cg: x was just written by another SM
-                } else if (i < j0 + w) {
-                    Dsm[wib][i - j0][c] = v; // diagonal block row
                 }
+                Tv xv[TB];
+#pragma unroll
+                for (int k = 0; k < TB; k++) xv[k] = dep[k] >= 0 ? __ldcg(x + xi[k]) : (Tv)0; // .cg: written by another SM
+#pragma unroll
+                for (int k = 0; k < TB; k++) acc = fma(v[k], xv[k], acc);
             }
         }
         for (int d = w; d < 32; d <<= 1) {

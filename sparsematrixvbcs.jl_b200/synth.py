@@ -140,3 +140,37 @@ def config_c4_triangular(n=2_000_000, u=4, w=4, S=79, dtype=np.float64, ti=np.in
     K, L = n // u, n // w
     offs = [0, -(S - 1), -S, -(S + 1), -(S * S)]
     return banded_blocks(K, L, u, w, offs, seed=seed, dtype=dtype, ti=ti, diag_boost=float(8 * len(offs) * u))
+
+
+def variable_block_matrix(n, per_stripe=8, g_max=6, band=2000, seed=SEED, dtype=np.float64, ti=np.int64):
+    """Square matrix with NATURAL variable blocks (FEM-like supernodes): columns fall into groups of 1..g_max
+    adjacent columns with identical patterns, rows likewise, and every column group holds `per_stripe` dense
+    blocks at random row groups within +-band rows of the diagonal.  Returns (A, natural Π, natural Φ)."""
+    rng = np.random.default_rng(seed)
+
+    def groups(total):
+        w = rng.integers(1, g_max + 1, size=total)
+        s = np.concatenate([[0], np.cumsum(w)])
+        s = s[s < total]
+        return np.append(s, total).astype(np.int64)
+    cs, rs = groups(n), groups(n)
+    L, K = len(cs) - 1, len(rs) - 1
+    rows_l, cols_l = [], []
+    centre = np.searchsorted(rs, cs[:-1], side="right") - 1         # row group under the stripe's first column
+    half = max(1, int(band / ((g_max + 1) / 2)))
+    cand = centre[:, None] + rng.integers(-half, half + 1, size=(L, per_stripe))
+    cand[:, 0] = centre                                             # keep the diagonal block
+    cand = np.clip(cand, 0, K - 1)
+    import scipy.sparse as sp
+    lk = np.unique(np.stack([np.repeat(np.arange(L), per_stripe), cand.reshape(-1)], axis=1), axis=0)
+    ls, ks = lk[:, 0], lk[:, 1]
+    u, w = (rs[ks + 1] - rs[ks]), (cs[ls + 1] - cs[ls])
+    cnt = u * w
+    tot = int(cnt.sum())
+    blk = np.repeat(np.arange(len(ls)), cnt)
+    off = np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    rr = rs[ks][blk] + off // w[blk]
+    cc = cs[ls][blk] + off % w[blk]
+    vals = entry_values(rr, cc, n, seed=seed, dtype=dtype)
+    A = SparseMatrixCSC.from_scipy(sp.csc_matrix((vals, (rr, cc)), shape=(n, n)), ti=ti, tv=dtype)
+    return A, SplitPartition((rs + 1).astype(ti)), SplitPartition((cs + 1).astype(ti))

@@ -370,7 +370,7 @@ def test_spmm_matches_column_by_column_oracle(fixtures):
     absS = abs(S)
     phi = vb.pack_stripe(A, vb.RandomChunker(8, 4))
     pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(4)))
-    piv, phiv = vb.pack_plaid(A, vb.AlternatingPacker(vb.RandomChunker(4, 7), vb.RandomChunker(12, 8)))
+    piv, phiv = vb.pack_plaid(A, vb.AlternatingPacker(vb.RandomChunker(12, 8), vb.RandomChunker(4, 7)))  # columns <= 12, rows <= 4
     mats = [(vb.SparseMatrix1DVBC[8](A, phi), oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 8)),
             (vb.SparseMatrixVBC[4, 4](A, pi, phi2), oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi2.spl, 4, 4)),
             (vb.SparseMatrixVBC[4, 12](A, piv, phiv), oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, piv.spl, phiv.spl, 4, 12))]

@@ -43,7 +43,8 @@ def test_random_chunker_is_a_valid_split(n, w):
 
 def test_alternating_packer_partitions_rows_and_columns():
     A = vb.SparseMatrixCSC.from_scipy(sp.random(9, 13, 0.3, random_state=2, format="csc"))
-    pi, phi = vb.pack_plaid(A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(3)))
+    # reference order: first method -> columns (Φ), second -> rows (Π)  (bin/test_table.jl:89)
+    pi, phi = vb.pack_plaid(A, vb.AlternatingPacker(vb.EquiChunker(3), vb.EquiChunker(4)))
     assert pi.spl.tolist() == [1, 5, 9, 10] and phi.spl.tolist() == [1, 4, 7, 10, 13, 14]
 
 
@@ -129,3 +130,58 @@ def test_memory_models_match_reference_formulas():
     m2 = costs.model_SparseMatrixVBC_memory(np.float32, np.int32)
     assert m2.block_value(4, 4) == 4 + 4 * 4 * 4  # |Ti| + u*w*|Tv|  (costs.jl:140)
     assert costs.model_SparseMatrix1DVBC_blocks().stripe_value(7, 13) == 13  # costs.jl:8
+
+
+def _brute_force_dp(A, stripe_cost, W):
+    """min over all contiguous partitions with widths <= W of sum stripe_cost(j0, j1); exponential-free O(n W) reference."""
+    n = A.n
+    best = [0.0] + [None] * n
+    for b in range(1, n + 1):
+        best[b] = min(best[b - w] + stripe_cost(b - w, b) for w in range(1, min(W, b) + 1))
+    return best[n]
+
+
+def test_window_distinct_counts_and_dynamic_total_chunker():
+    from vbc_b200 import costs
+    from vbc_b200.partition import DynamicTotalChunker, window_weight_sums
+    rng = np.random.default_rng(3)
+    M = sp.random(40, 31, 0.15, random_state=5, format="csc")
+    A = vb.SparseMatrixCSC.from_scipy(M)
+    S = M.tocsc()
+    W = 5
+    D = window_weight_sums(A, W)[:, :, 0]
+    for b in range(0, A.n + 1):
+        for w in range(1, min(W, b) + 1):
+            assert D[b, w - 1] == len(np.unique(S[:, b - w:b].tocoo().row)), (b, w)
+    # 1D: block-count and memory models against an exhaustive recurrence with set-based stripe costs
+    for mdl in (costs.model_SparseMatrix1DVBC_blocks(), costs.model_SparseMatrix1DVBC_memory(np.float64, np.int64)):
+        phi = vb.pack_stripe(A, DynamicTotalChunker(mdl, W))
+        spl = phi.spl.astype(np.int64) - 1
+        assert spl[0] == 0 and spl[-1] == A.n and np.all(np.diff(spl) >= 1) and np.diff(spl).max() <= W
+        cost = lambda a, b: mdl.stripe_value(b - a, len(np.unique(S[:, a:b].tocoo().row)))
+        got = sum(cost(a, b) for a, b in zip(spl[:-1], spl[1:]))
+        assert np.isclose(got, _brute_force_dp(A, cost, W))
+    # the memory model never does worse than Strict or Equi partitions of the same width limit
+    mem = costs.model_SparseMatrix1DVBC_memory(np.float64, np.int64)
+    def total(phi):
+        s_ = phi.spl.astype(np.int64) - 1
+        return sum(mem.stripe_value(b - a, len(np.unique(S[:, a:b].tocoo().row))) for a, b in zip(s_[:-1], s_[1:]))
+    best = total(vb.pack_stripe(A, DynamicTotalChunker(mem, W)))
+    assert best <= total(vb.pack_stripe(A, vb.StrictChunker(W))) and best <= total(vb.pack_stripe(A, vb.EquiChunker(W)))
+    # 2D: columns given a row partition, weighted distinct-part sums
+    pi = vb.pack_stripe(A.transpose(), vb.RandomChunker(4, 2))
+    m2 = costs.model_SparseMatrixVBC_memory(np.float64, np.int64)
+    phi2 = vb.pack_stripe(A, DynamicTotalChunker(m2, W), other=pi)
+    ps = pi.spl.astype(np.int64) - 1
+    heights = np.diff(ps)
+    def cost2(a, b):
+        parts = np.unique(np.searchsorted(ps, S[:, a:b].tocoo().row, side="right") - 1)
+        return 3 * 8 + sum(m2.block_value(heights[k], b - a) for k in parts)
+    s2 = phi2.spl.astype(np.int64) - 1
+    assert np.isclose(sum(cost2(a, b) for a, b in zip(s2[:-1], s2[1:])), _brute_force_dp(A, cost2, W))
+    # AlternatingPacker in the reference's order: columns, rows | columns, columns | rows ...
+    pi3, phi3 = vb.pack_plaid(A, vb.AlternatingPacker(DynamicTotalChunker(costs.model_SparseMatrix1DVBC_blocks(), W), vb.EquiChunker(1)))
+    assert len(pi3) == A.m and np.diff(phi3.spl).max() <= W
+    pi4, phi4 = vb.pack_plaid(A, vb.AlternatingPacker(vb.EquiChunker(1), vb.EquiChunker(1), DynamicTotalChunker(m2, W),
+                                                       DynamicTotalChunker(vb.partition.permutedims(m2), 4), DynamicTotalChunker(m2, W)))
+    assert np.diff(pi4.spl).max() <= 4 and np.diff(phi4.spl).max() <= W and pi4.spl[-1] == A.m + 1 and phi4.spl[-1] == A.n + 1
