@@ -11,6 +11,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # built artefacts are git-ignored: a fresh checkout has no libvbc.so / liboracle_vbc.so yet
+    lib = os.path.join(ROOT, "sparsematrixvbcs.jl_b200", "libvbc.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def pytest_collection_modifyitems(config, items):
