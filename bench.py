@@ -332,6 +332,7 @@ def run_ours(args, rank, world, local_rank):
                                                   "nccl": "torch.distributed all_gather_into_tensor after the multiply"}[args.exchange]),
             "exchange_mode": (args.exchange if world > 1 else None), "x_abs_sum_after_run": x_check,
             "exchange_sent_fraction": (peer.sent_fraction if peer is not None else None),
+            "exchange_flag_neighbors_rank0": (peer.neighbors if peer is not None else None),
             "exchange_sync": (None if peer is None else {0: "flag kernel after the multiply", 1: f"in-kernel, stripes {list(peer.interior)} run before the wait",
                                                                2: f"split launches, stripes {list(peer.interior)} run before the wait"}[args.sync_mode]),
         }

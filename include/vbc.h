@@ -192,6 +192,11 @@ int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, 
  * halos) -- x stays complete on every rank exactly where that rank reads it.  mask == NULL restores
  * full replication. */
 int vbc_peer_set_mask(vbc_peer *P, const void *mask, int64_t nchunks, int chunk_shift);
+/* Restrict the flag exchange to the ranks in `mask` (bit r = rank r).  With sparsity-aware replication a rank
+ * only has to synchronise with the ranks it sends y segments to (they must have finished reading the buffer it
+ * is about to overwrite) and the ranks it receives from (their segments must have landed) -- for a banded
+ * operator its two neighbours instead of everyone.  The relation must be symmetric across ranks. */
+int vbc_peer_set_neighbors(vbc_peer *P, unsigned mask);
 /* Overlapping the flag exchange with the multiply (optional).  enable = 2: barrier = 3 steps become four
  * launches -- [stripes i0..i1) | wait for the peers' previous step | remaining stripes | signal -- so the
  * wait (and the drift between ranks) hides behind the first launch; the default (enable = 0) is

@@ -23,6 +23,7 @@ struct vbc_peer {
                              // [stripes i0..i1] [wait] [the rest] [signal] so the wait hides behind the first launch
     int i0 = 0, i1 = 0;      // stripes [i0, i1): no peer involved (run before the in-kernel wait)
     unsigned *d_done = nullptr;
+    unsigned nbr_mask = 0xffffffffu; // ranks this rank exchanges flags with (bit r); default: everyone
     int64_t launches = 0;
 };
 
@@ -49,14 +50,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 //   wait  : spin until flags_me[r] >= epoch for every r (acquire), with a wall-clock bound so a
 //           dead peer cannot hang the GPU.
 __global__ void k_peer_flags(const __grid_constant__ FlagPtrs f, const int me, const int nranks, unsigned long long *__restrict__ d_epoch,
-                             const int do_signal, const int do_wait, int *__restrict__ timed_out)
+                             const int do_signal, const int do_wait, int *__restrict__ timed_out, const unsigned nbr_mask)
 {
     const int r = threadIdx.x;
     // epoch of this barrier: a signal opens a new epoch, a wait-only launch waits for the open one
     const unsigned long long epoch = *d_epoch + (do_signal ? 1ull : 0ull);
     __syncwarp();
     if (r == 0 && do_signal) *d_epoch = epoch;
-    if (r >= nranks) return;
+    if (r >= nranks || !((nbr_mask >> r) & 1u)) return; // only the ranks this one sends to or receives from
     if (do_signal) {
         __threadfence_system();
         st_release_sys(f.p[r] + me, epoch);
@@ -81,7 +82,7 @@ static int flags_launch(vbc_peer *P, cudaStream_t st, int barrier)
     if (!(barrier & 3)) return VBC_OK;
     FlagPtrs f;
     for (int r = 0; r < VBC_MAX_PEERS; r++) f.p[r] = r < P->nranks ? (unsigned long long *)P->bufs[r][2] : nullptr;
-    k_peer_flags<<<1, 32, 0, st>>>(f, P->rank, P->nranks, P->d_epoch, barrier & 1, (barrier & 2) ? 1 : 0, P->d_timeout);
+    k_peer_flags<<<1, 32, 0, st>>>(f, P->rank, P->nranks, P->d_epoch, barrier & 1, (barrier & 2) ? 1 : 0, P->d_timeout, P->nbr_mask | (1u << P->rank));
     P->launches++;
     VBC_CUDA(cudaGetLastError());
     return VBC_OK;
@@ -258,6 +259,13 @@ int vbc_peer_set_fused_sync(vbc_peer *P, int enable, int64_t i0, int64_t i1)
     P->fused_sync = enable;
     P->i0 = (int)i0;
     P->i1 = (int)i1;
+    return VBC_OK;
+}
+
+int vbc_peer_set_neighbors(vbc_peer *P, unsigned mask)
+{
+    if (!P) VBC_FAIL(VBC_EARG, "NULL argument");
+    P->nbr_mask = mask;
     return VBC_OK;
 }
 

@@ -201,6 +201,7 @@ class PeerExchangeOperator:
         self.Tv = B.Tv
         self._lib = _lib
         self.halo = False
+        self.neighbors = [r for r in range(world) if r != rank]
         self.sent_fraction = 1.0
         if rows_read is not None and world > 1:
             C = 1 << chunk_shift
@@ -228,6 +229,21 @@ class PeerExchangeOperator:
                 needed = need_all[r][lo] | need_all[r][hi]
                 mask |= (needed.astype(np.uint8) << i).astype(np.uint8)
             _lib.check(L.vbc_peer_set_mask(self._h, mask.ctypes.data_as(ctypes.c_void_p), nl, chunk_shift))
+            # flag exchange only with the ranks this one sends to or receives from (made symmetric by construction:
+            # every rank derives both directions from the same gathered `need_all`)
+            S_ = layout.S
+            nbr = 0
+            for r in range(world):
+                if r == rank:
+                    continue
+                g0, g1 = (r * S_) >> chunk_shift, min((r + 1) * S_ - 1, layout.padded_len - 1) >> chunk_shift
+                m0, m1 = (rank * S_) >> chunk_shift, min((rank + 1) * S_ - 1, layout.padded_len - 1) >> chunk_shift
+                i_read_r = bool(need_all[rank][g0:g1 + 1].any())   # I gather from r's slice -> r sends to me
+                r_reads_me = bool(need_all[r][m0:m1 + 1].any())    # r gathers from my slice -> I send to r
+                if i_read_r or r_reads_me:
+                    nbr |= 1 << r
+            _lib.check(L.vbc_peer_set_neighbors(self._h, nbr))
+            self.neighbors = [r for r in range(world) if (nbr >> r) & 1]
             self.halo = True
             bits = np.unpackbits(mask[:, None], axis=1).sum()
             self.sent_fraction = float(bits) / float(nl * world)
