@@ -29,19 +29,24 @@ __device__ __forceinline__ int row_xindex(const int *__restrict__ desc, const in
     return __ldg(desc + pos0 + r / u0) + r % u0;
 }
 
-// Adjoint SpMM.  One warp per stripe; rows are taken RB = 8 at a time: the 8 x indices are loaded by 8 lanes
-// and broadcast, the 8 X rows are 8 independent coalesced loads in flight per lane, the 8 x w val slab is
-// loaded coalesced (each value once per warp) and staged in shared memory, from where the FMAs read it
-// with warp-uniform (broadcast) LDS -- 128-bit when w is even.
+// Adjoint SpMM.  One warp per stripe; rows are taken RB at a time in a two-stage software pipeline: while
+// batch t is multiplied, batch t+1's X rows (RB independent coalesced loads per lane), its slab of val
+// (loaded coalesced, each value once per warp, parked in the other half of a shared-memory double buffer)
+// and batch t+2's x indices are already in flight.  The FMAs read val with warp-uniform (broadcast) LDS,
+// 128-bit when WB is even.
+#ifndef VBC_SPMM_RB
+#define VBC_SPMM_RB 4
+#endif
 template <typename Tv, int MODE, int WB, int KT>
 __global__ void __launch_bounds__(256, (WB * KT <= 8 ? 3 : 2)) k_spmm_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
-                                                   const Tv *__restrict__ val, const Tv *__restrict__ X, const long long ldx,
-                                                   Tv *__restrict__ Y, const long long ldy, const int L, const int k,
-                                                   const int u0, const int log2u, const Tv alpha, const Tv beta)
+                                                      const Tv *__restrict__ val, const Tv *__restrict__ X, const long long ldx,
+                                                      Tv *__restrict__ Y, const long long ldy, const int L, const int k,
+                                                      const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
-    constexpr int RB = 8;
-    __shared__ __align__(16) Tv vs_all[8][RB * WB];
-    Tv *vs = vs_all[threadIdx.x >> 5];
+    constexpr int RB = VBC_SPMM_RB;
+    constexpr int VPL = (RB * WB + 31) / 32; // staged values per lane and batch
+    __shared__ __align__(16) Tv vs_all[8][2][RB * WB];
+    Tv(*vs)[RB * WB] = vs_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
     for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); l < L; l += nwarps) {
@@ -51,56 +56,73 @@ __global__ void __launch_bounds__(256, (WB * KT <= 8 ? 3 : 2)) k_spmm_adj(const 
         const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
         for (int kb = 0; kb < k; kb += 32 * KT) {
             for (int wb = 0; wb < w; wb += WB) {
-                const int wc = min(WB, w - wb); // columns of this chunk
+                const int wc = min(WB, w - wb);
                 Tv acc[WB][KT];
 #pragma unroll
                 for (int dj = 0; dj < WB; dj++)
 #pragma unroll
                     for (int t = 0; t < KT; t++) acc[dj][t] = (Tv)0;
-                int nxi = lane < min(RB, R) ? row_xindex<MODE>(desc, a.pos, lane, u0, log2u) : 0; // x indices one batch ahead
-                for (int r = 0; r < R; r += RB) {
+
+                // issue the loads of one batch: X rows into xn, val slab into vreg; the x indices were loaded a batch earlier
+                Tv xn[RB][KT], vreg[VPL];
+                int xi_next = lane < min(RB, R) ? row_xindex<MODE>(desc, a.pos, lane, u0, log2u) : 0;
+                auto issue = [&](const int r) {
                     const int nr = min(RB, R - r);
-                    // stage val[r .. r+nr) x [wb .. wb+wc) as vs[j * WB + dj], zero-padded to RB x WB
-                    __syncwarp();
-                    for (int i = lane; i < RB * WB; i += 32) {
-                        const int j = i / WB, dj = i % WB;
-                        vs[i] = (j < nr && dj < wc) ? __ldcs(val + a.ofs + (long long)(r + j) * w + wb + dj) : (Tv)0;
-                    }
-                    const int myxi = nxi;
-                    nxi = (lane < RB && r + RB + lane < R) ? row_xindex<MODE>(desc, a.pos, r + RB + lane, u0, log2u) : 0;
-                    Tv xv[RB][KT];
+                    const int myxi = xi_next;
+                    xi_next = (lane < RB && r + RB + lane < R) ? row_xindex<MODE>(desc, a.pos, r + RB + lane, u0, log2u) : 0;
 #pragma unroll
                     for (int j = 0; j < RB; j++) {
                         const int xi = __shfl_sync(0xffffffffu, myxi, j);
 #pragma unroll
                         for (int t = 0; t < KT; t++) {
                             const int c = kb + t * 32 + lane;
-                            xv[j][t] = (j < nr && c < k) ? __ldg(X + (long long)xi * ldx + c) : (Tv)0;
+                            xn[j][t] = (j < nr && c < k) ? __ldg(X + (long long)xi * ldx + c) : (Tv)0;
                         }
                     }
+#pragma unroll
+                    for (int q = 0; q < VPL; q++) {
+                        const int i = lane + 32 * q, j = i / WB, dj = i % WB;
+                        vreg[q] = (i < RB * WB && j < nr && dj < wc) ? __ldcs(val + a.ofs + (long long)(r + j) * w + wb + dj) : (Tv)0;
+                    }
+                };
+                int buf = 0;
+                if (R > 0) issue(0);
+                for (int r = 0; r < R; r += RB) {
+                    // park batch r's values; take over its X rows
+                    Tv xc[RB][KT];
+#pragma unroll
+                    for (int j = 0; j < RB; j++)
+#pragma unroll
+                        for (int t = 0; t < KT; t++) xc[j][t] = xn[j][t];
+#pragma unroll
+                    for (int q = 0; q < VPL; q++)
+                        if (lane + 32 * q < RB * WB) vs[buf][lane + 32 * q] = vreg[q];
+                    if (r + RB < R) issue(r + RB); // next batch's loads fly while this one is multiplied
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < RB; j++) {
                         if constexpr (WB % 2 == 0 && sizeof(Tv) == 8) {
 #pragma unroll
                             for (int dj = 0; dj < WB; dj += 2) {
-                                const double2 v2 = *reinterpret_cast<const double2 *>(vs + j * WB + dj); // warp-uniform LDS.128
+                                const double2 v2 = *reinterpret_cast<const double2 *>(&vs[buf][j * WB + dj]); // warp-uniform LDS.128
 #pragma unroll
                                 for (int t = 0; t < KT; t++) {
-                                    acc[dj][t] = fma((Tv)v2.x, xv[j][t], acc[dj][t]);
-                                    acc[dj + 1][t] = fma((Tv)v2.y, xv[j][t], acc[dj + 1][t]);
+                                    acc[dj][t] = fma((Tv)v2.x, xc[j][t], acc[dj][t]);
+                                    acc[dj + 1][t] = fma((Tv)v2.y, xc[j][t], acc[dj + 1][t]);
                                 }
                             }
                         } else {
 #pragma unroll
                             for (int dj = 0; dj < WB; dj++) {
-                                const Tv v = vs[j * WB + dj];
+                                const Tv v = vs[buf][j * WB + dj];
 #pragma unroll
-                                for (int t = 0; t < KT; t++) acc[dj][t] = fma(v, xv[j][t], acc[dj][t]);
+                                for (int t = 0; t < KT; t++) acc[dj][t] = fma(v, xc[j][t], acc[dj][t]);
                             }
                         }
                     }
+                    buf ^= 1; // the other half is free: it was read two batches ago, and every lane has passed a __syncwarp since
                 }
+                __syncwarp();
 #pragma unroll
                 for (int dj = 0; dj < WB; dj++) {
                     if (dj < wc) {

@@ -141,6 +141,22 @@ def main():
             del X, Y
         B.close()
         del A
+    if want("c3b"):
+        # same sizes as C3 but a CONTIGUOUS 50-row band per stripe (adjacent stripes share 42 of their 50 rows)
+        K, L = 1_000_000, 125_000
+        A, _, phi = synth.banded_blocks(K, L, 1, 8, np.arange(-25, 25))
+        B = pack_time("C3b 1D f64 w=8 n=1M contiguous band", lambda: vb.SparseMatrix1DVBC[8](A, phi))
+        report("C3b 1D f64 w=8 n=1M contiguous band", B, A, groups=(8,))
+        for k in (32, 64):
+            X = torch.rand(A.m, k, dtype=torch.float64, device="cuda"); Y = torch.empty(A.n, k, dtype=torch.float64, device="cuda")
+            med, mn = tk(lambda: vb.mul_(Y, B.T, X), reps=10)
+            nb = B.format_bytes()[1] + 8 * k * (A.m + A.n)
+            rows.append(dict(workload="C3b 1D f64 w=8 n=1M contiguous band", kernel=f"spmm_adj k={k} rowmajor", group=32, us_med=med * 1e6, us_min=mn * 1e6,
+                             bytes=nb, gbs=nb / med / 1e9, gflops=2.0 * A.nnz * k / med / 1e9, nnz=A.nnz))
+            print(f"{'C3b SpMM adjoint k=%d rowmajor' % k:34s}          {med * 1e6:8.1f} us  {nb / med / 1e9:7.0f} GB/s  {2.0 * A.nnz * k / med / 1e9:8.1f} GFLOP/s", flush=True)
+            del X, Y
+        B.close()
+        del A
     if want("c1"):
         A, phi = synth.config_c1()
         B = pack_time("C1 1D f64 w=8 n=10k (L2-resident)", lambda: vb.SparseMatrix1DVBC[8](A, phi))
