@@ -51,9 +51,10 @@ enum vbc_option {
     VBC_OPT_GRID_MULT = 3,  /* CTAs per SM for the persistent grid-stride launch: 0 = auto                   */
     VBC_OPT_PARITY_MODE = 4, /* 1: multiply straight from the canonical Ti arrays (pos/idx/ofs/spl) with the
                                   generic kernel instead of the compact device layout                         */
-    VBC_OPT_FWD_MODE = 5     /* forward multiply: 0 = auto (owner-computes through a transposed unit index, built at first
+    VBC_OPT_FWD_MODE = 5,    /* forward multiply: 0 = auto (owner-computes through a transposed unit index, built at first
                                   use, for uniform 2D blocks; atomic scatter kernel otherwise), 1 = always the atomic
                                   scatter kernel, 2 = the transposed index whenever the layout allows it              */
+    VBC_OPT_SPMM_SIMT = 6    /* Float64 adjoint SpMM: 0 = FP64 tensor (DMMA m8n8k4) tiles, 1 = the SIMT (DFMA) kernel      */
 };
 
 const char *vbc_last_error(void);

@@ -376,6 +376,9 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
     case VBC_OPT_PARITY_MODE:
         A->opt_parity = value ? 1 : 0;
         return VBC_OK;
+    case VBC_OPT_SPMM_SIMT:
+        A->opt_spmm_simt = value ? 1 : 0;
+        return VBC_OK;
     case VBC_OPT_FWD_MODE:
         if (value < 0 || value > 2) VBC_FAIL(VBC_EARG, "forward mode must be 0 (auto), 1 (atomic scatter) or 2 (transposed index whenever possible)");
         A->opt_fwd_atomic = (int)value;
@@ -393,6 +396,7 @@ int vbc_get_option(const vbc_mat *A, int option, int64_t *value)
     case VBC_OPT_GRID_MULT: *value = A->opt_grid_mult; return VBC_OK;
     case VBC_OPT_PARITY_MODE: *value = A->opt_parity; return VBC_OK;
     case VBC_OPT_FWD_MODE: *value = A->opt_fwd_atomic; return VBC_OK;
+    case VBC_OPT_SPMM_SIMT: *value = A->opt_spmm_simt; return VBC_OK;
     }
     VBC_FAIL(VBC_EARG, "unknown option %d", option);
 }

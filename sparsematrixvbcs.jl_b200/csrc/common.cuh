@@ -87,6 +87,7 @@ struct vbc_mat {
     vbc_trsv_plan *trsv = nullptr; // level schedule of the triangular solve (vbc_trsv_analyse)
     vbc::TIndex *tindex = nullptr; // transposed unit index of the owner-computes forward multiply (built at first use)
     int opt_fwd_atomic = 0;        // 1: always use the atomic scatter kernel for the forward multiply
+    int opt_spmm_simt = 0;         // 1: Float64 adjoint SpMM on the SIMT (DFMA) kernel instead of the DMMA tiles
 };
 
 struct vbc_csc {

@@ -139,6 +139,77 @@ __global__ void __launch_bounds__(256, (WB * KT <= 8 ? 3 : 2)) k_spmm_adj(const 
     }
 }
 
+// Adjoint SpMM on the FP64 tensor path (DMMA).  For one stripe, Y[j:j+w, :] = V' * Xg with V the stripe's R x w
+// slab and Xg the R gathered rows of X: a real contraction over the stripe's rows, so it maps onto
+// mma.sync.m8n8k4.f64 tiles -- A = 8 stripe columns x 4 stripe rows (read straight from val, one value per
+// lane), B = 4 gathered X rows x 8 right-hand sides, C = 8 x 8 accumulators (2 per lane and N-tile).  One
+// warp per stripe, 4 N-tiles (32 right-hand sides) per pass: per 4 stripe rows a lane issues 1 val load,
+// 1 index load, 4 X loads and 4 DMMAs -- about 5 instructions per stripe row instead of ~45 in the SIMT
+// kernel, which is what bounds that one (issue slots, not HBM or DFMA rate).  No shared memory.
+// (On Blackwell FP64 tensor math still goes through the mma.sync-class DMMA path; tcgen05 has no FP64 kind.)
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, const double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_spmm_adj_dmma(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+                                                        const double *__restrict__ val, const double *__restrict__ X, const long long ldx,
+                                                        double *__restrict__ Y, const long long ldy, const int L, const int k,
+                                                        const int u0, const int log2u, const double alpha, const double beta)
+{
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); l < L; l += nwarps) {
+        const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
+        const int w = b.col - a.col;
+        if (w <= 0) continue;
+        const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
+        for (int kb = 0; kb < k; kb += 32) {
+            for (int wb = 0; wb < w; wb += 8) {
+                double c[4][2];
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) { c[nt][0] = 0.0; c[nt][1] = 0.0; }
+                const bool arow = wb + g < w; // this lane's A row (stripe column) exists
+                const double *vp = val + a.ofs + (long long)t * w + wb + g;
+                int xi_next = t < R ? row_xindex<MODE>(desc, a.pos, t, u0, log2u) : -1;
+                for (int r = 0; r < R; r += 8) { // two k-steps of 4 stripe rows per iteration, all loads first
+                    const int xi0 = xi_next;
+                    const int xi1 = (r + 4 + t < R) ? row_xindex<MODE>(desc, a.pos, r + 4 + t, u0, log2u) : -1;
+                    xi_next = (r + 8 + t < R) ? row_xindex<MODE>(desc, a.pos, r + 8 + t, u0, log2u) : -1;
+                    const double a0 = (arow && xi0 >= 0) ? __ldcs(vp) : 0.0;
+                    const double a1 = (arow && xi1 >= 0) ? __ldcs(vp + 4 * (long long)w) : 0.0;
+                    vp += 8 * (long long)w;
+                    double b0[4], b1[4];
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) {
+                        const int col = kb + nt * 8 + g;
+                        b0[nt] = (xi0 >= 0 && col < k) ? __ldg(X + (long long)xi0 * ldx + col) : 0.0;
+                        b1[nt] = (xi1 >= 0 && col < k) ? __ldg(X + (long long)xi1 * ldx + col) : 0.0;
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) {
+                        dmma_m8n8k4(c[nt], a0, b0[nt]);
+                        dmma_m8n8k4(c[nt], a1, b1[nt]);
+                    }
+                }
+                if (arow) {
+                    double *yp = Y + (long long)(a.col + wb + g) * ldy;
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) {
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int col = kb + nt * 8 + 2 * t + e;
+                            if (col < k) yp[col] = (beta == 0.0) ? alpha * c[nt][e] : alpha * c[nt][e] + beta * yp[col];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <typename Tv, int MODE, int WB, int KT>
 __global__ void __launch_bounds__(256) k_spmm_fwd(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                    const Tv *__restrict__ val, const Tv *__restrict__ X, const long long ldx,
@@ -230,6 +301,18 @@ static int launch_spmm_mode(vbc_mat *A, int trans, int k, Tv alpha, const Tv *X,
 #define SPMM_LAUNCH(KERNEL, WBv, KTv, ...) KERNEL<Tv, MODE, WBv, KTv><<<(unsigned)grid, 256, 0, A->stream>>>(__VA_ARGS__)
     if (trans) {
         if (L == 0) return VBC_OK;
+        if constexpr (sizeof(Tv) == 8) {
+            if (!A->opt_spmm_simt) { // Float64: tensor (DMMA) tiles
+                int64_t g2 = (int64_t)A->sm_count * 8;
+                if (g2 > need) g2 = need;
+                if (g2 < 1) g2 = 1;
+                k_spmm_adj_dmma<MODE><<<(unsigned)g2, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const double *)A->d_val, (const double *)X, ldx,
+                                                                           (double *)Y, ldy, L, k, A->u0, log2u, (double)alpha, (double)beta);
+                A->launches++;
+                VBC_CUDA(cudaGetLastError());
+                return VBC_OK;
+            }
+        }
         if (wide) { if (k2) SPMM_LAUNCH(k_spmm_adj, 16, 2, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta);
                     else    SPMM_LAUNCH(k_spmm_adj, 16, 1, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta); }
         else if (narrow) { if (k2) SPMM_LAUNCH(k_spmm_adj, 4, 2, A->d_meta, A->d_desc, (const Tv *)A->d_val, X, ldx, Y, ldy, L, k, A->u0, log2u, alpha, beta);

@@ -376,6 +376,7 @@ def test_spmm_matches_column_by_column_oracle(fixtures):
             (vb.SparseMatrixVBC[4, 12](A, piv, phiv), oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, piv.spl, phiv.spl, 4, 12))]
     for B, H in mats:
         for k in (1, 3, 32, 40, 70):
+            B.set_option(_lib.OPT_SPMM_SIMT, 1 if k in (3, 40) else 0)  # Float64 adjoint: SIMT kernel / DMMA tiles
             for order in ("C", "F"):
                 for trans in (False, True):
                     xr, yr = (A.m, A.n) if trans else (A.n, A.m)

@@ -147,13 +147,14 @@ def main():
         A, _, phi = synth.banded_blocks(K, L, 1, 8, np.arange(-25, 25))
         B = pack_time("C3b 1D f64 w=8 n=1M contiguous band", lambda: vb.SparseMatrix1DVBC[8](A, phi))
         report("C3b 1D f64 w=8 n=1M contiguous band", B, A, groups=(8,))
-        for k in (32, 64):
+        for k, simt in ((32, 0), (64, 0), (32, 1)):
+            B.set_option(_lib.OPT_SPMM_SIMT, simt)
             X = torch.rand(A.m, k, dtype=torch.float64, device="cuda"); Y = torch.empty(A.n, k, dtype=torch.float64, device="cuda")
             med, mn = tk(lambda: vb.mul_(Y, B.T, X), reps=10)
             nb = B.format_bytes()[1] + 8 * k * (A.m + A.n)
-            rows.append(dict(workload="C3b 1D f64 w=8 n=1M contiguous band", kernel=f"spmm_adj k={k} rowmajor", group=32, us_med=med * 1e6, us_min=mn * 1e6,
+            rows.append(dict(workload="C3b 1D f64 w=8 n=1M contiguous band", kernel=f"spmm_adj k={k} rowmajor {'simt' if simt else 'dmma'}", group=32, us_med=med * 1e6, us_min=mn * 1e6,
                              bytes=nb, gbs=nb / med / 1e9, gflops=2.0 * A.nnz * k / med / 1e9, nnz=A.nnz))
-            print(f"{'C3b SpMM adjoint k=%d rowmajor' % k:34s}          {med * 1e6:8.1f} us  {nb / med / 1e9:7.0f} GB/s  {2.0 * A.nnz * k / med / 1e9:8.1f} GFLOP/s", flush=True)
+            print(f"{'C3b SpMM adjoint k=%d %s' % (k, 'simt' if simt else 'dmma'):34s}          {med * 1e6:8.1f} us  {nb / med / 1e9:7.0f} GB/s  {2.0 * A.nnz * k / med / 1e9:8.1f} GFLOP/s", flush=True)
             del X, Y
         B.close()
         del A
