@@ -172,36 +172,27 @@ __global__ void __launch_bounds__(256) k_spmm_adj_dmma(const StripeMeta *__restr
 #pragma unroll
                 for (int nt = 0; nt < 4; nt++) { c[nt][0] = 0.0; c[nt][1] = 0.0; }
                 const bool arow = wb + g < w; // this lane's A row (stripe column) exists
-                // k-steps of 4 stripe rows, software-pipelined: the val / X loads of step s+1 are issued before the
-                // DMMAs of step s, and the x indices run two steps ahead of that.
-                const int S = (R + 3) >> 2;
-                auto idx_of = [&](const int s_) { const int r_ = 4 * s_ + t; return (s_ < S && r_ < R) ? row_xindex<MODE>(desc, a.pos, r_, u0, log2u) : -1; };
-                const double *vbase = val + a.ofs + (long long)t * w + wb + g;
-                auto load_step = [&](const int s_, const int xi, double &av, double (&bv)[4]) {
-                    av = (arow && xi >= 0) ? __ldcs(vbase + (long long)s_ * 4 * w) : 0.0;
+                const double *vp = val + a.ofs + (long long)t * w + wb + g;
+                int xi_next = t < R ? row_xindex<MODE>(desc, a.pos, t, u0, log2u) : -1;
+                for (int r = 0; r < R; r += 8) { // two k-steps of 4 stripe rows per iteration, all loads first
+                    const int xi0 = xi_next;
+                    const int xi1 = (r + 4 + t < R) ? row_xindex<MODE>(desc, a.pos, r + 4 + t, u0, log2u) : -1;
+                    xi_next = (r + 8 + t < R) ? row_xindex<MODE>(desc, a.pos, r + 8 + t, u0, log2u) : -1;
+                    const double a0 = (arow && xi0 >= 0) ? __ldcs(vp) : 0.0;
+                    const double a1 = (arow && xi1 >= 0) ? __ldcs(vp + 4 * (long long)w) : 0.0;
+                    vp += 8 * (long long)w;
+                    double b0[4], b1[4];
 #pragma unroll
                     for (int nt = 0; nt < 4; nt++) {
                         const int col = kb + nt * 8 + g;
-                        bv[nt] = (xi >= 0 && col < k) ? __ldg(X + (long long)xi * ldx + col) : 0.0;
-                    }
-                };
-                int xi_n = idx_of(0), xi_nn = idx_of(1);
-                double a_n, b_n[4];
-                load_step(0, xi_n, a_n, b_n);
-                xi_n = xi_nn;
-                xi_nn = idx_of(2);
-                for (int s_ = 0; s_ < S; s_++) {
-                    const double a_c = a_n;
-                    double b_c[4];
-#pragma unroll
-                    for (int nt = 0; nt < 4; nt++) b_c[nt] = b_n[nt];
-                    if (s_ + 1 < S) {
-                        load_step(s_ + 1, xi_n, a_n, b_n);
-                        xi_n = xi_nn;
-                        xi_nn = idx_of(s_ + 3);
+                        b0[nt] = (xi0 >= 0 && col < k) ? __ldg(X + (long long)xi0 * ldx + col) : 0.0;
+                        b1[nt] = (xi1 >= 0 && col < k) ? __ldg(X + (long long)xi1 * ldx + col) : 0.0;
                     }
 #pragma unroll
-                    for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], a_c, b_c[nt]);
+                    for (int nt = 0; nt < 4; nt++) {
+                        dmma_m8n8k4(c[nt], a0, b0[nt]);
+                        dmma_m8n8k4(c[nt], a1, b1[nt]);
+                    }
                 }
                 if (arow) {
                     double *yp = Y + (long long)(a.col + wb + g) * ldy;
