@@ -147,6 +147,9 @@ __global__ void __launch_bounds__(256, (WB * KT <= 8 ? 3 : 2)) k_spmm_adj(const 
 // 1 index load, 4 X loads and 4 DMMAs -- about 5 instructions per stripe row instead of ~45 in the SIMT
 // kernel, which is what bounds that one (issue slots, not HBM or DFMA rate).  No shared memory.
 // (On Blackwell FP64 tensor math still goes through the mma.sync-class DMMA path; tcgen05 has no FP64 kind.)
+#ifndef VBC_DMMA_KS
+#define VBC_DMMA_KS 4
+#endif
 __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, const double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -174,25 +177,28 @@ __global__ void __launch_bounds__(256) k_spmm_adj_dmma(const StripeMeta *__restr
                 const bool arow = wb + g < w; // this lane's A row (stripe column) exists
                 const double *vp = val + a.ofs + (long long)t * w + wb + g;
                 int xi_next = t < R ? row_xindex<MODE>(desc, a.pos, t, u0, log2u) : -1;
-                for (int r = 0; r < R; r += 8) { // two k-steps of 4 stripe rows per iteration, all loads first
-                    const int xi0 = xi_next;
-                    const int xi1 = (r + 4 + t < R) ? row_xindex<MODE>(desc, a.pos, r + 4 + t, u0, log2u) : -1;
-                    xi_next = (r + 8 + t < R) ? row_xindex<MODE>(desc, a.pos, r + 8 + t, u0, log2u) : -1;
-                    const double a0 = (arow && xi0 >= 0) ? __ldcs(vp) : 0.0;
-                    const double a1 = (arow && xi1 >= 0) ? __ldcs(vp + 4 * (long long)w) : 0.0;
-                    vp += 8 * (long long)w;
-                    double b0[4], b1[4];
+                constexpr int KS = VBC_DMMA_KS; // k-steps (of 4 stripe rows) per iteration: all their loads are issued first
+                for (int r = 0; r < R; r += 4 * KS) {
+                    int xi[KS];
+                    xi[0] = xi_next;
 #pragma unroll
-                    for (int nt = 0; nt < 4; nt++) {
-                        const int col = kb + nt * 8 + g;
-                        b0[nt] = (xi0 >= 0 && col < k) ? __ldg(X + (long long)xi0 * ldx + col) : 0.0;
-                        b1[nt] = (xi1 >= 0 && col < k) ? __ldg(X + (long long)xi1 * ldx + col) : 0.0;
-                    }
+                    for (int q = 1; q < KS; q++) xi[q] = (r + 4 * q + t < R) ? row_xindex<MODE>(desc, a.pos, r + 4 * q + t, u0, log2u) : -1;
+                    xi_next = (r + 4 * KS + t < R) ? row_xindex<MODE>(desc, a.pos, r + 4 * KS + t, u0, log2u) : -1;
+                    double av[KS], bv[KS][4];
 #pragma unroll
-                    for (int nt = 0; nt < 4; nt++) {
-                        dmma_m8n8k4(c[nt], a0, b0[nt]);
-                        dmma_m8n8k4(c[nt], a1, b1[nt]);
-                    }
+                    for (int q = 0; q < KS; q++) av[q] = (arow && xi[q] >= 0) ? __ldcs(vp + 4 * q * (long long)w) : 0.0;
+                    vp += 4 * KS * (long long)w;
+#pragma unroll
+                    for (int q = 0; q < KS; q++)
+#pragma unroll
+                        for (int nt = 0; nt < 4; nt++) {
+                            const int col = kb + nt * 8 + g;
+                            bv[q][nt] = (xi[q] >= 0 && col < k) ? __ldg(X + (long long)xi[q] * ldx + col) : 0.0;
+                        }
+#pragma unroll
+                    for (int q = 0; q < KS; q++)
+#pragma unroll
+                        for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], av[q], bv[q][nt]);
                 }
                 if (arow) {
                     double *yp = Y + (long long)(a.col + wb + g) * ldy;
