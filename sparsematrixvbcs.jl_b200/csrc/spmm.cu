@@ -147,8 +147,11 @@ __global__ void __launch_bounds__(256, (WB * KT <= 8 ? 3 : 2)) k_spmm_adj(const 
 // 1 index load, 4 X loads and 4 DMMAs -- about 5 instructions per stripe row instead of ~45 in the SIMT
 // kernel, which is what bounds that one (issue slots, not HBM or DFMA rate).  No shared memory.
 // (On Blackwell FP64 tensor math still goes through the mma.sync-class DMMA path; tcgen05 has no FP64 kind.)
+#ifndef VBC_DMMA_MINB
+#define VBC_DMMA_MINB 4
+#endif
 #ifndef VBC_DMMA_KS
-#define VBC_DMMA_KS 4
+#define VBC_DMMA_KS 2
 #endif
 __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, const double b)
 {
@@ -157,7 +160,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, cons
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) k_spmm_adj_dmma(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+__global__ void __launch_bounds__(256, VBC_DMMA_MINB) k_spmm_adj_dmma(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                         const double *__restrict__ val, const double *__restrict__ X, const long long ldx,
                                                         double *__restrict__ Y, const long long ldy, const int L, const int k,
                                                         const int u0, const int log2u, const double alpha, const double beta)
