@@ -353,15 +353,21 @@ static int finalize_t(vbc_mat *A, const void *h_pi_spl_v)
     A->u0 = uniform ? (int)u0 : 1;
     const int64_t nb = A->nidx;
     VBC_CUDA(cudaMalloc(&A->d_brow, sizeof(int) * (size_t)(nb > 0 ? nb : 1)));
-    int *d_bdesc = nullptr;
+    struct Scratch { // freed on every exit path
+        int *bdesc = nullptr, *rowbase = nullptr;
+        long long *rows = nullptr, *tmp = nullptr;
+        ~Scratch() { cudaFree(bdesc); cudaFree(rowbase); cudaFree(rows); cudaFree(tmp); }
+    } sc;
+    int *&d_bdesc = sc.bdesc;
+    long long *&d_rows = sc.rows;
     VBC_CUDA(cudaMalloc(&d_bdesc, sizeof(int) * (size_t)(nb > 0 ? nb : 1)));
-    long long *d_rows = nullptr;
     if (!uniform) VBC_CUDA(cudaMalloc(&d_rows, sizeof(long long) * (size_t)(L > 0 ? L : 1)));
     if (L > 0) { k_desc_blocks_2d<Ti><<<nblk(L, 128), 128, 0, st>>>(pos, idx, pi, L, d_bdesc, A->d_brow, d_rows); A->launches++; }
     VBC_CUDA(cudaGetLastError());
     if (uniform) {
         A->desc_mode = DESC_BLOCKS;
         A->d_desc = d_bdesc;
+        d_bdesc = nullptr; // ownership moved to the matrix
         A->ndesc = nb;
         k_meta<Ti, Ti><<<nblk(L + 1, 256), 256, 0, st>>>(ofs, pos, 1, phi, L, A->d_meta); A->launches++;
         VBC_CUDA(cudaGetLastError());
@@ -369,8 +375,9 @@ static int finalize_t(vbc_mat *A, const void *h_pi_spl_v)
     }
     // expanded rows
     A->desc_mode = DESC_ROWS;
-    int *d_rowbase = nullptr;
-    long long *d_tmp = nullptr, total = 0;
+    int *&d_rowbase = sc.rowbase;
+    long long *&d_tmp = sc.tmp;
+    long long total = 0;
     VBC_CUDA(cudaMalloc(&d_rowbase, sizeof(int) * (size_t)(L + 1)));
     VBC_CUDA(cudaMalloc(&d_tmp, sizeof(long long) * (size_t)scan_tmp_elems(L)));
     int rc = exclusive_scan<int>(d_rows, d_rowbase, L, 0, d_tmp, &total, st, &A->launches);
@@ -384,7 +391,6 @@ static int finalize_t(vbc_mat *A, const void *h_pi_spl_v)
         k_meta<Ti, int><<<nblk(L + 1, 256), 256, 0, st>>>(ofs, d_rowbase, 0, phi, L, A->d_meta); A->launches++;
         if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { set_error("finalize (expanded rows) kernels failed"); rc = VBC_ECUDA; }
     }
-    cudaFree(d_rowbase); cudaFree(d_tmp); cudaFree(d_rows); cudaFree(d_bdesc);
     return rc;
 }
 
