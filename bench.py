@@ -98,6 +98,15 @@ def cpu_reference_setup(A, pi, phi):
     return oracle, H
 
 
+def host_threads():
+    """All the host threads this process may use.  (torchrun exports OMP_NUM_THREADS=1, which would silently make the
+    reference arm single-threaded; the oracle's `num_threads` clause overrides it.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def time_cpu_reference(oracle, H, x, reps, warm, threads):
     y = np.empty(H.n, dtype=H.val.dtype)
     for _ in range(warm):
@@ -117,7 +126,7 @@ def run_reference(args, rank, world):
     from vbc_b200 import synth
     A, pi, phi = synth.config_c2(n=N_LOCAL)
     oracle, H = cpu_reference_setup(A, pi, phi)
-    threads = oracle.max_threads()
+    threads = host_threads()
     x = synth.vector(A.m, 1)
     ts, _ = time_cpu_reference(oracle, H, x, args.steps, args.warmup, threads)
     total = sum(ts)
@@ -338,7 +347,7 @@ def run_ours(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu_baseline:
             oracle, H = cpu_reference_setup(A, pi, phi)
-            threads = oracle.max_threads()
+            threads = host_threads()
             ts, y_cpu = time_cpu_reference(oracle, H, xg, 10, 2, threads)
             y_gpu = vb.mul_(np.empty(N_LOCAL), B.T, xg)
             err = float(np.max(np.abs(y_gpu - y_cpu) / np.maximum(np.abs(y_cpu), 1e-300)))
