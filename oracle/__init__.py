@@ -72,6 +72,12 @@ def max_threads() -> int:
     return int(lib().vbc_oracle_max_threads())
 
 
+def set_static_schedule(on: bool):
+    """False (default): the reference's one-stripe-per-grab self-scheduling; True: OpenMP static schedule
+    (not the reference's discipline -- only for stating what the same loops reach without the shared counter)."""
+    lib().vbc_oracle_set_static_schedule(ctypes.c_int(1 if on else 0))
+
+
 _TV = {np.dtype(np.float64): "f64", np.dtype(np.float32): "f32"}
 _TI = {np.dtype(np.int64): "i64", np.dtype(np.int32): "i32"}
 

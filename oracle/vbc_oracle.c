@@ -33,6 +33,20 @@
 #include <omp.h>
 #endif
 
+/* Loop schedule of the adjoint multiply.  0 (default) = schedule(dynamic, 1): one stripe per grab from a shared
+ * counter, the reference's discipline (`atomic_add!(l′, 1)` inside `@threads`, multiply_1DVBC.jl:169-177).
+ * 1 = schedule(static): NOT what the reference does; offered so a benchmark can also state what the same loops
+ * reach without the shared counter. */
+static int g_static_schedule = 0;
+void vbc_oracle_set_static_schedule(int on) { g_static_schedule = on ? 1 : 0; }
+static void vbc_oracle_apply_schedule(void)
+{
+#ifdef _OPENMP
+    if (g_static_schedule) omp_set_schedule(omp_sched_static, 0);
+    else omp_set_schedule(omp_sched_dynamic, 1);
+#endif
+}
+
 #define CAT3_(a, b, c) a##_##b##_##c
 #define CAT3(a, b, c) CAT3_(a, b, c)
 
