@@ -206,6 +206,9 @@ void vbc_destroy(vbc_mat *A)
     cudaFree(A->d_meta); cudaFree(A->d_desc); cudaFree(A->d_brow); cudaFree(A->d_order); cudaFree(A->d_px); cudaFree(A->d_py); cudaFree(A->d_x); cudaFree(A->d_y);
     destroy_trsv_plan(A->trsv);
     destroy_tindex(A->tindex);
+    if (A->copy_stream) cudaStreamDestroy(A->copy_stream);
+    for (int c = 0; c < 8; c++)
+        if (A->chunk_ev[c]) cudaEventDestroy(A->chunk_ev[c]);
     delete A;
 }
 
@@ -271,6 +274,42 @@ int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, d
     VBC_TRY(ensure_vec(&A->d_y, &A->y_cap, ylen, tv));
     if (xlen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_x, x, tv * (size_t)xlen, cudaMemcpyHostToDevice, A->stream));
     if (beta != 0.0 && ylen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_y, y, tv * (size_t)ylen, cudaMemcpyHostToDevice, A->stream));
+    // adjoint with a large y: launch the stripes in chunks and copy each finished y range back on a second stream
+    // while the next chunk computes (the D2H copy is as long as the whole kernel)
+    if (trans && !A->opt_parity && A->d_order == nullptr && A->nchunks == 0) {
+        A->nchunks = -1;
+        constexpr int NC = 8;
+        if (A->L >= 64 * NC && tv * (size_t)ylen >= (1u << 20)) {
+            bool ok = cudaStreamCreateWithFlags(&A->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+            for (int c = 0; c < NC && ok; c++) ok = cudaEventCreateWithFlags(&A->chunk_ev[c], cudaEventDisableTiming) == cudaSuccess;
+            for (int c = 0; c <= NC && ok; c++) {
+                A->chunk_l[c] = (int)(A->L * c / NC);
+                StripeMeta mt;
+                ok = cudaMemcpy(&mt, A->d_meta + A->chunk_l[c], sizeof(StripeMeta), cudaMemcpyDeviceToHost) == cudaSuccess;
+                A->chunk_col[c] = mt.col;
+            }
+            if (ok) A->nchunks = NC;
+            else cudaGetLastError();
+        }
+    }
+    if (trans && !A->opt_parity && A->nchunks > 0 && A->d_order == nullptr) {
+        int rc = VBC_OK;
+        for (int c = 0; c < A->nchunks && rc == VBC_OK; c++) {
+            A->range_l0 = A->chunk_l[c]; A->range_l1 = A->chunk_l[c + 1];
+            rc = launch_spmv(A, trans, alpha, A->d_x, beta, A->d_y);
+            if (rc == VBC_OK && cudaEventRecord(A->chunk_ev[c], A->stream) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = VBC_ECUDA; }
+        }
+        A->range_l0 = A->range_l1 = -1;
+        VBC_TRY(rc);
+        for (int c = 0; c < A->nchunks; c++) {
+            const int64_t c0 = A->chunk_col[c], c1 = A->chunk_col[c + 1];
+            VBC_CUDA(cudaStreamWaitEvent(A->copy_stream, A->chunk_ev[c], 0));
+            if (c1 > c0) VBC_CUDA(cudaMemcpyAsync((char *)y + tv * (size_t)c0, (char *)A->d_y + tv * (size_t)c0, tv * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, A->copy_stream));
+        }
+        VBC_CUDA(cudaStreamSynchronize(A->copy_stream));
+        VBC_CUDA(cudaStreamSynchronize(A->stream));
+        return VBC_OK;
+    }
     VBC_TRY(launch_spmv(A, trans, alpha, A->d_x, beta, A->d_y));
     if (ylen > 0) VBC_CUDA(cudaMemcpyAsync(y, A->d_y, tv * (size_t)ylen, cudaMemcpyDeviceToHost, A->stream));
     VBC_CUDA(cudaStreamSynchronize(A->stream));

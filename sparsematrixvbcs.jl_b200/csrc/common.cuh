@@ -84,6 +84,14 @@ struct vbc_mat {
     int opt_adj_group = 0, opt_fwd_group = 0, opt_grid_mult = 0, opt_parity = 0;
     int sm_count = 148;
     int64_t launches = 0;
+    // host-vector adjoint multiplies: the stripes are launched in chunks so the D2H copy of a finished y range
+    // overlaps the next chunk's kernel (second, non-blocking stream)
+    int range_l0 = -1, range_l1 = -1;      // stripe range of the next adjoint launch (-1: all)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_ev[8] = {};
+    int chunk_l[9] = {};                   // stripe boundaries of the chunks
+    int64_t chunk_col[9] = {};             // first column of each chunk
+    int nchunks = 0;                       // 0: not prepared, -1: chunking not applicable
     vbc_trsv_plan *trsv = nullptr; // level schedule of the triangular solve (vbc_trsv_analyse)
     vbc::TIndex *tindex = nullptr; // transposed unit index of the owner-computes forward multiply (built at first use)
     int opt_fwd_atomic = 0;        // 1: always use the atomic scatter kernel for the forward multiply

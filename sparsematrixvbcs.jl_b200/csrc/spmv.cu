@@ -541,10 +541,13 @@ static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y, const
     if (occ < 1) occ = 1;
     if (A->opt_grid_mult > 0) occ = A->opt_grid_mult;
     int64_t grid = (int64_t)A->sm_count * occ;
-    const int64_t need = (A->L * G + 255) / 256;
+    // a stripe range [l0, l1) is launched by offsetting meta: its entries are absolute (value offset, descriptor, column)
+    const bool ranged = !PEER && A->range_l0 >= 0 && A->d_order == nullptr;
+    const int64_t l0 = ranged ? A->range_l0 : 0, l1 = ranged ? A->range_l1 : A->L;
+    const int64_t need = ((l1 - l0) * G + 255) / 256;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    k_spmv_adj<Tv, G, MODE, PEER><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, y, dst, PEER ? nullptr : A->d_order, (int)A->L, A->u0, ilog2_exact(A->u0), alpha, beta);
+    k_spmv_adj<Tv, G, MODE, PEER><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta + l0, A->d_desc, (const Tv *)A->d_val, x, y, dst, PEER ? nullptr : A->d_order, (int)(l1 - l0), A->u0, ilog2_exact(A->u0), alpha, beta);
     A->launches++;
     VBC_CUDA(cudaGetLastError());
     return VBC_OK;
