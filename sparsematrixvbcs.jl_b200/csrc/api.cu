@@ -278,8 +278,9 @@ int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, d
     // while the next chunk computes (the D2H copy is as long as the whole kernel)
     if (trans && !A->opt_parity && A->d_order == nullptr && A->nchunks == 0) {
         A->nchunks = -1;
-        constexpr int NC = 8;
-        if (A->L >= 64 * NC && tv * (size_t)ylen >= (1u << 20)) {
+        int NC = 4;
+        if (const char *e = getenv("VBC_E2E_CHUNKS")) { NC = atoi(e); if (NC > 8) NC = 8; }
+        if (NC >= 2 && A->L >= 64 * NC && tv * (size_t)ylen >= (1u << 20)) {
             bool ok = cudaStreamCreateWithFlags(&A->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
             for (int c = 0; c < NC && ok; c++) ok = cudaEventCreateWithFlags(&A->chunk_ev[c], cudaEventDisableTiming) == cudaSuccess;
             for (int c = 0; c <= NC && ok; c++) {
