@@ -248,10 +248,17 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
             const int l = lbase + gid;
             const int lend = min(lbase + GPW, hi);
             const int colbase = ld_meta(meta + lbase).col, colend = ld_meta(meta + lend).col;
+            // sparsity-aware replication: when every column chunk of this run is read by this rank only, the
+            // results go straight to the own next-x buffer -- no staging, no flush (the common case for a banded operator)
+            bool self_only = false;
+            if (dst.mask != nullptr && colend > colbase) {
+                self_only = true;
+                for (int ch = colbase >> dst.chunk_shift; ch <= ((colend - 1) >> dst.chunk_shift); ch++) self_only = self_only && (__ldg(dst.mask + ch) == 1);
+            }
             if (l < hi) {
                 const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
                 const int w = b.col - a.col;
-                Tv *ys = stage - colbase; // the stripe bodies store y[a.col + ...]: lands in the staging run
+                Tv *ys = self_only ? reinterpret_cast<Tv *>(dst.p[0]) : stage - colbase; // the stripe bodies store y[a.col + ...]
                 if (w > 0) {
                     if ((w % VE) == 0 && (a.ofs % VE) == 0)
                         adj_dispatch_cpr<Tv, G, MODE, VE, false>(a, b, w, lane, gmask, desc, val, x, ys, none, u0, log2u, alpha, (Tv)0);
@@ -261,6 +268,7 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
                         adj_dispatch_cpr<Tv, G, MODE, 1, false>(a, b, w, lane, gmask, desc, val, x, ys, none, u0, log2u, alpha, (Tv)0);
                 }
             }
+            if (self_only) continue; // warp-uniform
             __syncwarp();
             const int ncols = colend - colbase;
             if (dst.mask == nullptr) { // full replication
