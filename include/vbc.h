@@ -146,6 +146,11 @@ void vbc_csc_destroy(vbc_csc *A);
  * (constructors_1DVBC.jl:1-2, test/runtests.jl:22-23); ChainPartitioners is not vendored, tie-breaking
  * parity is unpinned. */
 int vbc_dp_chunk(int64_t n, int W, const double *cost, int64_t *spl, int64_t *L_out);
+/* Greedy overlap chunker, a stand-in for ChainPartitioners' OverlapChunker(rho, w_max) (test/runtests.jl:21) under an
+ * ASSUMED definition: the next column joins the current stripe while it is narrower than w_max and the Jaccard
+ * similarity of its row pattern with the union of the stripe's patterns is >= rho.  colptr / rowval: 0-based int64
+ * CSC structure, rows ascending.  Writes the 1-based spl (at most n+1 entries) and its length. */
+int vbc_overlap_chunk(int64_t n, const int64_t *colptr, const int64_t *rowval, double rho, int w_max, int64_t *spl, int64_t *L_out);
 
 /* ---- execution control ---------------------------------------------------------------------*/
 int vbc_set_stream(vbc_mat *A, void *cuda_stream); /* a cudaStream_t; NULL = legacy default stream */

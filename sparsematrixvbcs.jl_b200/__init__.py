@@ -10,7 +10,7 @@ kernel (partition.py), synthetic workloads (synth.py) and the row-partitioned mu
 """
 from ._lib import ArgumentError, DimensionMismatch, VBCError, LIB_PATH  # noqa: F401
 from . import partition  # noqa: F401
-from .partition import (AlternatingPacker, DynamicTotalChunker, EquiChunker, RandomChunker, SparseMatrixCSC,  # noqa: F401
+from .partition import (AlternatingPacker, DynamicTotalChunker, EquiChunker, OverlapChunker, RandomChunker, SparseMatrixCSC,  # noqa: F401
                         SplitPartition, StrictChunker, pack_plaid, pack_stripe, permutedims)
 from .matrix import (Adjoint, CuSparseMatrixCSC, CuVBC1D, CuVBC2D, SparseMatrix1DVBC,  # noqa: F401
                      SparseMatrixVBC, TrSpMV_, adjoint, ldiv_lower_, mul_, size, trsv_analyse)
@@ -23,7 +23,7 @@ __all__ = [
     "SparseMatrix1DVBC", "SparseMatrixVBC", "CuVBC1D", "CuVBC2D", "CuSparseMatrixCSC", "Adjoint",
     "mul_", "TrSpMV_", "adjoint", "size", "ldiv_lower_", "trsv_analyse",
     "SparseMatrixCSC", "SplitPartition", "EquiChunker", "StrictChunker", "RandomChunker",
-    "AlternatingPacker", "DynamicTotalChunker", "permutedims", "pack_stripe", "pack_plaid",
+    "AlternatingPacker", "DynamicTotalChunker", "OverlapChunker", "permutedims", "pack_stripe", "pack_plaid",
     "DimensionMismatch", "ArgumentError", "VBCError", "synth", "costs",
     "model_SparseMatrix1DVBC_blocks", "model_SparseMatrix1DVBC_memory", "model_SparseMatrix1DVBC_TrSpMV_time",
     "model_SparseMatrixVBC_blocks", "model_SparseMatrixVBC_memory", "model_SparseMatrixVBC_TrSpMV_time", "total_value",

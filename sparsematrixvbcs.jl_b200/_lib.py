@@ -21,7 +21,7 @@ SYMBOLS = [
     "vbc_spmv", "vbc_spmm", "vbc_trsv_analyse", "vbc_trsv_levels", "vbc_trsv_lower",
     "vbc_csc_upload", "vbc_csc_trspmv", "vbc_csc_destroy",
     "vbc_set_stream", "vbc_csc_set_stream", "vbc_sync", "vbc_set_option", "vbc_get_option",
-    "vbc_launch_count", "vbc_dp_chunk",
+    "vbc_launch_count", "vbc_dp_chunk", "vbc_overlap_chunk",
     "vbc_peer_create", "vbc_peer_connect", "vbc_peer_connect_local", "vbc_peer_buffer", "vbc_peer_current",
     "vbc_peer_spmv_step", "vbc_peer_set_mask", "vbc_peer_set_fused_sync", "vbc_peer_set_neighbors", "vbc_peer_barrier", "vbc_peer_status", "vbc_peer_destroy",
 ]
@@ -97,6 +97,7 @@ def lib():
     L.vbc_get_option.argtypes = [c_vp, c_int, pi64]
     L.vbc_launch_count.argtypes = [c_vp, pi64]
     L.vbc_dp_chunk.argtypes = [c_i64, c_int, c_vp, c_vp, pi64]
+    L.vbc_overlap_chunk.argtypes = [c_i64, c_vp, c_vp, c_dbl, c_int, c_vp, pi64]
     L.vbc_peer_create.argtypes = [pp, c_int, c_i64, c_int, c_int, c_int, c_vp]
     L.vbc_peer_connect.argtypes = [c_vp, c_vp]
     L.vbc_peer_connect_local.argtypes = [c_vp, ctypes.POINTER(c_vp)]

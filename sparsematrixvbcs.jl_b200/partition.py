@@ -12,6 +12,7 @@ ChainPartitioners.jl (v1.1.6, un-vendored dependency; Manifest.toml:23-29) is NO
                         mdl, VertexCount(), w_max))`).  Restated from its definition: exact per-window
                         distinct-row (or weighted distinct-row-part) counts + the O(n W) recurrence
                         (libvbc's host function vbc_dp_chunk); tie-breaking parity unpinned.
+  OverlapChunker(rho, w_max)  greedy Jaccard-overlap grouping (test/runtests.jl:21) -- ASSUMED definition, unpinned
   AlternatingPacker(m1, m2, m3, ...)  the reference's order: m1 partitions the COLUMNS, m2 the ROWS
                         given the columns, m3 the columns again given the rows, ... (bin/test_table.jl:
                         89-111: `AlternatingPacker(DynamicTotalChunker(..1D..), EquiChunker(1))` is
@@ -112,6 +113,14 @@ class StrictChunker:
 class RandomChunker:
     w_max: int
     seed: int = 0
+
+
+@dataclass
+class OverlapChunker:
+    """`OverlapChunker(ρ, w_max)` (test/runtests.jl:21).  ASSUMED definition -- ChainPartitioners is not vendored:
+    greedy, the next column joins while Jaccard(pattern, union of the stripe's patterns) >= ρ and width < w_max."""
+    rho: float
+    w_max: int
 
 
 @dataclass
@@ -270,6 +279,16 @@ def pack_stripe(A: SparseMatrixCSC, method, other: SplitPartition = None) -> Spl
         return _random(A.n, method.w_max, method.seed, ti)
     if isinstance(method, DynamicTotalChunker):
         return _dynamic_total(A, method, other)
+    if isinstance(method, OverlapChunker):
+        import ctypes
+        from . import _lib
+        cp = np.ascontiguousarray(A.colptr.astype(np.int64) - 1)
+        rv = np.ascontiguousarray(A.rowval.astype(np.int64) - 1)
+        spl = np.empty(A.n + 1, dtype=np.int64)
+        L = ctypes.c_int64()
+        _lib.check(_lib.lib().vbc_overlap_chunk(A.n, cp.ctypes.data_as(ctypes.c_void_p), rv.ctypes.data_as(ctypes.c_void_p),
+                                                float(method.rho), int(method.w_max), spl.ctypes.data_as(ctypes.c_void_p), ctypes.byref(L)))
+        return SplitPartition(spl[: L.value + 1].astype(ti))
     raise TypeError(f"unsupported partitioner {method!r} (ChainPartitioners is not vendored; "
                     "pass a SplitPartition computed on the Julia side)")
 

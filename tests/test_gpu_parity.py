@@ -511,3 +511,22 @@ def test_gpu_time_model_autotuner_small():
     B1 = vb.SparseMatrix1DVBC[4](A, phi)
     assert costs.total_value(B1, costs.model_SparseMatrix1DVBC_blocks()) == B1.nidx
     assert costs.total_value(B1, costs.model_SparseMatrix1DVBC_memory(np.float64, np.int64)) == B1.format_bytes()[0] - 8 * 3
+
+
+@pytest.mark.parametrize("name", ["LPnetlib__lpi_itest6", "HB__west0132", "LPnetlib__lp_blend", "Pajek__GD99_c"])
+def test_runtests_jl_mirror(fixtures, name):
+    """test/runtests.jl:19-88 as written there: `B = SparseMatrix1DVBC{4}(A, method)` for its four 1D methods and
+    `SparseMatrixVBC{4, 4}(A, method)` for its two 2D packers, then `mul!(y_test, B, e_j, true, false) == mul!(y_ref, A, e_j, ...)`
+    for every unit vector, both orientations, exact equality."""
+    from test_oracle_golden import reference_methods_1d, reference_methods_2d
+    A = fixtures[name]
+    for method in reference_methods_1d():
+        B = vb.SparseMatrix1DVBC[4](A, method)
+        H = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, B.Phi.spl, 4)
+        assert_packed_equal(B, H)
+        onehot_check(A, B, H)
+    for method in reference_methods_2d():
+        B = vb.SparseMatrixVBC[4, 4](A, method)
+        H = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, B.Pi.spl, B.Phi.spl, 4, 4)
+        assert_packed_equal(B, H)
+        onehot_check(A, B, H)

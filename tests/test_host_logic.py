@@ -185,3 +185,21 @@ def test_window_distinct_counts_and_dynamic_total_chunker():
     pi4, phi4 = vb.pack_plaid(A, vb.AlternatingPacker(vb.EquiChunker(1), vb.EquiChunker(1), DynamicTotalChunker(m2, W),
                                                        DynamicTotalChunker(vb.partition.permutedims(m2), 4), DynamicTotalChunker(m2, W)))
     assert np.diff(pi4.spl).max() <= 4 and np.diff(phi4.spl).max() <= W and pi4.spl[-1] == A.m + 1 and phi4.spl[-1] == A.n + 1
+
+
+def test_overlap_chunker_assumed_definition():
+    # columns: a a' b b c   with a' = a plus one extra row (Jaccard 2/3), b identical twice, c empty
+    pats = [[0, 2], [0, 2, 5], [1, 3], [1, 3], []]
+    rows, cc = [], []
+    for j, p in enumerate(pats):
+        for r in p:
+            rows.append(r); cc.append(j)
+    A = vb.SparseMatrixCSC.from_scipy(sp.csc_matrix((np.ones(len(rows)), (rows, cc)), shape=(6, len(pats))))
+    assert vb.pack_stripe(A, vb.OverlapChunker(0.9, 4)).spl.tolist() == [1, 2, 3, 5, 6]   # only the identical pair merges
+    assert vb.pack_stripe(A, vb.OverlapChunker(0.6, 4)).spl.tolist() == [1, 3, 5, 6]      # a, a' merge at 2/3 >= 0.6
+    assert vb.pack_stripe(A, vb.OverlapChunker(0.0, 2)).spl.tolist() == [1, 3, 5, 6]      # width limit
+    assert vb.pack_stripe(A, vb.OverlapChunker(1.0, 8)).spl.tolist() == vb.pack_stripe(A, vb.StrictChunker(8)).spl.tolist()
+    M = sp.random(60, 200, 0.1, random_state=3, format="csc")
+    B = vb.SparseMatrixCSC.from_scipy(M)
+    spl = vb.pack_stripe(B, vb.OverlapChunker(0.3, 4)).spl
+    assert spl[0] == 1 and spl[-1] == 201 and np.diff(spl).min() >= 1 and np.diff(spl).max() <= 4

@@ -185,3 +185,31 @@ def test_memory_cost_models(fixtures):
     cost, extra = oracle.memory_cost(C)
     assert extra == 8 * C.K
     assert cost.sum() == 3 * 8 * C.L + 8 * len(C.idx) + 8 * len(C.val)
+
+
+def reference_methods_1d():
+    """The method list of test/runtests.jl:19-25 (W = 4)."""
+    from vbc_b200 import costs
+    return [vb.StrictChunker(4), vb.OverlapChunker(0.9, 4),
+            vb.DynamicTotalChunker(costs.model_SparseMatrix1DVBC_blocks(), 4),
+            vb.DynamicTotalChunker(costs.model_SparseMatrix1DVBC_memory(np.float64, np.int64), 4)]
+
+
+def reference_methods_2d():
+    """test/runtests.jl:56-59 (U = W = 4)."""
+    return [vb.AlternatingPacker(vb.StrictChunker(4), vb.StrictChunker(4)),
+            vb.AlternatingPacker(vb.OverlapChunker(0.9, 4), vb.OverlapChunker(0.9, 4))]
+
+
+@pytest.mark.parametrize("name", FIXTURE_NAMES)
+def test_runtests_jl_method_list_on_the_oracle(fixtures, name):
+    """test/runtests.jl:19-88 with its own partitioner list (stand-ins for the un-vendored ChainPartitioners; the
+    invariants are partition-agnostic, so they pin the pack + multiply, not the partitions)."""
+    A = fixtures[name]
+    for method in reference_methods_1d():
+        phi = vb.pack_stripe(A, method)
+        assert np.diff(phi.spl).max() <= 4
+        onehot_check(A, oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, 4))
+    for method in reference_methods_2d():
+        pi, phi = vb.pack_plaid(A, method)
+        onehot_check(A, oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, 4, 4))
