@@ -8,8 +8,8 @@ reference's `A = permutedims(sparse(mdopen(mtx).A))` (test_table.jl:27):
   2D methods   1D 2D, strict 2D, dynamic blocks 2D, dynamic memory 2D        (test_table.jl:88-127)
 columns: setup time (partition + pack, s), memory (bytes, the reference's format accounting), run time of
 `mul_(y, B.T, x, True, False)` (s, CUDA-graph minimum) and the time model's prediction (s); `y ≈ z` is asserted
-against scipy like test_table.jl:42/:84/:126.  OverlapChunker rows are absent (its definition lives in the
-un-vendored ChainPartitioners)."""
+against scipy like test_table.jl:42/:84/:126.  The partitioners are stand-ins restated from their definitions
+(ChainPartitioners is not vendored; OverlapChunker's definition is assumed), "dynamic time 2D" is left out."""
 import json
 import os
 import sys
@@ -53,7 +53,7 @@ def run_matrix(name, A, out):
     mdl_memory_2d = costs.model_SparseMatrixVBC_memory(np.float64, np.int64)
     DP = vb.DynamicTotalChunker
 
-    for key, method in (("strict", vb.StrictChunker(W_MAX)), ("min blocks", DP(mdl_blocks_1d, W_MAX)),
+    for key, method in (("strict", vb.StrictChunker(W_MAX)), ("overlap", vb.OverlapChunker(0.9, W_MAX)), ("min blocks", DP(mdl_blocks_1d, W_MAX)),
                         ("min memory", DP(mdl_memory_1d, W_MAX)), ("min time", DP(mdl_time_1d, W_MAX))):
         t0 = time.perf_counter()
         B = vb.SparseMatrix1DVBC[W_MAX](A, method)
@@ -67,6 +67,9 @@ def run_matrix(name, A, out):
     pd = vb.permutedims
     for key, method in (("1D 2D", vb.AlternatingPacker(DP(mdl_blocks_1d, W_MAX), vb.EquiChunker(1))),
                         ("strict 2D", vb.AlternatingPacker(vb.StrictChunker(W_MAX), vb.StrictChunker(W_MAX))),
+                        ("overlap 2D 0.9", vb.AlternatingPacker(vb.OverlapChunker(0.9, W_MAX), vb.OverlapChunker(0.9, W_MAX))),
+                        ("overlap 2D 0.8", vb.AlternatingPacker(vb.OverlapChunker(0.8, W_MAX), vb.OverlapChunker(0.8, W_MAX))),
+                        ("overlap 2D 0.7", vb.AlternatingPacker(vb.OverlapChunker(0.7, W_MAX), vb.OverlapChunker(0.7, W_MAX))),
                         ("dynamic blocks 2D", vb.AlternatingPacker(DP(mdl_blocks_1d, W_MAX), DP(pd(mdl_blocks_2d), W_MAX), DP(mdl_blocks_2d, W_MAX))),
                         ("dynamic memory 2D", vb.AlternatingPacker(vb.EquiChunker(1), vb.EquiChunker(1), DP(mdl_memory_2d, W_MAX),
                                                                    DP(pd(mdl_memory_2d), W_MAX), DP(mdl_memory_2d, W_MAX)))):
