@@ -166,7 +166,11 @@ def run_ours(args, rank, world, local_rank):
     dev = local_rank
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = os.environ.get("VBC_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
+        # keep NCCL's version banner off stdout (one JSON line only): it is printed at NCCL_DEBUG >= VERSION
+        if "VBC_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["VBC_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     u = w = 4
