@@ -244,19 +244,10 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
         const PeerDst none{};
         const int warp0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
         auto run_range = [&](const int lo, const int hi) {
-        int lbase = lo + warp0 * GPW;
-        if (lbase >= hi) return;
-        StripeMeta na, nb; // this group's next stripe, loaded one iteration ahead
-        if (lbase + gid < hi) { na = ld_meta(meta + lbase + gid); nb = ld_meta(meta + lbase + gid + 1); }
-        else { na = StripeMeta{0, 0, 0}; nb = na; }
-        for (; lbase < hi; lbase += nwarps * GPW) {
+        for (int lbase = lo + warp0 * GPW; lbase < hi; lbase += nwarps * GPW) {
             const int l = lbase + gid;
-            const StripeMeta a = na, b = nb;
-            const int ln = l + nwarps * GPW;
-            if (ln < hi) { na = ld_meta(meta + ln); nb = ld_meta(meta + ln + 1); }
-            // the run of columns this warp produces: first column of its first stripe .. end of its last valid stripe
-            const int nvalid = min(GPW, hi - lbase);
-            const int colbase = __shfl_sync(0xffffffffu, a.col, 0), colend = __shfl_sync(0xffffffffu, b.col, (nvalid - 1) * G);
+            const int lend = min(lbase + GPW, hi);
+            const int colbase = ld_meta(meta + lbase).col, colend = ld_meta(meta + lend).col;
             // sparsity-aware replication: when every column chunk of this run is read by this rank only, the
             // results go straight to the own next-x buffer -- no staging, no flush (the common case for a banded operator)
             bool self_only = false;
@@ -265,6 +256,7 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
                 for (int ch = colbase >> dst.chunk_shift; ch <= ((colend - 1) >> dst.chunk_shift); ch++) self_only = self_only && (__ldg(dst.mask + ch) == 1);
             }
             if (l < hi) {
+                const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
                 const int w = b.col - a.col;
                 Tv *ys = self_only ? reinterpret_cast<Tv *>(dst.p[0]) : stage - colbase; // the stripe bodies store y[a.col + ...]
                 if (w > 0) {
