@@ -158,6 +158,13 @@ def main():
             del X, Y
         B.close()
         del A
+    if want("c5"):
+        n5 = 4_000_000
+        A, pi, phi = synth.banded_blocks(n5 // 4, n5 // 4, 4, 4, [0, 1, -1, 2, -2, 57, -57, 58, -58, 3249], dtype=np.float32, ti=np.int32)
+        B = pack_time("C5 slab 2D f32/i32 4x4 10 blk/stripe n=4M", lambda: vb.SparseMatrixVBC[4, 4](A, pi, phi))
+        report("C5 slab 2D f32/i32 4x4 10 blk/stripe n=4M", B, A, groups=(4, 8, 16, 32))
+        B.close()
+        del A
     if want("c1"):
         A, phi = synth.config_c1()
         B = pack_time("C1 1D f64 w=8 n=10k (L2-resident)", lambda: vb.SparseMatrix1DVBC[8](A, phi))
