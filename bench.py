@@ -391,8 +391,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-mode", type=int, default=0, choices=[0, 1, 2],
-                    help="peer/halo flag exchange: 0 = one flag kernel (signal+wait) after the multiply; 1 = inside the multiply "
-                         "kernel; 2 = split launches [interior stripes][wait][other stripes][signal] (halo only)")
+                    help="peer/halo flag exchange: 0 = one flag kernel (signal+wait) after the multiply; 1 = (removed: same as 0); "
+                         "2 = split launches [interior stripes][wait][other stripes][signal] (halo only)")
     ap.add_argument("--exchange", default="halo", choices=["halo", "peer", "nccl"],
                     help="N > 1, how x_{t+1} reaches the ranks: 'halo' (default) = exchange fused into the multiply kernel through "
                          "NVLink peer stores, each y segment sent to exactly the ranks whose stripes read it; 'peer' = same kernel, "

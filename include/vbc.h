@@ -206,7 +206,8 @@ int vbc_peer_set_neighbors(vbc_peer *P, unsigned mask);
 /* Overlapping the flag exchange with the multiply (optional).  enable = 2: barrier = 3 steps become four
  * launches -- [stripes i0..i1) | wait for the peers' previous step | remaining stripes | signal -- so the
  * wait (and the drift between ranks) hides behind the first launch; the default (enable = 0) is
- * [all stripes | signal + wait].  enable = 1: vbc_peer_spmv_step(..., barrier = 3) launches ONE
+ * [all stripes | signal + wait].  enable = 1 (REMOVED, now the same as 0; it measured slower and quadrupled the
+ * kernel's code size): vbc_peer_spmv_step(..., barrier = 3) launched ONE
  * kernel per iteration: it first runs the stripes [i0, i1) -- which must gather only from this rank's
  * own slice and (under the mask) feed only this rank -- then waits for the peers' flags of the
  * previous iteration, runs the remaining stripes, and the last CTA to finish publishes this rank's

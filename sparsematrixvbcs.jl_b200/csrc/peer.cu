@@ -209,14 +209,7 @@ int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, 
     if (P->d_mask && A->n > 0 && ((A->n - 1) >> P->chunk_shift) >= P->mask_len)
         VBC_FAIL(VBC_EDIM, "peer mask covers %lld chunks, the y slice needs %lld", (long long)P->mask_len, (long long)(((A->n - 1) >> P->chunk_shift) + 1));
     // the mask is indexed by (column in the y slice) >> shift; the kernel indexes by slab column, so no offset is needed
-    if (P->fused_sync == 1 && barrier == 3) {
-        PeerSyncArgs sa;
-        sa.nranks = P->nranks; sa.me = P->rank;
-        for (int r = 0; r < VBC_MAX_PEERS; r++) sa.flags[r] = r < P->nranks ? (unsigned long long *)P->bufs[r][2] : nullptr;
-        sa.d_epoch = P->d_epoch; sa.d_done = P->d_done; sa.timed_out = P->d_timeout;
-        sa.i0 = P->i0; sa.i1 = P->i1;
-        VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, &sa, nullptr));
-    } else if (P->fused_sync == 2 && barrier == 3 && P->i1 > P->i0) {
+    if (P->fused_sync == 2 && barrier == 3 && P->i1 > P->i0) {
         const int L = (int)A->L;
         const int ra[4] = {P->i0, P->i1, 0, 0}, rc[4] = {0, P->i0, P->i1, L};
         VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, nullptr, ra));
@@ -251,6 +244,7 @@ int vbc_peer_set_fused_sync(vbc_peer *P, int enable, int64_t i0, int64_t i1)
 {
     if (!P) VBC_FAIL(VBC_EARG, "NULL argument");
     if (i0 < 0 || i1 < i0 || enable < 0 || enable > 2) VBC_FAIL(VBC_EARG, "bad interior range / mode");
+    if (enable == 1) enable = 0; // the in-kernel flag exchange lost to the separate flag kernel and quadrupled the kernel's code size; removed
     DeviceGuard guard(P->device);
     if (enable && !P->d_done) {
         VBC_CUDA(cudaMalloc(&P->d_done, sizeof(unsigned)));

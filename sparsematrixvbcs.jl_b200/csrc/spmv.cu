@@ -287,46 +287,8 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
             __syncwarp();
         }
         };
-        if (dst.sync_n == 0) {
-            run_range(dst.ra0, min(dst.ra1, L));
-            run_range(dst.rb0, min(dst.rb1, L));
-        } else {
-            // (A) stripes that gather only from this rank's own slice and feed only this rank: no peer involved
-            run_range(dst.i0, dst.i1);
-            // (B) every other stripe reads x entries written by peers in their previous step: wait for their flags
-            if (lane32 == 0) {
-                const unsigned long long want = *dst.d_epoch;
-                for (int r = 0; r < dst.sync_n; r++) {
-                    if (r == dst.me) continue;
-                    if (ld_acquire_sys_u64(dst.flags[dst.me] + r) < want) {
-                        unsigned long long t0, t1;
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                        while (ld_acquire_sys_u64(dst.flags[dst.me] + r) < want) {
-                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                            if (t1 - t0 > 4000000000ull) { atomicExch(dst.timed_out, 1); break; }
-                            __nanosleep(64);
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            // (C) the rest
-            run_range(0, dst.i0);
-            run_range(dst.i1, L);
-            // (D) the last CTA to finish publishes the new epoch to every rank
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence_system();
-                if (atomicAdd(dst.d_done, 1u) == gridDim.x - 1) {
-                    *dst.d_done = 0;
-                    const unsigned long long e = *dst.d_epoch + 1;
-                    *dst.d_epoch = e;
-                    __threadfence_system();
-                    for (int r = 0; r < dst.sync_n; r++)
-                        if (r != dst.me) st_release_sys_u64(dst.flags[r] + dst.me, e);
-                }
-            }
-        }
+        // one copy of the stripe bodies: the (at most two) ranges of this launch are walked by the same loop
+        for (int part = 0; part < 2; part++) run_range(part ? dst.rb0 : dst.ra0, min(part ? dst.rb1 : dst.ra1, L));
         return;
     }
     int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G);
