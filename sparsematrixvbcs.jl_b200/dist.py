@@ -125,6 +125,68 @@ def longest_true_run(flags):
     return int(starts[k]), int(ends[k])
 
 
+def stripe_memory_costs(A: SparseMatrixCSC, phi: SplitPartition, pi: SplitPartition = None, tv_size=8, ti_size=8):
+    """Exact per-stripe cost of the packed format under the reference's memory model (costs.jl:10 1D, :140 2D), from
+    the CSC structure alone (before any packing): 3|Ti| + units*|Ti| + stored_rows*w*|Tv|, with units = distinct rows
+    (1D) or distinct row parts (2D) of the stripe and stored_rows = the rows they cover."""
+    from .partition import window_weight_sums
+    spl = phi.spl.astype(np.int64) - 1
+    widths = np.diff(spl)
+    W = int(widths.max()) if len(widths) else 1
+    if pi is None:
+        D = window_weight_sums(A, W)
+        units = rows = D[spl[1:], np.maximum(widths, 1) - 1, 0]
+    else:
+        heights = np.diff(pi.spl).astype(np.float64)
+        D = window_weight_sums(A, W, pi, np.stack([np.ones(len(heights)), heights]))
+        units = D[spl[1:], np.maximum(widths, 1) - 1, 0]
+        rows = D[spl[1:], np.maximum(widths, 1) - 1, 1]
+    units = np.where(widths > 0, units, 0.0)
+    rows = np.where(widths > 0, rows, 0.0)
+    return (3 * ti_size + units * ti_size + rows * widths * tv_size).astype(np.int64)
+
+
+def distribute(A: SparseMatrixCSC, phi: SplitPartition, pi: SplitPartition = None, world=1, rank=0):
+    """Row-block partition of the adjoint multiply of a SQUARE operator over `world` ranks, balanced by the
+    reference's memory model: -> (local slab CSC with rows in padded coordinates, local Π (or None), local Φ,
+    PaddedLayout, stripe bounds).  Rank r owns the stripes [b[r], b[r+1]) and the matching slice of the vectors.
+    For 2D the rank boundaries must fall on row-part boundaries of Π (they do when Π and Φ share those split points)."""
+    if A.m != A.n:
+        raise ValueError("the iterated row-partitioned multiply needs a square operator")
+    ti = A.colptr.dtype.type
+    cost = stripe_memory_costs(A, phi, pi, A.nzval.dtype.itemsize, A.colptr.dtype.itemsize)
+    b = split_by_cost(cost, world)
+    spl = phi.spl.astype(np.int64) - 1
+    col_bounds = spl[b]
+    layout = PaddedLayout(col_bounds)
+    if pi is not None:
+        ps = pi.spl.astype(np.int64) - 1
+        if not np.all(np.isin(col_bounds, ps)):
+            raise ValueError("rank boundaries do not fall on row-part boundaries of Π")
+    c0, c1 = int(col_bounds[rank]), int(col_bounds[rank + 1])
+    cp = A.colptr.astype(np.int64) - 1
+    lo, hi = cp[c0], cp[c1]
+    slab = SparseMatrixCSC(A.m, c1 - c0, (cp[c0:c1 + 1] - lo + 1).astype(ti), A.rowval[lo:hi], A.nzval[lo:hi])
+    slab = remap_rows_to_padded(slab, layout)
+    phi_loc = SplitPartition((spl[b[rank]:b[rank + 1] + 1] - c0 + 1).astype(ti))
+    pi_loc = None
+    if pi is not None:  # Π in padded coordinates: every rank slice keeps its own parts, the padding becomes extra (empty) parts
+        pieces = []
+        for r in range(world):
+            inside = ps[(ps >= col_bounds[r]) & (ps <= col_bounds[r + 1])] - col_bounds[r] + r * layout.S
+            pieces.append(inside)
+        flat = np.unique(np.concatenate(pieces + [np.array([layout.padded_len])]))
+        # split padding gaps so that no part is taller than the tallest real part
+        umax = int(np.diff(ps).max())
+        out = [flat[0]]
+        for v in flat[1:]:
+            while v - out[-1] > umax:
+                out.append(out[-1] + umax)
+            out.append(v)
+        pi_loc = SplitPartition((np.array(out, dtype=np.int64) + 1).astype(ti))
+    return slab, pi_loc, phi_loc, layout, b
+
+
 class RowPartitionedOperator:
     """One rank's share of the iterated adjoint multiply x <- alpha * A' x with the x exchange done by
     a torch.distributed all-gather (NCCL on GPUs; gloo in the CPU tests).
