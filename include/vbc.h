@@ -113,6 +113,14 @@ int vbc_memory_cost(const vbc_mat *A, int64_t *cost, int64_t *row_term);
 int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, double beta,
              void *y, int64_t ylen, int on_device);
 
+/* Same multiply with vectors of a wider type than the stored values: vec_vt is the type of x AND y.
+ * The reference converts values and x to eltype(y) before multiplying (multiply_1DVBC.jl:23/27/34, :102;
+ * multiply_VBC.jl:40-45, :131), so a Float32 matrix with Float64 vectors accumulates in Float64.
+ * vec_vt == the matrix' value type: identical to vbc_spmv.  Float32 matrix + VBC_F64 vectors: dedicated
+ * kernels (csrc/mixed.cu).  Float64 matrix + VBC_F32 vectors: VBC_EARG (narrowing is not offered). */
+int vbc_spmv_mixed(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, double beta,
+                   void *y, int64_t ylen, int vec_vt, int on_device);
+
 /* k right-hand sides: Y <- alpha * op(A) * X + beta * Y, X: cols(op(A)) x k, Y: rows(op(A)) x k.
  * Stands in for `*(A, B::DenseMatrix)` (multiply_1DVBC.jl:184-185, multiply_VBC.jl:196-197), which the
  * reference declares but cannot execute (no matrix `mul!` method) -- new functionality,

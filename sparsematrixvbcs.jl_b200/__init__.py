@@ -14,7 +14,7 @@ from .partition import (AlternatingPacker, DynamicTotalChunker, EquiChunker, Ove
                         SplitPartition, StrictChunker, pack_plaid, pack_stripe, permutedims)
 from .matrix import (Adjoint, CuSparseMatrixCSC, CuVBC1D, CuVBC2D, SparseMatrix1DVBC,  # noqa: F401
                      SparseMatrixVBC, TrSpMV_, adjoint, ldiv_lower_, mul_, size, trsv_analyse)
-from . import costs, synth  # noqa: F401
+from . import costs, solvers, synth  # noqa: F401
 from .costs import (model_SparseMatrix1DVBC_blocks, model_SparseMatrix1DVBC_memory,  # noqa: F401
                     model_SparseMatrix1DVBC_TrSpMV_time, model_SparseMatrixVBC_blocks,
                     model_SparseMatrixVBC_memory, model_SparseMatrixVBC_TrSpMV_time, total_value)
@@ -24,7 +24,7 @@ __all__ = [
     "mul_", "TrSpMV_", "adjoint", "size", "ldiv_lower_", "trsv_analyse",
     "SparseMatrixCSC", "SplitPartition", "EquiChunker", "StrictChunker", "RandomChunker",
     "AlternatingPacker", "DynamicTotalChunker", "OverlapChunker", "permutedims", "pack_stripe", "pack_plaid",
-    "DimensionMismatch", "ArgumentError", "VBCError", "synth", "costs",
+    "DimensionMismatch", "ArgumentError", "VBCError", "synth", "costs", "solvers",
     "model_SparseMatrix1DVBC_blocks", "model_SparseMatrix1DVBC_memory", "model_SparseMatrix1DVBC_TrSpMV_time",
     "model_SparseMatrixVBC_blocks", "model_SparseMatrixVBC_memory", "model_SparseMatrixVBC_TrSpMV_time", "total_value",
 ]

@@ -18,7 +18,7 @@ SYMBOLS = [
     "vbc_last_error", "vbc_version", "vbc_device_count",
     "vbc_pack_csc", "vbc_pack_csc_dev", "vbc_upload", "vbc_destroy",
     "vbc_shape", "vbc_sizes", "vbc_download", "vbc_format_bytes", "vbc_memory_cost",
-    "vbc_spmv", "vbc_spmm", "vbc_trsv_analyse", "vbc_trsv_levels", "vbc_trsv_lower",
+    "vbc_spmv", "vbc_spmv_mixed", "vbc_spmm", "vbc_trsv_analyse", "vbc_trsv_levels", "vbc_trsv_lower",
     "vbc_csc_upload", "vbc_csc_trspmv", "vbc_csc_destroy",
     "vbc_set_stream", "vbc_csc_set_stream", "vbc_sync", "vbc_set_option", "vbc_get_option",
     "vbc_launch_count", "vbc_dp_chunk", "vbc_overlap_chunk",
@@ -82,6 +82,7 @@ def lib():
     L.vbc_format_bytes.argtypes = [c_vp, pi64]
     L.vbc_memory_cost.argtypes = [c_vp, c_vp, pi64]
     L.vbc_spmv.argtypes = [c_vp, c_int, c_dbl, c_vp, c_i64, c_dbl, c_vp, c_i64, c_int]
+    L.vbc_spmv_mixed.argtypes = [c_vp, c_int, c_dbl, c_vp, c_i64, c_dbl, c_vp, c_i64, c_int, c_int]
     L.vbc_spmm.argtypes = [c_vp, c_int, c_i64, c_dbl, c_vp, c_i64, c_dbl, c_vp, c_i64, c_int, c_int]
     L.vbc_trsv_analyse.argtypes = [c_vp, pint]
     L.vbc_trsv_levels.argtypes = [c_vp, pint]

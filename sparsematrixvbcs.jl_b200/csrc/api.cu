@@ -317,6 +317,37 @@ int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, d
     return VBC_OK;
 }
 
+int vbc_spmv_mixed(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, double beta, void *y, int64_t ylen, int vec_vt, int on_device)
+{
+    if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
+    if (vec_vt != VBC_F32 && vec_vt != VBC_F64) VBC_FAIL(VBC_EARG, "vector type must be VBC_F32 or VBC_F64");
+    if (vec_vt == A->vt) return vbc_spmv(A, trans, alpha, x, xlen, beta, y, ylen, on_device);
+    if (vec_vt == VBC_F32) VBC_FAIL(VBC_EARG, "ArgumentError: Float64 values with Float32 vectors (narrowing) is not offered");
+    const int64_t need_x = trans ? A->m : A->n, need_y = trans ? A->n : A->m;
+    if (xlen != need_x || ylen != need_y)
+        VBC_FAIL(VBC_EDIM, "DimensionMismatch: op(A) is %lld x %lld, x has %lld, y has %lld", (long long)need_y, (long long)need_x, (long long)xlen, (long long)ylen);
+    if ((!x && xlen > 0) || (!y && ylen > 0)) VBC_FAIL(VBC_EARG, "NULL vector");
+    DeviceGuard guard(A->device);
+    if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", A->device);
+    if (on_device) return launch_spmv_mixed(A, trans, alpha, x, beta, y);
+    const size_t tu = vt_size(vec_vt);
+    void *dx = nullptr, *dy = nullptr; // wider than the handle's staging vectors: call-local buffers
+    int rc = VBC_OK;
+    do {
+        if (cudaMalloc(&dx, tu * (size_t)(xlen > 0 ? xlen : 1)) != cudaSuccess || cudaMalloc(&dy, tu * (size_t)(ylen > 0 ? ylen : 1)) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of the staging vectors failed"); rc = VBC_ENOMEM; break; }
+        cudaError_t e = cudaSuccess;
+        if (xlen > 0) e = cudaMemcpyAsync(dx, x, tu * (size_t)xlen, cudaMemcpyHostToDevice, A->stream);
+        if (e == cudaSuccess && ylen > 0 && beta != 0.0) e = cudaMemcpyAsync(dy, y, tu * (size_t)ylen, cudaMemcpyHostToDevice, A->stream);
+        if (e != cudaSuccess) { set_error("host-to-device copy failed: %s", cudaGetErrorString(e)); rc = VBC_ECUDA; break; }
+        if ((rc = launch_spmv_mixed(A, trans, alpha, dx, beta, dy)) != VBC_OK) break;
+        if (ylen > 0) e = cudaMemcpyAsync(y, dy, tu * (size_t)ylen, cudaMemcpyDeviceToHost, A->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(A->stream);
+        if (e != cudaSuccess) { set_error("device-to-host copy failed: %s", cudaGetErrorString(e)); rc = VBC_ECUDA; }
+    } while (0);
+    cudaFree(dx); cudaFree(dy);
+    return rc;
+}
+
 int vbc_csc_upload(vbc_csc **out, int vt, int it, int64_t m, int64_t n, const void *colptr, const void *rowval, const void *nzval, int device)
 {
     if (!out) VBC_FAIL(VBC_EARG, "out is NULL");

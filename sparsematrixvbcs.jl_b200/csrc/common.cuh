@@ -138,6 +138,8 @@ struct PeerSyncArgs { // in-kernel flag exchange of the fused multiply + all-gat
 };
 int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs, const unsigned char *d_mask, int chunk_shift,
                          const PeerSyncArgs *sync, const int *ranges /* {a0,a1,b0,b1} or null = all */);
+// mixed.cu
+int launch_spmv_mixed(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y);
 // fwdt.cu
 int ensure_tindex(vbc_mat *A);
 int launch_fwdt(vbc_mat *A, double alpha, const void *x, double beta, void *y);

@@ -138,6 +138,18 @@ function _cuvbc_mul!(y::StridedVector{Tv}, A::CuVBC{U, W, Tv}, x::StridedVector{
     return y
 end
 
+# eltype(y) wider than the stored values: the reference converts values and x to eltype(y) before multiplying
+# (multiply_1DVBC.jl:23/27/34, :102) -> Float64 accumulation over a Float32 matrix (csrc/mixed.cu)
+function _cuvbc_mul!(y::StridedVector{Float64}, A::CuVBC{U, W, Float32}, x::StridedVector{Tx}, α::Number, β::Number, trans::Bool) where {U, W, Tx <: Union{Float32, Float64}}
+    xw = Tx === Float64 ? x : convert(Vector{Float64}, x)
+    GC.@preserve xw y begin
+        vbc_check(ccall((:vbc_spmv_mixed, libvbc), Cint,
+            (Ptr{Cvoid}, Cint, Cdouble, Ptr{Cvoid}, Int64, Cdouble, Ptr{Cvoid}, Int64, Cint, Cint),
+            A.handle, trans, Float64(α), xw, length(xw), Float64(β), y, length(y), 1 #= VBC_F64 =#, 0))
+    end
+    return y
+end
+
 LinearAlgebra.mul!(y::StridedVector, A::CuVBC, x::StridedVector, α::Number, β::Number) =
     _cuvbc_mul!(y, A, x, α, β, false)
 LinearAlgebra.mul!(y::StridedVector, adjA::Union{Adjoint{<:Any, <:CuVBC}, Transpose{<:Any, <:CuVBC}}, x::StridedVector, α::Number, β::Number) =

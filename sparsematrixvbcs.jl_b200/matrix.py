@@ -43,6 +43,13 @@ def _is_torch(t):
     return type(t).__module__.startswith("torch")
 
 
+def _is_f64(v):
+    if _is_torch(v):
+        import torch
+        return v.dtype == torch.float64
+    return np.asarray(v).dtype == np.dtype(np.float64)
+
+
 def _vec_args(handle_dtype, v, name):
     """-> (pointer, length, on_device, keepalive)"""
     if _is_torch(v):
@@ -375,6 +382,20 @@ def mul_(y, A, x, alpha=True, beta=False):
         raise TypeError("mul_ expects a SparseMatrix1DVBC / SparseMatrixVBC or its adjoint")
     if getattr(x, "ndim", 1) == 2:
         return _mul_panel(y, B, trans, x, alpha, beta)
+    if B.Tv == np.dtype(np.float32) and _is_f64(y):
+        # eltype(y) wider than Tv: values and x are converted to eltype(y) before multiplying
+        # (multiply_1DVBC.jl:23/27, :102) -- Float64 accumulation over the Float32 matrix
+        f64 = np.dtype(np.float64)
+        if not _is_f64(x):
+            x = x.double() if _is_torch(x) else np.asarray(x, dtype=f64)
+        xp, xlen, xdev, _kx = _vec_args(f64, x, "x")
+        yp, ylen, ydev, _ky = _vec_args(f64, y, "y")
+        if xdev != ydev:
+            raise TypeError("x and y must both be host arrays or both be device tensors")
+        if xdev:
+            B._use_torch_stream()
+        check(_lib.lib().vbc_spmv_mixed(B._h, 1 if trans else 0, float(alpha), xp, xlen, float(beta), yp, ylen, _lib.VBC_F64, xdev))
+        return y
     xp, xlen, xdev, _kx = _vec_args(B.Tv, x, "x")
     yp, ylen, ydev, _ky = _vec_args(B.Tv, y, "y")
     if xdev != ydev:

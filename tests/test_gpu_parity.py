@@ -530,3 +530,90 @@ def test_runtests_jl_mirror(fixtures, name):
         H = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, B.Pi.spl, B.Phi.spl, 4, 4)
         assert_packed_equal(B, H)
         onehot_check(A, B, H)
+
+
+def test_float32_matrix_with_float64_vectors_accumulates_in_float64():
+    """eltype(y) decides the arithmetic: values and x are converted to eltype(y) before multiplying
+    (multiply_1DVBC.jl:23/27/34, :102; multiply_VBC.jl:40-45, :131).  A Float32 matrix applied to Float64
+    vectors must therefore agree with the Float64 product of the (exactly representable) Float32 values to
+    Float64 accuracy -- a Float32 accumulation would miss this bound by seven orders of magnitude."""
+    import torch
+    rng = np.random.default_rng(21)
+    for (m, n, u, w) in ((57, 41, 4, 4), (40, 37, 3, 5), (64, 64, 1, 8), (30, 50, 8, 2)):
+        A = sprand(m, n, 0.3, rng).astype(np.float32)
+        S = A.to_scipy().astype(np.float64)
+        absS = abs(S)
+        phi = vb.pack_stripe(A, vb.EquiChunker(w))
+        pi = vb.pack_stripe(A.transpose(), vb.EquiChunker(u))
+        pir, phir = vb.pack_plaid(A, vb.AlternatingPacker(vb.RandomChunker(w, seed=m), vb.RandomChunker(u, seed=n)))
+        mats = [vb.SparseMatrix1DVBC[w](A, phi), vb.SparseMatrixVBC[u, w](A, pi, phi), vb.SparseMatrixVBC[max(u, w), max(u, w)](A, pir, phir)]
+        for B in mats:
+            assert B.Tv == np.dtype(np.float32)
+            for trans in (False, True):
+                xlen, ylen = (m, n) if trans else (n, m)
+                op, Sop, aSop = (B.T, S.T, absS.T) if trans else (B, S, absS)
+                x = rng.random(xlen)
+                y0 = rng.random(ylen)
+                bound = aSop @ np.abs(x)
+                y = vb.mul_(np.full(ylen, np.nan), op, x, True, False)
+                assert y.dtype == np.float64
+                assert np.all(np.abs(y - Sop @ x) <= 1e-12 * bound + 1e-300)
+                # BLAS alpha / beta on the same path
+                y = vb.mul_(y0.copy(), op, x, 2.0, -0.25)
+                assert np.all(np.abs(y - (2.0 * (Sop @ x) - 0.25 * y0)) <= 1e-12 * (2 * bound + np.abs(y0)) + 1e-300)
+                # a Float32 x is widened like the values are
+                x32 = x.astype(np.float32)
+                y = vb.mul_(np.empty(ylen), op, x32)
+                assert np.all(np.abs(y - Sop @ x32.astype(np.float64)) <= 1e-12 * bound + 1e-300)
+                # device tensors
+                xd = torch.from_numpy(x).cuda()
+                yd = torch.full((ylen,), float("nan"), dtype=torch.float64, device="cuda")
+                vb.mul_(yd, op, xd)
+                torch.cuda.synchronize()
+                assert np.all(np.abs(yd.cpu().numpy() - Sop @ x) <= 1e-12 * bound + 1e-300)
+            # same-type call on the same handle still runs the Float32 kernels
+            x = rng.random(n).astype(np.float32)
+            y = vb.mul_(np.empty(m, dtype=np.float32), B, x)
+            assert np.all(np.abs(y - S @ x.astype(np.float64)) <= 4e-5 * (absS @ np.abs(x.astype(np.float64))) + 1e-30)
+            with pytest.raises(vb.DimensionMismatch):
+                vb.mul_(np.empty(m + 1), B, rng.random(n))
+    # narrowing (Float64 values, Float32 vectors) is refused at the ABI
+    A64 = sprand(9, 9, 0.5, rng)
+    B64 = vb.SparseMatrix1DVBC[4](A64, vb.EquiChunker(4))
+    x32, y32 = np.ones(9, dtype=np.float32), np.empty(9, dtype=np.float32)
+    rc = _lib.lib().vbc_spmv_mixed(B64._h, 0, 1.0, x32.ctypes.data, 9, 0.0, y32.ctypes.data, 9, _lib.VBC_F32, 0)
+    assert rc == _lib.VBC_EARG
+
+
+def _spd_blocked(n, rng):
+    import scipy.sparse as sp
+    R = sp.random(n, n, density=6.0 / n, random_state=np.random.RandomState(int(rng.integers(1 << 30))), format="csr")
+    band = sp.diags([rng.random(n - 1), rng.random(n - 4)], [1, 4], format="csr")
+    S = R + band
+    S = S + S.T
+    d = np.asarray(abs(S).sum(axis=1)).ravel() + 1.0
+    d[7] = 5.0 * d.max()  # one dominant entry: a clear spectral gap for the power iteration
+    return (S + sp.diags(d)).tocsc()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_device_resident_cg_and_power_iteration(graph):
+    """the adjoint multiply inside device-resident iterations (eager and CUDA-graph replay)."""
+    import scipy.sparse.linalg as spla
+    import torch
+    from vbc_b200 import solvers
+    rng = np.random.default_rng(33)
+    n = 3000
+    S = _spd_blocked(n, rng)
+    A = vb.SparseMatrixCSC.from_scipy(S)
+    for B in (vb.SparseMatrixVBC[4, 4](A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(4))), vb.SparseMatrix1DVBC[8](A, vb.EquiChunker(8))):
+        b = rng.random(n)
+        x, its, res = solvers.cg(B.T, b, iters=500, rtol=1e-12, check_every=5, graph=graph)
+        torch.cuda.synchronize()
+        assert res <= 1e-12 and its < 500
+        xs = spla.spsolve(S.T.tocsc(), b)
+        assert np.allclose(x.cpu().numpy(), xs, rtol=1e-9, atol=1e-12)
+        lam, v, its = solvers.power_iteration(B.T, iters=400, tol=1e-13, check_every=20, graph=graph)
+        top = spla.eigsh(S, k=1, which="LA", return_eigenvectors=False)[0]
+        assert abs(lam - top) <= 1e-6 * top
+        assert abs(float(torch.linalg.vector_norm(v)) - 1.0) < 1e-12
