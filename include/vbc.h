@@ -54,7 +54,10 @@ enum vbc_option {
     VBC_OPT_FWD_MODE = 5,    /* forward multiply: 0 = auto (owner-computes through a transposed unit index, built at first
                                   use, for uniform 2D blocks; atomic scatter kernel otherwise), 1 = always the atomic
                                   scatter kernel, 2 = the transposed index whenever the layout allows it              */
-    VBC_OPT_SPMM_SIMT = 6    /* Float64 adjoint SpMM: 0 = FP64 tensor (DMMA m8n8k4) tiles, 1 = the SIMT (DFMA) kernel      */
+    VBC_OPT_SPMM_SIMT = 6    /* Float64 adjoint SpMM: 0 = auto (FP64 tensor DMMA m8n8k4 tiles), 1 = the SIMT (DFMA) kernel,
+                              * 2 = DMMA with scalar X loads (what 0 selects), 3 = DMMA with 256-bit X-row loads, 4 = DMMA tiles fed
+                              * through shared memory by bulk copies, 5 = by cp.async (3-5: experiments, profiles/r01_spmm_ncu.md;
+                              * they fall back to 2 when the panels are not suitably aligned) */
 };
 
 const char *vbc_last_error(void);

@@ -448,7 +448,8 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
         A->opt_parity = value ? 1 : 0;
         return VBC_OK;
     case VBC_OPT_SPMM_SIMT:
-        A->opt_spmm_simt = value ? 1 : 0;
+        if (value < 0 || value > 5) VBC_FAIL(VBC_EARG, "SpMM kernel must be 0 (auto), 1 (SIMT), 2 (DMMA, scalar X loads), 3 (DMMA, 256-bit X-row loads), 4 (DMMA fed by bulk copies) or 5 (DMMA fed by cp.async)");
+        A->opt_spmm_simt = (int)value;
         return VBC_OK;
     case VBC_OPT_FWD_MODE:
         if (value < 0 || value > 2) VBC_FAIL(VBC_EARG, "forward mode must be 0 (auto), 1 (atomic scatter) or 2 (transposed index whenever possible)");
