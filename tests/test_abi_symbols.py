@@ -79,3 +79,38 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text, f
+
+
+def build_c_client(tmp_path):
+    """gcc -std=c99 build of tests/c_abi/abi_smoke.c against include/vbc.h and libvbc.so -> (exe, env)."""
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(vb.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi", "abi_smoke.c"), "-o", exe, "-L", libdir, "-lvbc",
+                    "-Wl,-rpath," + libdir, "-Wl,--allow-shlib-undefined"], check=True)
+    # the CUDA runtime the library was linked against (pip-installed next to torch, not on the default loader path)
+    ldd = subprocess.run(["ldd", vb.LIB_PATH], capture_output=True, text=True).stdout
+    dirs = {os.path.dirname(m) for m in re.findall(r"=> (\S+libcudart\S*)", ldd)}
+    try:
+        import nvidia.cuda_runtime
+        dirs.add(os.path.join(os.path.dirname(nvidia.cuda_runtime.__file__), "lib"))
+    except ImportError:
+        pass
+    dirs.add("/usr/local/cuda/lib64")
+    env = dict(os.environ, LD_LIBRARY_PATH=":".join(sorted(dirs) + [os.environ.get("LD_LIBRARY_PATH", "")]))
+    return exe, env
+
+
+def test_header_is_c99_and_a_plain_c_client_links(tmp_path):
+    """The drop-in boundary is a C ABI: a C99 translation unit includes the header, links the library and gets the
+    documented status codes from argument validation (no GPU needed)."""
+    exe, env = build_c_client(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "abi_smoke ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_client_packs_and_multiplies_on_the_gpu(tmp_path):
+    exe, env = build_c_client(tmp_path)
+    out = subprocess.run([exe, "gpu"], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "abi_smoke ok" in out.stdout, out.stdout + out.stderr
