@@ -54,10 +54,13 @@ enum vbc_option {
     VBC_OPT_FWD_MODE = 5,    /* forward multiply: 0 = auto (owner-computes through a transposed unit index, built at first
                                   use, for uniform 2D blocks; atomic scatter kernel otherwise), 1 = always the atomic
                                   scatter kernel, 2 = the transposed index whenever the layout allows it              */
-    VBC_OPT_SPMM_SIMT = 6    /* Float64 adjoint SpMM: 0 = auto (FP64 tensor DMMA m8n8k4 tiles), 1 = the SIMT (DFMA) kernel,
+    VBC_OPT_SPMM_SIMT = 6,   /* Float64 adjoint SpMM: 0 = auto (FP64 tensor DMMA m8n8k4 tiles), 1 = the SIMT (DFMA) kernel,
                               * 2 = DMMA with scalar X loads (what 0 selects), 3 = DMMA with 256-bit X-row loads, 4 = DMMA tiles fed
                               * through shared memory by bulk copies, 5 = by cp.async (3-5: experiments, profiles/r01_spmm_ncu.md;
                               * they fall back to 2 when the panels are not suitably aligned) */
+    VBC_OPT_E2E_PIPELINE = 7 /* host-vector adjoint multiplies: 1 = upload x in pieces, each chunk of stripes starting as soon as the
+                              * x rows it gathers from have arrived (pays when the matrix is banded); 0 = upload x first (default).
+                              * Experimental in round 1: not yet run on a GPU. */
 };
 
 const char *vbc_last_error(void);

@@ -129,6 +129,55 @@ static int ensure_vec(void **buf, int64_t *cap, int64_t len, size_t esz)
 
 using namespace vbc;
 
+// largest x index gathered by the descriptors [d0, d1) -> *out (atomicMax), for the chunked host-vector multiply
+static __global__ void __launch_bounds__(256) k_desc_max(const int *__restrict__ desc, const long long d0, const long long d1, int *out)
+{
+    int mx = -1;
+    for (long long i = d0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d1; i += (long long)gridDim.x * blockDim.x) mx = max(mx, desc[i]);
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(out, mx);
+}
+
+// chunk_xhi[c] = one past the largest x index the stripes of chunks 0..c gather from (cumulative, clamped to m)
+static int prepare_x_ranges(vbc_mat *A)
+{
+    A->xhi_ready = -1;
+    const int NC = A->nchunks;
+    int *d_mx = nullptr;
+    VBC_CUDA(cudaMalloc(&d_mx, sizeof(int) * 8));
+    int rc = VBC_OK;
+    int h_mx[8];
+    do {
+        if (cudaMemsetAsync(d_mx, 0xff, sizeof(int) * 8, A->stream) != cudaSuccess) { rc = VBC_ECUDA; break; } // -1
+        for (int c = 0; c < NC && rc == VBC_OK; c++) {
+            StripeMeta m0, m1;
+            if (cudaMemcpy(&m0, A->d_meta + A->chunk_l[c], sizeof(StripeMeta), cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(&m1, A->d_meta + A->chunk_l[c + 1], sizeof(StripeMeta), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = VBC_ECUDA; break; }
+            const long long n = (long long)m1.pos - m0.pos;
+            if (n <= 0) continue;
+            long long g = (n + 255) / 256;
+            if (g > (long long)A->sm_count * 8) g = (long long)A->sm_count * 8;
+            k_desc_max<<<(unsigned)g, 256, 0, A->stream>>>(A->d_desc, m0.pos, m1.pos, d_mx + c);
+        }
+        if (rc != VBC_OK) break;
+        if (cudaMemcpyAsync(h_mx, d_mx, sizeof(int) * 8, cudaMemcpyDeviceToHost, A->stream) != cudaSuccess || cudaStreamSynchronize(A->stream) != cudaSuccess) { rc = VBC_ECUDA; break; }
+    } while (0);
+    cudaFree(d_mx);
+    if (rc != VBC_OK) { cudaGetLastError(); set_error("x-range analysis of the chunked multiply failed"); return rc; }
+    // a block descriptor is the FIRST x index of a block of up to u0 rows (DESC_BLOCKS); a row descriptor is the index itself
+    const int64_t reach = (A->desc_mode == DESC_BLOCKS) ? A->u0 : 1;
+    int64_t hi = 0;
+    for (int c = 0; c < NC; c++) {
+        if (h_mx[c] >= 0 && (int64_t)h_mx[c] + reach > hi) hi = (int64_t)h_mx[c] + reach;
+        if (hi > A->m) hi = A->m;
+        A->chunk_xhi[c] = hi;
+    }
+    A->xhi_ready = 1;
+    return VBC_OK;
+}
+
+using namespace vbc;
+
 extern "C" {
 
 const char *vbc_last_error(void) { return get_error(); }
@@ -207,6 +256,9 @@ void vbc_destroy(vbc_mat *A)
     destroy_trsv_plan(A->trsv);
     destroy_tindex(A->tindex);
     if (A->copy_stream) cudaStreamDestroy(A->copy_stream);
+    if (A->h2d_stream) cudaStreamDestroy(A->h2d_stream);
+    for (int c = 0; c < 8; c++)
+        if (A->h2d_ev[c]) cudaEventDestroy(A->h2d_ev[c]);
     for (int c = 0; c < 8; c++)
         if (A->chunk_ev[c]) cudaEventDestroy(A->chunk_ev[c]);
     delete A;
@@ -272,7 +324,9 @@ int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, d
     const size_t tv = vt_size(A->vt);
     VBC_TRY(ensure_vec(&A->d_x, &A->x_cap, xlen, tv));
     VBC_TRY(ensure_vec(&A->d_y, &A->y_cap, ylen, tv));
-    if (xlen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_x, x, tv * (size_t)xlen, cudaMemcpyHostToDevice, A->stream));
+    // x is uploaded up front unless the pipelined path below takes it over (decided after the chunks are prepared)
+    const bool want_pipeline = trans && A->opt_e2e_pipeline && !A->opt_parity && A->d_order == nullptr && xlen > 0;
+    if (xlen > 0 && !want_pipeline) VBC_CUDA(cudaMemcpyAsync(A->d_x, x, tv * (size_t)xlen, cudaMemcpyHostToDevice, A->stream));
     if (beta != 0.0 && ylen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_y, y, tv * (size_t)ylen, cudaMemcpyHostToDevice, A->stream));
     // adjoint with a large y: launch the stripes in chunks and copy each finished y range back on a second stream
     // while the next chunk computes (the D2H copy is as long as the whole kernel)
@@ -293,9 +347,30 @@ int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, d
             else cudaGetLastError();
         }
     }
+    // pipelined upload: needs the chunks, the x ranges and a third stream; anything missing -> plain upload now
+    bool pipeline = false;
+    if (want_pipeline) {
+        if (A->nchunks > 0 && A->xhi_ready == 0) {
+            bool ok = cudaStreamCreateWithFlags(&A->h2d_stream, cudaStreamNonBlocking) == cudaSuccess;
+            for (int c = 0; c < A->nchunks && ok; c++) ok = cudaEventCreateWithFlags(&A->h2d_ev[c], cudaEventDisableTiming) == cudaSuccess;
+            if (ok) ok = prepare_x_ranges(A) == VBC_OK;
+            if (!ok) { cudaGetLastError(); A->xhi_ready = -1; }
+        }
+        pipeline = A->nchunks > 0 && A->xhi_ready == 1;
+        if (!pipeline) VBC_CUDA(cudaMemcpyAsync(A->d_x, x, tv * (size_t)xlen, cudaMemcpyHostToDevice, A->stream));
+    }
     if (trans && !A->opt_parity && A->nchunks > 0 && A->d_order == nullptr) {
         int rc = VBC_OK;
+        int64_t xcopied = 0;
         for (int c = 0; c < A->nchunks && rc == VBC_OK; c++) {
+            if (pipeline) { // the piece of x this chunk still lacks, on the upload stream; the chunk's kernel waits for it
+                const int64_t hi = A->chunk_xhi[c];
+                cudaError_t e = cudaSuccess;
+                if (hi > xcopied) { e = cudaMemcpyAsync((char *)A->d_x + tv * (size_t)xcopied, (const char *)x + tv * (size_t)xcopied, tv * (size_t)(hi - xcopied), cudaMemcpyHostToDevice, A->h2d_stream); xcopied = hi; }
+                if (e == cudaSuccess) e = cudaEventRecord(A->h2d_ev[c], A->h2d_stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(A->stream, A->h2d_ev[c], 0);
+                if (e != cudaSuccess) { set_error("pipelined upload failed: %s", cudaGetErrorString(e)); rc = VBC_ECUDA; break; }
+            }
             A->range_l0 = A->chunk_l[c]; A->range_l1 = A->chunk_l[c + 1];
             rc = launch_spmv(A, trans, alpha, A->d_x, beta, A->d_y);
             if (rc == VBC_OK && cudaEventRecord(A->chunk_ev[c], A->stream) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = VBC_ECUDA; }
@@ -309,6 +384,7 @@ int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, d
         }
         VBC_CUDA(cudaStreamSynchronize(A->copy_stream));
         VBC_CUDA(cudaStreamSynchronize(A->stream));
+        if (pipeline) VBC_CUDA(cudaStreamSynchronize(A->h2d_stream));
         return VBC_OK;
     }
     VBC_TRY(launch_spmv(A, trans, alpha, A->d_x, beta, A->d_y));
@@ -451,6 +527,9 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
         if (value < 0 || value > 5) VBC_FAIL(VBC_EARG, "SpMM kernel must be 0 (auto), 1 (SIMT), 2 (DMMA, scalar X loads), 3 (DMMA, 256-bit X-row loads), 4 (DMMA fed by bulk copies) or 5 (DMMA fed by cp.async)");
         A->opt_spmm_simt = (int)value;
         return VBC_OK;
+    case VBC_OPT_E2E_PIPELINE:
+        A->opt_e2e_pipeline = value ? 1 : 0;
+        return VBC_OK;
     case VBC_OPT_FWD_MODE:
         if (value < 0 || value > 2) VBC_FAIL(VBC_EARG, "forward mode must be 0 (auto), 1 (atomic scatter) or 2 (transposed index whenever possible)");
         A->opt_fwd_atomic = (int)value;
@@ -469,6 +548,7 @@ int vbc_get_option(const vbc_mat *A, int option, int64_t *value)
     case VBC_OPT_PARITY_MODE: *value = A->opt_parity; return VBC_OK;
     case VBC_OPT_FWD_MODE: *value = A->opt_fwd_atomic; return VBC_OK;
     case VBC_OPT_SPMM_SIMT: *value = A->opt_spmm_simt; return VBC_OK;
+    case VBC_OPT_E2E_PIPELINE: *value = A->opt_e2e_pipeline; return VBC_OK;
     }
     VBC_FAIL(VBC_EARG, "unknown option %d", option);
 }

@@ -92,6 +92,12 @@ struct vbc_mat {
     int chunk_l[9] = {};                   // stripe boundaries of the chunks
     int64_t chunk_col[9] = {};             // first column of each chunk
     int nchunks = 0;                       // 0: not prepared, -1: chunking not applicable
+    // optional (VBC_OPT_E2E_PIPELINE): x is uploaded in pieces on its own stream; chunk c starts once x[0, chunk_xhi[c]) is there
+    int opt_e2e_pipeline = 0;
+    cudaStream_t h2d_stream = nullptr;
+    cudaEvent_t h2d_ev[8] = {};
+    int64_t chunk_xhi[8] = {};             // cumulative: one past the largest x index gathered by the stripes of chunks 0..c
+    int xhi_ready = 0;                     // 0: not computed, 1: ready, -1: failed (pipeline off)
     vbc_trsv_plan *trsv = nullptr; // level schedule of the triangular solve (vbc_trsv_analyse)
     vbc::TIndex *tindex = nullptr; // transposed unit index of the owner-computes forward multiply (built at first use)
     int opt_fwd_atomic = 0;        // 1: always use the atomic scatter kernel for the forward multiply
