@@ -58,9 +58,11 @@ enum vbc_option {
                               * 2 = DMMA with scalar X loads (what 0 selects), 3 = DMMA with 256-bit X-row loads, 4 = DMMA tiles fed
                               * through shared memory by bulk copies, 5 = by cp.async (3-5: experiments, profiles/r01_spmm_ncu.md;
                               * they fall back to 2 when the panels are not suitably aligned) */
-    VBC_OPT_E2E_PIPELINE = 7 /* host-vector adjoint multiplies: 1 = upload x in pieces, each chunk of stripes starting as soon as the
+    VBC_OPT_E2E_PIPELINE = 7, /* host-vector adjoint multiplies: 1 = upload x in pieces, each chunk of stripes starting as soon as the
                               * x rows it gathers from have arrived (pays when the matrix is banded); 0 = upload x first (default).
+                              * Only x[lo, hi) with lo / hi the smallest / largest index any stripe gathers from is uploaded at all.
                               * Experimental in round 1: not yet run on a GPU. */
+    VBC_OPT_E2E_UPLOAD_ELEMS = 8 /* read-only: x elements the last host-vector multiply copied to the device */
 };
 
 const char *vbc_last_error(void);

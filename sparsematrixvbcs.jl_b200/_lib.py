@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_DIR, "libvbc.so")
 VBC_F32, VBC_F64 = 0, 1
 VBC_I32, VBC_I64 = 0, 1
 VBC_OK, VBC_EDIM, VBC_EARG, VBC_ELIMIT, VBC_ECUDA, VBC_ENCCL, VBC_ENOMEM = range(7)
-OPT_ADJ_GROUP, OPT_FWD_GROUP, OPT_GRID_MULT, OPT_PARITY_MODE, OPT_FWD_MODE, OPT_SPMM_SIMT, OPT_E2E_PIPELINE = 1, 2, 3, 4, 5, 6, 7
+OPT_ADJ_GROUP, OPT_FWD_GROUP, OPT_GRID_MULT, OPT_PARITY_MODE, OPT_FWD_MODE, OPT_SPMM_SIMT, OPT_E2E_PIPELINE, OPT_E2E_UPLOAD_ELEMS = 1, 2, 3, 4, 5, 6, 7, 8
 
 # every symbol include/vbc.h declares (tests/test_abi_symbols.py checks header <-> this list <-> .so)
 SYMBOLS = [

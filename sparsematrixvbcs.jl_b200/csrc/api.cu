@@ -130,12 +130,19 @@ static int ensure_vec(void **buf, int64_t *cap, int64_t len, size_t esz)
 using namespace vbc;
 
 // largest x index gathered by the descriptors [d0, d1) -> *out (atomicMax), for the chunked host-vector multiply
-static __global__ void __launch_bounds__(256) k_desc_max(const int *__restrict__ desc, const long long d0, const long long d1, int *out)
+static __global__ void __launch_bounds__(256) k_desc_max(const int *__restrict__ desc, const long long d0, const long long d1, int *out, int *out_min)
 {
-    int mx = -1;
-    for (long long i = d0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d1; i += (long long)gridDim.x * blockDim.x) mx = max(mx, desc[i]);
-    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(out, mx);
+    int mx = -1, mn = 0x7fffffff;
+    for (long long i = d0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d1; i += (long long)gridDim.x * blockDim.x) {
+        const int v = desc[i];
+        mx = max(mx, v);
+        mn = min(mn, v);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+    }
+    if ((threadIdx.x & 31) == 0 && mx >= 0) { atomicMax(out, mx); atomicMin(out_min, mn); }
 }
 
 // chunk_xhi[c] = one past the largest x index the stripes of chunks 0..c gather from (cumulative, clamped to m)
@@ -144,11 +151,13 @@ static int prepare_x_ranges(vbc_mat *A)
     A->xhi_ready = -1;
     const int NC = A->nchunks;
     int *d_mx = nullptr;
-    VBC_CUDA(cudaMalloc(&d_mx, sizeof(int) * 8));
+    VBC_CUDA(cudaMalloc(&d_mx, sizeof(int) * 9)); // [0..7]: per-chunk max, [8]: global min
     int rc = VBC_OK;
-    int h_mx[8];
+    int h_mx[9];
     do {
-        if (cudaMemsetAsync(d_mx, 0xff, sizeof(int) * 8, A->stream) != cudaSuccess) { rc = VBC_ECUDA; break; } // -1
+        const int big = 0x7fffffff;
+        if (cudaMemsetAsync(d_mx, 0xff, sizeof(int) * 8, A->stream) != cudaSuccess ||  // -1
+            cudaMemcpyAsync(d_mx + 8, &big, sizeof(int), cudaMemcpyHostToDevice, A->stream) != cudaSuccess) { rc = VBC_ECUDA; break; }
         for (int c = 0; c < NC && rc == VBC_OK; c++) {
             StripeMeta m0, m1;
             if (cudaMemcpy(&m0, A->d_meta + A->chunk_l[c], sizeof(StripeMeta), cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -157,10 +166,10 @@ static int prepare_x_ranges(vbc_mat *A)
             if (n <= 0) continue;
             long long g = (n + 255) / 256;
             if (g > (long long)A->sm_count * 8) g = (long long)A->sm_count * 8;
-            k_desc_max<<<(unsigned)g, 256, 0, A->stream>>>(A->d_desc, m0.pos, m1.pos, d_mx + c);
+            k_desc_max<<<(unsigned)g, 256, 0, A->stream>>>(A->d_desc, m0.pos, m1.pos, d_mx + c, d_mx + 8);
         }
         if (rc != VBC_OK) break;
-        if (cudaMemcpyAsync(h_mx, d_mx, sizeof(int) * 8, cudaMemcpyDeviceToHost, A->stream) != cudaSuccess || cudaStreamSynchronize(A->stream) != cudaSuccess) { rc = VBC_ECUDA; break; }
+        if (cudaMemcpyAsync(h_mx, d_mx, sizeof(int) * 9, cudaMemcpyDeviceToHost, A->stream) != cudaSuccess || cudaStreamSynchronize(A->stream) != cudaSuccess) { rc = VBC_ECUDA; break; }
     } while (0);
     cudaFree(d_mx);
     if (rc != VBC_OK) { cudaGetLastError(); set_error("x-range analysis of the chunked multiply failed"); return rc; }
@@ -172,6 +181,8 @@ static int prepare_x_ranges(vbc_mat *A)
         if (hi > A->m) hi = A->m;
         A->chunk_xhi[c] = hi;
     }
+    A->x_lo = (h_mx[8] != 0x7fffffff && h_mx[8] > 0) ? h_mx[8] : 0; // nothing below the smallest gathered index is ever read
+    if (A->x_lo > hi) A->x_lo = hi;
     A->xhi_ready = 1;
     return VBC_OK;
 }
@@ -361,7 +372,7 @@ int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, d
     }
     if (trans && !A->opt_parity && A->nchunks > 0 && A->d_order == nullptr) {
         int rc = VBC_OK;
-        int64_t xcopied = 0;
+        int64_t xcopied = pipeline ? A->x_lo : 0;
         for (int c = 0; c < A->nchunks && rc == VBC_OK; c++) {
             if (pipeline) { // the piece of x this chunk still lacks, on the upload stream; the chunk's kernel waits for it
                 const int64_t hi = A->chunk_xhi[c];
@@ -385,11 +396,13 @@ int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, d
         VBC_CUDA(cudaStreamSynchronize(A->copy_stream));
         VBC_CUDA(cudaStreamSynchronize(A->stream));
         if (pipeline) VBC_CUDA(cudaStreamSynchronize(A->h2d_stream));
+        A->last_upload_elems = pipeline ? xcopied - A->x_lo : xlen;
         return VBC_OK;
     }
     VBC_TRY(launch_spmv(A, trans, alpha, A->d_x, beta, A->d_y));
     if (ylen > 0) VBC_CUDA(cudaMemcpyAsync(y, A->d_y, tv * (size_t)ylen, cudaMemcpyDeviceToHost, A->stream));
     VBC_CUDA(cudaStreamSynchronize(A->stream));
+    A->last_upload_elems = xlen;
     return VBC_OK;
 }
 
@@ -530,6 +543,8 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
     case VBC_OPT_E2E_PIPELINE:
         A->opt_e2e_pipeline = value ? 1 : 0;
         return VBC_OK;
+    case VBC_OPT_E2E_UPLOAD_ELEMS:
+        VBC_FAIL(VBC_EARG, "VBC_OPT_E2E_UPLOAD_ELEMS is read-only");
     case VBC_OPT_FWD_MODE:
         if (value < 0 || value > 2) VBC_FAIL(VBC_EARG, "forward mode must be 0 (auto), 1 (atomic scatter) or 2 (transposed index whenever possible)");
         A->opt_fwd_atomic = (int)value;
@@ -549,6 +564,7 @@ int vbc_get_option(const vbc_mat *A, int option, int64_t *value)
     case VBC_OPT_FWD_MODE: *value = A->opt_fwd_atomic; return VBC_OK;
     case VBC_OPT_SPMM_SIMT: *value = A->opt_spmm_simt; return VBC_OK;
     case VBC_OPT_E2E_PIPELINE: *value = A->opt_e2e_pipeline; return VBC_OK;
+    case VBC_OPT_E2E_UPLOAD_ELEMS: *value = A->last_upload_elems; return VBC_OK;
     }
     VBC_FAIL(VBC_EARG, "unknown option %d", option);
 }

@@ -98,6 +98,8 @@ struct vbc_mat {
     cudaEvent_t h2d_ev[8] = {};
     int64_t chunk_xhi[8] = {};             // cumulative: one past the largest x index gathered by the stripes of chunks 0..c
     int xhi_ready = 0;                     // 0: not computed, 1: ready, -1: failed (pipeline off)
+    int64_t x_lo = 0;                      // smallest x index any stripe gathers from
+    int64_t last_upload_elems = 0;         // x elements the last host-vector multiply copied to the device
     vbc_trsv_plan *trsv = nullptr; // level schedule of the triangular solve (vbc_trsv_analyse)
     vbc::TIndex *tindex = nullptr; // transposed unit index of the owner-computes forward multiply (built at first use)
     int opt_fwd_atomic = 0;        // 1: always use the atomic scatter kernel for the forward multiply

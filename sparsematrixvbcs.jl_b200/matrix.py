@@ -160,6 +160,11 @@ class _CuVBC:
     def set_option(self, option, value):
         check(_lib.lib().vbc_set_option(self._h, int(option), int(value)))
 
+    def get_option(self, option):
+        v = ctypes.c_int64()
+        check(_lib.lib().vbc_get_option(self._h, int(option), v))
+        return v.value
+
     def launch_count(self):
         c = ctypes.c_int64()
         check(_lib.lib().vbc_launch_count(self._h, c))

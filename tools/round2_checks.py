@@ -130,6 +130,7 @@ def _():
     res["plain_us_med_min"] = e2e_time(B, x, yp0)
     B.set_option(_lib.OPT_E2E_PIPELINE, 1)
     res["pipelined_us_med_min"] = e2e_time(B, x, yp1)
+    res["uploaded_x_elements"] = B.get_option(_lib.OPT_E2E_UPLOAD_ELEMS)
     res["max_abs_diff"] = float(np.abs(yp0 - yp1).max())
     # alpha / beta through the pipelined path
     yb = yp1.copy()
