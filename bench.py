@@ -236,7 +236,7 @@ def run_ours(args, rank, world, local_rank):
         with torch.cuda.graph(graph, stream=side):
             for _ in range(args.steps):
                 step()
-        flag_launches = 0 if peer is None else {0: 1, 1: 0, 2: (2 if peer.interior[1] > peer.interior[0] else 1)}[args.sync_mode]
+        flag_launches = 0 if peer is None else {0: 1, 1: 0, 2: (2 if peer.interior[1] > peer.interior[0] else 1), 3: 1}[args.sync_mode]
         gpu_launches = B.launch_count() - launches_before + args.steps * flag_launches  # + flag kernel(s) per step
         torch.cuda.synchronize()
         if world > 1:
@@ -347,7 +347,8 @@ def run_ours(args, rank, world, local_rank):
             "exchange_sent_fraction": (peer.sent_fraction if peer is not None else None),
             "exchange_flag_neighbors_rank0": (peer.neighbors if peer is not None else None),
             "exchange_sync": (None if peer is None else {0: "flag kernel after the multiply", 1: f"in-kernel, stripes {list(peer.interior)} run before the wait",
-                                                               2: f"split launches, stripes {list(peer.interior)} run before the wait"}[args.sync_mode]),
+                                                               2: f"split launches, stripes {list(peer.interior)} run before the wait",
+                                                               3: "plain multiply into the own buffer, then one push-the-read-chunks + flag kernel"}[args.sync_mode]),
         }
         if world == 1 and not args.no_cpu_baseline:
             oracle, H = cpu_reference_setup(A, pi, phi)
@@ -390,9 +391,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sync-mode", type=int, default=0, choices=[0, 1, 2],
+    ap.add_argument("--sync-mode", type=int, default=0, choices=[0, 1, 2, 3],
                     help="peer/halo flag exchange: 0 = one flag kernel (signal+wait) after the multiply; 1 = (removed: same as 0); "
-                         "2 = split launches [interior stripes][wait][other stripes][signal] (halo only)")
+                         "2 = split launches [interior stripes][wait][other stripes][signal] (halo only); 3 = plain multiply kernel into the own "
+                         "buffer, then one kernel that pushes the chunks other ranks read and exchanges flags (halo only; experimental)")
     ap.add_argument("--exchange", default="halo", choices=["halo", "peer", "nccl"],
                     help="N > 1, how x_{t+1} reaches the ranks: 'halo' (default) = exchange fused into the multiply kernel through "
                          "NVLink peer stores, each y segment sent to exactly the ranks whose stripes read it; 'peer' = same kernel, "

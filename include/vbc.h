@@ -228,7 +228,10 @@ int vbc_peer_set_neighbors(vbc_peer *P, unsigned mask);
  * own slice and (under the mask) feed only this rank -- then waits for the peers' flags of the
  * previous iteration, runs the remaining stripes, and the last CTA to finish publishes this rank's
  * flag.  The wait is hidden behind the work of [i0, i1), and ranks may drift by that much.  With full
- * replication pass i0 == i1 (nothing can run before the wait). */
+ * replication pass i0 == i1 (nothing can run before the wait).
+ * enable = 3 (needs a mask; experimental, not yet run on a GPU): the step is the PLAIN adjoint kernel writing the
+ * rank's slice into its own next-x buffer, then ONE kernel in which every CTA copies its share of the column chunks
+ * some other rank reads to those ranks and the last CTA to finish runs the signal + wait. */
 int vbc_peer_set_fused_sync(vbc_peer *P, int enable, int64_t i0, int64_t i1);
 /* the flag kernel alone (barrier = 1 | 2 | 3 as above); does not flip cur */
 int vbc_peer_barrier(vbc_peer *P, void *cuda_stream, int barrier);

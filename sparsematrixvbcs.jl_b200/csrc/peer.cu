@@ -19,11 +19,15 @@ struct vbc_peer {
     unsigned char *d_mask = nullptr; // per column chunk of this rank's slice: which destinations read it
     int chunk_shift = 0;
     int64_t mask_len = 0;
-    int fused_sync = 0;      // 0: multiply, then k_peer_flags; 1: flags inside the multiply kernel; 2: split launches
-                             // [stripes i0..i1] [wait] [the rest] [signal] so the wait hides behind the first launch
+    int fused_sync = 0;      // 0: multiply, then k_peer_flags; 1: flags inside the multiply kernel (removed); 2: split launches
+                             // [stripes i0..i1] [wait] [the rest] [signal] so the wait hides behind the first launch;
+                             // 3: plain multiply into the own buffer, then ONE kernel that pushes the chunks other ranks read
+                             //    and does the flag exchange (sparsity-aware mode only; experimental, not yet run on a GPU)
     int i0 = 0, i1 = 0;      // stripes [i0, i1): no peer involved (run before the in-kernel wait)
     unsigned *d_done = nullptr;
     unsigned nbr_mask = 0xffffffffu; // ranks this rank exchanges flags with (bit r); default: everyone
+    int *d_push = nullptr;           // fused_sync 3: the column chunks of this rank's slice that some OTHER rank reads
+    int npush = 0;
     int64_t launches = 0;
 };
 
@@ -74,6 +78,58 @@ __global__ void k_peer_flags(const __grid_constant__ FlagPtrs f, const int me, c
             }
             __nanosleep(64);
         }
+    }
+}
+
+// fused_sync 3.  The multiply has written this rank's whole y slice into its own next-x buffer with the plain
+// kernel; only the column chunks some other rank gathers from (push[0..npush), usually a fraction of a percent for a
+// banded operator) still have to travel.  Every CTA copies its share of those chunks to the ranks that read them;
+// the last CTA to finish then runs the flag exchange of k_peer_flags (signal, wait).
+struct PushDst {
+    void *p[VBC_MAX_PEERS]; // destination i of the rotated order of vbc_peer_spmv_step (p[0] = own buffer, unused here)
+    int n;
+};
+template <typename Tv>
+__global__ void __launch_bounds__(256) k_peer_push_flags(const Tv *__restrict__ src, const __grid_constant__ PushDst dst, const unsigned char *__restrict__ mask,
+                                                         const int chunk_shift, const int ncols, const int *__restrict__ push, const int npush,
+                                                         const __grid_constant__ FlagPtrs f, const int me, const int nranks, unsigned long long *__restrict__ d_epoch,
+                                                         unsigned *__restrict__ d_done, int *__restrict__ timed_out, const unsigned nbr_mask)
+{
+    for (int idx = blockIdx.x; idx < npush; idx += gridDim.x) {
+        const int ch = push[idx];
+        const unsigned mk = mask[ch];
+        const int c0 = ch << chunk_shift, c1 = min(ncols, c0 + (1 << chunk_shift));
+        for (int c = c0 + (int)threadIdx.x; c < c1; c += (int)blockDim.x) {
+            const Tv v = src[c];
+            for (int i = 1; i < dst.n; i++)
+                if ((mk >> i) & 1u) reinterpret_cast<Tv *>(dst.p[i])[c] = v;
+        }
+    }
+    __threadfence_system(); // this thread's peer stores are visible system-wide before the CTA is counted as done
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(d_done, 1u);
+        last = prev == gridDim.x - 1;
+        if (last) *d_done = 0; // ready for the next launch (stream order)
+    }
+    __syncthreads();
+    if (!last || threadIdx.x >= 32) return;
+    __threadfence();
+    const int r = threadIdx.x;
+    const unsigned long long epoch = *d_epoch + 1ull;
+    __syncwarp();
+    if (r == 0) *d_epoch = epoch;
+    if (r >= nranks || !((nbr_mask >> r) & 1u)) return;
+    __threadfence_system();
+    st_release_sys(f.p[r] + me, epoch);
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(f.p[me] + r) < epoch) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) { atomicExch(timed_out, 1); break; }
+        __nanosleep(64);
     }
 }
 
@@ -209,7 +265,25 @@ int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, 
     if (P->d_mask && A->n > 0 && ((A->n - 1) >> P->chunk_shift) >= P->mask_len)
         VBC_FAIL(VBC_EDIM, "peer mask covers %lld chunks, the y slice needs %lld", (long long)P->mask_len, (long long)(((A->n - 1) >> P->chunk_shift) + 1));
     // the mask is indexed by (column in the y slice) >> shift; the kernel indexes by slab column, so no offset is needed
-    if (P->fused_sync == 2 && barrier == 3 && P->i1 > P->i0) {
+    if (P->fused_sync == 3 && barrier == 3 && P->d_mask && P->d_done) {
+        // plain kernel into the own next-x buffer, then push + flags in one launch
+        VBC_TRY(launch_spmv(A, 1, alpha, P->own[P->cur], 0.0, dst[0]));
+        PushDst pd;
+        pd.n = n;
+        for (int i = 0; i < VBC_MAX_PEERS; i++) pd.p[i] = i < n ? dst[i] : nullptr;
+        FlagPtrs f;
+        for (int r = 0; r < VBC_MAX_PEERS; r++) f.p[r] = r < P->nranks ? (unsigned long long *)P->bufs[r][2] : nullptr;
+        int grid = P->npush < 1 ? 1 : (P->npush > 64 ? 64 : P->npush);
+        const unsigned nbr = P->nbr_mask | (1u << P->rank);
+        if (P->vt == VBC_F64)
+            k_peer_push_flags<double><<<grid, 256, 0, A->stream>>>((const double *)dst[0], pd, P->d_mask, P->chunk_shift, (int)A->n, P->d_push, P->npush, f, P->rank,
+                                                                   P->nranks, P->d_epoch, P->d_done, P->d_timeout, nbr);
+        else
+            k_peer_push_flags<float><<<grid, 256, 0, A->stream>>>((const float *)dst[0], pd, P->d_mask, P->chunk_shift, (int)A->n, P->d_push, P->npush, f, P->rank,
+                                                                  P->nranks, P->d_epoch, P->d_done, P->d_timeout, nbr);
+        P->launches++;
+        VBC_CUDA(cudaGetLastError());
+    } else if (P->fused_sync == 2 && barrier == 3 && P->i1 > P->i0) {
         const int L = (int)A->L;
         const int ra[4] = {P->i0, P->i1, 0, 0}, rc[4] = {0, P->i0, P->i1, L};
         VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, nullptr, ra));
@@ -229,21 +303,33 @@ int vbc_peer_set_mask(vbc_peer *P, const void *mask, int64_t nchunks, int chunk_
     if (!P) VBC_FAIL(VBC_EARG, "NULL argument");
     DeviceGuard guard(P->device);
     cudaFree(P->d_mask);
-    cudaFree(P->d_done);
-    P->d_mask = nullptr; P->mask_len = 0; P->chunk_shift = 0;
+    cudaFree(P->d_push);
+    P->d_mask = nullptr; P->d_push = nullptr; P->npush = 0; P->mask_len = 0; P->chunk_shift = 0;
     if (!mask) return VBC_OK; // back to full replication
     if (nchunks < 1 || chunk_shift < 0 || chunk_shift > 30) VBC_FAIL(VBC_EARG, "bad mask geometry");
     VBC_CUDA(cudaMalloc(&P->d_mask, (size_t)nchunks));
     VBC_CUDA(cudaMemcpy(P->d_mask, mask, (size_t)nchunks, cudaMemcpyHostToDevice));
     P->mask_len = nchunks;
     P->chunk_shift = chunk_shift;
+    { // chunks with a reader other than this rank (bit 0 is the own buffer in the rotated destination order)
+        int *list = new (std::nothrow) int[(size_t)nchunks];
+        if (!list) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
+        int np = 0;
+        for (int64_t c = 0; c < nchunks; c++)
+            if (((const unsigned char *)mask)[c] & 0xfeu) list[np++] = (int)c;
+        cudaError_t e = cudaMalloc(&P->d_push, sizeof(int) * (size_t)(np > 0 ? np : 1));
+        if (e == cudaSuccess && np > 0) e = cudaMemcpy(P->d_push, list, sizeof(int) * (size_t)np, cudaMemcpyHostToDevice);
+        delete[] list;
+        if (e != cudaSuccess) VBC_FAIL(VBC_ECUDA, "vbc_peer_set_mask: push list upload failed: %s", cudaGetErrorString(e));
+        P->npush = np;
+    }
     return VBC_OK;
 }
 
 int vbc_peer_set_fused_sync(vbc_peer *P, int enable, int64_t i0, int64_t i1)
 {
     if (!P) VBC_FAIL(VBC_EARG, "NULL argument");
-    if (i0 < 0 || i1 < i0 || enable < 0 || enable > 2) VBC_FAIL(VBC_EARG, "bad interior range / mode");
+    if (i0 < 0 || i1 < i0 || enable < 0 || enable > 3) VBC_FAIL(VBC_EARG, "bad interior range / mode");
     if (enable == 1) enable = 0; // the in-kernel flag exchange lost to the separate flag kernel and quadrupled the kernel's code size; removed
     DeviceGuard guard(P->device);
     if (enable && !P->d_done) {
@@ -292,6 +378,7 @@ void vbc_peer_destroy(vbc_peer *P)
     cudaFree(P->d_epoch);
     cudaFree(P->d_mask);
     cudaFree(P->d_done);
+    cudaFree(P->d_push);
     delete P;
 }
 
