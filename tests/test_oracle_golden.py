@@ -213,3 +213,67 @@ def test_runtests_jl_method_list_on_the_oracle(fixtures, name):
     for method in reference_methods_2d():
         pi, phi = vb.pack_plaid(A, method)
         onehot_check(A, oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, 4, 4))
+
+
+# ---- the format DEFINITION, stated with sets instead of merges, against the oracle's packers (property test) ----------
+def _split(rng_ints, dim, cap):
+    """split points of a random contiguous partition of 1..dim with parts <= cap (from a list of random ints)"""
+    spl, pos, i = [1], 0, 0
+    while pos < dim:
+        step = 1 + rng_ints[i % len(rng_ints)] % cap
+        i += 1
+        pos = min(dim, pos + step)
+        spl.append(pos + 1)
+    return np.array(spl)
+
+
+def _definition_pack(m, n, colptr, rowval, nzval, pi_spl, phi_spl):
+    """SparseMatrixVBCs.jl:36-43 / :62-70 read as a definition: per stripe, the ascending distinct rows (1D) or row
+    parts (2D) that hold a STORED entry; every unit is a dense row-major block, zero where nothing is stored."""
+    dense = {}
+    for j in range(n):
+        for t in range(colptr[j] - 1, colptr[j + 1] - 1):
+            dense[(int(rowval[t]), j + 1)] = nzval[t]
+    part_of = None
+    if pi_spl is not None:
+        part_of = {}
+        for k in range(len(pi_spl) - 1):
+            for i in range(pi_spl[k], pi_spl[k + 1]):
+                part_of[int(i)] = k + 1
+    pos, ofs, idx, val = [1], [1], [], []
+    for l in range(len(phi_spl) - 1):
+        cols = range(int(phi_spl[l]), int(phi_spl[l + 1]))
+        rows = sorted({i for (i, j) in dense if j in cols})
+        units = rows if part_of is None else sorted({part_of[i] for i in rows})
+        for uid in units:
+            idx.append(uid)
+            urows = [uid] if part_of is None else range(int(pi_spl[uid - 1]), int(pi_spl[uid]))
+            for i in urows:
+                for j in cols:
+                    val.append(dense.get((int(i), j), 0))
+        pos.append(len(idx) + 1)
+        ofs.append(len(val) + 1)
+    return np.array(pos), np.array(idx, dtype=np.int64), np.array(ofs), np.array(val, dtype=np.float64)
+
+
+def test_packers_match_the_set_definition_of_the_format():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=120, deadline=None, derandomize=True)
+    @given(m=st.integers(1, 13), n=st.integers(1, 13), seed=st.integers(0, 2**31 - 1), density=st.sampled_from([0.0, 0.1, 0.3, 0.7, 1.0]),
+           ints=st.lists(st.integers(0, 1000), min_size=4, max_size=12), cap=st.integers(1, 5), ti=st.sampled_from([np.int64, np.int32]))
+    def check(m, n, seed, density, ints, cap, ti):
+        rng = np.random.default_rng(seed)
+        A = sprand(m, n, density, rng)
+        colptr, rowval = A.colptr.astype(ti), A.rowval.astype(ti)
+        phi = _split(ints, n, cap).astype(ti)
+        pi = _split(ints[::-1], m, cap).astype(ti)
+        H1 = oracle.pack_1d(m, n, colptr, rowval, A.nzval, phi, cap)
+        p, i, o, v = _definition_pack(m, n, colptr, rowval, A.nzval, None, phi)
+        assert np.array_equal(H1.pos, p) and np.array_equal(H1.idx, i) and np.array_equal(H1.ofs, o) and np.array_equal(H1.val, v)
+        H2 = oracle.pack_2d(m, n, colptr, rowval, A.nzval, pi, phi, cap, cap)
+        p, i, o, v = _definition_pack(m, n, colptr, rowval, A.nzval, pi, phi)
+        assert np.array_equal(H2.pos, p) and np.array_equal(H2.idx, i) and np.array_equal(H2.ofs, o) and np.array_equal(H2.val, v)
+        assert H1.pos.dtype == np.dtype(ti) and H2.idx.dtype == np.dtype(ti)
+
+    check()
