@@ -265,8 +265,15 @@ __global__ void __launch_bounds__(256, VBC_DMMA_MINB) k_spmm_adj_dmma(const Stri
 // fragments are read back with conflict-free LDS.64 (rows padded to 288 bytes).  One warp = one private
 // ring of ST stages x CH rows; the ring keeps running across stripe boundaries, row indices and stripe
 // meta are fetched one step ahead, so nothing in the loop waits on a global load.
-#define VBC_TMA_CH 16
-#define VBC_TMA_ST 2
+#ifndef VBC_TMA_CH
+#define VBC_TMA_CH 16     // rows per stage (multiple of 4, at most 32)
+#endif
+#ifndef VBC_TMA_ST
+#define VBC_TMA_ST 2      // stages per warp
+#endif
+#ifndef VBC_TMA_MINB
+#define VBC_TMA_MINB 2    // CTAs per SM the register allocation is bounded for (the ring: 8 warps x ST x (CH x 352) bytes per CTA)
+#endif
 #define VBC_TMA_ROWB 288  // bytes between staged rows: 256 + 32, i.e. 8 banks of shift per row -> the 4 rows x 8 doubles of a half-warp hit 32 distinct banks
 #define VBC_TMA_STAGE (VBC_TMA_CH * VBC_TMA_ROWB + VBC_TMA_CH * 8 * 8)
 #define VBC_TMA_SMEM (8 * VBC_TMA_ST * VBC_TMA_STAGE + 8 * VBC_TMA_ST * 8)
@@ -292,7 +299,7 @@ __device__ __forceinline__ bool mbar_try_wait(const uint32_t bar, const uint32_t
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) k_spmm_adj_tma(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+__global__ void __launch_bounds__(256, VBC_TMA_MINB) k_spmm_adj_tma(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                        const double *__restrict__ val, const double *__restrict__ X, const long long ldx,
                                                        double *__restrict__ Y, const long long ldy, const int L, const int k,
                                                        const int u0, const int log2u, const double alpha, const double beta)
@@ -430,7 +437,7 @@ __device__ __forceinline__ void cp_async16(const uint32_t dst, const void *src)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) k_spmm_adj_cpasync(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+__global__ void __launch_bounds__(256, VBC_TMA_MINB) k_spmm_adj_cpasync(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                            const double *__restrict__ val, const double *__restrict__ X, const long long ldx,
                                                            double *__restrict__ Y, const long long ldy, const int L, const int k,
                                                            const int u0, const int log2u, const double alpha, const double beta)
@@ -656,7 +663,7 @@ static int launch_spmm_mode(vbc_mat *A, int trans, int k, Tv alpha, const Tv *X,
                         else VBC_CUDA(cudaFuncSetAttribute(k_spmm_adj_cpasync<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, VBC_TMA_SMEM));
                         attr_set[bulk][MODE][A->device & 63] = true;
                     }
-                    int64_t g3 = (int64_t)A->sm_count * 2;
+                    int64_t g3 = (int64_t)A->sm_count * VBC_TMA_MINB;
                     if (g3 > need) g3 = need;
                     if (g3 < 1) g3 = 1;
                     dim3 grid3((unsigned)g3, (unsigned)((k + 31) / 32));
