@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libvbc.so")
+# VBC_LIBRARY: another build of the same library (kernel-variant experiments, tools/build_variants.sh); default = the in-tree one
+LIB_PATH = os.environ.get("VBC_LIBRARY") or os.path.join(_DIR, "libvbc.so")
 
 VBC_F32, VBC_F64 = 0, 1
 VBC_I32, VBC_I64 = 0, 1
