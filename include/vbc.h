@@ -40,7 +40,7 @@ enum vbc_status {
     VBC_ELIMIT = 3, /* AssertionError `w <= W` constructors_1DVBC.jl:46 / constructors_VBC.jl:65, `u <= U` :58-60;
                        also: sizes beyond the device layout's 32-bit fields                                        */
     VBC_ECUDA = 4,  /* a CUDA runtime call failed (message has the CUDA error string)                            */
-    VBC_ENCCL = 5,  /* reserved for the multi-GPU layer                                                          */
+    VBC_ENCCL = 5,  /* an NCCL call failed, or libnccl could not be loaded (vbc_dist_* with the NCCL exchange)     */
     VBC_ENOMEM = 6  /* host or device allocation failed                                                          */
 };
 
@@ -54,14 +54,12 @@ enum vbc_option {
     VBC_OPT_FWD_MODE = 5,    /* forward multiply: 0 = auto (owner-computes through a transposed unit index, built at first
                                   use, for uniform 2D blocks; atomic scatter kernel otherwise), 1 = always the atomic
                                   scatter kernel, 2 = the transposed index whenever the layout allows it              */
-    VBC_OPT_SPMM_SIMT = 6,   /* Float64 adjoint SpMM: 0 = auto (FP64 tensor DMMA m8n8k4 tiles), 1 = the SIMT (DFMA) kernel,
-                              * 2 = DMMA with scalar X loads (what 0 selects), 3 = DMMA with 256-bit X-row loads, 4 = DMMA tiles fed
-                              * through shared memory by bulk copies, 5 = by cp.async (3-5: experiments, profiles/r01_spmm_ncu.md;
-                              * they fall back to 2 when the panels are not suitably aligned) */
-    VBC_OPT_E2E_PIPELINE = 7, /* host-vector adjoint multiplies: 1 = upload x in pieces, each chunk of stripes starting as soon as the
-                              * x rows it gathers from have arrived (pays when the matrix is banded); 0 = upload x first (default).
-                              * Only x[lo, hi) with lo / hi the smallest / largest index any stripe gathers from is uploaded at all.
-                              * Experimental in round 1: not yet run on a GPU. */
+    VBC_OPT_SPMM_SIMT = 6,   /* Float64 adjoint SpMM: 0 = FP64 tensor (DMMA m8n8k4) tiles, 1 = the SIMT (DFMA) kernel            */
+    VBC_OPT_E2E_PIPELINE = 7, /* host-vector adjoint multiplies: 1 (default) = x is uploaded in pieces on its own stream and each
+                              * chunk of stripes starts as soon as the x rows it gathers from have arrived, while the y ranges of
+                              * finished chunks are already on their way back (pays when the matrix is banded; any matrix stays
+                              * correct: a chunk that reaches far simply waits for more of x); 0 = upload all of x first.  Either way
+                              * only x[lo, hi), lo / hi the smallest / largest index any stripe gathers from, is uploaded.          */
     VBC_OPT_E2E_UPLOAD_ELEMS = 8 /* read-only: x elements the last host-vector multiply copied to the device */
 };
 
@@ -177,66 +175,69 @@ int vbc_get_option(const vbc_mat *A, int option, int64_t *value);
 /* number of kernel launches this handle has made since creation (bench.py's gpu_launches) */
 int vbc_launch_count(const vbc_mat *A, int64_t *count);
 
-/* ---- multi-GPU: row-block partition with x replicated through peer memory ---------------------
+/* ---- multi-GPU: row-block partition with the x exchange fused into the multiply ---------------
  * north_star (e): stripes (the row blocks of A') are split across the GPUs of one box; every rank
- * needs the whole x for its gathers, so each iteration x_{t+1} <- alpha * A' x_t ends with an
- * all-gather of the y slices.  Here that all-gather is FUSED into the multiply: the adjoint kernel
- * stores each finished y segment straight into the next-x buffer of every rank (its own and, over
- * NVLink peer mappings, the others'), and a one-CTA flag kernel is the only cross-rank step.
- * One process per GPU; the handles are exchanged by the host (torch.distributed / MPI / files).
- * No reference counterpart: the reference is single-process. */
+ * needs the x entries its stripes gather from, so each iteration x_{t+1} <- alpha * A' x_t ends with an
+ * exchange of the y slices.  Here that exchange is FUSED into the multiply: one kernel per iteration
+ * runs the rank's interior stripes like the single-GPU kernel, and its boundary stripes store their
+ * results straight into the next-x buffers of the ranks that read them (own HBM + NVLink peer
+ * mappings) and publish a per-step flag -- no collective call, no separate exchange launch.
+ * Two front ends share it: vbc_peer_* (one process per GPU; the IPC handles are exchanged by the
+ * host: torch.distributed / MPI / files) and vbc_dist_* (one process driving all GPUs, below).
+ * No reference counterpart: the reference is single-process; the loop it scales is
+ * the @threads stripe loop of multiply_1DVBC.jl:169-177 / multiply_VBC.jl:182-189. */
 typedef struct vbc_peer vbc_peer;
 #define VBC_IPC_HANDLE_BYTES 64
 #define VBC_PEER_HANDLES 3 /* x buffer 0, x buffer 1, flag block */
 #define VBC_MAX_PEERS 8
 
 /* Allocates this rank's two x buffers (xlen elements of vt each, zero-filled) and flag block on
- * `device`, and writes VBC_PEER_HANDLES CUDA IPC handles to handles_out (3 * 64 bytes). */
+ * `device`, and writes VBC_PEER_HANDLES CUDA IPC handles to handles_out (3 * 64 bytes; may be NULL
+ * when the ranks share a process). */
 int vbc_peer_create(vbc_peer **out, int vt, int64_t xlen, int rank, int nranks, int device, void *handles_out);
 /* all_handles: nranks * 3 * 64 bytes, rank-major, as gathered from every rank.  Maps the peers. */
 int vbc_peer_connect(vbc_peer *P, const void *all_handles);
-/* Same-process variant (tests, one process driving several "ranks"): raw device pointers,
- * ptrs[r * 3 + k] = buffer k of rank r. */
+/* Same-process variant (vbc_dist_*, tests): raw device pointers, ptrs[r * 3 + k] = buffer k of rank r
+ * (peer access between the devices must already be enabled). */
 int vbc_peer_connect_local(vbc_peer *P, void *const *ptrs);
 /* raw device pointers of this rank's buffers (k = 0, 1: x buffers; 2: flags) and the current x index */
 int vbc_peer_buffer(vbc_peer *P, int k, void **ptr);
 int vbc_peer_current(const vbc_peer *P, int *cur);
-/* One iteration: y = alpha * A' * x_cur on this rank's stripes, stored at element offset y_offset of
- * x_{1-cur} on EVERY rank; then signal + wait for all ranks (flags), then cur flips.  A->n columns
- * are written; A->m must equal xlen.  Enqueued on A's stream.  `barrier`: 3 = signal and wait
- * (normal), 1 = signal only, 2 = wait only, 0 = neither (same-process tests must not wait inside
- * one stream for a signal that a later launch of the same stream produces). */
+/* One iteration, one kernel launch on A's stream: y = alpha * A' * x_cur on this rank's stripes, stored at
+ * element offset y_offset of x_{1-cur} on this rank and on every rank that reads it (all ranks without a
+ * mask); then cur flips.  A->n columns are written; A->m must equal xlen.  `barrier` bit 2 (wait): the
+ * boundary stripes start only when every neighbour has published its previous step (its halo has landed
+ * here, and it no longer reads the buffer about to be overwritten); bit 1 (signal): the step is published
+ * to the neighbours when the last boundary stripe has been stored.  3 = both (normal); 0 = neither
+ * (same-process tests, or when vbc_peer_barrier is used between the steps instead).
+ * After the last iteration, vbc_peer_barrier(P, stream, 2) waits until the neighbours' final halos are in. */
 int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, int barrier);
 /* Sparsity-aware replication (optional).  mask[c >> chunk_shift] (c = column inside this rank's slab,
  * nchunks bytes) has bit i set when the i-th destination reads that chunk of columns; destination 0 is
- * this rank itself, destination i is rank (rank + i) % nranks.  With a mask the fused epilogue sends a
- * y segment only to the ranks whose stripes gather from it (for a banded operator: the neighbours'
- * halos) -- x stays complete on every rank exactly where that rank reads it.  mask == NULL restores
- * full replication. */
+ * this rank itself (always written), destination i is rank (rank + i) % nranks.  With a mask a y segment is
+ * sent only to the ranks whose stripes gather from it (for a banded operator: the neighbours' halos) -- x
+ * stays complete on every rank exactly where that rank reads it.  mask == NULL restores full replication. */
 int vbc_peer_set_mask(vbc_peer *P, const void *mask, int64_t nchunks, int chunk_shift);
 /* Restrict the flag exchange to the ranks in `mask` (bit r = rank r).  With sparsity-aware replication a rank
  * only has to synchronise with the ranks it sends y segments to (they must have finished reading the buffer it
  * is about to overwrite) and the ranks it receives from (their segments must have landed) -- for a banded
  * operator its two neighbours instead of everyone.  The relation must be symmetric across ranks. */
 int vbc_peer_set_neighbors(vbc_peer *P, unsigned mask);
-/* Overlapping the flag exchange with the multiply (optional).  enable = 2: barrier = 3 steps become four
- * launches -- [stripes i0..i1) | wait for the peers' previous step | remaining stripes | signal -- so the
- * wait (and the drift between ranks) hides behind the first launch; the default (enable = 0) is
- * [all stripes | signal + wait].  enable = 1 (REMOVED, now the same as 0; it measured slower and quadrupled the
- * kernel's code size): vbc_peer_spmv_step(..., barrier = 3) launched ONE
- * kernel per iteration: it first runs the stripes [i0, i1) -- which must gather only from this rank's
- * own slice and (under the mask) feed only this rank -- then waits for the peers' flags of the
- * previous iteration, runs the remaining stripes, and the last CTA to finish publishes this rank's
- * flag.  The wait is hidden behind the work of [i0, i1), and ranks may drift by that much.  With full
- * replication pass i0 == i1 (nothing can run before the wait).
- * enable = 3 (needs a mask; experimental, not yet run on a GPU): the step is the PLAIN adjoint kernel writing the
- * rank's slice into its own next-x buffer, then ONE kernel in which every CTA copies its share of the column chunks
- * some other rank reads to those ranks and the last CTA to finish runs the signal + wait. */
-int vbc_peer_set_fused_sync(vbc_peer *P, int enable, int64_t i0, int64_t i1);
-/* the flag kernel alone (barrier = 1 | 2 | 3 as above); does not flip cur */
+/* Interior stripes [i0, i1) (0-based, of the matrix passed to vbc_peer_spmv_step): stripes that gather only
+ * from this rank's own slice of x and (under the mask) feed only this rank.  They run before and independently
+ * of the flag exchange; all other stripes are boundary stripes.  Default: none (i0 == i1 == 0). */
+int vbc_peer_set_interior(vbc_peer *P, int64_t i0, int64_t i1);
+/* Derives the interior range on the device from the packed matrix and the mask set so far (the longest run of
+ * stripes whose gathers stay inside x[y_offset, y_offset + n) and whose columns only this rank reads), installs
+ * it and reports it (i0_out / i1_out may be NULL).  Without a mask, or with one rank, see vbc_peer_set_mask. */
+int vbc_peer_auto_interior(vbc_peer *P, vbc_mat *A, int64_t y_offset, int64_t *i0_out, int64_t *i1_out);
+/* the flag exchange alone, as one tiny kernel (barrier = 1 signal | 2 wait | 3 both); does not flip cur */
 int vbc_peer_barrier(vbc_peer *P, void *cuda_stream, int barrier);
 /* 0 if no flag wait has timed out since creation (checked after a stream sync by the caller) */
 int vbc_peer_status(vbc_peer *P, int *timed_out);
+/* stats[0] = steps published, [1] = ns spent spinning in in-kernel flag waits (summed over waiting lanes),
+ * [2] = waits that had to spin at all, [3] = longest single wait in ns; reset != 0 clears [1..3].  Synchronous. */
+int vbc_peer_wait_stats(vbc_peer *P, uint64_t stats[4], int reset);
 void vbc_peer_destroy(vbc_peer *P);
 
 #ifdef __cplusplus

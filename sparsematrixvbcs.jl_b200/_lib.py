@@ -24,7 +24,8 @@ SYMBOLS = [
     "vbc_set_stream", "vbc_csc_set_stream", "vbc_sync", "vbc_set_option", "vbc_get_option",
     "vbc_launch_count", "vbc_dp_chunk", "vbc_overlap_chunk",
     "vbc_peer_create", "vbc_peer_connect", "vbc_peer_connect_local", "vbc_peer_buffer", "vbc_peer_current",
-    "vbc_peer_spmv_step", "vbc_peer_set_mask", "vbc_peer_set_fused_sync", "vbc_peer_set_neighbors", "vbc_peer_barrier", "vbc_peer_status", "vbc_peer_destroy",
+    "vbc_peer_spmv_step", "vbc_peer_set_mask", "vbc_peer_set_interior", "vbc_peer_auto_interior", "vbc_peer_set_neighbors", "vbc_peer_barrier", "vbc_peer_status",
+    "vbc_peer_wait_stats", "vbc_peer_destroy",
 ]
 
 IPC_HANDLE_BYTES, PEER_HANDLES, MAX_PEERS = 64, 3, 8
@@ -107,7 +108,9 @@ def lib():
     L.vbc_peer_current.argtypes = [c_vp, pint]
     L.vbc_peer_spmv_step.argtypes = [c_vp, c_vp, c_dbl, c_i64, c_int]
     L.vbc_peer_set_mask.argtypes = [c_vp, c_vp, c_i64, c_int]
-    L.vbc_peer_set_fused_sync.argtypes = [c_vp, c_int, c_i64, c_i64]
+    L.vbc_peer_set_interior.argtypes = [c_vp, c_i64, c_i64]
+    L.vbc_peer_auto_interior.argtypes = [c_vp, c_vp, c_i64, pi64, pi64]
+    L.vbc_peer_wait_stats.argtypes = [c_vp, ctypes.POINTER(ctypes.c_uint64), c_int]
     L.vbc_peer_set_neighbors.argtypes = [c_vp, ctypes.c_uint]
     L.vbc_peer_barrier.argtypes = [c_vp, c_vp, c_int]
     L.vbc_peer_status.argtypes = [c_vp, pint]

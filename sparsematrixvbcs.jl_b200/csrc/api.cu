@@ -537,7 +537,7 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
         A->opt_parity = value ? 1 : 0;
         return VBC_OK;
     case VBC_OPT_SPMM_SIMT:
-        if (value < 0 || value > 5) VBC_FAIL(VBC_EARG, "SpMM kernel must be 0 (auto), 1 (SIMT), 2 (DMMA, scalar X loads), 3 (DMMA, 256-bit X-row loads), 4 (DMMA fed by bulk copies) or 5 (DMMA fed by cp.async)");
+        if (value < 0 || value > 1) VBC_FAIL(VBC_EARG, "SpMM kernel must be 0 (FP64 tensor tiles) or 1 (SIMT)");
         A->opt_spmm_simt = (int)value;
         return VBC_OK;
     case VBC_OPT_E2E_PIPELINE:

@@ -92,8 +92,8 @@ struct vbc_mat {
     int chunk_l[9] = {};                   // stripe boundaries of the chunks
     int64_t chunk_col[9] = {};             // first column of each chunk
     int nchunks = 0;                       // 0: not prepared, -1: chunking not applicable
-    // optional (VBC_OPT_E2E_PIPELINE): x is uploaded in pieces on its own stream; chunk c starts once x[0, chunk_xhi[c]) is there
-    int opt_e2e_pipeline = 0;
+    // VBC_OPT_E2E_PIPELINE (default on): x is uploaded in pieces on its own stream; chunk c starts once x[0, chunk_xhi[c]) is there
+    int opt_e2e_pipeline = 1;
     cudaStream_t h2d_stream = nullptr;
     cudaEvent_t h2d_ev[8] = {};
     int64_t chunk_xhi[8] = {};             // cumulative: one past the largest x index gathered by the stripes of chunks 0..c
@@ -136,16 +136,19 @@ int finalize_layout(vbc_mat *A, const void *h_pi_spl /* host copy, may be null f
 int memory_cost_device(const vbc_mat *A, int64_t *h_cost, int64_t *row_term);
 // spmv.cu
 int launch_spmv(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y);
-struct PeerSyncArgs { // in-kernel flag exchange of the fused multiply + all-gather (peer.cu -> spmv.cu)
-    int nranks, me;
+struct HaloLaunch { // one step of the row-partitioned iteration (peer.cu -> spmv.cu, k_spmv_adj_halo)
+    int n;                                     // destinations; dst[0] = own next-x buffer, dst[i] = rank (me + i) % n
+    void *dst[VBC_MAX_PEERS];
+    const unsigned char *d_mask; int chunk_shift;
+    int i0, i1;                                // interior stripes [i0, i1)
+    int me, nranks, do_wait, do_signal;
+    unsigned nbr_mask;
     unsigned long long *flags[VBC_MAX_PEERS];
-    unsigned long long *d_epoch;
-    unsigned *d_done;
+    unsigned long long *ctl;                   // claim counter, finished-claim counter, epoch
     int *timed_out;
-    int i0, i1;
+    unsigned long long *last_T;                // host: claim period of the previous launch on these counters (0: none yet)
 };
-int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs, const unsigned char *d_mask, int chunk_shift,
-                         const PeerSyncArgs *sync, const int *ranges /* {a0,a1,b0,b1} or null = all */);
+int launch_spmv_adj_halo(vbc_mat *A, double alpha, const void *d_x, const HaloLaunch *hl);
 // mixed.cu
 int launch_spmv_mixed(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y);
 // fwdt.cu

@@ -36,6 +36,25 @@ __global__ void k_check_spl(const Ti *__restrict__ spl, int64_t P, int64_t dim, 
     }
 }
 
+// CSC validation (the reference trusts SparseMatrixCSC's invariants; here a malformed index would send the merge, the
+// value scatter and later every multiply out of bounds): colptr[1] == 1, colptr nondecreasing and ending at nnz + 1,
+// 1 <= rowval <= m, rows strictly ascending within a column.  8 lanes per column.
+template <typename Ti>
+__global__ void __launch_bounds__(256) k_check_csc(const Ti *__restrict__ colptr, const Ti *__restrict__ rowval, int64_t n, int64_t m, int64_t nnz, int *err)
+{
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int lane = threadIdx.x & 7;
+    if (j >= n) return;
+    const int64_t b = (int64_t)colptr[j] - 1, e = (int64_t)colptr[j + 1] - 1;
+    if ((j == 0 && b != 0) || b < 0 || e < b || e > nnz) { if (lane == 0) atomicMax(err, PERR_CSC); return; }
+    bool bad = false;
+    for (int64_t t = b + lane; t < e; t += 8) {
+        const int64_t r = (int64_t)rowval[t];
+        if (r < 1 || r > m || (t > b && (int64_t)rowval[t - 1] >= r)) bad = true;
+    }
+    if (bad) atomicMax(err, PERR_CSC);
+}
+
 // asg[i] = 0-based part of row i  (`convert(MapPartition, Π).asg`, constructors_VBC.jl:22)
 template <typename Ti>
 __global__ void k_build_map(const Ti *__restrict__ spl, int64_t P, int64_t dim, int *__restrict__ asg)
@@ -421,6 +440,15 @@ static int pack_t(vbc_mat *A, const Ti *colptr, const Ti *rowval, const Tv *nzva
     int herr = 0;
     VBC_CUDA(cudaMemcpyAsync(&herr, t.err, sizeof(int), cudaMemcpyDeviceToHost, st));
     VBC_CUDA(cudaStreamSynchronize(st));
+    if (herr == 0 && n > 0) { // CSC arrays (the partitions are valid, so the kernels below index them safely)
+        int64_t nnz_h = 0;
+        { Ti last; VBC_CUDA(cudaMemcpy(&last, colptr + n, sizeof(Ti), cudaMemcpyDeviceToHost)); nnz_h = (int64_t)last - 1; }
+        if (nnz_h < 0) VBC_FAIL(VBC_EARG, "ArgumentError: colptr[end] < 1");
+        k_check_csc<Ti><<<nblk(n * 8, 256), 256, 0, st>>>(colptr, rowval, n, m, nnz_h, t.err); A->launches++;
+        VBC_CUDA(cudaMemcpyAsync(&herr, t.err, sizeof(int), cudaMemcpyDeviceToHost, st));
+        VBC_CUDA(cudaStreamSynchronize(st));
+        if (herr == PERR_CSC) VBC_FAIL(VBC_EARG, "ArgumentError: malformed SparseMatrixCSC (colptr must start at 1 and be nondecreasing, rowval must lie in 1:%lld and ascend strictly within each column)", (long long)m);
+    }
     if (herr == PERR_SPL) VBC_FAIL(VBC_EARG, "partition is not a SplitPartition of the matrix dimension (spl[1]==1, nondecreasing, spl[end]==dim+1)");
     if (herr == PERR_W) VBC_FAIL(VBC_ELIMIT, "AssertionError: w <= W (a stripe is wider than W=%d)", A->W);
     if (herr == PERR_U) VBC_FAIL(VBC_ELIMIT, "AssertionError: u <= U (a row part is taller than U=%d)", A->U);

@@ -1,9 +1,13 @@
-// peer.cu -- row-partitioned multiply across the GPUs of one box: x replicated through peer
-// memory (CUDA IPC over NVLink / NVSwitch), the all-gather fused into the adjoint kernel's
-// epilogue (spmv.cu, PeerDst), and a flag kernel as the only cross-rank step.
+// peer.cu -- row-partitioned multiply across the GPUs of one box: x lives in peer-mapped buffers
+// (CUDA IPC between processes, or plain peer access inside one process), and the exchange of the new
+// x is fused into the adjoint kernel (spmv.cu, k_spmv_adj_halo): boundary stripes store their results
+// straight into the buffers of the ranks that read them over NVLink / NVSwitch and the last one
+// publishes a flag; there is no collective call and no separate exchange launch in an iteration.
 #include <new>
 
 #include "common.cuh"
+
+#define VBC_PEER_CTL_WORDS 8 // claim counter, finished-claim counter, epoch, wait ns, waits that spun, longest wait, 2 spare
 
 struct vbc_peer {
     int vt = VBC_F64, rank = 0, nranks = 1, device = 0;
@@ -13,21 +17,15 @@ struct vbc_peer {
     bool ipc_opened[VBC_MAX_PEERS][VBC_PEER_HANDLES] = {};
     bool connected = false;
     int cur = 0;
-    unsigned long long *d_epoch = nullptr; // device-side epoch counter: the flag kernel advances it itself, so a
-                                           // captured CUDA graph of steps stays correct when replayed
+    unsigned long long *d_ctl = nullptr;   // device-side counters (VBC_PEER_CTL_WORDS): the kernels advance the epoch themselves,
+                                           // so a captured CUDA graph of steps stays correct when replayed
+    unsigned long long last_T = 0;         // claim period of the last fused launch on d_ctl (spmv.cu)
     int *d_timeout = nullptr;
     unsigned char *d_mask = nullptr; // per column chunk of this rank's slice: which destinations read it
     int chunk_shift = 0;
     int64_t mask_len = 0;
-    int fused_sync = 0;      // 0: multiply, then k_peer_flags; 1: flags inside the multiply kernel (removed); 2: split launches
-                             // [stripes i0..i1] [wait] [the rest] [signal] so the wait hides behind the first launch;
-                             // 3: plain multiply into the own buffer, then ONE kernel that pushes the chunks other ranks read
-                             //    and does the flag exchange (sparsity-aware mode only; experimental, not yet run on a GPU)
-    int i0 = 0, i1 = 0;      // stripes [i0, i1): no peer involved (run before the in-kernel wait)
-    unsigned *d_done = nullptr;
+    int i0 = 0, i1 = 0;              // interior stripes [i0, i1): gather only from this rank's slice, feed only this rank
     unsigned nbr_mask = 0xffffffffu; // ranks this rank exchanges flags with (bit r); default: everyone
-    int *d_push = nullptr;           // fused_sync 3: the column chunks of this rank's slice that some OTHER rank reads
-    int npush = 0;
     int64_t launches = 0;
 };
 
@@ -48,9 +46,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-// One CTA of 32 threads; thread r talks to rank r.
-//   signal: flags_r[me] = epoch  (release, system scope: this rank's earlier stores -- the y
-//           segments written by the preceding multiply on this stream -- are visible first)
+// The flag exchange on its own (vbc_peer_barrier): one CTA of 32 threads; thread r talks to rank r.
+//   signal: flags_r[me] = epoch  (release, system scope: this rank's earlier stores on this stream are visible first)
 //   wait  : spin until flags_me[r] >= epoch for every r (acquire), with a wall-clock bound so a
 //           dead peer cannot hang the GPU.
 __global__ void k_peer_flags(const __grid_constant__ FlagPtrs f, const int me, const int nranks, unsigned long long *__restrict__ d_epoch,
@@ -61,7 +58,7 @@ __global__ void k_peer_flags(const __grid_constant__ FlagPtrs f, const int me, c
     const unsigned long long epoch = *d_epoch + (do_signal ? 1ull : 0ull);
     __syncwarp();
     if (r == 0 && do_signal) *d_epoch = epoch;
-    if (r >= nranks || !((nbr_mask >> r) & 1u)) return; // only the ranks this one sends to or receives from
+    if (r >= nranks || r == me || !((nbr_mask >> r) & 1u)) return; // only the ranks this one sends to or receives from
     if (do_signal) {
         __threadfence_system();
         st_release_sys(f.p[r] + me, epoch);
@@ -81,56 +78,23 @@ __global__ void k_peer_flags(const __grid_constant__ FlagPtrs f, const int me, c
     }
 }
 
-// fused_sync 3.  The multiply has written this rank's whole y slice into its own next-x buffer with the plain
-// kernel; only the column chunks some other rank gathers from (push[0..npush), usually a fraction of a percent for a
-// banded operator) still have to travel.  Every CTA copies its share of those chunks to the ranks that read them;
-// the last CTA to finish then runs the flag exchange of k_peer_flags (signal, wait).
-struct PushDst {
-    void *p[VBC_MAX_PEERS]; // destination i of the rotated order of vbc_peer_spmv_step (p[0] = own buffer, unused here)
-    int n;
-};
-template <typename Tv>
-__global__ void __launch_bounds__(256) k_peer_push_flags(const Tv *__restrict__ src, const __grid_constant__ PushDst dst, const unsigned char *__restrict__ mask,
-                                                         const int chunk_shift, const int ncols, const int *__restrict__ push, const int npush,
-                                                         const __grid_constant__ FlagPtrs f, const int me, const int nranks, unsigned long long *__restrict__ d_epoch,
-                                                         unsigned *__restrict__ d_done, int *__restrict__ timed_out, const unsigned nbr_mask)
+// interior[l] = 1 when stripe l gathers only from x[own_lo, own_hi) and every column chunk it writes is read by this rank alone
+__global__ void __launch_bounds__(256) k_mark_interior(const StripeMeta *__restrict__ meta, const int *__restrict__ desc, const int L, const int reach,
+                                                        const long long own_lo, const long long own_hi, const unsigned char *__restrict__ mask,
+                                                        const int chunk_shift, const int full_replication, unsigned char *__restrict__ interior)
 {
-    for (int idx = blockIdx.x; idx < npush; idx += gridDim.x) {
-        const int ch = push[idx];
-        const unsigned mk = mask[ch];
-        const int c0 = ch << chunk_shift, c1 = min(ncols, c0 + (1 << chunk_shift));
-        for (int c = c0 + (int)threadIdx.x; c < c1; c += (int)blockDim.x) {
-            const Tv v = src[c];
-            for (int i = 1; i < dst.n; i++)
-                if ((mk >> i) & 1u) reinterpret_cast<Tv *>(dst.p[i])[c] = v;
-        }
+    const int l = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3), lane = threadIdx.x & 7; // 8 lanes per stripe
+    if (l >= L) return;
+    const StripeMeta a = meta[l], b = meta[l + 1];
+    bool ok = !full_replication;
+    for (int q = a.pos + lane; ok && q < b.pos; q += 8) {
+        const long long i = desc[q];
+        ok = i >= own_lo && i + reach <= own_hi;
     }
-    __threadfence_system(); // this thread's peer stores are visible system-wide before the CTA is counted as done
-    __shared__ bool last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned prev = atomicAdd(d_done, 1u);
-        last = prev == gridDim.x - 1;
-        if (last) *d_done = 0; // ready for the next launch (stream order)
-    }
-    __syncthreads();
-    if (!last || threadIdx.x >= 32) return;
-    __threadfence();
-    const int r = threadIdx.x;
-    const unsigned long long epoch = *d_epoch + 1ull;
-    __syncwarp();
-    if (r == 0) *d_epoch = epoch;
-    if (r >= nranks || !((nbr_mask >> r) & 1u)) return;
-    __threadfence_system();
-    st_release_sys(f.p[r] + me, epoch);
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (ld_acquire_sys(f.p[me] + r) < epoch) {
-        unsigned long long t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 4000000000ull) { atomicExch(timed_out, 1); break; }
-        __nanosleep(64);
-    }
+    if (ok && mask != nullptr && b.col > a.col && lane == 0)
+        for (int ch = a.col >> chunk_shift; ch <= ((b.col - 1) >> chunk_shift); ch++) ok = ok && ((mask[ch] | 1u) == 1u);
+    ok = __all_sync(0xffu << ((threadIdx.x & 31) & ~7), ok);
+    if (lane == 0) interior[l] = ok ? 1 : 0;
 }
 
 static int flags_launch(vbc_peer *P, cudaStream_t st, int barrier)
@@ -138,7 +102,7 @@ static int flags_launch(vbc_peer *P, cudaStream_t st, int barrier)
     if (!(barrier & 3)) return VBC_OK;
     FlagPtrs f;
     for (int r = 0; r < VBC_MAX_PEERS; r++) f.p[r] = r < P->nranks ? (unsigned long long *)P->bufs[r][2] : nullptr;
-    k_peer_flags<<<1, 32, 0, st>>>(f, P->rank, P->nranks, P->d_epoch, barrier & 1, (barrier & 2) ? 1 : 0, P->d_timeout, P->nbr_mask | (1u << P->rank));
+    k_peer_flags<<<1, 32, 0, st>>>(f, P->rank, P->nranks, P->d_ctl + 2, barrier & 1, (barrier & 2) ? 1 : 0, P->d_timeout, P->nbr_mask);
     P->launches++;
     VBC_CUDA(cudaGetLastError());
     return VBC_OK;
@@ -171,8 +135,9 @@ int vbc_peer_create(vbc_peer **out, int vt, int64_t xlen, int rank, int nranks, 
             rc = VBC_ENOMEM;
         }
     }
-    if (rc == VBC_OK && (cudaMalloc(&P->d_epoch, sizeof(unsigned long long)) != cudaSuccess || cudaMemset(P->d_epoch, 0, sizeof(unsigned long long)) != cudaSuccess)) {
-        set_error("vbc_peer_create: epoch allocation failed");
+    if (rc == VBC_OK && (cudaMalloc(&P->d_ctl, sizeof(unsigned long long) * VBC_PEER_CTL_WORDS) != cudaSuccess ||
+                         cudaMemset(P->d_ctl, 0, sizeof(unsigned long long) * VBC_PEER_CTL_WORDS) != cudaSuccess)) {
+        set_error("vbc_peer_create: counter allocation failed");
         rc = VBC_ENOMEM;
     }
     if (rc == VBC_OK && (cudaMalloc(&P->d_timeout, sizeof(int)) != cudaSuccess || cudaMemset(P->d_timeout, 0, sizeof(int)) != cudaSuccess)) {
@@ -247,53 +212,37 @@ int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, 
 {
     if (!P || !A) VBC_FAIL(VBC_EARG, "NULL argument");
     if (!P->connected) VBC_FAIL(VBC_EARG, "vbc_peer_connect has not been called");
+    if (barrier < 0 || barrier > 3) VBC_FAIL(VBC_EARG, "barrier must be 0..3");
     if (A->vt != P->vt) VBC_FAIL(VBC_EARG, "matrix and exchange buffers have different element types");
     if (A->m != P->xlen) VBC_FAIL(VBC_EDIM, "DimensionMismatch: A' needs x of length %lld, exchange buffers hold %lld", (long long)A->m, (long long)P->xlen);
     if (y_offset < 0 || y_offset + A->n > P->xlen) VBC_FAIL(VBC_EDIM, "DimensionMismatch: y slice [%lld, %lld) outside x of length %lld", (long long)y_offset, (long long)(y_offset + A->n), (long long)P->xlen);
+    if (P->i1 > A->L) VBC_FAIL(VBC_EDIM, "interior stripe range [%d, %d) outside the %lld stripes of the matrix", P->i0, P->i1, (long long)A->L);
     DeviceGuard guard(P->device);
     if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", P->device);
     const size_t tv = vt_size(P->vt);
-    void *dst[VBC_MAX_PEERS];
     const int nxt = 1 - P->cur;
-    // own buffer first: its stores are local; then the peers, starting after this rank so the
-    // ranks do not all hit the same destination at the same moment
-    int n = 0;
-    for (int i = 0; i < P->nranks; i++) {
-        const int r = (P->rank + i) % P->nranks;
-        dst[n++] = (char *)P->bufs[r][nxt] + tv * (size_t)y_offset;
-    }
     if (P->d_mask && A->n > 0 && ((A->n - 1) >> P->chunk_shift) >= P->mask_len)
         VBC_FAIL(VBC_EDIM, "peer mask covers %lld chunks, the y slice needs %lld", (long long)P->mask_len, (long long)(((A->n - 1) >> P->chunk_shift) + 1));
-    // the mask is indexed by (column in the y slice) >> shift; the kernel indexes by slab column, so no offset is needed
-    if (P->fused_sync == 3 && barrier == 3 && P->d_mask && P->d_done) {
-        // plain kernel into the own next-x buffer, then push + flags in one launch
-        VBC_TRY(launch_spmv(A, 1, alpha, P->own[P->cur], 0.0, dst[0]));
-        PushDst pd;
-        pd.n = n;
-        for (int i = 0; i < VBC_MAX_PEERS; i++) pd.p[i] = i < n ? dst[i] : nullptr;
-        FlagPtrs f;
-        for (int r = 0; r < VBC_MAX_PEERS; r++) f.p[r] = r < P->nranks ? (unsigned long long *)P->bufs[r][2] : nullptr;
-        int grid = P->npush < 1 ? 1 : (P->npush > 64 ? 64 : P->npush);
-        const unsigned nbr = P->nbr_mask | (1u << P->rank);
-        if (P->vt == VBC_F64)
-            k_peer_push_flags<double><<<grid, 256, 0, A->stream>>>((const double *)dst[0], pd, P->d_mask, P->chunk_shift, (int)A->n, P->d_push, P->npush, f, P->rank,
-                                                                   P->nranks, P->d_epoch, P->d_done, P->d_timeout, nbr);
-        else
-            k_peer_push_flags<float><<<grid, 256, 0, A->stream>>>((const float *)dst[0], pd, P->d_mask, P->chunk_shift, (int)A->n, P->d_push, P->npush, f, P->rank,
-                                                                  P->nranks, P->d_epoch, P->d_done, P->d_timeout, nbr);
-        P->launches++;
-        VBC_CUDA(cudaGetLastError());
-    } else if (P->fused_sync == 2 && barrier == 3 && P->i1 > P->i0) {
-        const int L = (int)A->L;
-        const int ra[4] = {P->i0, P->i1, 0, 0}, rc[4] = {0, P->i0, P->i1, L};
-        VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, nullptr, ra));
-        VBC_TRY(flags_launch(P, A->stream, 2)); // wait for the peers' previous step
-        VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, nullptr, rc));
-        VBC_TRY(flags_launch(P, A->stream, 1)); // publish this step
-    } else {
-        VBC_TRY(launch_spmv_adj_peer(A, alpha, P->own[P->cur], n, dst, P->d_mask, P->chunk_shift, nullptr, nullptr));
-        VBC_TRY(flags_launch(P, A->stream, barrier));
+    HaloLaunch hl{};
+    // own buffer first: its stores are local; then the peers, starting after this rank so the
+    // ranks do not all hit the same destination at the same moment
+    hl.n = P->nranks;
+    for (int i = 0; i < P->nranks; i++) {
+        const int r = (P->rank + i) % P->nranks;
+        hl.dst[i] = (char *)P->bufs[r][nxt] + tv * (size_t)y_offset;
     }
+    // the mask is indexed by (column in the y slice) >> shift; the kernel indexes by slab column, so no offset is needed
+    hl.d_mask = P->d_mask; hl.chunk_shift = P->chunk_shift;
+    hl.i0 = P->i0; hl.i1 = P->i1;
+    hl.me = P->rank; hl.nranks = P->nranks;
+    hl.do_signal = barrier & 1; hl.do_wait = (barrier & 2) ? 1 : 0;
+    hl.nbr_mask = P->nbr_mask;
+    for (int r = 0; r < VBC_MAX_PEERS; r++) hl.flags[r] = r < P->nranks ? (unsigned long long *)P->bufs[r][2] : nullptr;
+    hl.ctl = P->d_ctl;
+    hl.timed_out = P->d_timeout;
+    hl.last_T = &P->last_T;
+    VBC_TRY(launch_spmv_adj_halo(A, alpha, P->own[P->cur], &hl));
+    P->launches++;
     P->cur = nxt;
     return VBC_OK;
 }
@@ -303,42 +252,63 @@ int vbc_peer_set_mask(vbc_peer *P, const void *mask, int64_t nchunks, int chunk_
     if (!P) VBC_FAIL(VBC_EARG, "NULL argument");
     DeviceGuard guard(P->device);
     cudaFree(P->d_mask);
-    cudaFree(P->d_push);
-    P->d_mask = nullptr; P->d_push = nullptr; P->npush = 0; P->mask_len = 0; P->chunk_shift = 0;
+    P->d_mask = nullptr; P->mask_len = 0; P->chunk_shift = 0;
     if (!mask) return VBC_OK; // back to full replication
     if (nchunks < 1 || chunk_shift < 0 || chunk_shift > 30) VBC_FAIL(VBC_EARG, "bad mask geometry");
     VBC_CUDA(cudaMalloc(&P->d_mask, (size_t)nchunks));
     VBC_CUDA(cudaMemcpy(P->d_mask, mask, (size_t)nchunks, cudaMemcpyHostToDevice));
     P->mask_len = nchunks;
     P->chunk_shift = chunk_shift;
-    { // chunks with a reader other than this rank (bit 0 is the own buffer in the rotated destination order)
-        int *list = new (std::nothrow) int[(size_t)nchunks];
-        if (!list) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
-        int np = 0;
-        for (int64_t c = 0; c < nchunks; c++)
-            if (((const unsigned char *)mask)[c] & 0xfeu) list[np++] = (int)c;
-        cudaError_t e = cudaMalloc(&P->d_push, sizeof(int) * (size_t)(np > 0 ? np : 1));
-        if (e == cudaSuccess && np > 0) e = cudaMemcpy(P->d_push, list, sizeof(int) * (size_t)np, cudaMemcpyHostToDevice);
-        delete[] list;
-        if (e != cudaSuccess) VBC_FAIL(VBC_ECUDA, "vbc_peer_set_mask: push list upload failed: %s", cudaGetErrorString(e));
-        P->npush = np;
-    }
     return VBC_OK;
 }
 
-int vbc_peer_set_fused_sync(vbc_peer *P, int enable, int64_t i0, int64_t i1)
+int vbc_peer_set_interior(vbc_peer *P, int64_t i0, int64_t i1)
 {
     if (!P) VBC_FAIL(VBC_EARG, "NULL argument");
-    if (i0 < 0 || i1 < i0 || enable < 0 || enable > 3) VBC_FAIL(VBC_EARG, "bad interior range / mode");
-    if (enable == 1) enable = 0; // the in-kernel flag exchange lost to the separate flag kernel and quadrupled the kernel's code size; removed
-    DeviceGuard guard(P->device);
-    if (enable && !P->d_done) {
-        VBC_CUDA(cudaMalloc(&P->d_done, sizeof(unsigned)));
-        VBC_CUDA(cudaMemset(P->d_done, 0, sizeof(unsigned)));
-    }
-    P->fused_sync = enable;
+    if (i0 < 0 || i1 < i0 || i1 > 0x7fffffff) VBC_FAIL(VBC_EARG, "bad interior range [%lld, %lld)", (long long)i0, (long long)i1);
     P->i0 = (int)i0;
     P->i1 = (int)i1;
+    return VBC_OK;
+}
+
+int vbc_peer_auto_interior(vbc_peer *P, vbc_mat *A, int64_t y_offset, int64_t *i0_out, int64_t *i1_out)
+{
+    if (!P || !A) VBC_FAIL(VBC_EARG, "NULL argument");
+    if (A->m != P->xlen || y_offset < 0 || y_offset + A->n > P->xlen) VBC_FAIL(VBC_EDIM, "DimensionMismatch: the matrix does not fit the exchange buffers");
+    if (A->opt_parity) VBC_FAIL(VBC_EARG, "needs the compact layout (parity mode is on)");
+    DeviceGuard guard(P->device);
+    if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", P->device);
+    const int L = (int)A->L;
+    int64_t best0 = 0, best1 = 0;
+    if (L > 0 && P->nranks > 1) {
+        unsigned char *d_f = nullptr;
+        VBC_CUDA(cudaMalloc(&d_f, (size_t)L));
+        unsigned char *h_f = new (std::nothrow) unsigned char[(size_t)L];
+        if (!h_f) { cudaFree(d_f); VBC_FAIL(VBC_ENOMEM, "host allocation failed"); }
+        const int reach = A->desc_mode == DESC_BLOCKS ? A->u0 : 1;
+        const long long grid = ((long long)L * 8 + 255) / 256;
+        // without a mask every stripe feeds every rank: nothing is interior
+        k_mark_interior<<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, L, reach, (long long)y_offset, (long long)(y_offset + A->n), P->d_mask,
+                                                                P->chunk_shift, P->d_mask == nullptr ? 1 : 0, d_f);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_f, d_f, (size_t)L, cudaMemcpyDeviceToHost, A->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(A->stream);
+        cudaFree(d_f);
+        if (e != cudaSuccess) { delete[] h_f; VBC_FAIL(VBC_ECUDA, "vbc_peer_auto_interior: %s", cudaGetErrorString(e)); }
+        for (int64_t l = 0; l < L;) { // longest run of interior stripes
+            if (!h_f[l]) { l++; continue; }
+            int64_t e1 = l;
+            while (e1 < L && h_f[e1]) e1++;
+            if (e1 - l > best1 - best0) { best0 = l; best1 = e1; }
+            l = e1;
+        }
+        delete[] h_f;
+    } else if (P->nranks == 1) {
+        best0 = 0; best1 = L; // a single rank has no boundary
+    }
+    P->i0 = (int)best0; P->i1 = (int)best1;
+    if (i0_out) *i0_out = best0;
+    if (i1_out) *i1_out = best1;
     return VBC_OK;
 }
 
@@ -355,6 +325,17 @@ int vbc_peer_barrier(vbc_peer *P, void *cuda_stream, int barrier)
     if (!P->connected) VBC_FAIL(VBC_EARG, "vbc_peer_connect has not been called");
     DeviceGuard guard(P->device);
     return flags_launch(P, (cudaStream_t)cuda_stream, barrier);
+}
+
+int vbc_peer_wait_stats(vbc_peer *P, uint64_t stats[4], int reset)
+{
+    if (!P || !stats) VBC_FAIL(VBC_EARG, "NULL argument");
+    DeviceGuard guard(P->device);
+    unsigned long long h[VBC_PEER_CTL_WORDS];
+    VBC_CUDA(cudaMemcpy(h, P->d_ctl, sizeof(h), cudaMemcpyDeviceToHost));
+    stats[0] = h[2]; stats[1] = h[3]; stats[2] = h[4]; stats[3] = h[5];
+    if (reset) VBC_CUDA(cudaMemset(P->d_ctl + 3, 0, 3 * sizeof(unsigned long long)));
+    return VBC_OK;
 }
 
 int vbc_peer_status(vbc_peer *P, int *timed_out)
@@ -375,10 +356,8 @@ void vbc_peer_destroy(vbc_peer *P)
             if (P->ipc_opened[r][k]) cudaIpcCloseMemHandle(P->bufs[r][k]);
     for (int k = 0; k < VBC_PEER_HANDLES; k++) cudaFree(P->own[k]);
     cudaFree(P->d_timeout);
-    cudaFree(P->d_epoch);
+    cudaFree(P->d_ctl);
     cudaFree(P->d_mask);
-    cudaFree(P->d_done);
-    cudaFree(P->d_push);
     delete P;
 }
 

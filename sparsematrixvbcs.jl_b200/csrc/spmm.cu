@@ -153,25 +153,13 @@ __global__ void __launch_bounds__(256, (WB * KT <= 8 ? 3 : 2)) k_spmm_adj(const 
 #ifndef VBC_DMMA_KS
 #define VBC_DMMA_KS 2
 #endif
-#ifndef VBC_DMMA_VEC_DEFAULT
-#define VBC_DMMA_VEC_DEFAULT 0 // 1: the 256-bit X-row loads are the default whenever the panels are aligned
-#endif
 __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, const double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// VEC: the right-hand sides are permuted over the N-tiles -- fragment column n of tile nt is right-hand side
-// kb + 4 n + nt -- so the four B values of a lane are 32 contiguous bytes of one X row (one 256-bit load, the
-// eight lanes of a k-row cover the whole 256-byte row) and its C values are two runs of 4 contiguous Y entries.
-// Needs k % 4 == 0 and 32-byte aligned rows (checked at launch).
-__device__ __forceinline__ void ld_row4(const double *p, double (&v)[4])
-{
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-}
-
-template <int MODE, bool VEC>
+template <int MODE>
 __global__ void __launch_bounds__(256, VBC_DMMA_MINB) k_spmm_adj_dmma(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                         const double *__restrict__ val, const double *__restrict__ X, const long long ldx,
                                                         double *__restrict__ Y, const long long ldy, const int L, const int k,
@@ -205,16 +193,10 @@ __global__ void __launch_bounds__(256, VBC_DMMA_MINB) k_spmm_adj_dmma(const Stri
                     vp += 4 * KS * (long long)w;
 #pragma unroll
                     for (int q = 0; q < KS; q++) {
-                        if constexpr (VEC) {
-                            const int col = kb + 4 * g;
-                            if (xi[q] >= 0 && col < k) ld_row4(X + (long long)xi[q] * ldx + col, bv[q]);
-                            else { bv[q][0] = 0.0; bv[q][1] = 0.0; bv[q][2] = 0.0; bv[q][3] = 0.0; }
-                        } else {
 #pragma unroll
-                            for (int nt = 0; nt < 4; nt++) {
-                                const int col = kb + nt * 8 + g;
-                                bv[q][nt] = (xi[q] >= 0 && col < k) ? __ldg(X + (long long)xi[q] * ldx + col) : 0.0;
-                            }
+                        for (int nt = 0; nt < 4; nt++) {
+                            const int col = kb + nt * 8 + g;
+                            bv[q][nt] = (xi[q] >= 0 && col < k) ? __ldg(X + (long long)xi[q] * ldx + col) : 0.0;
                         }
                     }
 #pragma unroll
@@ -224,338 +206,18 @@ __global__ void __launch_bounds__(256, VBC_DMMA_MINB) k_spmm_adj_dmma(const Stri
                 }
                 if (arow) {
                     double *yp = Y + (long long)(a.col + wb + g) * ldy;
-                    if constexpr (VEC) {
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) {
 #pragma unroll
                         for (int e = 0; e < 2; e++) {
-                            const int col = kb + 4 * (2 * t + e);
-                            if (col < k) {
-                                double2 *y2 = reinterpret_cast<double2 *>(yp + col);
-                                double2 lo = make_double2(alpha * c[0][e], alpha * c[1][e]), hi = make_double2(alpha * c[2][e], alpha * c[3][e]);
-                                if (beta != 0.0) {
-                                    const double2 o0 = y2[0], o1 = y2[1];
-                                    lo.x += beta * o0.x; lo.y += beta * o0.y; hi.x += beta * o1.x; hi.y += beta * o1.y;
-                                }
-                                y2[0] = lo; y2[1] = hi;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int nt = 0; nt < 4; nt++) {
-#pragma unroll
-                            for (int e = 0; e < 2; e++) {
-                                const int col = kb + nt * 8 + 2 * t + e;
-                                if (col < k) yp[col] = (beta == 0.0) ? alpha * c[nt][e] : alpha * c[nt][e] + beta * yp[col];
-                            }
+                            const int col = kb + nt * 8 + 2 * t + e;
+                            if (col < k) yp[col] = (beta == 0.0) ? alpha * c[nt][e] : alpha * c[nt][e] + beta * yp[col];
                         }
                     }
                 }
             }
         }
     }
-}
-
-// Adjoint SpMM, DMMA tiles fed through shared memory by the bulk-copy engine (TMA).
-//
-// ncu on the two kernels above (profiles/r01_spmm_ncu.md): both sit at ~90 % of the L1 data pipe
-// (l1tex__data_pipe_lsu_wavefronts) with DRAM and L2 far below their peaks.  The m8n8k4 B fragment puts FOUR
-// DIFFERENT gathered X rows in adjacent lanes, so every 32-byte sector of a register load is its own
-// data-pipe wavefront (one sector per clock and SM), hit or miss, scalar or 256-bit.  Here the X rows never
-// pass through the load/store data pipe: each stored row is one `cp.async.bulk` (global -> shared, 256 bytes,
-// completion counted on an mbarrier), the stripe's slab of val is one more bulk copy per chunk, and the
-// fragments are read back with conflict-free LDS.64 (rows padded to 288 bytes).  One warp = one private
-// ring of ST stages x CH rows; the ring keeps running across stripe boundaries, row indices and stripe
-// meta are fetched one step ahead, so nothing in the loop waits on a global load.
-#ifndef VBC_TMA_CH
-#define VBC_TMA_CH 16     // rows per stage (multiple of 4, at most 32)
-#endif
-#ifndef VBC_TMA_ST
-#define VBC_TMA_ST 2      // stages per warp
-#endif
-#ifndef VBC_TMA_MINB
-#define VBC_TMA_MINB 2    // CTAs per SM the register allocation is bounded for (the ring: 8 warps x ST x (CH x 352) bytes per CTA)
-#endif
-#define VBC_TMA_ROWB 288  // bytes between staged rows: 256 + 32, i.e. 8 banks of shift per row -> the 4 rows x 8 doubles of a half-warp hit 32 distinct banks
-#define VBC_TMA_STAGE (VBC_TMA_CH * VBC_TMA_ROWB + VBC_TMA_CH * 8 * 8)
-#define VBC_TMA_SMEM (8 * VBC_TMA_ST * VBC_TMA_STAGE + 8 * VBC_TMA_ST * 8)
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(const uint32_t bar, const uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(const uint32_t bar, const uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(const uint32_t dst, const void *src, const uint32_t bytes, const uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(const uint32_t bar, const uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(256, VBC_TMA_MINB) k_spmm_adj_tma(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
-                                                       const double *__restrict__ val, const double *__restrict__ X, const long long ldx,
-                                                       double *__restrict__ Y, const long long ldy, const int L, const int k,
-                                                       const int u0, const int log2u, const double alpha, const double beta)
-{
-    constexpr int CH = VBC_TMA_CH, ST = VBC_TMA_ST, ROWB = VBC_TMA_ROWB, STAGE = VBC_TMA_STAGE;
-    extern __shared__ __align__(128) unsigned char tma_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    unsigned char *ring = tma_smem + (size_t)warp * (ST * STAGE);
-    const uint32_t ring_u32 = smem_u32(ring);
-    const uint32_t bar_u32 = smem_u32(tma_smem + 8 * ST * STAGE) + (uint32_t)warp * ST * 8;
-    if (lane == 0)
-        for (int s = 0; s < ST; s++) mbar_init(bar_u32 + 8 * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    const int kb = (int)blockIdx.y * 32;
-    const int kc = min(32, k - kb);
-    const uint32_t rowbytes = (uint32_t)kc * 8u;
-    const double *Xk = X + kb;
-    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
-    const int l0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-
-    // ---- producer: a cursor (stripe pl, row pr) over this warp's stripes, one chunk of up to CH rows per step
-    int pl = l0, pr = 0, pR = 0, pw = 0, xi_pref = 0, issued = 0;
-    StripeMeta pa{}, na{}, nb{};
-    auto rows_of = [&](const StripeMeta &a, const StripeMeta &b, int &w) {
-        w = b.col - a.col;
-        return (w > 0) ? ((MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w)) : 0;
-    };
-    auto fetch_meta = [&](const int l) { // the meta of stripe l rides ahead of its use
-        if (l < L) { na = ld_meta(meta + l); nb = ld_meta(meta + l + 1); }
-    };
-    auto settle = [&]() { // pl points at a stripe whose meta is in (na, nb): skip stripes without rows, then prefetch indices
-        while (pl < L) {
-            pa = na;
-            pR = rows_of(na, nb, pw);
-            fetch_meta(pl + nwarps);
-            if (pR > 0) break;
-            pl += nwarps;
-        }
-        pr = 0;
-        xi_pref = (pl < L && lane < min(CH, pR)) ? row_xindex<MODE>(desc, pa.pos, lane, u0, log2u) : 0;
-    };
-    fetch_meta(pl);
-    settle();
-    auto issue = [&]() {
-        if (pl >= L) return;
-        const int s = issued % ST;
-        const int nr = min(CH, pR - pr);
-        const uint32_t bar = bar_u32 + 8u * s, dst = ring_u32 + (uint32_t)(s * STAGE);
-        const bool val_bulk = ((pa.ofs | (long long)pw) & 1) == 0; // 16-byte aligned slab chunks
-        const int xi = xi_pref;
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)nr * rowbytes + (val_bulk ? (uint32_t)(nr * pw) * 8u : 0u));
-        __syncwarp();
-        if (lane < nr) bulk_g2s(dst + (uint32_t)(lane * ROWB), Xk + (long long)xi * ldx, rowbytes, bar);
-        if (lane == 0 && val_bulk) bulk_g2s(dst + (uint32_t)(CH * ROWB), val + pa.ofs + (long long)pr * pw, (uint32_t)(nr * pw) * 8u, bar);
-        issued++;
-        pr += CH;
-        if (pr >= pR) { pl += nwarps; settle(); }
-        else xi_pref = (lane < min(CH, pR - pr)) ? row_xindex<MODE>(desc, pa.pos, pr + lane, u0, log2u) : 0;
-    };
-    for (int i = 0; i < ST; i++) issue();
-
-    // ---- consumer: the same stripes in the same order
-    int consumed = 0;
-    for (int l = l0; l < L; l += nwarps) {
-        const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
-        int w;
-        const int R = rows_of(a, b, w);
-        if (w <= 0) continue;
-        const bool val_bulk = ((a.ofs | (long long)w) & 1) == 0;
-        const bool arow = g < w; // this lane's A row (stripe column) exists
-        double c[4][2];
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) { c[nt][0] = 0.0; c[nt][1] = 0.0; }
-        for (int r = 0; r < R; r += CH) {
-            const int s = consumed % ST;
-            const uint32_t parity = (uint32_t)((consumed / ST) & 1);
-            const unsigned char *sp = ring + s * STAGE;
-            double av[CH / 4];
-            if (!val_bulk) { // odd slab start or odd width: the A values come straight from global
-#pragma unroll
-                for (int q = 0; q < CH / 4; q++)
-                    av[q] = (arow && r + 4 * q + t < R) ? __ldcs(val + a.ofs + (long long)(r + 4 * q + t) * w + g) : 0.0;
-            }
-            {
-                unsigned spins = 0;
-                while (!mbar_try_wait(bar_u32 + 8u * s, parity))
-                    if (++spins > (1u << 22)) __trap(); // a lost copy must not hang the GPU
-            }
-            if (val_bulk) {
-                const double *vs = reinterpret_cast<const double *>(sp + CH * ROWB);
-#pragma unroll
-                for (int q = 0; q < CH / 4; q++) av[q] = (arow && r + 4 * q + t < R) ? vs[(4 * q + t) * w + g] : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < CH / 4; q++) {
-                const bool rok = r + 4 * q + t < R;
-                const unsigned char *rp = sp + (4 * q + t) * ROWB + g * 8;
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) {
-                    const double bv = (rok && nt * 8 + g < kc) ? *reinterpret_cast<const double *>(rp + nt * 64) : 0.0;
-                    dmma_m8n8k4(c[nt], av[q], bv);
-                }
-            }
-            __syncwarp();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the stage is handed back to the copy engine
-            consumed++;
-            issue();
-        }
-        if (arow) {
-            double *yp = Y + (long long)(a.col + g) * ldy;
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int col = kb + nt * 8 + 2 * t + e;
-                    if (col < k) yp[col] = (beta == 0.0) ? alpha * c[nt][e] : alpha * c[nt][e] + beta * yp[col];
-                }
-            }
-        }
-    }
-}
-
-// Same ring, filled with LDGSTS (cp.async, 16 bytes per lane) instead of bulk copies.  NOT YET RUN ON A GPU
-// (written after the round's GPU budget was spent; option 5, never selected automatically).  Why it should beat
-// the bulk-copy kernel: ncu shows that kernel spending a third of its instructions and most of its "wait" stalls
-// in the compiler's per-lane ELECT / R2UR / UBLKCP loop (one 256-byte copy per ~10 instructions, operands in
-// uniform registers).  Here 16 adjacent lanes copy one X row, 32 lanes two rows per instruction, with ordinary
-// per-lane addresses: 8 instructions per 16-row chunk, and the natural lane order keeps the data pipe at one
-// wavefront per 128 bytes.  Completion is counted with cp.async groups (one group per chunk, always committed).
-__device__ __forceinline__ void cp_async16(const uint32_t dst, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(256, VBC_TMA_MINB) k_spmm_adj_cpasync(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
-                                                           const double *__restrict__ val, const double *__restrict__ X, const long long ldx,
-                                                           double *__restrict__ Y, const long long ldy, const int L, const int k,
-                                                           const int u0, const int log2u, const double alpha, const double beta)
-{
-    constexpr int CH = VBC_TMA_CH, ST = VBC_TMA_ST, ROWB = VBC_TMA_ROWB, STAGE = VBC_TMA_STAGE;
-    extern __shared__ __align__(128) unsigned char tma_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    unsigned char *ring = tma_smem + (size_t)warp * (ST * STAGE);
-    const uint32_t ring_u32 = smem_u32(ring);
-    const int kb = (int)blockIdx.y * 32;
-    const int kc = min(32, k - kb);
-    const int ppr = kc >> 1; // 16-byte pieces per staged row
-    const double *Xk = X + kb;
-    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
-    const int l0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-
-    int pl = l0, pr = 0, pR = 0, pw = 0, xi_pref = 0, issued = 0;
-    StripeMeta pa{}, na{}, nb{};
-    auto rows_of = [&](const StripeMeta &a, const StripeMeta &b, int &w) {
-        w = b.col - a.col;
-        return (w > 0) ? ((MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w)) : 0;
-    };
-    auto fetch_meta = [&](const int l) {
-        if (l < L) { na = ld_meta(meta + l); nb = ld_meta(meta + l + 1); }
-    };
-    auto settle = [&]() {
-        while (pl < L) {
-            pa = na;
-            pR = rows_of(na, nb, pw);
-            fetch_meta(pl + nwarps);
-            if (pR > 0) break;
-            pl += nwarps;
-        }
-        pr = 0;
-        xi_pref = (pl < L && lane < min(CH, pR)) ? row_xindex<MODE>(desc, pa.pos, lane, u0, log2u) : 0;
-    };
-    fetch_meta(pl);
-    settle();
-    auto issue = [&]() {
-        if (pl < L) {
-            const int s = issued % ST;
-            const int nr = min(CH, pR - pr);
-            const uint32_t dst = ring_u32 + (uint32_t)(s * STAGE);
-            const int npieces = nr * ppr;
-            for (int i0 = 0; i0 < npieces; i0 += 32) { // uniform trip count: the shuffle below needs the whole warp
-                const int i = i0 + lane;
-                const int row = (ppr == 16) ? (i >> 4) : (i / ppr);
-                const int piece = i - row * ppr;
-                const int xi = __shfl_sync(0xffffffffu, xi_pref, min(row, nr - 1));
-                if (i < npieces) cp_async16(dst + (uint32_t)(row * ROWB + piece * 16), Xk + (long long)xi * ldx + 2 * piece);
-            }
-            if (((pa.ofs | (long long)pw) & 1) == 0) { // the chunk of the stripe's slab, when 16-byte aligned
-                const double *src = val + pa.ofs + (long long)pr * pw;
-                for (int i = lane; i < (nr * pw) >> 1; i += 32) cp_async16(dst + (uint32_t)(CH * ROWB + i * 16), src + 2 * i);
-            }
-            issued++;
-            pr += CH;
-            if (pr >= pR) { pl += nwarps; settle(); }
-            else xi_pref = (lane < min(CH, pR - pr)) ? row_xindex<MODE>(desc, pa.pos, pr + lane, u0, log2u) : 0;
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory"); // one group per call, empty at the tail, so the wait below can count
-    };
-    for (int i = 0; i < ST; i++) issue();
-
-    int consumed = 0;
-    for (int l = l0; l < L; l += nwarps) {
-        const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
-        int w;
-        const int R = rows_of(a, b, w);
-        if (w <= 0) continue;
-        const bool val_staged = ((a.ofs | (long long)w) & 1) == 0;
-        const bool arow = g < w;
-        double c[4][2];
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) { c[nt][0] = 0.0; c[nt][1] = 0.0; }
-        for (int r = 0; r < R; r += CH) {
-            const int s = consumed % ST;
-            const unsigned char *sp = ring + s * STAGE;
-            double av[CH / 4];
-            if (!val_staged) {
-#pragma unroll
-                for (int q = 0; q < CH / 4; q++)
-                    av[q] = (arow && r + 4 * q + t < R) ? __ldcs(val + a.ofs + (long long)(r + 4 * q + t) * w + g) : 0.0;
-            }
-            asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory"); // this lane's copies of the oldest chunk have landed
-            __syncwarp();                                                     // ... and so have every other lane's
-            if (val_staged) {
-                const double *vs = reinterpret_cast<const double *>(sp + CH * ROWB);
-#pragma unroll
-                for (int q = 0; q < CH / 4; q++) av[q] = (arow && r + 4 * q + t < R) ? vs[(4 * q + t) * w + g] : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < CH / 4; q++) {
-                const bool rok = r + 4 * q + t < R;
-                const unsigned char *rp = sp + (4 * q + t) * ROWB + g * 8;
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) {
-                    const double bv = (rok && nt * 8 + g < kc) ? *reinterpret_cast<const double *>(rp + nt * 64) : 0.0;
-                    dmma_m8n8k4(c[nt], av[q], bv);
-                }
-            }
-            __syncwarp(); // every lane is done reading the stage before it is refilled
-            consumed++;
-            issue();
-        }
-        if (arow) {
-            double *yp = Y + (long long)(a.col + g) * ldy;
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int col = kb + nt * 8 + 2 * t + e;
-                    if (col < k) yp[col] = (beta == 0.0) ? alpha * c[nt][e] : alpha * c[nt][e] + beta * yp[col];
-                }
-            }
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 template <typename Tv, int MODE, int WB, int KT>
@@ -654,38 +316,8 @@ static int launch_spmm_mode(vbc_mat *A, int trans, int k, Tv alpha, const Tv *X,
                 int64_t g2 = (int64_t)A->sm_count * 8;
                 if (g2 > need) g2 = need;
                 if (g2 < 1) g2 = 1;
-                // tiles fed through shared memory (4: bulk copies, 5: cp.async -- experimental): stripes at most 8 wide, 16-byte aligned X rows
-                if ((A->opt_spmm_simt == 4 || A->opt_spmm_simt == 5) && A->W <= 8 && (k % 2) == 0 && (ldx % 2) == 0 && ((uintptr_t)X % 16) == 0) {
-                    const bool bulk = A->opt_spmm_simt == 4;
-                    static bool attr_set[2][2][64] = {}; // per kernel instance and device; first call, outside any stream capture
-                    if (!attr_set[bulk][MODE][A->device & 63]) {
-                        if (bulk) VBC_CUDA(cudaFuncSetAttribute(k_spmm_adj_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, VBC_TMA_SMEM));
-                        else VBC_CUDA(cudaFuncSetAttribute(k_spmm_adj_cpasync<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, VBC_TMA_SMEM));
-                        attr_set[bulk][MODE][A->device & 63] = true;
-                    }
-                    int64_t g3 = (int64_t)A->sm_count * VBC_TMA_MINB;
-                    if (g3 > need) g3 = need;
-                    if (g3 < 1) g3 = 1;
-                    dim3 grid3((unsigned)g3, (unsigned)((k + 31) / 32));
-                    if (bulk)
-                        k_spmm_adj_tma<MODE><<<grid3, 256, VBC_TMA_SMEM, A->stream>>>(A->d_meta, A->d_desc, (const double *)A->d_val, (const double *)X, ldx,
-                                                                                     (double *)Y, ldy, L, k, A->u0, log2u, (double)alpha, (double)beta);
-                    else
-                        k_spmm_adj_cpasync<MODE><<<grid3, 256, VBC_TMA_SMEM, A->stream>>>(A->d_meta, A->d_desc, (const double *)A->d_val, (const double *)X, ldx,
-                                                                                         (double *)Y, ldy, L, k, A->u0, log2u, (double)alpha, (double)beta);
-                    A->launches++;
-                    VBC_CUDA(cudaGetLastError());
-                    return VBC_OK;
-                }
-                // 256-bit X-row loads when every row of both panels is 32-byte aligned (opt_spmm_simt: 2 forces the scalar loads, 3 the vector loads)
-                const bool aligned = (k % 4) == 0 && (ldx % 4) == 0 && (ldy % 4) == 0 && ((uintptr_t)X % 32) == 0 && ((uintptr_t)Y % 32) == 0;
-                const bool vec = aligned && (A->opt_spmm_simt == 3 || (A->opt_spmm_simt == 0 && VBC_DMMA_VEC_DEFAULT));
-                if (vec)
-                    k_spmm_adj_dmma<MODE, true><<<(unsigned)g2, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const double *)A->d_val, (const double *)X, ldx,
-                                                                                 (double *)Y, ldy, L, k, A->u0, log2u, (double)alpha, (double)beta);
-                else
-                    k_spmm_adj_dmma<MODE, false><<<(unsigned)g2, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const double *)A->d_val, (const double *)X, ldx,
-                                                                                  (double *)Y, ldy, L, k, A->u0, log2u, (double)alpha, (double)beta);
+                k_spmm_adj_dmma<MODE><<<(unsigned)g2, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const double *)A->d_val, (const double *)X, ldx,
+                                                                          (double *)Y, ldy, L, k, A->u0, log2u, (double)alpha, (double)beta);
                 A->launches++;
                 VBC_CUDA(cudaGetLastError());
                 return VBC_OK;
@@ -788,18 +420,20 @@ extern "C" int vbc_spmm(vbc_mat *A, int trans, int64_t k, double alpha, const vo
     DeviceGuard guard(A->device);
     if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", A->device);
     if (on_device) return launch_spmm(A, trans, k, alpha, X, ldx, beta, Y, ldy, layout);
-    // host panels: copy the ld-strided storage as is (outer x ld elements)
+    // host panels: an ld-strided buffer holds (outer - 1) * ld + inner elements (BLAS convention), so the copies are 2-D:
+    // `inner` elements per row of the panel, pitch ld on both sides; the padding between rows is neither read nor written
     const size_t tv = vt_size(A->vt);
     const int64_t xo = layout == 0 ? xr : k, yo = layout == 0 ? yr : k; // outer extents
+    const int64_t xi = layout == 0 ? k : xr, yi = layout == 0 ? k : yr; // inner extents
     void *dX = nullptr, *dY = nullptr;
     VBC_CUDA(cudaMalloc(&dX, tv * (size_t)(xo * ldx > 0 ? xo * ldx : 1)));
     if (cudaMalloc(&dY, tv * (size_t)(yo * ldy > 0 ? yo * ldy : 1)) != cudaSuccess) { cudaFree(dX); VBC_FAIL(VBC_ENOMEM, "spmm panel allocation failed"); }
     int rc = VBC_OK;
     cudaError_t e = cudaSuccess;
-    if (xo * ldx > 0) e = cudaMemcpyAsync(dX, X, tv * (size_t)(xo * ldx), cudaMemcpyHostToDevice, A->stream);
-    if (e == cudaSuccess && yo * ldy > 0) e = cudaMemcpyAsync(dY, Y, tv * (size_t)(yo * ldy), cudaMemcpyHostToDevice, A->stream); // keeps ld padding intact
+    if (xo > 0 && xi > 0) e = cudaMemcpy2DAsync(dX, tv * (size_t)ldx, X, tv * (size_t)ldx, tv * (size_t)xi, (size_t)xo, cudaMemcpyHostToDevice, A->stream);
+    if (e == cudaSuccess && yo > 0 && yi > 0 && beta != 0.0) e = cudaMemcpy2DAsync(dY, tv * (size_t)ldy, Y, tv * (size_t)ldy, tv * (size_t)yi, (size_t)yo, cudaMemcpyHostToDevice, A->stream);
     if (e == cudaSuccess) rc = launch_spmm(A, trans, k, alpha, dX, ldx, beta, dY, ldy, layout);
-    if (e == cudaSuccess && rc == VBC_OK && yo * ldy > 0) e = cudaMemcpyAsync(Y, dY, tv * (size_t)(yo * ldy), cudaMemcpyDeviceToHost, A->stream);
+    if (e == cudaSuccess && rc == VBC_OK && yo > 0 && yi > 0) e = cudaMemcpy2DAsync(Y, tv * (size_t)ldy, dY, tv * (size_t)ldy, tv * (size_t)yi, (size_t)yo, cudaMemcpyDeviceToHost, A->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(A->stream);
     cudaFree(dX); cudaFree(dY);
     if (e != cudaSuccess) VBC_FAIL(VBC_ECUDA, "vbc_spmm: %s", cudaGetErrorString(e));

@@ -75,22 +75,23 @@ template <> struct Ld<float, 1> { static __device__ __forceinline__ void s(const
 template <> struct Ld<float, 2> { static __device__ __forceinline__ void s(const float *p, float (&v)[2]) { const float2 t = ld_val(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; } };
 template <> struct Ld<float, 4> { static __device__ __forceinline__ void s(const float *p, float (&v)[4]) { const float4 t = ld_val(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
 
-// Destinations of the adjoint result.  n == 0: the caller's y (alpha/beta applied).  n > 0: the
-// fused all-gather of the row-partitioned multiply -- every finished y segment is stored into the
-// next-x buffer of each of the n ranks (own HBM and NVLink peer mappings); beta is not applied.
-struct PeerDst {
-    int n;
+// Row-partitioned multiply with the x exchange fused into the kernel (peer.cu, vbc_peer_spmv_step).
+// Destination 0 is this rank's own next-x buffer, destination i the buffer of rank (me + i) % n, mapped
+// over NVLink; all pointers are already offset to this rank's first column.
+struct HaloArgs {
+    int n;                                   // destinations
     void *p[VBC_MAX_PEERS];
-    const unsigned char *mask; // optional: mask[(col >> chunk_shift)] bit i set <=> destination i reads that column chunk
+    const unsigned char *mask;               // optional: mask[col >> chunk_shift] bit i set <=> destination i reads that column chunk
     int chunk_shift;
-    // in-kernel cross-rank synchronisation (fused flag exchange); sync_n == 0: none (the caller launches k_peer_flags)
-    int sync_n, me;                               // ranks, this rank
-    unsigned long long *flags[VBC_MAX_PEERS];     // flag block of every rank (flags[me] is local)
-    unsigned long long *d_epoch;                  // epoch signalled at the end of this rank's previous step
-    unsigned *d_done;                             // CTAs finished in this launch
+    int i0, i1;                              // interior stripes [i0, i1): gather only from this rank's slice, feed only this rank
+    int nrunsA, nruns;                       // boundary runs of 32/G adjacent stripes: [0, nrunsA) cover [0, i0), the rest cover [i1, L)
+    int rpc, nclaims;                        // runs per claim, number of claims
+    unsigned long long T;                    // claims per launch including the failing one of every warp: nclaims + warps in the grid
+    int me, nranks, do_wait, do_signal;
+    unsigned nbr_mask;                       // ranks this rank exchanges flags with
+    unsigned long long *flags[VBC_MAX_PEERS]; // flag block of every rank (flags[me] is local)
+    unsigned long long *ctl;                 // [0] claim counter, [1] finished-claim counter, [2] epoch (steps published so far), [3..5] wait statistics
     int *timed_out;
-    int i0, i1;                                   // stripes [i0, i1) need nothing from other ranks and feed only this rank
-    int ra0, ra1, rb0, rb1;                       // sync_n == 0: the stripe ranges this launch covers ([ra0,ra1) then [rb0,rb1))
 };
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
@@ -103,32 +104,36 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-
-template <typename Tv, int EPV, bool PEER>
-__device__ __forceinline__ void store_y(Tv *__restrict__ y, const PeerDst &dst, const int col, const Tv (&acc)[EPV], const Tv alpha, const Tv beta)
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long *p)
 {
-    if constexpr (PEER) {
-        Tv v[EPV];
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// x gathers.  XC = false: read-only path (x does not change while the kernel runs).  XC = true: the halo part of x is
+// written by other GPUs while this kernel runs (and only read after an acquire of their flag): L2 is the point of
+// coherence for those peer writes, so the load must not be served from a line L1 might still hold.
+template <typename Tv, bool XC> __device__ __forceinline__ Tv ld_x(const Tv *p)
+{
+    if constexpr (XC) return __ldcg(p);
+    else return __ldg(p);
+}
+
+template <typename Tv, int EPV>
+__device__ __forceinline__ void store_y(Tv *__restrict__ y, const int col, const Tv (&acc)[EPV], const Tv alpha, const Tv beta)
+{
+    Tv *yp = y + col;
 #pragma unroll
-        for (int e = 0; e < EPV; e++) v[e] = alpha * acc[e];
-        for (int i = 0; i < dst.n; i++) {
-            Tv *yp = reinterpret_cast<Tv *>(dst.p[i]) + col;
-#pragma unroll
-            for (int e = 0; e < EPV; e++) yp[e] = v[e];
-        }
-    } else {
-        Tv *yp = y + col;
-#pragma unroll
-        for (int e = 0; e < EPV; e++) yp[e] = (beta == (Tv)0) ? alpha * acc[e] : alpha * acc[e] + beta * yp[e];
-    }
+    for (int e = 0; e < EPV; e++) yp[e] = (beta == (Tv)0) ? alpha * acc[e] : alpha * acc[e] + beta * yp[e];
 }
 
 // ---- adjoint ----------------------------------------------------------------------------------
 // CPR > 0: compile-time vectors per row (power of two, <= G).  CPR == 0: runtime cpr <= G.
-template <typename Tv, int G, int MODE, int EPV, int CPR, bool PEER>
+template <typename Tv, int G, int MODE, int EPV, int CPR, bool XC>
 __device__ __forceinline__ void adj_stripe(const StripeMeta a, const StripeMeta b, const int w, const int lane, const unsigned gmask,
                                            const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
-                                           Tv *__restrict__ y, const PeerDst &dst, const int u0, const int log2u, const Tv alpha, const Tv beta)
+                                           Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
     int cpr, rps, c, r0;
     if constexpr (CPR > 0) { cpr = CPR; rps = G / CPR; c = lane % CPR; r0 = lane / CPR; }
@@ -166,7 +171,7 @@ __device__ __forceinline__ void adj_stripe(const StripeMeta a, const StripeMeta 
 #pragma unroll
         for (int k = 0; k < UNR; k++) xi[k] = walk.next_if(ok[k]);
 #pragma unroll
-        for (int k = 0; k < UNR; k++) xv[k] = ok[k] ? __ldg(x + xi[k]) : (Tv)0;
+        for (int k = 0; k < UNR; k++) xv[k] = ok[k] ? ld_x<Tv, XC>(x + xi[k]) : (Tv)0;
 #pragma unroll
         for (int k = 0; k < UNR; k++)
 #pragma unroll
@@ -187,14 +192,14 @@ __device__ __forceinline__ void adj_stripe(const StripeMeta a, const StripeMeta 
             }
     }
     // y[j + Δj] = tmp[Δj]  (multiply_1DVBC.jl:114-116), with BLAS alpha/beta
-    if (lane < cpr) store_y<Tv, EPV, PEER>(y, dst, a.col + lane * EPV, acc, alpha, beta);
+    if (lane < cpr) store_y<Tv, EPV>(y, a.col + lane * EPV, acc, alpha, beta);
 }
 
 // wide stripes (more vectors per row than lanes): one lane per column, serial over rows
-template <typename Tv, int G, int MODE, bool PEER>
+template <typename Tv, int G, int MODE, bool XC>
 __device__ __noinline__ void adj_stripe_wide(const StripeMeta a, const StripeMeta b, const int w, const int lane,
                                              const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
-                                             Tv *__restrict__ y, const PeerDst &dst, const int u0, const Tv alpha, const Tv beta)
+                                             Tv *__restrict__ y, const int u0, const Tv alpha, const Tv beta)
 {
     const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
     for (int col = lane; col < w; col += G) {
@@ -202,123 +207,187 @@ __device__ __noinline__ void adj_stripe_wide(const StripeMeta a, const StripeMet
         RowWalk<MODE> walk;
         walk.init(desc, a.pos, 0, 1, u0, -1);
         const Tv *vp = val + a.ofs + col;
-        for (int r = 0; r < R; r++) { acc = fma(__ldcs(vp), __ldg(x + walk.next()), acc); vp += w; }
+        for (int r = 0; r < R; r++) { acc = fma(__ldcs(vp), ld_x<Tv, XC>(x + walk.next()), acc); vp += w; }
         const Tv accv[1] = {acc};
-        store_y<Tv, 1, PEER>(y, dst, a.col + col, accv, alpha, beta);
+        store_y<Tv, 1>(y, a.col + col, accv, alpha, beta);
     }
 }
 
-template <typename Tv, int G, int MODE, int EPV, bool PEER>
+template <typename Tv, int G, int MODE, int EPV, bool XC>
 __device__ __forceinline__ void adj_dispatch_cpr(const StripeMeta a, const StripeMeta b, const int w, const int lane, const unsigned gmask,
                                                  const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
-                                                 Tv *__restrict__ y, const PeerDst &dst, const int u0, const int log2u, const Tv alpha, const Tv beta)
+                                                 Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
     const int cpr = w / EPV;
-    if (cpr == 1) adj_stripe<Tv, G, MODE, EPV, 1, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
-    else if (cpr == 2) adj_stripe<Tv, G, MODE, EPV, 2, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
-    else if (cpr == 4) adj_stripe<Tv, G, MODE, EPV, 4, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
-    else if (cpr <= G) adj_stripe<Tv, G, MODE, EPV, 0, PEER>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
-    else adj_stripe_wide<Tv, G, MODE, PEER>(a, b, w, lane, desc, val, x, y, dst, u0, alpha, beta);
+    if (cpr == 1) adj_stripe<Tv, G, MODE, EPV, 1, XC>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    else if (cpr == 2) adj_stripe<Tv, G, MODE, EPV, 2, XC>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    else if (cpr == 4) adj_stripe<Tv, G, MODE, EPV, 4, XC>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    else if (cpr <= G) adj_stripe<Tv, G, MODE, EPV, 0, XC>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    else adj_stripe_wide<Tv, G, MODE, XC>(a, b, w, lane, desc, val, x, y, u0, alpha, beta);
 }
 
-template <typename Tv, int G, int MODE, bool PEER>
-__global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
-                                                   const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ y,
-                                                   const __grid_constant__ PeerDst dst, const int *__restrict__ order,
-                                                   const int L, const int u0, const int log2u, const Tv alpha, const Tv beta)
+// one stripe, body class chosen from its width and the alignment of its slab (the analogue of le_nest, util.jl:28-38)
+template <typename Tv, int G, int MODE, bool XC>
+__device__ __forceinline__ void adj_one_stripe(const StripeMeta a, const StripeMeta b, const int lane, const unsigned gmask,
+                                               const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
+                                               Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
     constexpr int VE = 16 / (int)sizeof(Tv);
+    const int w = b.col - a.col;
+    if (w <= 0) return;
+#if VBC_WIDE_LD
+    if (sizeof(Tv) == 8 && (w % 4) == 0 && (a.ofs % 4) == 0)
+        adj_dispatch_cpr<Tv, G, MODE, (sizeof(Tv) == 8 ? 4 : VE), XC>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    else
+#endif
+    if ((w % VE) == 0 && (a.ofs % VE) == 0)
+        adj_dispatch_cpr<Tv, G, MODE, VE, XC>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0)
+        adj_dispatch_cpr<Tv, G, MODE, (VE == 4 ? 2 : 1), XC>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    else
+        adj_dispatch_cpr<Tv, G, MODE, 1, XC>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+}
+
+// stripes [lo, hi) dealt round-robin to the groups of the grid.  order == null: stripes in index order, next stripe's
+// meta prefetched.  order != null (mixed widths): position l holds stripe order[l], stripes of one body class are
+// adjacent, so a warp's groups agree.  (One loop for both, so the stripe bodies exist once in the kernel.)
+template <typename Tv, int G, int MODE>
+__device__ __forceinline__ void adj_range(const StripeMeta *__restrict__ meta, const int *__restrict__ order, const int lo, const int hi,
+                                          const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
+                                          Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta)
+{
     const int lane = threadIdx.x % G;
     const unsigned gmask = group_mask<G>();
     const int ngroups = (int)((gridDim.x * blockDim.x) / G);
-    if constexpr (PEER) {
-        // Fused all-gather: the warp's groups own adjacent stripes, i.e. one contiguous run of columns.
-        // Their results are staged in shared memory and flushed to every destination (own next-x buffer
-        // and the peers' over NVLink) with full-warp coalesced stores -- 128-256 B per store instruction
-        // instead of one 16-32 B store per group, which is what NVLink write packets want.
-        constexpr int GPW = 32 / G;
-        __shared__ Tv stage_all[8][GPW * 32];
-        Tv *stage = stage_all[threadIdx.x >> 5];
-        const int lane32 = threadIdx.x & 31, gid = lane32 / G;
-        const int nwarps = ngroups / GPW;
-        const PeerDst none{};
-        const int warp0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-        auto run_range = [&](const int lo, const int hi) {
-        for (int lbase = lo + warp0 * GPW; lbase < hi; lbase += nwarps * GPW) {
-            const int l = lbase + gid;
-            const int lend = min(lbase + GPW, hi);
-            const int colbase = ld_meta(meta + lbase).col, colend = ld_meta(meta + lend).col;
-            // sparsity-aware replication: when every column chunk of this run is read by this rank only, the
-            // results go straight to the own next-x buffer -- no staging, no flush (the common case for a banded operator)
-            bool self_only = false;
-            if (dst.mask != nullptr && colend > colbase) {
-                self_only = true;
-                for (int ch = colbase >> dst.chunk_shift; ch <= ((colend - 1) >> dst.chunk_shift); ch++) self_only = self_only && (__ldg(dst.mask + ch) == 1);
-            }
-            if (l < hi) {
-                const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
-                const int w = b.col - a.col;
-                Tv *ys = self_only ? reinterpret_cast<Tv *>(dst.p[0]) : stage - colbase; // the stripe bodies store y[a.col + ...]
-                if (w > 0) {
-                    if ((w % VE) == 0 && (a.ofs % VE) == 0)
-                        adj_dispatch_cpr<Tv, G, MODE, VE, false>(a, b, w, lane, gmask, desc, val, x, ys, none, u0, log2u, alpha, (Tv)0);
-                    else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0)
-                        adj_dispatch_cpr<Tv, G, MODE, (VE == 4 ? 2 : 1), false>(a, b, w, lane, gmask, desc, val, x, ys, none, u0, log2u, alpha, (Tv)0);
-                    else
-                        adj_dispatch_cpr<Tv, G, MODE, 1, false>(a, b, w, lane, gmask, desc, val, x, ys, none, u0, log2u, alpha, (Tv)0);
-                }
-            }
-            if (self_only) continue; // warp-uniform
-            __syncwarp();
-            const int ncols = colend - colbase;
-            if (dst.mask == nullptr) { // full replication
-                for (int i = 0; i < dst.n; i++) {
-                    Tv *d = reinterpret_cast<Tv *>(dst.p[i]) + colbase;
-                    for (int c = lane32; c < ncols; c += 32) d[c] = stage[c];
-                }
-            } else { // sparsity-aware replication: a destination gets only the column chunks it gathers from
-                for (int c = lane32; c < ncols; c += 32) {
-                    const unsigned mk = __ldg(dst.mask + ((colbase + c) >> dst.chunk_shift));
-                    const Tv v = stage[c];
-                    for (int i = 0; i < dst.n; i++)
-                        if ((mk >> i) & 1u) reinterpret_cast<Tv *>(dst.p[i])[colbase + c] = v;
-                }
-            }
-            __syncwarp();
-        }
-        };
-        // one copy of the stripe bodies: the (at most two) ranges of this launch are walked by the same loop
-        for (int part = 0; part < 2; part++) run_range(part ? dst.rb0 : dst.ra0, min(part ? dst.rb1 : dst.ra1, L));
-        return;
-    }
-    int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) / G);
-    if (l >= L) return;
-    // order == null: stripes in index order, next stripe's meta prefetched.  order != null (mixed widths):
-    // position l holds stripe order[l], stripes of one body class are adjacent, so a warp's groups agree.
+    int l = lo + (int)((blockIdx.x * blockDim.x + threadIdx.x) / G);
+    if (l >= hi) return;
     StripeMeta na, nb;
     if (order == nullptr) { na = ld_meta(meta + l); nb = ld_meta(meta + l + 1); }
-    for (; l < L; l += ngroups) {
+    for (; l < hi; l += ngroups) {
         StripeMeta a, b;
         if (order == nullptr) {
             a = na; b = nb;
-            if (l + ngroups < L) { na = ld_meta(meta + l + ngroups); nb = ld_meta(meta + l + ngroups + 1); } // next stripe's meta rides along
+            if (l + ngroups < hi) { na = ld_meta(meta + l + ngroups); nb = ld_meta(meta + l + ngroups + 1); } // next stripe's meta rides along
         } else {
             const int ls = __ldg(order + l);
             a = ld_meta(meta + ls); b = ld_meta(meta + ls + 1);
         }
-        const int w = b.col - a.col;
-        if (w <= 0) continue;
-#if VBC_WIDE_LD
-        if (sizeof(Tv) == 8 && (w % 4) == 0 && (a.ofs % 4) == 0)
-            adj_dispatch_cpr<Tv, G, MODE, (sizeof(Tv) == 8 ? 4 : VE), false>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
-        else
-#endif
-        if ((w % VE) == 0 && (a.ofs % VE) == 0)
-            adj_dispatch_cpr<Tv, G, MODE, VE, false>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
-        else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0)
-            adj_dispatch_cpr<Tv, G, MODE, (VE == 4 ? 2 : 1), false>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
-        else
-            adj_dispatch_cpr<Tv, G, MODE, 1, false>(a, b, w, lane, gmask, desc, val, x, y, dst, u0, log2u, alpha, beta);
+        adj_one_stripe<Tv, G, MODE, false>(a, b, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+    }
+}
+
+template <typename Tv, int G, int MODE>
+__global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+                                          const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ y,
+                                          const int *__restrict__ order, const int L, const int u0, const int log2u, const Tv alpha, const Tv beta)
+{
+    adj_range<Tv, G, MODE>(meta, order, 0, L, desc, val, x, y, u0, log2u, alpha, beta);
+}
+
+// ---- adjoint with the x exchange of the row-partitioned iteration fused in (north_star (e)) -------------------------
+// One launch per iteration x_{t+1} <- alpha * A' x_t on this rank's stripes.
+//   interior stripes [i0, i1) gather only from this rank's own slice of x and feed only this rank: they run first, exactly
+//     like the plain kernel, storing into the own next-x buffer.  Nothing here depends on another GPU.
+//   boundary stripes (the rest; for a banded operator the few hundred at both ends of the slab) read x entries that the
+//     neighbours produced in their previous step and produce entries the neighbours read in their next one.  They are cut
+//     into runs of 32/G adjacent stripes and CLAIMED (one atomic per claim) by whichever warps finish their interior share
+//     first, so they fill the tail of the launch instead of lengthening it.  A claiming warp first waits (acquire, system
+//     scope) until every neighbour has published the previous step -- by then that happened a whole kernel ago, the wait
+//     only ever spins when the ranks have drifted by more than one step -- computes its stripes with L2-coherent x loads,
+//     stages the run's results in shared memory and stores them with full-warp coalesced stores into the own next-x buffer
+//     and into the buffers of exactly the ranks that gather from those columns (mask), over NVLink.  The warp that
+//     finishes the last claim publishes the step to the neighbours (release, system scope).
+// Counters never need a reset: every warp makes exactly one failing claim, so a launch advances the claim counter by
+// T = nclaims + warps and `old % T` is the claim index in every launch; the epoch (ctl[2]) is read by a warp only between
+// its successful claim and its completion, and written only after all claims have completed.
+template <typename Tv, int G, int MODE>
+__device__ __noinline__ void adj_boundary_run(const StripeMeta *__restrict__ meta, const int lbase, const int lend, const int *__restrict__ desc,
+                                              const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ stage, const HaloArgs &h,
+                                              const int u0, const int log2u, const Tv alpha)
+{
+    const int lane = threadIdx.x % G, lane32 = threadIdx.x & 31, gid = lane32 / G;
+    const unsigned gmask = group_mask<G>();
+    const int colbase = ld_meta(meta + lbase).col, colend = ld_meta(meta + lend).col;
+    const int l = lbase + gid;
+    if (l < lend) // the stripe bodies store y[a.col + ...]: point them at the staging row of this run
+        adj_one_stripe<Tv, G, MODE, true>(ld_meta(meta + l), ld_meta(meta + l + 1), lane, gmask, desc, val, x, stage - colbase, u0, log2u, alpha, (Tv)0);
+    __syncwarp();
+    const int ncols = colend - colbase;
+    if (h.mask == nullptr) { // full replication: every destination gets the run
+        for (int i = 0; i < h.n; i++) {
+            Tv *d = reinterpret_cast<Tv *>(h.p[i]) + colbase;
+            for (int c = lane32; c < ncols; c += 32) d[c] = stage[c];
+        }
+    } else { // sparsity-aware replication: a destination gets only the column chunks it gathers from
+        for (int c = lane32; c < ncols; c += 32) {
+            const unsigned mk = __ldg(h.mask + ((colbase + c) >> h.chunk_shift)) | 1u;
+            const Tv v = stage[c];
+            for (int i = 0; i < h.n; i++)
+                if ((mk >> i) & 1u) reinterpret_cast<Tv *>(h.p[i])[colbase + c] = v;
+        }
+    }
+    __syncwarp();
+}
+
+template <typename Tv, int G, int MODE>
+__global__ void VBC_ADJ_BOUNDS k_spmv_adj_halo(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+                                               const Tv *__restrict__ val, const Tv *__restrict__ x, const __grid_constant__ HaloArgs h,
+                                               const int L, const int u0, const int log2u, const Tv alpha)
+{
+    constexpr int GPW = 32 / G;
+    adj_range<Tv, G, MODE>(meta, nullptr, h.i0, h.i1, desc, val, x, reinterpret_cast<Tv *>(h.p[0]), u0, log2u, alpha, (Tv)0);
+    if (h.nclaims == 0) return;
+    __shared__ Tv stage_all[8][GPW * 32];
+    Tv *stage = stage_all[threadIdx.x >> 5];
+    const int lane32 = threadIdx.x & 31;
+    bool waited = false;
+    unsigned long long epoch = 0;
+    __syncwarp();
+    for (;;) {
+        unsigned long long old = 0;
+        if (lane32 == 0) old = atomicAdd(h.ctl + 0, 1ull);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        const int claim = (int)(old % h.T);
+        if (claim >= h.nclaims) break; // the one failing claim of this warp
+        if (!waited) {
+            waited = true;
+            epoch = ld_relaxed_gpu_u64(h.ctl + 2); // steps this rank has published: the neighbours must have published as many
+            if (h.do_wait && lane32 < h.nranks && lane32 != h.me && ((h.nbr_mask >> lane32) & 1u)) {
+                unsigned long long t0, t1 = 0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                bool spun = false;
+                while (ld_acquire_sys_u64(h.flags[h.me] + lane32) < epoch) {
+                    spun = true;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 4000000000ull) { atomicExch(h.timed_out, 1); break; } // 4 s: a dead peer must not hang the GPU
+                    __nanosleep(32);
+                }
+                if (spun) { // wait statistics (vbc_peer_wait_stats): total ns, waits that spun, longest
+                    atomicAdd(h.ctl + 3, t1 - t0);
+                    atomicAdd(h.ctl + 4, 1ull);
+                    atomicMax(h.ctl + 5, t1 - t0);
+                }
+            }
+            __syncwarp();
+        }
+        for (int run = claim * h.rpc; run < min((claim + 1) * h.rpc, h.nruns); run++) {
+            int lbase, lend;
+            if (run < h.nrunsA) { lbase = run * GPW; lend = min(lbase + GPW, h.i0); }
+            else { lbase = h.i1 + (run - h.nrunsA) * GPW; lend = min(lbase + GPW, L); }
+            adj_boundary_run<Tv, G, MODE>(meta, lbase, lend, desc, val, x, stage, h, u0, log2u, alpha);
+        }
+        __threadfence_system(); // this lane's stores (own HBM and peers) are visible system-wide before the claim counts as done
+        __syncwarp();
+        unsigned long long fin = 0;
+        if (lane32 == 0) fin = atomicAdd(h.ctl + 1, 1ull);
+        fin = __shfl_sync(0xffffffffu, fin, 0);
+        if ((fin % (unsigned long long)h.nclaims) == (unsigned long long)(h.nclaims - 1)) { // last claim of this launch: publish the step
+            // (do_signal == 0: a separate flag kernel publishes and advances the epoch -- vbc_peer_barrier)
+            __threadfence_system();
+            if (h.do_signal && lane32 == 0) *reinterpret_cast<volatile unsigned long long *>(h.ctl + 2) = epoch + 1ull;
+            if (h.do_signal && lane32 < h.nranks && lane32 != h.me && ((h.nbr_mask >> lane32) & 1u))
+                st_release_sys_u64(h.flags[lane32] + h.me, epoch + 1ull);
+        }
     }
 }
 
@@ -503,21 +572,53 @@ static int auto_group(const vbc_mat *A)
     return G;
 }
 
-template <typename Tv, int G, int MODE, bool PEER>
-static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y, const PeerDst &dst)
+template <typename Tv, int G, int MODE>
+static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
 {
     int occ = 0;
-    VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_adj<Tv, G, MODE, PEER>, 256, 0));
+    VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_adj<Tv, G, MODE>, 256, 0));
     if (occ < 1) occ = 1;
     if (A->opt_grid_mult > 0) occ = A->opt_grid_mult;
     int64_t grid = (int64_t)A->sm_count * occ;
     // a stripe range [l0, l1) is launched by offsetting meta: its entries are absolute (value offset, descriptor, column)
-    const bool ranged = !PEER && A->range_l0 >= 0 && A->d_order == nullptr;
+    const bool ranged = A->range_l0 >= 0 && A->d_order == nullptr;
     const int64_t l0 = ranged ? A->range_l0 : 0, l1 = ranged ? A->range_l1 : A->L;
     const int64_t need = ((l1 - l0) * G + 255) / 256;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    k_spmv_adj<Tv, G, MODE, PEER><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta + l0, A->d_desc, (const Tv *)A->d_val, x, y, dst, PEER ? nullptr : A->d_order, (int)(l1 - l0), A->u0, ilog2_exact(A->u0), alpha, beta);
+    k_spmv_adj<Tv, G, MODE><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta + l0, A->d_desc, (const Tv *)A->d_val, x, y, A->d_order, (int)(l1 - l0), A->u0, ilog2_exact(A->u0), alpha, beta);
+    A->launches++;
+    VBC_CUDA(cudaGetLastError());
+    return VBC_OK;
+}
+
+// the fused multiply + exchange: a persistent grid of exactly the resident capacity (the boundary claims assume every warp runs)
+template <typename Tv, int G, int MODE>
+static int launch_halo_t(vbc_mat *A, Tv alpha, const Tv *x, HaloArgs &h, unsigned long long *last_T)
+{
+    int occ = 0;
+    VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_adj_halo<Tv, G, MODE>, 256, 0));
+    if (occ < 1) occ = 1;
+    int64_t grid = (int64_t)A->sm_count * occ;
+    const int64_t need = (A->L * G + 255) / 256;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    constexpr int GPW = 32 / G;
+    const int L = (int)A->L;
+    h.nrunsA = (h.i0 + GPW - 1) / GPW;
+    h.nruns = h.nrunsA + (L - h.i1 + GPW - 1) / GPW;
+    const int64_t warps = grid * 8;
+    h.rpc = (int)((h.nruns + 2 * warps - 1) / (2 * warps)); // at most two claims per warp on average: the claim counter is one address
+    if (h.rpc < 1) h.rpc = 1;
+    h.nclaims = (h.nruns + h.rpc - 1) / h.rpc;
+    h.T = (unsigned long long)h.nclaims + (unsigned long long)warps;
+    // the claim arithmetic (`old % T`) needs counters that are multiples of T at launch: when the geometry changes
+    // (another matrix, another interior range), the two counters restart from zero in stream order; the epoch stays
+    if (last_T && *last_T != h.T) {
+        if (*last_T != 0) VBC_CUDA(cudaMemsetAsync(h.ctl, 0, 2 * sizeof(unsigned long long), A->stream));
+        *last_T = h.T;
+    }
+    k_spmv_adj_halo<Tv, G, MODE><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, h, L, A->u0, ilog2_exact(A->u0), alpha);
     A->launches++;
     VBC_CUDA(cudaGetLastError());
     return VBC_OK;
@@ -540,15 +641,26 @@ static int launch_fwd_t(vbc_mat *A, Tv alpha, const Tv *x, Tv *y)
     return VBC_OK;
 }
 
-template <typename Tv, bool PEER>
-static int launch_adj_any(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y, const PeerDst &dst)
+template <typename Tv>
+static int launch_adj_any(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
 {
     const bool rows = A->desc_mode == DESC_ROWS;
     const int G = A->opt_adj_group ? A->opt_adj_group : auto_group(A);
-    if (G >= 32) return rows ? launch_adj_t<Tv, 32, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 32, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
-    if (G >= 16) return rows ? launch_adj_t<Tv, 16, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 16, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
-    if (G >= 8) return rows ? launch_adj_t<Tv, 8, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 8, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
-    return rows ? launch_adj_t<Tv, 4, DESC_ROWS, PEER>(A, alpha, x, beta, y, dst) : launch_adj_t<Tv, 4, DESC_BLOCKS, PEER>(A, alpha, x, beta, y, dst);
+    if (G >= 32) return rows ? launch_adj_t<Tv, 32, DESC_ROWS>(A, alpha, x, beta, y) : launch_adj_t<Tv, 32, DESC_BLOCKS>(A, alpha, x, beta, y);
+    if (G >= 16) return rows ? launch_adj_t<Tv, 16, DESC_ROWS>(A, alpha, x, beta, y) : launch_adj_t<Tv, 16, DESC_BLOCKS>(A, alpha, x, beta, y);
+    if (G >= 8) return rows ? launch_adj_t<Tv, 8, DESC_ROWS>(A, alpha, x, beta, y) : launch_adj_t<Tv, 8, DESC_BLOCKS>(A, alpha, x, beta, y);
+    return rows ? launch_adj_t<Tv, 4, DESC_ROWS>(A, alpha, x, beta, y) : launch_adj_t<Tv, 4, DESC_BLOCKS>(A, alpha, x, beta, y);
+}
+
+template <typename Tv>
+static int launch_halo_any(vbc_mat *A, Tv alpha, const Tv *x, HaloArgs &h, unsigned long long *last_T)
+{
+    const bool rows = A->desc_mode == DESC_ROWS;
+    const int G = A->opt_adj_group ? A->opt_adj_group : auto_group(A);
+    if (G >= 32) return rows ? launch_halo_t<Tv, 32, DESC_ROWS>(A, alpha, x, h, last_T) : launch_halo_t<Tv, 32, DESC_BLOCKS>(A, alpha, x, h, last_T);
+    if (G >= 16) return rows ? launch_halo_t<Tv, 16, DESC_ROWS>(A, alpha, x, h, last_T) : launch_halo_t<Tv, 16, DESC_BLOCKS>(A, alpha, x, h, last_T);
+    if (G >= 8) return rows ? launch_halo_t<Tv, 8, DESC_ROWS>(A, alpha, x, h, last_T) : launch_halo_t<Tv, 8, DESC_BLOCKS>(A, alpha, x, h, last_T);
+    return rows ? launch_halo_t<Tv, 4, DESC_ROWS>(A, alpha, x, h, last_T) : launch_halo_t<Tv, 4, DESC_BLOCKS>(A, alpha, x, h, last_T);
 }
 
 template <typename Tv>
@@ -599,7 +711,7 @@ static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, 
     const bool rows = A->desc_mode == DESC_ROWS;
     if (trans) {
         if (A->L == 0) return VBC_OK; // n == 0: nothing to write
-        return launch_adj_any<Tv, false>(A, alpha, x, beta, y, PeerDst{});
+        return launch_adj_any<Tv>(A, alpha, x, beta, y);
     }
     if (A->opt_fwd_atomic != 1) { // owner-computes forward through the transposed unit index (fwdt.cu)
         VBC_TRY(ensure_tindex(A));
@@ -613,31 +725,29 @@ static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, 
     return rows ? launch_fwd_t<Tv, 8, DESC_ROWS>(A, alpha, x, y) : launch_fwd_t<Tv, 8, DESC_BLOCKS>(A, alpha, x, y);
 }
 
-// adjoint multiply whose result goes to `n` destination buffers (each already offset to this
-// rank's first column): the compute half of vbc_peer_spmv_step.
-int launch_spmv_adj_peer(vbc_mat *A, double alpha, const void *d_x, int n, void *const *dst_ptrs, const unsigned char *d_mask, int chunk_shift,
-                         const PeerSyncArgs *sync, const int *ranges)
+// One step of the row-partitioned iteration: the adjoint multiply of this rank's slab with the exchange of the new x
+// fused in (k_spmv_adj_halo).  dst_ptrs[i]: next-x buffer of destination i, already offset to this rank's first column.
+int launch_spmv_adj_halo(vbc_mat *A, double alpha, const void *d_x, const HaloLaunch *hl)
 {
     if (A->opt_parity) VBC_FAIL(VBC_EARG, "peer multiply needs the compact layout (parity mode is on)");
-    if (n < 1 || n > VBC_MAX_PEERS) VBC_FAIL(VBC_EARG, "peer count %d out of 1..%d", n, VBC_MAX_PEERS);
+    if (hl->n < 1 || hl->n > VBC_MAX_PEERS) VBC_FAIL(VBC_EARG, "peer count %d out of 1..%d", hl->n, VBC_MAX_PEERS);
+    if (A->W > 32) VBC_FAIL(VBC_ELIMIT, "the fused multiply + exchange stages a run of stripes in shared memory: stripes may be at most 32 columns wide (W = %d)", A->W);
+    if (A->d_order != nullptr) VBC_FAIL(VBC_ELIMIT, "the fused multiply + exchange walks the stripes in index order: matrices whose stripes were regrouped by width class are not supported");
     if (A->L == 0) return VBC_OK;
-    PeerDst dst{};
-    dst.n = n;
-    for (int i = 0; i < VBC_MAX_PEERS; i++) dst.p[i] = i < n ? dst_ptrs[i] : nullptr;
-    dst.mask = d_mask;
-    dst.chunk_shift = chunk_shift;
-    dst.sync_n = 0;
-    dst.ra0 = 0; dst.ra1 = (int)A->L; dst.rb0 = dst.rb1 = 0;
-    if (ranges) { dst.ra0 = ranges[0]; dst.ra1 = ranges[1]; dst.rb0 = ranges[2]; dst.rb1 = ranges[3]; }
-    if (sync) {
-        dst.sync_n = sync->nranks; dst.me = sync->me;
-        for (int r = 0; r < VBC_MAX_PEERS; r++) dst.flags[r] = r < sync->nranks ? sync->flags[r] : nullptr;
-        dst.d_epoch = sync->d_epoch; dst.d_done = sync->d_done; dst.timed_out = sync->timed_out;
-        dst.i0 = sync->i0 < 0 ? 0 : (sync->i0 > (int)A->L ? (int)A->L : sync->i0);
-        dst.i1 = sync->i1 < dst.i0 ? dst.i0 : (sync->i1 > (int)A->L ? (int)A->L : sync->i1);
-    }
-    if (A->vt == VBC_F64) return launch_adj_any<double, true>(A, alpha, (const double *)d_x, 0.0, nullptr, dst);
-    return launch_adj_any<float, true>(A, (float)alpha, (const float *)d_x, 0.0f, nullptr, dst);
+    HaloArgs h{};
+    h.n = hl->n;
+    for (int i = 0; i < VBC_MAX_PEERS; i++) h.p[i] = i < hl->n ? hl->dst[i] : nullptr;
+    h.mask = hl->d_mask;
+    h.chunk_shift = hl->chunk_shift;
+    const int L = (int)A->L;
+    h.i0 = hl->i0 < 0 ? 0 : (hl->i0 > L ? L : hl->i0);
+    h.i1 = hl->i1 < h.i0 ? h.i0 : (hl->i1 > L ? L : hl->i1);
+    h.me = hl->me; h.nranks = hl->nranks; h.do_wait = hl->do_wait; h.do_signal = hl->do_signal; h.nbr_mask = hl->nbr_mask;
+    for (int r = 0; r < VBC_MAX_PEERS; r++) h.flags[r] = r < hl->nranks ? hl->flags[r] : nullptr;
+    h.ctl = hl->ctl;
+    h.timed_out = hl->timed_out;
+    if (A->vt == VBC_F64) return launch_halo_any<double>(A, alpha, (const double *)d_x, h, hl->last_T);
+    return launch_halo_any<float>(A, (float)alpha, (const float *)d_x, h, hl->last_T);
 }
 
 int launch_spmv(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y)

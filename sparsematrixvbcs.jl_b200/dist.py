@@ -187,6 +187,59 @@ def distribute(A: SparseMatrixCSC, phi: SplitPartition, pi: SplitPartition = Non
     return slab, pi_loc, phi_loc, layout, b
 
 
+def _allgather_u8(arr):
+    """all_gather of a uint8 numpy array over torch.distributed (any backend) -> [rank, ...]"""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return np.stack([a.cpu().numpy() for a in out])
+
+
+def halo_mask(rows_read, layout: PaddedLayout, rank, world, n_local, chunk_shift, pad, allgather):
+    """Sparsity-aware replication plan of one rank (`vbc_peer_set_mask` / `vbc_peer_set_neighbors`).
+
+    rows_read: 0-based padded x indices this rank's stripes gather from; pad: a 2D block reads all u rows of its
+    row part, stored or zero-filled, so the need is widened by U-1 rows both ways.  allgather(need_u8) -> [rank, chunk].
+    Returns (mask, nbr): mask[c] bit i set <=> destination i (rank (rank+i) % world) gathers from column chunk c of this
+    rank's slab; nbr bit r set <=> this rank sends to or receives from rank r (symmetric: every rank derives both
+    directions from the same gathered table)."""
+    C = 1 << chunk_shift
+    ng = (layout.padded_len + C - 1) // C
+    need = np.zeros(ng, dtype=np.uint8)
+    rr = np.asarray(rows_read, dtype=np.int64)
+    if len(rr):
+        need[rr >> chunk_shift] = 1
+        if pad:
+            need[np.maximum(rr - pad, 0) >> chunk_shift] = 1
+            need[np.minimum(rr + pad, layout.padded_len - 1) >> chunk_shift] = 1
+    need_all = allgather(need)  # [rank, global chunk]
+    y_offset = rank * layout.S
+    nl = (n_local + C - 1) // C
+    lo = (y_offset + np.arange(nl, dtype=np.int64) * C) >> chunk_shift
+    hi = np.minimum(y_offset + (np.arange(nl, dtype=np.int64) + 1) * C - 1, layout.padded_len - 1) >> chunk_shift
+    mask = np.ones(nl, dtype=np.uint8)  # bit 0: this rank always keeps its own slice
+    for i in range(1, world):
+        r = (rank + i) % world
+        needed = need_all[r][lo] | need_all[r][hi]
+        mask |= (needed.astype(np.uint8) << i).astype(np.uint8)
+    S_ = layout.S
+    nbr = 0
+    for r in range(world):
+        if r == rank:
+            continue
+        g0, g1 = (r * S_) >> chunk_shift, min((r + 1) * S_ - 1, layout.padded_len - 1) >> chunk_shift
+        m0, m1 = (rank * S_) >> chunk_shift, min((rank + 1) * S_ - 1, layout.padded_len - 1) >> chunk_shift
+        i_read_r = bool(need_all[rank][g0:g1 + 1].any())   # I gather from r's slice -> r sends to me
+        r_reads_me = bool(need_all[r][m0:m1 + 1].any())    # r gathers from my slice -> I send to r
+        if i_read_r or r_reads_me:
+            nbr |= 1 << r
+    return mask, nbr
+
+
 class RowPartitionedOperator:
     """One rank's share of the iterated adjoint multiply x <- alpha * A' x with the x exchange done by
     a torch.distributed all-gather (NCCL on GPUs; gloo in the CPU tests).
@@ -229,16 +282,19 @@ class RowPartitionedOperator:
 
 
 class PeerExchangeOperator:
-    """Same iteration with the all-gather FUSED into the multiply (libvbc `vbc_peer_*`): the adjoint
-    kernel stores every finished y segment into the next-x buffer of all ranks through CUDA-IPC
-    peer mappings (NVLink), and a one-CTA flag kernel is the only cross-rank step.  x is double
-    buffered inside libvbc; handles are exchanged once with torch.distributed (any backend)."""
+    """Same iteration with the exchange FUSED into the multiply (libvbc `vbc_peer_*`): one kernel per
+    iteration runs the interior stripes like the single-GPU kernel, while its boundary stripes store their
+    results into the next-x buffers of the ranks that read them through CUDA-IPC peer mappings (NVLink)
+    and publish a per-step flag.  x is double buffered inside libvbc; handles are exchanged once with
+    torch.distributed (any backend)."""
 
     def __init__(self, B, layout: PaddedLayout, rank, world, device, alpha=1.0, rows_read=None, chunk_shift=7, row_pad=None,
-                 fused_sync=False, stripe_ranges=None):
+                 sync_mode=0):
         """rows_read: optional 0-based (padded) x indices this rank's stripes gather from (e.g. the slab's
         CSC rowval - 1).  When every rank passes it, replication becomes sparsity-aware: a y segment is
-        stored only into the ranks that read it (`vbc_peer_set_mask`); otherwise x is fully replicated."""
+        stored only into the ranks that read it (`vbc_peer_set_mask`); otherwise x is fully replicated.
+        sync_mode 0: flags inside the multiply kernel (default); 1: a separate flag kernel (signal + wait)
+        after every multiply -- the comparator the fused form is measured against."""
         import ctypes
 
         import torch
@@ -246,6 +302,7 @@ class PeerExchangeOperator:
 
         from . import _lib
         self.B, self.layout, self.rank, self.world, self.alpha = B, layout, rank, world, float(alpha)
+        self.sync_mode = int(sync_mode)
         self._h = ctypes.c_void_p()
         L = _lib.lib()
         vt = _lib.VBC_F64 if B.Tv == np.dtype(np.float64) else _lib.VBC_F32
@@ -266,64 +323,19 @@ class PeerExchangeOperator:
         self.neighbors = [r for r in range(world) if r != rank]
         self.sent_fraction = 1.0
         if rows_read is not None and world > 1:
-            C = 1 << chunk_shift
-            ng = (layout.padded_len + C - 1) // C
-            need = np.zeros(ng, dtype=np.uint8)
-            rr = np.asarray(rows_read, dtype=np.int64)
-            # a 2D block reads all u rows of its row part, stored or zero-filled: widen by U-1 rows both ways
-            pad = (max(int(B.U), 1) - 1) if row_pad is None else int(row_pad)
-            need[rr >> chunk_shift] = 1
-            if pad:
-                need[np.maximum(rr - pad, 0) >> chunk_shift] = 1
-                need[np.minimum(rr + pad, layout.padded_len - 1) >> chunk_shift] = 1
-            t = torch.from_numpy(need)
-            if dist.get_backend() == "nccl":
-                t = t.cuda()
-            alln = [torch.zeros_like(t) for _ in range(world)]
-            dist.all_gather(alln, t)
-            need_all = np.stack([a.cpu().numpy() for a in alln])  # [rank, global chunk]
-            nl = (B.n + C - 1) // C
-            lo = (self.y_offset + np.arange(nl, dtype=np.int64) * C) >> chunk_shift
-            hi = np.minimum(self.y_offset + (np.arange(nl, dtype=np.int64) + 1) * C - 1, layout.padded_len - 1) >> chunk_shift
-            mask = np.ones(nl, dtype=np.uint8)  # bit 0: this rank always keeps its own slice
-            for i in range(1, world):
-                r = (rank + i) % world
-                needed = need_all[r][lo] | need_all[r][hi]
-                mask |= (needed.astype(np.uint8) << i).astype(np.uint8)
-            _lib.check(L.vbc_peer_set_mask(self._h, mask.ctypes.data_as(ctypes.c_void_p), nl, chunk_shift))
-            # flag exchange only with the ranks this one sends to or receives from (made symmetric by construction:
-            # every rank derives both directions from the same gathered `need_all`)
-            S_ = layout.S
-            nbr = 0
-            for r in range(world):
-                if r == rank:
-                    continue
-                g0, g1 = (r * S_) >> chunk_shift, min((r + 1) * S_ - 1, layout.padded_len - 1) >> chunk_shift
-                m0, m1 = (rank * S_) >> chunk_shift, min((rank + 1) * S_ - 1, layout.padded_len - 1) >> chunk_shift
-                i_read_r = bool(need_all[rank][g0:g1 + 1].any())   # I gather from r's slice -> r sends to me
-                r_reads_me = bool(need_all[r][m0:m1 + 1].any())    # r gathers from my slice -> I send to r
-                if i_read_r or r_reads_me:
-                    nbr |= 1 << r
+            mask, nbr = halo_mask(rows_read, layout, rank, world, B.n, chunk_shift,
+                                  (max(int(B.U), 1) - 1) if row_pad is None else int(row_pad), _allgather_u8)
+            _lib.check(L.vbc_peer_set_mask(self._h, mask.ctypes.data_as(ctypes.c_void_p), len(mask), chunk_shift))
             _lib.check(L.vbc_peer_set_neighbors(self._h, nbr))
             self.neighbors = [r for r in range(world) if (nbr >> r) & 1]
             self.halo = True
             bits = np.unpackbits(mask[:, None], axis=1).sum()
-            self.sent_fraction = float(bits) / float(nl * world)
+            self.sent_fraction = float(bits) / float(len(mask) * world)
             self._mask, self._chunk_shift = mask, chunk_shift
-        self.interior = (0, 0)
-        if fused_sync:
-            i0 = i1 = 0
-            if self.halo and stripe_ranges is not None:
-                rmin, rmax = stripe_ranges
-                own_lo, own_hi = self.y_offset, self.y_offset + int(layout.lens[rank])
-                reads_own = (rmax < 0) | ((rmin >= own_lo) & (rmax < own_hi))
-                spl0 = B.Phi.spl.astype(np.int64) - 1
-                c_lo = spl0[:-1] >> self._chunk_shift
-                c_hi = np.maximum(spl0[1:] - 1, spl0[:-1]) >> self._chunk_shift
-                feeds_self = (self._mask[np.minimum(c_lo, len(self._mask) - 1)] == 1) & (self._mask[np.minimum(c_hi, len(self._mask) - 1)] == 1)
-                i0, i1 = longest_true_run(reads_own & feeds_self)
-            _lib.check(L.vbc_peer_set_fused_sync(self._h, int(fused_sync), i0, i1))
-            self.interior = (i0, i1)
+        # interior stripes (gather only from the own slice, feed only this rank): derived on the device from the packed matrix
+        i0, i1 = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(L.vbc_peer_auto_interior(self._h, B._h, self.y_offset, ctypes.byref(i0), ctypes.byref(i1)))
+        self.interior = (int(i0.value), int(i1.value))
 
     def _buf_ptr(self, k):
         import ctypes
@@ -355,7 +367,30 @@ class PeerExchangeOperator:
 
     def step(self, barrier=3):
         self.B._use_torch_stream()
-        self._lib.check(self._lib.lib().vbc_peer_spmv_step(self._h, self.B._h, self.alpha, self.y_offset, barrier))
+        L = self._lib.lib()
+        if self.sync_mode == 1 and barrier == 3:
+            import ctypes
+
+            import torch
+            self._lib.check(L.vbc_peer_spmv_step(self._h, self.B._h, self.alpha, self.y_offset, 0))
+            self._lib.check(L.vbc_peer_barrier(self._h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), 3))
+            return
+        self._lib.check(L.vbc_peer_spmv_step(self._h, self.B._h, self.alpha, self.y_offset, barrier))
+
+    def finish(self):
+        """After the last step: wait (on the current stream) until the neighbours' final halos have landed."""
+        import ctypes
+
+        import torch
+        if self.world > 1 and self.sync_mode == 0:
+            self._lib.check(self._lib.lib().vbc_peer_barrier(self._h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), 2))
+
+    def wait_stats(self, reset=False):
+        """dict(steps, wait_ns, waits_that_spun, longest_wait_ns) of the in-kernel flag waits (vbc_peer_wait_stats)."""
+        import ctypes
+        st = (ctypes.c_uint64 * 4)()
+        self._lib.check(self._lib.lib().vbc_peer_wait_stats(self._h, st, 1 if reset else 0))
+        return {"steps": int(st[0]), "wait_ns": int(st[1]), "waits_that_spun": int(st[2]), "longest_wait_ns": int(st[3])}
 
     def timed_out(self):
         import ctypes
@@ -372,6 +407,8 @@ class PeerExchangeOperator:
         mine = cur[self.y_offset: self.y_offset + self.layout.S].clone()
         if self.world == 1:
             return self.layout.gather(mine.cpu().numpy())
+        if dist.get_backend() != "nccl":
+            mine = mine.cpu()
         parts = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(parts, mine)
         return self.layout.gather(torch.cat(parts).cpu().numpy())

@@ -440,9 +440,9 @@ def test_triangular_solve_extension():
         vb.ldiv_lower_(np.zeros(5), B.T, np.zeros(5))
 
 
-def test_peer_fused_sync_single_rank():
-    """The one-kernel-per-step variant (in-kernel wait + last-CTA signal) with a single rank: phases A/C/D
-    and the mask path run, nothing to wait for."""
+def test_peer_single_rank_interior_and_boundary():
+    """The fused step with a single rank: interior range + claimed boundary runs + the mask path all execute,
+    there is nobody to wait for; two interior choices and the auto-derived one give the same iterate."""
     import ctypes
     import torch
     n, u, w = 12_000, 4, 4
@@ -450,30 +450,42 @@ def test_peer_fused_sync_single_rank():
     S = A.to_scipy()
     B = vb.SparseMatrixVBC[u, w](A, pi, phi)
     Lh = _lib.lib()
-    h = ctypes.c_void_p()
-    _lib.check(Lh.vbc_peer_create(ctypes.byref(h), _lib.VBC_F64, n, 0, 1, 0, None))
-    mask = np.ones((n + 127) // 128, dtype=np.uint8)
-    _lib.check(Lh.vbc_peer_set_mask(h, mask.ctypes.data_as(ctypes.c_void_p), len(mask), 7))
-    _lib.check(Lh.vbc_peer_set_fused_sync(h, 1, 1000, 2001))
-    p = ctypes.c_void_p()
-    _lib.check(Lh.vbc_peer_buffer(h, 0, ctypes.byref(p)))
-    x0 = synth.vector(n, 4)
     rt = ctypes.CDLL("libcudart.so")
-    rt.cudaMemcpy(ctypes.c_void_p(p.value), ctypes.c_void_p(x0.ctypes.data), ctypes.c_size_t(x0.nbytes), 1)
-    ref = x0.copy()
-    for _ in range(3):
-        _lib.check(Lh.vbc_peer_spmv_step(h, B._h, 0.04, 0, 3))
-        ref = 0.04 * (S.T @ ref)
-    torch.cuda.synchronize()
-    cur, to = ctypes.c_int(), ctypes.c_int()
-    _lib.check(Lh.vbc_peer_current(h, ctypes.byref(cur)))
-    _lib.check(Lh.vbc_peer_status(h, ctypes.byref(to)))
-    assert cur.value == 1 and to.value == 0
-    _lib.check(Lh.vbc_peer_buffer(h, 1, ctypes.byref(p)))
-    out = np.empty(n)
-    rt.cudaMemcpy(ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(p.value), ctypes.c_size_t(out.nbytes), 2)
-    assert np.allclose(out, ref, rtol=1e-12, atol=0)
-    Lh.vbc_peer_destroy(h)
+    x0 = synth.vector(n, 4)
+    outs = []
+    for interior in ((1000, 2001), (0, 0), None):
+        h = ctypes.c_void_p()
+        _lib.check(Lh.vbc_peer_create(ctypes.byref(h), _lib.VBC_F64, n, 0, 1, 0, None))
+        mask = np.ones((n + 127) // 128, dtype=np.uint8)
+        _lib.check(Lh.vbc_peer_set_mask(h, mask.ctypes.data_as(ctypes.c_void_p), len(mask), 7))
+        if interior is None:
+            i0, i1 = ctypes.c_int64(), ctypes.c_int64()
+            _lib.check(Lh.vbc_peer_auto_interior(h, B._h, 0, ctypes.byref(i0), ctypes.byref(i1)))
+            assert (i0.value, i1.value) == (0, B.L)
+        else:
+            _lib.check(Lh.vbc_peer_set_interior(h, *interior))
+        p = ctypes.c_void_p()
+        _lib.check(Lh.vbc_peer_buffer(h, 0, ctypes.byref(p)))
+        rt.cudaMemcpy(ctypes.c_void_p(p.value), ctypes.c_void_p(x0.ctypes.data), ctypes.c_size_t(x0.nbytes), 1)
+        ref = x0.copy()
+        for _ in range(3):
+            _lib.check(Lh.vbc_peer_spmv_step(h, B._h, 0.04, 0, 3))
+            ref = 0.04 * (S.T @ ref)
+        torch.cuda.synchronize()
+        cur, to = ctypes.c_int(), ctypes.c_int()
+        _lib.check(Lh.vbc_peer_current(h, ctypes.byref(cur)))
+        _lib.check(Lh.vbc_peer_status(h, ctypes.byref(to)))
+        assert cur.value == 1 and to.value == 0
+        _lib.check(Lh.vbc_peer_buffer(h, 1, ctypes.byref(p)))
+        out = np.empty(n)
+        rt.cudaMemcpy(ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(p.value), ctypes.c_size_t(out.nbytes), 2)
+        assert np.allclose(out, ref, rtol=1e-12, atol=0)
+        st = (ctypes.c_uint64 * 4)()
+        _lib.check(Lh.vbc_peer_wait_stats(h, st, 0))
+        assert st[0] == (0 if interior is None else 3)  # steps published (no boundary claims <=> nothing to publish)
+        outs.append(out)
+        Lh.vbc_peer_destroy(h)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])  # same stripe bodies, same bits
 
 
 def test_pack_from_device_resident_csc(fixtures):
@@ -617,3 +629,73 @@ def test_device_resident_cg_and_power_iteration(graph):
         top = spla.eigsh(S, k=1, which="LA", return_eigenvectors=False)[0]
         assert abs(lam - top) <= 1e-6 * top
         assert abs(float(torch.linalg.vector_norm(v)) - 1.0) < 1e-12
+
+
+def test_host_vector_pipeline_matches_plain_upload():
+    """VBC_OPT_E2E_PIPELINE (default on): x uploaded in pieces, chunks of stripes started as their rows arrive, y ranges
+    copied back while later chunks run -- same bits as upload-everything-first, for a banded matrix, for one whose first
+    stripes reach the LAST rows (the first piece must then be all of x) and for a slab that reads only a row window
+    (only that window is uploaded)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+
+    def both(B, x, n, alpha=True, beta=False, y0=None):
+        outs = []
+        for mode in (0, 1):
+            B.set_option(_lib.OPT_E2E_PIPELINE, mode)
+            y = np.full(n, np.nan) if y0 is None else y0.copy()
+            outs.append(vb.mul_(y, B.T, x, alpha, beta))
+        return outs
+
+    # banded 2D blocks, large enough for the chunked path (y >= 1 MiB)
+    A, pi, phi = synth.config_c2(n=200_000, S=23)
+    B = vb.SparseMatrixVBC[4, 4](A, pi, phi)
+    assert B.get_option(_lib.OPT_E2E_PIPELINE) == 1
+    x = rng.random(A.m)
+    ya, yb = both(B, x, A.n)
+    assert np.array_equal(ya, yb)
+    assert B.get_option(_lib.OPT_E2E_UPLOAD_ELEMS) == A.m
+    assert np.allclose(ya, A.to_scipy().T @ x, rtol=1e-12)
+    y0 = rng.random(A.n)
+    ya, yb = both(B, x, A.n, 2.0, -0.5, y0)
+    assert np.array_equal(ya, yb)
+    # far-reaching first stripes
+    n = 400_000
+    S = sp.diags([rng.random(n), rng.random(n - 3)], [0, -3], format="lil")
+    S[n - 1, 0] = 2.0
+    S[n - 2, 5] = 3.0
+    A = vb.SparseMatrixCSC.from_scipy(S.tocsc())
+    B = vb.SparseMatrix1DVBC[4](A, vb.EquiChunker(4))
+    x = rng.random(n)
+    ya, yb = both(B, x, n)
+    assert np.array_equal(ya, yb) and np.allclose(ya, S.T @ x, rtol=1e-12)
+    # a slab like one rank of the row-partitioned multiply: gathers only from rows [100k, 300k) of 400k
+    m, n = 400_000, 200_000
+    S = sp.diags([rng.random(n), rng.random(n), rng.random(n)], [-100_000, -100_007, -99_990], shape=(m, n), format="csc")
+    A = vb.SparseMatrixCSC.from_scipy(S)
+    pi, phi = vb.pack_plaid(A, vb.AlternatingPacker(vb.EquiChunker(4), vb.EquiChunker(4)))
+    B = vb.SparseMatrixVBC[4, 4](A, pi, phi)
+    x = rng.random(m)
+    ya, yb = both(B, x, n)
+    assert np.array_equal(ya, yb) and np.allclose(ya, S.T @ x, rtol=1e-12)
+    assert B.get_option(_lib.OPT_E2E_UPLOAD_ELEMS) < 0.6 * m
+
+
+def test_spmm_host_panels_with_leading_dimension_padding():
+    """a host panel with ld > inner holds (outer-1)*ld + inner elements; the copies must not touch more."""
+    rng = np.random.default_rng(8)
+    A = sprand(60, 45, 0.2, rng)
+    B = vb.SparseMatrix1DVBC[4](A, vb.EquiChunker(4))
+    k, ldx, ldy = 5, 9, 11
+    Xbuf = rng.random((A.m - 1) * ldx + k)            # exactly the BLAS-sized buffers: one element more would fault under a sanitizer
+    Ybuf = np.full((A.n - 1) * ldy + k, -7.0)
+    X = np.lib.stride_tricks.as_strided(Xbuf, shape=(A.m, k), strides=(8 * ldx, 8))
+    L = _lib.lib()
+    import ctypes
+    _lib.check(L.vbc_spmm(B._h, 1, k, 1.0, ctypes.c_void_p(Xbuf.ctypes.data), ldx, 0.0, ctypes.c_void_p(Ybuf.ctypes.data), ldy, 0, 0))
+    Y = np.lib.stride_tricks.as_strided(Ybuf, shape=(A.n, k), strides=(8 * ldy, 8))
+    assert np.allclose(Y, A.to_scipy().T @ X, rtol=1e-12)
+    pad = np.ones(len(Ybuf), dtype=bool)
+    for r in range(A.n):
+        pad[r * ldy: r * ldy + k] = False
+    assert np.all(Ybuf[pad] == -7.0)  # the gaps between the rows of Y were not written
