@@ -60,7 +60,11 @@ enum vbc_option {
                               * finished chunks are already on their way back (pays when the matrix is banded; any matrix stays
                               * correct: a chunk that reaches far simply waits for more of x); 0 = upload all of x first.  Either way
                               * only x[lo, hi), lo / hi the smallest / largest index any stripe gathers from, is uploaded.          */
-    VBC_OPT_E2E_UPLOAD_ELEMS = 8 /* read-only: x elements the last host-vector multiply copied to the device */
+    VBC_OPT_E2E_UPLOAD_ELEMS = 8, /* read-only: x elements the last host-vector multiply copied to the device */
+    VBC_OPT_E2E_GRAPH = 9     /* host-vector adjoint multiplies: 1 (default) = when the same PINNED x and y (and alpha, beta) come back --
+                              * an iterative caller's `mul!(y, A', x)` -- the second call captures the copies, chunk kernels and their
+                              * dependencies into one CUDA graph on an internal stream and later calls replay it (one launch instead of
+                              * ~50 runtime calls); pageable buffers and changing pointers take the eager path.  get: 2 once a graph exists. */
 };
 
 const char *vbc_last_error(void);
@@ -166,6 +170,21 @@ int vbc_dp_chunk(int64_t n, int W, const double *cost, int64_t *spl, int64_t *L_
  * CSC structure, rows ascending.  Writes the 1-based spl (at most n+1 entries) and its length. */
 int vbc_overlap_chunk(int64_t n, const int64_t *colptr, const int64_t *rowval, double rho, int w_max, int64_t *spl, int64_t *L_out);
 
+/* ---- benchmark support: synthetic matrices generated on the device -----------------------------
+ * The block-banded generator of the benchmark configs (modelled on the reference's own generators for its
+ * time-model experiments, costs.jl:63-85 / :200-222): global stripe l holds a dense u x w block at every row
+ * part l*K/L + offsets[t] inside [0, K); values = hash of the entry's global (row, col) and the seed, in [0, 1),
+ * so any slab [l0, l1) can be produced by the rank that owns it and any entry re-derived on the host.
+ * Writes a SparseMatrixCSC slab ((l1-l0)*w columns, K*u rows) into freshly allocated DEVICE arrays (1-based
+ * Ti colptr / rowval, Tv nzval) for vbc_pack_csc_dev; release them with vbc_gen_free.  offsets ascend strictly. */
+int vbc_gen_banded_csc(int vt, int it, int64_t K, int64_t L, int u, int w, const int64_t *offsets, int noffsets,
+                       int64_t l0, int64_t l1, uint64_t seed, double diag_boost,
+                       void **colptr, void **rowval, void **nzval, int64_t *nnz, int device);
+int vbc_gen_free(void *colptr, void *rowval, void *nzval, int device);
+/* need[c] = 1 when an adjoint multiply of A gathers from x[c << chunk_shift, (c+1) << chunk_shift) (host array of
+ * nchunks >= ceil(m / 2^chunk_shift) bytes): the input of the sparsity-aware exchange plan (vbc_peer_set_mask). */
+int vbc_read_chunks(vbc_mat *A, int chunk_shift, unsigned char *need, int64_t nchunks);
+
 /* ---- execution control ---------------------------------------------------------------------*/
 int vbc_set_stream(vbc_mat *A, void *cuda_stream); /* a cudaStream_t; NULL = legacy default stream */
 int vbc_csc_set_stream(vbc_csc *A, void *cuda_stream);
@@ -227,6 +246,7 @@ int vbc_peer_set_neighbors(vbc_peer *P, unsigned mask);
  * from this rank's own slice of x and (under the mask) feed only this rank.  They run before and independently
  * of the flag exchange; all other stripes are boundary stripes.  Default: none (i0 == i1 == 0). */
 int vbc_peer_set_interior(vbc_peer *P, int64_t i0, int64_t i1);
+int vbc_peer_get_interior(const vbc_peer *P, int64_t *i0, int64_t *i1);
 /* Derives the interior range on the device from the packed matrix and the mask set so far (the longest run of
  * stripes whose gathers stay inside x[y_offset, y_offset + n) and whose columns only this rank reads), installs
  * it and reports it (i0_out / i1_out may be NULL).  Without a mask, or with one rank, see vbc_peer_set_mask. */
@@ -239,6 +259,29 @@ int vbc_peer_status(vbc_peer *P, int *timed_out);
  * [2] = waits that had to spin at all, [3] = longest single wait in ns; reset != 0 clears [1..3].  Synchronous. */
 int vbc_peer_wait_stats(vbc_peer *P, uint64_t stats[4], int reset);
 void vbc_peer_destroy(vbc_peer *P);
+
+/* ---- multi-GPU, one process driving all devices (the form a Julia host uses) -------------------
+ * The iterated adjoint multiply x_{t+1} <- alpha * A' x_t of a SQUARE operator over `ngpus` devices of this box:
+ * the stripes (row blocks of A') are split into contiguous ranges balanced by the reference's memory cost model
+ * (costs.jl:10 / :140), every range is packed on its device from the host CSC + partitions (same arguments as
+ * vbc_pack_csc, m == n), x lives in peer-mapped buffers and an iteration is one launch per device
+ * (VBC_EXCH_FUSED: the exchange of the new x is fused into the multiply, see vbc_peer_*), or the plain multiply
+ * followed by ncclAllGather (VBC_EXCH_NCCL: the unfused comparator; libnccl.so.2 is loaded at first use and its
+ * failures are reported as VBC_ENCCL).  devices == NULL: devices 0..ngpus-1; the same device may appear twice. */
+typedef struct vbc_dist vbc_dist;
+enum vbc_exchange { VBC_EXCH_FUSED = 0, VBC_EXCH_NCCL = 1 };
+int vbc_dist_create(vbc_dist **out, int ngpus, const int *devices, int vt, int it, int64_t n, int U, int W,
+                    const void *colptr, const void *rowval, const void *nzval,
+                    const void *pi_spl, int64_t K, const void *phi_spl, int64_t L, int exchange);
+/* the partition chosen: slice_len = padded slice length S; stripe_bounds[ngpus+1]; cost_per_gpu[ngpus] (bytes under
+ * the memory model); interior[2*ngpus] = interior stripe range of every rank (any pointer may be NULL) */
+int vbc_dist_info(const vbc_dist *D, int *ngpus, int64_t *slice_len, int64_t *stripe_bounds, int64_t *cost_per_gpu, int64_t *interior);
+int vbc_dist_set_x(vbc_dist *D, const void *x);      /* host vector of n entries -> every device */
+/* `iters` iterations, device-resident, synchronous on return; *ms_per_iter (may be NULL) = device time per iteration,
+ * maximum over the devices (CUDA events).  Fused exchange: the iterations are captured into one CUDA graph per device. */
+int vbc_dist_spmv_iter(vbc_dist *D, int iters, double alpha, double *ms_per_iter);
+int vbc_dist_gather_x(vbc_dist *D, void *x);         /* current x (n entries) assembled from the owners' slices */
+void vbc_dist_destroy(vbc_dist *D);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("VBC_LIBRARY") or os.path.join(_DIR, "libvbc.so")
 VBC_F32, VBC_F64 = 0, 1
 VBC_I32, VBC_I64 = 0, 1
 VBC_OK, VBC_EDIM, VBC_EARG, VBC_ELIMIT, VBC_ECUDA, VBC_ENCCL, VBC_ENOMEM = range(7)
-OPT_ADJ_GROUP, OPT_FWD_GROUP, OPT_GRID_MULT, OPT_PARITY_MODE, OPT_FWD_MODE, OPT_SPMM_SIMT, OPT_E2E_PIPELINE, OPT_E2E_UPLOAD_ELEMS = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_ADJ_GROUP, OPT_FWD_GROUP, OPT_GRID_MULT, OPT_PARITY_MODE, OPT_FWD_MODE, OPT_SPMM_SIMT, OPT_E2E_PIPELINE, OPT_E2E_UPLOAD_ELEMS, OPT_E2E_GRAPH = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 # every symbol include/vbc.h declares (tests/test_abi_symbols.py checks header <-> this list <-> .so)
 SYMBOLS = [
@@ -26,7 +26,10 @@ SYMBOLS = [
     "vbc_peer_create", "vbc_peer_connect", "vbc_peer_connect_local", "vbc_peer_buffer", "vbc_peer_current",
     "vbc_peer_spmv_step", "vbc_peer_set_mask", "vbc_peer_set_interior", "vbc_peer_auto_interior", "vbc_peer_set_neighbors", "vbc_peer_barrier", "vbc_peer_status",
     "vbc_peer_wait_stats", "vbc_peer_destroy",
+    "vbc_gen_banded_csc", "vbc_gen_free", "vbc_read_chunks", "vbc_peer_get_interior",
+    "vbc_dist_create", "vbc_dist_info", "vbc_dist_set_x", "vbc_dist_spmv_iter", "vbc_dist_gather_x", "vbc_dist_destroy",
 ]
+EXCH_FUSED, EXCH_NCCL = 0, 1
 
 IPC_HANDLE_BYTES, PEER_HANDLES, MAX_PEERS = 64, 3, 8
 
@@ -115,10 +118,22 @@ def lib():
     L.vbc_peer_barrier.argtypes = [c_vp, c_vp, c_int]
     L.vbc_peer_status.argtypes = [c_vp, pint]
     L.vbc_peer_destroy.argtypes = [c_vp]
+    L.vbc_gen_banded_csc.argtypes = [c_int, c_int, c_i64, c_i64, c_int, c_int, c_vp, c_int, c_i64, c_i64, ctypes.c_uint64, c_dbl,
+                                     pp, pp, pp, pi64, c_int]
+    L.vbc_gen_free.argtypes = [c_vp, c_vp, c_vp, c_int]
+    L.vbc_read_chunks.argtypes = [c_vp, c_int, c_vp, c_i64]
+    L.vbc_peer_get_interior.argtypes = [c_vp, pi64, pi64]
+    L.vbc_dist_create.argtypes = [pp, c_int, pint, c_int, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int]
+    L.vbc_dist_info.argtypes = [c_vp, pint, pi64, pi64, pi64, pi64]
+    L.vbc_dist_set_x.argtypes = [c_vp, c_vp]
+    L.vbc_dist_spmv_iter.argtypes = [c_vp, c_int, c_dbl, ctypes.POINTER(c_dbl)]
+    L.vbc_dist_gather_x.argtypes = [c_vp, c_vp]
+    L.vbc_dist_destroy.argtypes = [c_vp]
+    L.vbc_dist_destroy.restype = None
     L.vbc_peer_destroy.restype = None
     for name in SYMBOLS:
         f = getattr(L, name)
-        if name not in ("vbc_last_error", "vbc_destroy", "vbc_csc_destroy", "vbc_peer_destroy"):
+        if name not in ("vbc_last_error", "vbc_destroy", "vbc_csc_destroy", "vbc_peer_destroy", "vbc_dist_destroy"):
             f.restype = c_int
     _lib = L
     return L

@@ -266,6 +266,10 @@ void vbc_destroy(vbc_mat *A)
     cudaFree(A->d_meta); cudaFree(A->d_desc); cudaFree(A->d_brow); cudaFree(A->d_order); cudaFree(A->d_px); cudaFree(A->d_py); cudaFree(A->d_x); cudaFree(A->d_y);
     destroy_trsv_plan(A->trsv);
     destroy_tindex(A->tindex);
+    if (A->e2e_exec) cudaGraphExecDestroy(A->e2e_exec);
+    if (A->e2e_stream) cudaStreamDestroy(A->e2e_stream);
+    for (int k = 0; k < 3; k++)
+        if (A->e2e_ev[k]) cudaEventDestroy(A->e2e_ev[k]);
     if (A->copy_stream) cudaStreamDestroy(A->copy_stream);
     if (A->h2d_stream) cudaStreamDestroy(A->h2d_stream);
     for (int c = 0; c < 8; c++)
@@ -322,7 +326,110 @@ int vbc_memory_cost(const vbc_mat *A, int64_t *cost, int64_t *row_term)
     return memory_cost_device(A, cost, row_term);
 }
 
-int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, double beta, void *y, int64_t ylen, int on_device)
+// Host-vector adjoint multiply, chunked: enqueues (no synchronisation) the upload of x -- in pieces on h2d_stream when
+// `pipeline`, each chunk of stripes waiting only for the rows it gathers from -- the chunk kernels on A->stream and the
+// copies of the finished y ranges on copy_stream.  Used eagerly and under stream capture (the replayed graph below).
+static int host_adjoint_enqueue(vbc_mat *A, double alpha, const void *x, int64_t xlen, double beta, void *y, int64_t ylen, bool pipeline, int64_t *uploaded)
+{
+    const size_t tv = vt_size(A->vt);
+    if (!pipeline && xlen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_x, x, tv * (size_t)xlen, cudaMemcpyHostToDevice, A->stream));
+    if (beta != 0.0 && ylen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_y, y, tv * (size_t)ylen, cudaMemcpyHostToDevice, A->stream));
+    int rc = VBC_OK;
+    int64_t xcopied = pipeline ? A->x_lo : 0;
+    for (int c = 0; c < A->nchunks && rc == VBC_OK; c++) {
+        if (pipeline) { // the piece of x this chunk still lacks, on the upload stream; the chunk's kernel waits for it
+            const int64_t hi = A->chunk_xhi[c];
+            cudaError_t e = cudaSuccess;
+            if (hi > xcopied) { e = cudaMemcpyAsync((char *)A->d_x + tv * (size_t)xcopied, (const char *)x + tv * (size_t)xcopied, tv * (size_t)(hi - xcopied), cudaMemcpyHostToDevice, A->h2d_stream); xcopied = hi; }
+            if (e == cudaSuccess) e = cudaEventRecord(A->h2d_ev[c], A->h2d_stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(A->stream, A->h2d_ev[c], 0);
+            if (e != cudaSuccess) { set_error("pipelined upload failed: %s", cudaGetErrorString(e)); rc = VBC_ECUDA; break; }
+        }
+        A->range_l0 = A->chunk_l[c]; A->range_l1 = A->chunk_l[c + 1];
+        rc = launch_spmv(A, 1, alpha, A->d_x, beta, A->d_y);
+        if (rc == VBC_OK && cudaEventRecord(A->chunk_ev[c], A->stream) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = VBC_ECUDA; }
+    }
+    A->range_l0 = A->range_l1 = -1;
+    VBC_TRY(rc);
+    for (int c = 0; c < A->nchunks; c++) {
+        const int64_t c0 = A->chunk_col[c], c1 = A->chunk_col[c + 1];
+        VBC_CUDA(cudaStreamWaitEvent(A->copy_stream, A->chunk_ev[c], 0));
+        if (c1 > c0) VBC_CUDA(cudaMemcpyAsync((char *)y + tv * (size_t)c0, (char *)A->d_y + tv * (size_t)c0, tv * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, A->copy_stream));
+    }
+    *uploaded = pipeline ? xcopied - A->x_lo : xlen;
+    return VBC_OK;
+}
+
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static void drop_e2e_graph(vbc_mat *A)
+{
+    if (A->e2e_exec) { cudaGraphExecDestroy(A->e2e_exec); A->e2e_exec = nullptr; }
+    A->e2e_x = nullptr; A->e2e_y = nullptr; A->e2e_seen = 0;
+}
+
+// The same work as ONE replayed CUDA graph.  An iterative caller multiplies with the same pinned x and y again and again
+// (`mul!(y, A', x)` in a loop): the second call with the same pointers and scalars captures the enqueue above -- copies,
+// chunk kernels and their cross-stream dependencies -- into a graph on an internal stream, and every later call is a
+// single cudaGraphLaunch instead of ~50 runtime calls, which on a PCIe-bound path is most of the host time.
+static int host_adjoint_graph(vbc_mat *A, double alpha, const void *x, int64_t xlen, double beta, void *y, int64_t ylen, bool pipeline, bool *done)
+{
+    *done = false;
+    if (!A->opt_e2e_graph) return VBC_OK;
+    if (A->e2e_x != x || A->e2e_y != y || A->e2e_alpha != alpha || A->e2e_beta != beta || A->e2e_pipeline != (int)pipeline) {
+        drop_e2e_graph(A);
+        A->e2e_x = x; A->e2e_y = y; A->e2e_alpha = alpha; A->e2e_beta = beta; A->e2e_pipeline = (int)pipeline;
+        A->e2e_seen = 1;
+        return VBC_OK; // first sighting: run eagerly
+    }
+    if (!A->e2e_exec) {
+        if (A->e2e_seen < 0) return VBC_OK; // capture failed before for these buffers: stay eager
+        if (!is_pinned_host(x) || !is_pinned_host(y)) { A->e2e_seen = -1; return VBC_OK; }
+        if (!A->e2e_stream && cudaStreamCreateWithFlags(&A->e2e_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); A->e2e_seen = -1; return VBC_OK; }
+        for (int k = 0; k < 3; k++)
+            if (!A->e2e_ev[k] && cudaEventCreateWithFlags(&A->e2e_ev[k], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); A->e2e_seen = -1; return VBC_OK; }
+        cudaStream_t user = A->stream;
+        VBC_CUDA(cudaStreamSynchronize(user)); // earlier device work of this handle is finished before the internal stream takes over
+        A->stream = A->e2e_stream;
+        cudaGraph_t g = nullptr;
+        int64_t up = 0;
+        cudaError_t e = cudaStreamBeginCapture(A->e2e_stream, cudaStreamCaptureModeThreadLocal);
+        int rc = VBC_OK;
+        if (e == cudaSuccess) {
+            e = cudaEventRecord(A->e2e_ev[0], A->e2e_stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(A->copy_stream, A->e2e_ev[0], 0);
+            if (e == cudaSuccess && A->h2d_stream) e = cudaStreamWaitEvent(A->h2d_stream, A->e2e_ev[0], 0);
+            if (e == cudaSuccess) rc = host_adjoint_enqueue(A, alpha, x, xlen, beta, y, ylen, pipeline, &up);
+            if (e == cudaSuccess && rc == VBC_OK) e = cudaEventRecord(A->e2e_ev[1], A->copy_stream);
+            if (e == cudaSuccess && rc == VBC_OK) e = cudaStreamWaitEvent(A->e2e_stream, A->e2e_ev[1], 0);
+            if (e == cudaSuccess && rc == VBC_OK && A->h2d_stream) { e = cudaEventRecord(A->e2e_ev[2], A->h2d_stream); if (e == cudaSuccess) e = cudaStreamWaitEvent(A->e2e_stream, A->e2e_ev[2], 0); }
+            cudaError_t e2 = cudaStreamEndCapture(A->e2e_stream, &g);
+            if (e == cudaSuccess) e = e2;
+        }
+        A->stream = user;
+        if (e == cudaSuccess && rc == VBC_OK && g) e = cudaGraphInstantiate(&A->e2e_exec, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e != cudaSuccess || rc != VBC_OK || !A->e2e_exec) { // capture is an optimisation: fall back to the eager path for good
+            cudaGetLastError();
+            A->e2e_exec = nullptr;
+            A->e2e_seen = -1;
+            return VBC_OK;
+        }
+        A->e2e_upload = up;
+    }
+    VBC_CUDA(cudaGraphLaunch(A->e2e_exec, A->e2e_stream));
+    VBC_CUDA(cudaStreamSynchronize(A->e2e_stream));
+    A->last_upload_elems = A->e2e_upload;
+    *done = true;
+    return VBC_OK;
+}
+
+extern "C" int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, double beta, void *y, int64_t ylen, int on_device)
 {
     if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
     const int64_t need_x = trans ? A->m : A->n, need_y = trans ? A->n : A->m;
@@ -335,15 +442,12 @@ int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, d
     const size_t tv = vt_size(A->vt);
     VBC_TRY(ensure_vec(&A->d_x, &A->x_cap, xlen, tv));
     VBC_TRY(ensure_vec(&A->d_y, &A->y_cap, ylen, tv));
-    // x is uploaded up front unless the pipelined path below takes it over (decided after the chunks are prepared)
-    const bool want_pipeline = trans && A->opt_e2e_pipeline && !A->opt_parity && A->d_order == nullptr && xlen > 0;
-    if (xlen > 0 && !want_pipeline) VBC_CUDA(cudaMemcpyAsync(A->d_x, x, tv * (size_t)xlen, cudaMemcpyHostToDevice, A->stream));
-    if (beta != 0.0 && ylen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_y, y, tv * (size_t)ylen, cudaMemcpyHostToDevice, A->stream));
+    const bool chunkable = trans && !A->opt_parity && A->d_order == nullptr;
     // adjoint with a large y: launch the stripes in chunks and copy each finished y range back on a second stream
     // while the next chunk computes (the D2H copy is as long as the whole kernel)
-    if (trans && !A->opt_parity && A->d_order == nullptr && A->nchunks == 0) {
+    if (chunkable && A->nchunks == 0) {
         A->nchunks = -1;
-        int NC = 4;
+        int NC = 8;
         if (const char *e = getenv("VBC_E2E_CHUNKS")) { NC = atoi(e); if (NC > 8) NC = 8; }
         if (NC >= 2 && A->L >= 64 * NC && tv * (size_t)ylen >= (1u << 20)) {
             bool ok = cudaStreamCreateWithFlags(&A->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -358,47 +462,31 @@ int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, d
             else cudaGetLastError();
         }
     }
-    // pipelined upload: needs the chunks, the x ranges and a third stream; anything missing -> plain upload now
-    bool pipeline = false;
-    if (want_pipeline) {
-        if (A->nchunks > 0 && A->xhi_ready == 0) {
-            bool ok = cudaStreamCreateWithFlags(&A->h2d_stream, cudaStreamNonBlocking) == cudaSuccess;
-            for (int c = 0; c < A->nchunks && ok; c++) ok = cudaEventCreateWithFlags(&A->h2d_ev[c], cudaEventDisableTiming) == cudaSuccess;
-            if (ok) ok = prepare_x_ranges(A) == VBC_OK;
-            if (!ok) { cudaGetLastError(); A->xhi_ready = -1; }
-        }
-        pipeline = A->nchunks > 0 && A->xhi_ready == 1;
-        if (!pipeline) VBC_CUDA(cudaMemcpyAsync(A->d_x, x, tv * (size_t)xlen, cudaMemcpyHostToDevice, A->stream));
-    }
-    if (trans && !A->opt_parity && A->nchunks > 0 && A->d_order == nullptr) {
-        int rc = VBC_OK;
-        int64_t xcopied = pipeline ? A->x_lo : 0;
-        for (int c = 0; c < A->nchunks && rc == VBC_OK; c++) {
-            if (pipeline) { // the piece of x this chunk still lacks, on the upload stream; the chunk's kernel waits for it
-                const int64_t hi = A->chunk_xhi[c];
-                cudaError_t e = cudaSuccess;
-                if (hi > xcopied) { e = cudaMemcpyAsync((char *)A->d_x + tv * (size_t)xcopied, (const char *)x + tv * (size_t)xcopied, tv * (size_t)(hi - xcopied), cudaMemcpyHostToDevice, A->h2d_stream); xcopied = hi; }
-                if (e == cudaSuccess) e = cudaEventRecord(A->h2d_ev[c], A->h2d_stream);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(A->stream, A->h2d_ev[c], 0);
-                if (e != cudaSuccess) { set_error("pipelined upload failed: %s", cudaGetErrorString(e)); rc = VBC_ECUDA; break; }
+    if (chunkable && A->nchunks > 0) {
+        // pipelined upload: needs the x ranges of the chunks and a third stream; anything missing -> plain upload first
+        bool pipeline = false;
+        if (A->opt_e2e_pipeline && xlen > 0) {
+            if (A->xhi_ready == 0) {
+                bool ok = cudaStreamCreateWithFlags(&A->h2d_stream, cudaStreamNonBlocking) == cudaSuccess;
+                for (int c = 0; c < A->nchunks && ok; c++) ok = cudaEventCreateWithFlags(&A->h2d_ev[c], cudaEventDisableTiming) == cudaSuccess;
+                if (ok) ok = prepare_x_ranges(A) == VBC_OK;
+                if (!ok) { cudaGetLastError(); A->xhi_ready = -1; }
             }
-            A->range_l0 = A->chunk_l[c]; A->range_l1 = A->chunk_l[c + 1];
-            rc = launch_spmv(A, trans, alpha, A->d_x, beta, A->d_y);
-            if (rc == VBC_OK && cudaEventRecord(A->chunk_ev[c], A->stream) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = VBC_ECUDA; }
+            pipeline = A->xhi_ready == 1;
         }
-        A->range_l0 = A->range_l1 = -1;
-        VBC_TRY(rc);
-        for (int c = 0; c < A->nchunks; c++) {
-            const int64_t c0 = A->chunk_col[c], c1 = A->chunk_col[c + 1];
-            VBC_CUDA(cudaStreamWaitEvent(A->copy_stream, A->chunk_ev[c], 0));
-            if (c1 > c0) VBC_CUDA(cudaMemcpyAsync((char *)y + tv * (size_t)c0, (char *)A->d_y + tv * (size_t)c0, tv * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, A->copy_stream));
-        }
+        bool done = false;
+        VBC_TRY(host_adjoint_graph(A, alpha, x, xlen, beta, y, ylen, pipeline, &done));
+        if (done) return VBC_OK;
+        int64_t up = 0;
+        VBC_TRY(host_adjoint_enqueue(A, alpha, x, xlen, beta, y, ylen, pipeline, &up));
         VBC_CUDA(cudaStreamSynchronize(A->copy_stream));
         VBC_CUDA(cudaStreamSynchronize(A->stream));
         if (pipeline) VBC_CUDA(cudaStreamSynchronize(A->h2d_stream));
-        A->last_upload_elems = pipeline ? xcopied - A->x_lo : xlen;
+        A->last_upload_elems = up;
         return VBC_OK;
     }
+    if (xlen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_x, x, tv * (size_t)xlen, cudaMemcpyHostToDevice, A->stream));
+    if (beta != 0.0 && ylen > 0) VBC_CUDA(cudaMemcpyAsync(A->d_y, y, tv * (size_t)ylen, cudaMemcpyHostToDevice, A->stream));
     VBC_TRY(launch_spmv(A, trans, alpha, A->d_x, beta, A->d_y));
     if (ylen > 0) VBC_CUDA(cudaMemcpyAsync(y, A->d_y, tv * (size_t)ylen, cudaMemcpyDeviceToHost, A->stream));
     VBC_CUDA(cudaStreamSynchronize(A->stream));
@@ -406,7 +494,7 @@ int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, d
     return VBC_OK;
 }
 
-int vbc_spmv_mixed(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, double beta, void *y, int64_t ylen, int vec_vt, int on_device)
+extern "C" int vbc_spmv_mixed(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, double beta, void *y, int64_t ylen, int vec_vt, int on_device)
 {
     if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
     if (vec_vt != VBC_F32 && vec_vt != VBC_F64) VBC_FAIL(VBC_EARG, "vector type must be VBC_F32 or VBC_F64");
@@ -543,6 +631,10 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
     case VBC_OPT_E2E_PIPELINE:
         A->opt_e2e_pipeline = value ? 1 : 0;
         return VBC_OK;
+    case VBC_OPT_E2E_GRAPH:
+        A->opt_e2e_graph = value ? 1 : 0;
+        if (!value) { DeviceGuard guard(A->device); drop_e2e_graph(A); }
+        return VBC_OK;
     case VBC_OPT_E2E_UPLOAD_ELEMS:
         VBC_FAIL(VBC_EARG, "VBC_OPT_E2E_UPLOAD_ELEMS is read-only");
     case VBC_OPT_FWD_MODE:
@@ -564,6 +656,7 @@ int vbc_get_option(const vbc_mat *A, int option, int64_t *value)
     case VBC_OPT_FWD_MODE: *value = A->opt_fwd_atomic; return VBC_OK;
     case VBC_OPT_SPMM_SIMT: *value = A->opt_spmm_simt; return VBC_OK;
     case VBC_OPT_E2E_PIPELINE: *value = A->opt_e2e_pipeline; return VBC_OK;
+    case VBC_OPT_E2E_GRAPH: *value = A->e2e_exec ? 2 : A->opt_e2e_graph; return VBC_OK;
     case VBC_OPT_E2E_UPLOAD_ELEMS: *value = A->last_upload_elems; return VBC_OK;
     }
     VBC_FAIL(VBC_EARG, "unknown option %d", option);

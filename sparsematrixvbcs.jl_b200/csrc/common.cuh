@@ -100,6 +100,15 @@ struct vbc_mat {
     int xhi_ready = 0;                     // 0: not computed, 1: ready, -1: failed (pipeline off)
     int64_t x_lo = 0;                      // smallest x index any stripe gathers from
     int64_t last_upload_elems = 0;         // x elements the last host-vector multiply copied to the device
+    // VBC_OPT_E2E_GRAPH (default on): repeated host-vector adjoint multiplies with the same pinned x / y replay one captured graph
+    int opt_e2e_graph = 1;
+    cudaGraphExec_t e2e_exec = nullptr;
+    cudaStream_t e2e_stream = nullptr;
+    cudaEvent_t e2e_ev[3] = {};
+    const void *e2e_x = nullptr; void *e2e_y = nullptr;
+    double e2e_alpha = 0.0, e2e_beta = 0.0;
+    int e2e_pipeline = 0, e2e_seen = 0;    // seen: 1 after the first call with these buffers, -1 if they cannot be captured
+    int64_t e2e_upload = 0;
     vbc_trsv_plan *trsv = nullptr; // level schedule of the triangular solve (vbc_trsv_analyse)
     vbc::TIndex *tindex = nullptr; // transposed unit index of the owner-computes forward multiply (built at first use)
     int opt_fwd_atomic = 0;        // 1: always use the atomic scatter kernel for the forward multiply
@@ -144,9 +153,8 @@ struct HaloLaunch { // one step of the row-partitioned iteration (peer.cu -> spm
     int me, nranks, do_wait, do_signal;
     unsigned nbr_mask;
     unsigned long long *flags[VBC_MAX_PEERS];
-    unsigned long long *ctl;                   // claim counter, finished-claim counter, epoch
+    unsigned long long *ctl;                   // [1] finished boundary warps, [2] epoch, [3..5] wait statistics
     int *timed_out;
-    unsigned long long *last_T;                // host: claim period of the previous launch on these counters (0: none yet)
 };
 int launch_spmv_adj_halo(vbc_mat *A, double alpha, const void *d_x, const HaloLaunch *hl);
 // mixed.cu

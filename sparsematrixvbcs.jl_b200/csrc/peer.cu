@@ -7,7 +7,7 @@
 
 #include "common.cuh"
 
-#define VBC_PEER_CTL_WORDS 8 // claim counter, finished-claim counter, epoch, wait ns, waits that spun, longest wait, 2 spare
+#define VBC_PEER_CTL_WORDS 8 // [1] finished boundary warps (running total), [2] epoch, [3] wait ns, [4] waits that spun, [5] longest wait
 
 struct vbc_peer {
     int vt = VBC_F64, rank = 0, nranks = 1, device = 0;
@@ -19,7 +19,6 @@ struct vbc_peer {
     int cur = 0;
     unsigned long long *d_ctl = nullptr;   // device-side counters (VBC_PEER_CTL_WORDS): the kernels advance the epoch themselves,
                                            // so a captured CUDA graph of steps stays correct when replayed
-    unsigned long long last_T = 0;         // claim period of the last fused launch on d_ctl (spmv.cu)
     int *d_timeout = nullptr;
     unsigned char *d_mask = nullptr; // per column chunk of this rank's slice: which destinations read it
     int chunk_shift = 0;
@@ -240,7 +239,6 @@ int vbc_peer_spmv_step(vbc_peer *P, vbc_mat *A, double alpha, int64_t y_offset, 
     for (int r = 0; r < VBC_MAX_PEERS; r++) hl.flags[r] = r < P->nranks ? (unsigned long long *)P->bufs[r][2] : nullptr;
     hl.ctl = P->d_ctl;
     hl.timed_out = P->d_timeout;
-    hl.last_T = &P->last_T;
     VBC_TRY(launch_spmv_adj_halo(A, alpha, P->own[P->cur], &hl));
     P->launches++;
     P->cur = nxt;
@@ -268,6 +266,14 @@ int vbc_peer_set_interior(vbc_peer *P, int64_t i0, int64_t i1)
     if (i0 < 0 || i1 < i0 || i1 > 0x7fffffff) VBC_FAIL(VBC_EARG, "bad interior range [%lld, %lld)", (long long)i0, (long long)i1);
     P->i0 = (int)i0;
     P->i1 = (int)i1;
+    return VBC_OK;
+}
+
+int vbc_peer_get_interior(const vbc_peer *P, int64_t *i0, int64_t *i1)
+{
+    if (!P || !i0 || !i1) VBC_FAIL(VBC_EARG, "NULL argument");
+    *i0 = P->i0;
+    *i1 = P->i1;
     return VBC_OK;
 }
 

@@ -18,6 +18,8 @@
 // Where the reference unrolls one body per width class (le_nest over ws, util.jl:28-38), the
 // kernels here instantiate one body per (elements-per-load EPV, vectors-per-row CPR) class
 // and select it per stripe.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "walk.cuh"
 
@@ -38,6 +40,9 @@ namespace vbc {
 #endif
 #ifndef VBC_LD_MODE
 #define VBC_LD_MODE 0      // val loads: 0 = ld.global.cs (streaming), 1 = ld.global.nc, 2 = ld.global.nc.L1::no_allocate
+#endif
+#ifndef VBC_HALO_RUN_INLINE
+#define VBC_HALO_RUN_INLINE __forceinline__ // the boundary-run body of k_spmv_adj_halo: inlined (a call in that kernel slows its interior loop)
 #endif
 #ifndef VBC_WIDE_LD
 #define VBC_WIDE_LD 0      // 1: 256-bit loads (sm_100+ LDG.256) for Float64 stripes whose width is a multiple of 4
@@ -85,12 +90,14 @@ struct HaloArgs {
     int chunk_shift;
     int i0, i1;                              // interior stripes [i0, i1): gather only from this rank's slice, feed only this rank
     int nrunsA, nruns;                       // boundary runs of 32/G adjacent stripes: [0, nrunsA) cover [0, i0), the rest cover [i1, L)
-    int rpc, nclaims;                        // runs per claim, number of claims
-    unsigned long long T;                    // claims per launch including the failing one of every warp: nclaims + warps in the grid
+    int first_warp, nbwarps;                 // boundary run r belongs to warp (first_warp + r) % warps; nbwarps = min(nruns, warps) warps own any
+    int ifence, imid;                        // interior is walked as [i0, ifence) (then boundary warps count themselves done), [ifence, imid) by
+                                             // every warp and [imid, i1) by the warps without boundary runs
+    int stage_elems;                         // staging row per warp, in elements: 32/G stripes x W columns
     int me, nranks, do_wait, do_signal;
     unsigned nbr_mask;                       // ranks this rank exchanges flags with
     unsigned long long *flags[VBC_MAX_PEERS]; // flag block of every rank (flags[me] is local)
-    unsigned long long *ctl;                 // [0] claim counter, [1] finished-claim counter, [2] epoch (steps published so far), [3..5] wait statistics
+    unsigned long long *ctl;                 // [1] boundary warps finished (running total), [2] epoch (steps published so far), [3..5] wait statistics
     int *timed_out;
 };
 
@@ -253,13 +260,13 @@ __device__ __forceinline__ void adj_one_stripe(const StripeMeta a, const StripeM
 // adjacent, so a warp's groups agree.  (One loop for both, so the stripe bodies exist once in the kernel.)
 template <typename Tv, int G, int MODE>
 __device__ __forceinline__ void adj_range(const StripeMeta *__restrict__ meta, const int *__restrict__ order, const int lo, const int hi,
+                                          const int group, const int ngroups,
                                           const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
                                           Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
     const int lane = threadIdx.x % G;
     const unsigned gmask = group_mask<G>();
-    const int ngroups = (int)((gridDim.x * blockDim.x) / G);
-    int l = lo + (int)((blockIdx.x * blockDim.x + threadIdx.x) / G);
+    int l = lo + group;
     if (l >= hi) return;
     StripeMeta na, nb;
     if (order == nullptr) { na = ld_meta(meta + l); nb = ld_meta(meta + l + 1); }
@@ -281,27 +288,28 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
                                           const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ y,
                                           const int *__restrict__ order, const int L, const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
-    adj_range<Tv, G, MODE>(meta, order, 0, L, desc, val, x, y, u0, log2u, alpha, beta);
+    adj_range<Tv, G, MODE>(meta, order, 0, L, (int)((blockIdx.x * blockDim.x + threadIdx.x) / G), (int)((gridDim.x * blockDim.x) / G),
+                           desc, val, x, y, u0, log2u, alpha, beta);
 }
 
 // ---- adjoint with the x exchange of the row-partitioned iteration fused in (north_star (e)) -------------------------
 // One launch per iteration x_{t+1} <- alpha * A' x_t on this rank's stripes.
-//   interior stripes [i0, i1) gather only from this rank's own slice of x and feed only this rank: they run first, exactly
-//     like the plain kernel, storing into the own next-x buffer.  Nothing here depends on another GPU.
-//   boundary stripes (the rest; for a banded operator the few hundred at both ends of the slab) read x entries that the
-//     neighbours produced in their previous step and produce entries the neighbours read in their next one.  They are cut
-//     into runs of 32/G adjacent stripes and CLAIMED (one atomic per claim) by whichever warps finish their interior share
-//     first, so they fill the tail of the launch instead of lengthening it.  A claiming warp first waits (acquire, system
-//     scope) until every neighbour has published the previous step -- by then that happened a whole kernel ago, the wait
-//     only ever spins when the ranks have drifted by more than one step -- computes its stripes with L2-coherent x loads,
-//     stages the run's results in shared memory and stores them with full-warp coalesced stores into the own next-x buffer
-//     and into the buffers of exactly the ranks that gather from those columns (mask), over NVLink.  The warp that
-//     finishes the last claim publishes the step to the neighbours (release, system scope).
-// Counters never need a reset: every warp makes exactly one failing claim, so a launch advances the claim counter by
-// T = nclaims + warps and `old % T` is the claim index in every launch; the epoch (ctl[2]) is read by a warp only between
-// its successful claim and its completion, and written only after all claims have completed.
+//   boundary stripes (for a banded operator the few thousand at both ends of the slab) read x entries that the neighbours
+//     produced in their previous step and produce entries the neighbours read in their next one.  They are cut into runs
+//     of 32/G adjacent stripes and dealt to the warps as the continuation of the interior round-robin, but every warp
+//     runs its boundary runs FIRST: the halo leaves for the neighbours in the first microseconds of the launch, spread
+//     over as many warps as there are runs, while all other warps already stream interior stripes.  A boundary warp
+//     first waits (acquire, system scope) until every neighbour has published the previous step -- that happened a whole
+//     kernel ago, the wait only spins when the ranks have drifted by more than one step -- computes its stripes with
+//     L2-coherent x loads, stages each run's results in shared memory and stores them with full-warp coalesced stores into
+//     the own next-x buffer and into the buffers of exactly the ranks that gather from those columns (mask), over NVLink.
+//     The warp that finishes last publishes the step to the neighbours (release, system scope).
+//   interior stripes [i0, i1) gather only from this rank's own slice of x and feed only this rank: exactly the loop of
+//     the plain kernel, storing into the own next-x buffer.  Nothing here depends on another GPU.
+// The epoch (ctl[2]) is read by a boundary warp before it counts itself done and written only after all have: no reset,
+// no host-side counter, so a captured CUDA graph of steps replays correctly.
 template <typename Tv, int G, int MODE>
-__device__ __noinline__ void adj_boundary_run(const StripeMeta *__restrict__ meta, const int lbase, const int lend, const int *__restrict__ desc,
+__device__ VBC_HALO_RUN_INLINE void adj_boundary_run(const StripeMeta *__restrict__ meta, const int lbase, const int lend, const int *__restrict__ desc,
                                               const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ stage, const HaloArgs &h,
                                               const int u0, const int log2u, const Tv alpha)
 {
@@ -335,58 +343,77 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj_halo(const StripeMeta *__restrict__ me
                                                const int L, const int u0, const int log2u, const Tv alpha)
 {
     constexpr int GPW = 32 / G;
-    adj_range<Tv, G, MODE>(meta, nullptr, h.i0, h.i1, desc, val, x, reinterpret_cast<Tv *>(h.p[0]), u0, log2u, alpha, (Tv)0);
-    if (h.nclaims == 0) return;
-    __shared__ Tv stage_all[8][GPW * 32];
-    Tv *stage = stage_all[threadIdx.x >> 5];
-    const int lane32 = threadIdx.x & 31;
-    bool waited = false;
+    extern __shared__ __align__(16) unsigned char halo_smem[]; // 8 warps x (32/G stripes x W columns) staged results
+    const int lane32 = threadIdx.x & 31, gid = lane32 / G;
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    int w2 = warp - h.first_warp; // position in the deal of the boundary runs
+    if (w2 < 0) w2 += nwarps;
+    const bool bwarp = w2 < h.nruns; // this warp owns boundary runs w2, w2 + nwarps, ...
     unsigned long long epoch = 0;
-    __syncwarp();
-    for (;;) {
-        unsigned long long old = 0;
-        if (lane32 == 0) old = atomicAdd(h.ctl + 0, 1ull);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        const int claim = (int)(old % h.T);
-        if (claim >= h.nclaims) break; // the one failing claim of this warp
-        if (!waited) {
-            waited = true;
-            epoch = ld_relaxed_gpu_u64(h.ctl + 2); // steps this rank has published: the neighbours must have published as many
-            if (h.do_wait && lane32 < h.nranks && lane32 != h.me && ((h.nbr_mask >> lane32) & 1u)) {
-                unsigned long long t0, t1 = 0;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                bool spun = false;
-                while (ld_acquire_sys_u64(h.flags[h.me] + lane32) < epoch) {
-                    spun = true;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                    if (t1 - t0 > 4000000000ull) { atomicExch(h.timed_out, 1); break; } // 4 s: a dead peer must not hang the GPU
-                    __nanosleep(32);
-                }
-                if (spun) { // wait statistics (vbc_peer_wait_stats): total ns, waits that spun, longest
-                    atomicAdd(h.ctl + 3, t1 - t0);
-                    atomicAdd(h.ctl + 4, 1ull);
-                    atomicMax(h.ctl + 5, t1 - t0);
-                }
+    if (bwarp) {
+        Tv *stage = reinterpret_cast<Tv *>(halo_smem) + (threadIdx.x >> 5) * h.stage_elems;
+        // the neighbours' flags and this rank's epoch are fetched together; the comparison waits for both
+        unsigned long long flag = ~0ull;
+        const bool waits = h.do_wait && lane32 < h.nranks && lane32 != h.me && ((h.nbr_mask >> lane32) & 1u);
+        if (waits) flag = ld_acquire_sys_u64(h.flags[h.me] + lane32);
+        epoch = ld_relaxed_gpu_u64(h.ctl + 2); // steps this rank has published: the neighbours must have published as many
+        if (waits && flag < epoch) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            t1 = t0;
+            while (ld_acquire_sys_u64(h.flags[h.me] + lane32) < epoch) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 4000000000ull) { atomicExch(h.timed_out, 1); break; } // 4 s: a dead peer must not hang the GPU
+                __nanosleep(32);
             }
-            __syncwarp();
+            // wait statistics (vbc_peer_wait_stats): total ns, waits that spun, longest
+            atomicAdd(h.ctl + 3, t1 - t0);
+            atomicAdd(h.ctl + 4, 1ull);
+            atomicMax(h.ctl + 5, t1 - t0);
         }
-        for (int run = claim * h.rpc; run < min((claim + 1) * h.rpc, h.nruns); run++) {
+        __syncwarp();
+        for (int r = w2; r < h.nruns; r += nwarps) {
             int lbase, lend;
-            if (run < h.nrunsA) { lbase = run * GPW; lend = min(lbase + GPW, h.i0); }
-            else { lbase = h.i1 + (run - h.nrunsA) * GPW; lend = min(lbase + GPW, L); }
+            if (r < h.nrunsA) { lbase = r * GPW; lend = min(lbase + GPW, h.i0); }
+            else { lbase = h.i1 + (r - h.nrunsA) * GPW; lend = min(lbase + GPW, L); }
             adj_boundary_run<Tv, G, MODE>(meta, lbase, lend, desc, val, x, stage, h, u0, log2u, alpha);
         }
-        __threadfence_system(); // this lane's stores (own HBM and peers) are visible system-wide before the claim counts as done
-        __syncwarp();
-        unsigned long long fin = 0;
-        if (lane32 == 0) fin = atomicAdd(h.ctl + 1, 1ull);
-        fin = __shfl_sync(0xffffffffu, fin, 0);
-        if ((fin % (unsigned long long)h.nclaims) == (unsigned long long)(h.nclaims - 1)) { // last claim of this launch: publish the step
-            // (do_signal == 0: a separate flag kernel publishes and advances the epoch -- vbc_peer_barrier)
-            __threadfence_system();
-            if (h.do_signal && lane32 == 0) *reinterpret_cast<volatile unsigned long long *>(h.ctl + 2) = epoch + 1ull;
-            if (h.do_signal && lane32 < h.nranks && lane32 != h.me && ((h.nbr_mask >> lane32) & 1u))
-                st_release_sys_u64(h.flags[lane32] + h.me, epoch + 1ull);
+    }
+    // Interior stripes, in three parts walked by ONE copy of the loop:
+    //   [i0, ifence)   every warp; after it a boundary warp counts itself done (fence + atomic) -- by then its peer stores
+    //                  have long been acknowledged, so the fence has nothing to wait for, and the step is still published
+    //                  tens of microseconds before any neighbour needs it;
+    //   [ifence, imid) every warp;
+    //   [imid, i1)     only the warps WITHOUT boundary runs: a boundary run costs about two interior runs (L2-coherent
+    //                  loads, staging, peer stores, fence), so the boundary warps get that much less of the interior deal
+    //                  and all warps finish together.
+#pragma unroll 1
+    for (int part = 0; part < 3; part++) {
+        int lo, hi, group, ngroups;
+        if (part < 2) {
+            lo = part == 0 ? h.i0 : h.ifence; hi = part == 0 ? h.ifence : h.imid;
+            group = warp * GPW + gid; ngroups = nwarps * GPW;
+        } else {
+            if (bwarp) break;
+            lo = h.imid; hi = h.i1;
+            group = (w2 - h.nbwarps) * GPW + gid; ngroups = (nwarps - h.nbwarps) * GPW; // dealt over the warps without boundary runs
+        }
+        adj_range<Tv, G, MODE>(meta, nullptr, lo, hi, group, ngroups, desc, val, x, reinterpret_cast<Tv *>(h.p[0]), u0, log2u, alpha, (Tv)0);
+        if (part == 0 && bwarp) {
+            __syncwarp();
+            __threadfence_system(); // this lane's stores (own HBM and peers) are visible system-wide before the warp counts as done
+            __syncwarp();
+            unsigned long long fin = 0;
+            if (lane32 == 0) fin = atomicAdd(h.ctl + 1, 1ull);
+            fin = __shfl_sync(0xffffffffu, fin, 0);
+            if ((fin % (unsigned long long)h.nbwarps) == (unsigned long long)(h.nbwarps - 1)) { // last boundary warp of this launch: publish the step
+                // (do_signal == 0: a separate flag kernel publishes and advances the epoch -- vbc_peer_barrier)
+                __threadfence_system();
+                if (h.do_signal && lane32 == 0) *reinterpret_cast<volatile unsigned long long *>(h.ctl + 2) = epoch + 1ull;
+                if (h.do_signal && lane32 < h.nranks && lane32 != h.me && ((h.nbr_mask >> lane32) & 1u))
+                    st_release_sys_u64(h.flags[lane32] + h.me, epoch + 1ull);
+            }
         }
     }
 }
@@ -592,12 +619,12 @@ static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
     return VBC_OK;
 }
 
-// the fused multiply + exchange: a persistent grid of exactly the resident capacity (the boundary claims assume every warp runs)
+// the fused multiply + exchange: same persistent grid as the plain kernel
 template <typename Tv, int G, int MODE>
-static int launch_halo_t(vbc_mat *A, Tv alpha, const Tv *x, HaloArgs &h, unsigned long long *last_T)
+static int launch_halo_t(vbc_mat *A, Tv alpha, const Tv *x, HaloArgs &h)
 {
     int occ = 0;
-    VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_adj_halo<Tv, G, MODE>, 256, 0));
+    VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_adj_halo<Tv, G, MODE>, 256, 8 * (32 / G) * 32 * sizeof(Tv)));
     if (occ < 1) occ = 1;
     int64_t grid = (int64_t)A->sm_count * occ;
     const int64_t need = (A->L * G + 255) / 256;
@@ -608,17 +635,34 @@ static int launch_halo_t(vbc_mat *A, Tv alpha, const Tv *x, HaloArgs &h, unsigne
     h.nrunsA = (h.i0 + GPW - 1) / GPW;
     h.nruns = h.nrunsA + (L - h.i1 + GPW - 1) / GPW;
     const int64_t warps = grid * 8;
-    h.rpc = (int)((h.nruns + 2 * warps - 1) / (2 * warps)); // at most two claims per warp on average: the claim counter is one address
-    if (h.rpc < 1) h.rpc = 1;
-    h.nclaims = (h.nruns + h.rpc - 1) / h.rpc;
-    h.T = (unsigned long long)h.nclaims + (unsigned long long)warps;
-    // the claim arithmetic (`old % T`) needs counters that are multiples of T at launch: when the geometry changes
-    // (another matrix, another interior range), the two counters restart from zero in stream order; the epoch stays
-    if (last_T && *last_T != h.T) {
-        if (*last_T != 0) VBC_CUDA(cudaMemsetAsync(h.ctl, 0, 2 * sizeof(unsigned long long), A->stream));
-        *last_T = h.T;
+    // interior runs are dealt round-robin from warp 0 (adj_range); the boundary runs continue that deal, so the warps that
+    // got one interior run fewer take the boundary runs
+    const int64_t int_runs = (h.i1 - h.i0 + GPW - 1) / GPW;
+    h.first_warp = (int)(int_runs % warps);
+    h.nbwarps = (int)(h.nruns < warps ? h.nruns : warps);
+    const int64_t ngroups = warps * GPW;
+    // a boundary run is weighted as `bw` interior runs: the boundary warps take part in `common` rounds of the interior deal,
+    // the rest of the interior goes to the other warps only
+    static int bw_env = -1;
+    if (bw_env < 0) { const char *e = getenv("VBC_HALO_BOUNDARY_WEIGHT"); bw_env = e ? atoi(e) : 3; if (bw_env < 0 || bw_env > 16) bw_env = 3; }
+    const int64_t bw = bw_env;
+    int64_t common = int_runs / warps; // rounds every warp can take part in
+    if (h.nbwarps > 0 && h.nbwarps < warps) {
+        const int64_t rb = (h.nruns + h.nbwarps - 1) / h.nbwarps; // boundary runs per boundary warp
+        int64_t c = (int_runs + bw * h.nruns) / warps - bw * rb;
+        if (c < 0) c = 0;
+        if (c < common) common = c;
+    } else if (h.nbwarps >= warps) {
+        common = (int_runs + warps - 1) / warps; // every warp is a boundary warp: the whole interior is common
     }
-    k_spmv_adj_halo<Tv, G, MODE><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, h, L, A->u0, ilog2_exact(A->u0), alpha);
+    const int64_t mid = (int64_t)h.i0 + common * ngroups;
+    h.imid = (int)(mid < h.i1 ? mid : h.i1);
+    const int64_t fence_at = (int64_t)h.i0 + 2 * ngroups; // two rounds of the interior deal
+    h.ifence = (int)(fence_at < h.imid ? fence_at : h.imid);
+    const int wmax = A->W < 1 ? 1 : (A->W > 32 ? 32 : A->W);
+    h.stage_elems = GPW * wmax;
+    const size_t smem = (size_t)8 * h.stage_elems * sizeof(Tv);
+    k_spmv_adj_halo<Tv, G, MODE><<<(unsigned)grid, 256, smem, A->stream>>>(A->d_meta, A->d_desc, (const Tv *)A->d_val, x, h, L, A->u0, ilog2_exact(A->u0), alpha);
     A->launches++;
     VBC_CUDA(cudaGetLastError());
     return VBC_OK;
@@ -653,14 +697,14 @@ static int launch_adj_any(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
 }
 
 template <typename Tv>
-static int launch_halo_any(vbc_mat *A, Tv alpha, const Tv *x, HaloArgs &h, unsigned long long *last_T)
+static int launch_halo_any(vbc_mat *A, Tv alpha, const Tv *x, HaloArgs &h)
 {
     const bool rows = A->desc_mode == DESC_ROWS;
     const int G = A->opt_adj_group ? A->opt_adj_group : auto_group(A);
-    if (G >= 32) return rows ? launch_halo_t<Tv, 32, DESC_ROWS>(A, alpha, x, h, last_T) : launch_halo_t<Tv, 32, DESC_BLOCKS>(A, alpha, x, h, last_T);
-    if (G >= 16) return rows ? launch_halo_t<Tv, 16, DESC_ROWS>(A, alpha, x, h, last_T) : launch_halo_t<Tv, 16, DESC_BLOCKS>(A, alpha, x, h, last_T);
-    if (G >= 8) return rows ? launch_halo_t<Tv, 8, DESC_ROWS>(A, alpha, x, h, last_T) : launch_halo_t<Tv, 8, DESC_BLOCKS>(A, alpha, x, h, last_T);
-    return rows ? launch_halo_t<Tv, 4, DESC_ROWS>(A, alpha, x, h, last_T) : launch_halo_t<Tv, 4, DESC_BLOCKS>(A, alpha, x, h, last_T);
+    if (G >= 32) return rows ? launch_halo_t<Tv, 32, DESC_ROWS>(A, alpha, x, h) : launch_halo_t<Tv, 32, DESC_BLOCKS>(A, alpha, x, h);
+    if (G >= 16) return rows ? launch_halo_t<Tv, 16, DESC_ROWS>(A, alpha, x, h) : launch_halo_t<Tv, 16, DESC_BLOCKS>(A, alpha, x, h);
+    if (G >= 8) return rows ? launch_halo_t<Tv, 8, DESC_ROWS>(A, alpha, x, h) : launch_halo_t<Tv, 8, DESC_BLOCKS>(A, alpha, x, h);
+    return rows ? launch_halo_t<Tv, 4, DESC_ROWS>(A, alpha, x, h) : launch_halo_t<Tv, 4, DESC_BLOCKS>(A, alpha, x, h);
 }
 
 template <typename Tv>
@@ -746,8 +790,8 @@ int launch_spmv_adj_halo(vbc_mat *A, double alpha, const void *d_x, const HaloLa
     for (int r = 0; r < VBC_MAX_PEERS; r++) h.flags[r] = r < hl->nranks ? hl->flags[r] : nullptr;
     h.ctl = hl->ctl;
     h.timed_out = hl->timed_out;
-    if (A->vt == VBC_F64) return launch_halo_any<double>(A, alpha, (const double *)d_x, h, hl->last_T);
-    return launch_halo_any<float>(A, (float)alpha, (const float *)d_x, h, hl->last_T);
+    if (A->vt == VBC_F64) return launch_halo_any<double>(A, alpha, (const double *)d_x, h);
+    return launch_halo_any<float>(A, (float)alpha, (const float *)d_x, h);
 }
 
 int launch_spmv(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y)

@@ -199,23 +199,16 @@ def _allgather_u8(arr):
     return np.stack([a.cpu().numpy() for a in out])
 
 
-def halo_mask(rows_read, layout: PaddedLayout, rank, world, n_local, chunk_shift, pad, allgather):
+def halo_mask(need, layout: PaddedLayout, rank, world, n_local, chunk_shift, allgather):
     """Sparsity-aware replication plan of one rank (`vbc_peer_set_mask` / `vbc_peer_set_neighbors`).
 
-    rows_read: 0-based padded x indices this rank's stripes gather from; pad: a 2D block reads all u rows of its
-    row part, stored or zero-filled, so the need is widened by U-1 rows both ways.  allgather(need_u8) -> [rank, chunk].
+    need[c] = 1 where this rank's stripes gather from chunk c of the padded x (`B.read_chunks(chunk_shift)`, computed
+    on the device from the packed matrix); allgather(need_u8) -> [rank, chunk].
     Returns (mask, nbr): mask[c] bit i set <=> destination i (rank (rank+i) % world) gathers from column chunk c of this
     rank's slab; nbr bit r set <=> this rank sends to or receives from rank r (symmetric: every rank derives both
     directions from the same gathered table)."""
     C = 1 << chunk_shift
-    ng = (layout.padded_len + C - 1) // C
-    need = np.zeros(ng, dtype=np.uint8)
-    rr = np.asarray(rows_read, dtype=np.int64)
-    if len(rr):
-        need[rr >> chunk_shift] = 1
-        if pad:
-            need[np.maximum(rr - pad, 0) >> chunk_shift] = 1
-            need[np.minimum(rr + pad, layout.padded_len - 1) >> chunk_shift] = 1
+    need = np.ascontiguousarray(need, dtype=np.uint8)
     need_all = allgather(need)  # [rank, global chunk]
     y_offset = rank * layout.S
     nl = (n_local + C - 1) // C
@@ -288,11 +281,10 @@ class PeerExchangeOperator:
     and publish a per-step flag.  x is double buffered inside libvbc; handles are exchanged once with
     torch.distributed (any backend)."""
 
-    def __init__(self, B, layout: PaddedLayout, rank, world, device, alpha=1.0, rows_read=None, chunk_shift=7, row_pad=None,
-                 sync_mode=0):
-        """rows_read: optional 0-based (padded) x indices this rank's stripes gather from (e.g. the slab's
-        CSC rowval - 1).  When every rank passes it, replication becomes sparsity-aware: a y segment is
-        stored only into the ranks that read it (`vbc_peer_set_mask`); otherwise x is fully replicated.
+    def __init__(self, B, layout: PaddedLayout, rank, world, device, alpha=1.0, halo=True, chunk_shift=7, sync_mode=0):
+        """halo=True (every rank must agree): replication is sparsity-aware -- each rank publishes which chunks of x
+        its stripes gather from (`vbc_read_chunks`, from the packed matrix on the device) and a y segment is stored
+        only into the ranks that read it (`vbc_peer_set_mask`); halo=False: x is fully replicated (a fused all-gather).
         sync_mode 0: flags inside the multiply kernel (default); 1: a separate flag kernel (signal + wait)
         after every multiply -- the comparator the fused form is measured against."""
         import ctypes
@@ -322,9 +314,8 @@ class PeerExchangeOperator:
         self.halo = False
         self.neighbors = [r for r in range(world) if r != rank]
         self.sent_fraction = 1.0
-        if rows_read is not None and world > 1:
-            mask, nbr = halo_mask(rows_read, layout, rank, world, B.n, chunk_shift,
-                                  (max(int(B.U), 1) - 1) if row_pad is None else int(row_pad), _allgather_u8)
+        if halo and world > 1:
+            mask, nbr = halo_mask(B.read_chunks(chunk_shift), layout, rank, world, B.n, chunk_shift, _allgather_u8)
             _lib.check(L.vbc_peer_set_mask(self._h, mask.ctypes.data_as(ctypes.c_void_p), len(mask), chunk_shift))
             _lib.check(L.vbc_peer_set_neighbors(self._h, nbr))
             self.neighbors = [r for r in range(world) if (nbr >> r) & 1]

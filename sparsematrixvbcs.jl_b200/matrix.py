@@ -157,6 +157,13 @@ class _CuVBC:
         check(_lib.lib().vbc_memory_cost(self._h, _vp(cost), row_term))
         return cost, row_term.value
 
+    def read_chunks(self, chunk_shift):
+        """need[c] = 1 where an adjoint multiply gathers from x chunk c (vbc_read_chunks)."""
+        n = (self.m + (1 << chunk_shift) - 1) >> chunk_shift
+        need = np.zeros(max(n, 1), dtype=np.uint8)
+        check(_lib.lib().vbc_read_chunks(self._h, int(chunk_shift), _vp(need), len(need)))
+        return need[:n]
+
     def set_option(self, option, value):
         check(_lib.lib().vbc_set_option(self._h, int(option), int(value)))
 

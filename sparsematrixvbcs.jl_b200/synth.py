@@ -174,3 +174,58 @@ def variable_block_matrix(n, per_stripe=8, g_max=6, band=2000, seed=SEED, dtype=
     vals = entry_values(rr, cc, n, seed=seed, dtype=dtype)
     A = SparseMatrixCSC.from_scipy(sp.csc_matrix((vals, (rr, cc)), shape=(n, n)), ti=ti, tv=dtype)
     return A, SplitPartition((rs + 1).astype(ti)), SplitPartition((cs + 1).astype(ti))
+
+
+class DeviceCSC:
+    """A SparseMatrixCSC slab living in device memory, produced by libvbc's generator (`vbc_gen_banded_csc`):
+    colptr / rowval / nzval are torch CUDA tensors viewing memory owned by this object."""
+
+    def __init__(self, m, n, nnz, ptrs, tv, ti, device):
+        import torch
+        self.m, self.n, self.nnz, self._ptrs, self.device = int(m), int(n), int(nnz), ptrs, int(device)
+        self.tv, self.ti = np.dtype(tv), np.dtype(ti)
+
+        def view(ptr, count, dt):
+            class _W:
+                pass
+            o = _W()
+            o.__cuda_array_interface__ = {"shape": (max(int(count), 1),), "typestr": np.dtype(dt).str, "data": (int(ptr), False), "version": 2}
+            return torch.as_tensor(o, device=f"cuda:{device}")[: int(count)]
+        self.colptr = view(ptrs[0], self.n + 1, ti)
+        self.rowval = view(ptrs[1], self.nnz, ti)
+        self.nzval = view(ptrs[2], self.nnz, tv)
+
+    def free(self):
+        if self._ptrs is not None:
+            import ctypes
+
+            from . import _lib
+            self.colptr = self.rowval = self.nzval = None
+            _lib.lib().vbc_gen_free(ctypes.c_void_p(self._ptrs[0]), ctypes.c_void_p(self._ptrs[1]), ctypes.c_void_p(self._ptrs[2]), self.device)
+            self._ptrs = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def banded_blocks_device(K, L, u, w, offsets, seed=SEED, dtype=np.float64, ti=np.int64, stripes=None, diag_boost=0.0, device=0):
+    """`banded_blocks` generated on the device (same matrix, same values): -> DeviceCSC slab of stripes [l0, l1)."""
+    import ctypes
+
+    from . import _lib
+    offs = np.array(sorted(set(int(o) for o in offsets)), dtype=np.int64)
+    l0, l1 = (0, L) if stripes is None else stripes
+    vt = _lib.VBC_F64 if np.dtype(dtype) == np.dtype(np.float64) else _lib.VBC_F32
+    it = _lib.VBC_I64 if np.dtype(ti) == np.dtype(np.int64) else _lib.VBC_I32
+    cp, rv, nz = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    nnz = ctypes.c_int64()
+    _lib.check(_lib.lib().vbc_gen_banded_csc(vt, it, int(K), int(L), int(u), int(w), ctypes.c_void_p(offs.ctypes.data), len(offs), int(l0), int(l1),
+                                            ctypes.c_uint64(seed), float(diag_boost), ctypes.byref(cp), ctypes.byref(rv), ctypes.byref(nz),
+                                            ctypes.byref(nnz), int(device)))
+    return DeviceCSC(K * u, (l1 - l0) * w, nnz.value, (cp.value, rv.value, nz.value), dtype, ti, device)
+
+
+C5_OFFSETS = (0, 1, -1, 2, -2, 57, -57, 58, -58, 3249)  # BASELINE.json configs[4]: 10 blocks per stripe, banded

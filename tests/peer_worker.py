@@ -35,7 +35,7 @@ def main():
     B = vb.SparseMatrixVBC[u, w](Ar, vdist.padded_row_partition(layout, u, np.int64), phir, device=dev)
     x0 = synth.vector(n, 5)
 
-    peer = vdist.PeerExchangeOperator(B, layout, rank, world, dev, alpha=alpha, rows_read=Ar.rowval.astype(np.int64) - 1)
+    peer = vdist.PeerExchangeOperator(B, layout, rank, world, dev, alpha=alpha, halo=True)
     peer.set_x(x0)
     dist.barrier()
     for _ in range(steps):

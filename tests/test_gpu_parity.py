@@ -699,3 +699,76 @@ def test_spmm_host_panels_with_leading_dimension_padding():
     for r in range(A.n):
         pad[r * ldy: r * ldy + k] = False
     assert np.all(Ybuf[pad] == -7.0)  # the gaps between the rows of Y were not written
+
+
+def test_device_generator_matches_host_generator():
+    """vbc_gen_banded_csc: the slab generated on the device equals synth.banded_blocks bit for bit (structure and values),
+    for both element / index types, a slab in the middle and the clipped edges; and packs to the same VBC arrays."""
+    import torch
+    K = L = 3000
+    for tv, ti in ((np.float64, np.int64), (np.float32, np.int32)):
+        for stripes in ((0, 700), (1100, 1900), (2500, 3000), None):
+            H, pi, phi = synth.banded_blocks(K, L, 4, 4, synth.C5_OFFSETS, dtype=tv, ti=ti, stripes=stripes, diag_boost=2.5)
+            D = synth.banded_blocks_device(K, L, 4, 4, synth.C5_OFFSETS, dtype=tv, ti=ti, stripes=stripes, diag_boost=2.5)
+            assert (D.m, D.n, D.nnz) == (H.m, H.n, H.nnz)
+            assert np.array_equal(D.colptr.cpu().numpy(), H.colptr)
+            assert np.array_equal(D.rowval.cpu().numpy(), H.rowval)
+            assert np.array_equal(D.nzval.cpu().numpy(), H.nzval)
+            d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+            B = vb.SparseMatrixVBC.from_device_csc(4, 4, D.m, D.n, D.colptr, D.rowval, D.nzval, d(pi.spl), d(phi.spl))
+            Hp = oracle.pack_2d(H.m, H.n, H.colptr, H.rowval, H.nzval, pi.spl, phi.spl, 4, 4)
+            assert_packed_equal(B, Hp)
+            D.free()
+
+
+def test_malformed_csc_is_refused_on_the_device():
+    """rowval outside 1:m, descending rows, a broken colptr -> ArgumentError before any kernel indexes with them."""
+    import torch
+    A = sprand(40, 30, 0.3, np.random.default_rng(2))
+    phi = vb.pack_stripe(A, vb.EquiChunker(4))
+    pi = vb.pack_stripe(A.transpose(), vb.EquiChunker(4))
+    bad = []
+    rv = A.rowval.copy(); rv[5] = A.m + 1; bad.append((A.colptr, rv))
+    rv = A.rowval.copy(); rv[7] = 0; bad.append((A.colptr, rv))
+    j = int(np.argmax(np.diff(A.colptr) >= 2)); b = A.colptr[j] - 1
+    rv = A.rowval.copy(); rv[b], rv[b + 1] = rv[b + 1], rv[b]; bad.append((A.colptr, rv))
+    cp = A.colptr.copy(); cp[3] = cp[-1] + 5; bad.append((cp, A.rowval))
+    for cpb, rvb in bad:
+        M = vb.SparseMatrixCSC(A.m, A.n, cpb, rvb, A.nzval)
+        for ctor in (lambda: vb.SparseMatrix1DVBC[4](M, phi), lambda: vb.SparseMatrixVBC[4, 4](M, pi, phi)):
+            with pytest.raises(vb.ArgumentError):
+                ctor()
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        with pytest.raises(vb.ArgumentError):
+            vb.SparseMatrix1DVBC.from_device_csc(4, A.m, A.n, d(cpb), d(rvb), d(A.nzval), d(phi.spl))
+    B = vb.SparseMatrix1DVBC[4](A, phi)  # the device is still healthy
+    assert np.allclose(vb.mul_(np.empty(A.n), B.T, np.ones(A.m)), A.to_scipy().T @ np.ones(A.m))
+
+
+def test_host_vector_multiply_replays_a_graph_for_repeated_pinned_buffers():
+    """VBC_OPT_E2E_GRAPH: the iterative caller's `mul!(y, A', x)` with the same pinned x / y is captured at the second call and
+    replayed afterwards -- the results follow the CONTENTS of the buffers; pageable buffers and changing pointers stay eager."""
+    import torch
+    rng = np.random.default_rng(17)
+    A, pi, phi = synth.config_c2(n=200_000, S=23)
+    S = A.to_scipy()
+    B = vb.SparseMatrixVBC[4, 4](A, pi, phi)
+    x = torch.empty(A.m, dtype=torch.float64).pin_memory().numpy()
+    y = torch.empty(A.n, dtype=torch.float64).pin_memory().numpy()
+    for it in range(5):
+        x[:] = rng.random(A.m)
+        y[:] = np.nan
+        vb.mul_(y, B.T, x)
+        assert np.allclose(y, S.T @ x, rtol=1e-12), it
+        assert B.get_option(_lib.OPT_E2E_GRAPH) == (2 if it >= 1 else 1)
+    eager = vb.mul_(np.empty(A.n), B.T, x.copy())          # pageable buffers: eager path, same bits
+    assert np.array_equal(eager, y) and B.get_option(_lib.OPT_E2E_GRAPH) == 1
+    y0 = rng.random(A.n)
+    for it in range(3):                                        # alpha / beta are part of the captured work
+        y[:] = y0
+        vb.mul_(y, B.T, x, 2.0, -0.5)
+        assert np.allclose(y, 2.0 * (S.T @ x) - 0.5 * y0, rtol=1e-12)
+    B.set_option(_lib.OPT_E2E_GRAPH, 0)
+    y[:] = np.nan
+    vb.mul_(y, B.T, x)
+    assert np.array_equal(y, eager) and B.get_option(_lib.OPT_E2E_GRAPH) == 0

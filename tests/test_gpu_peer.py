@@ -58,18 +58,16 @@ def _run_ranks_one_process(n, S, P, steps, alpha, shift_bounds, Tv=np.float64, h
     interiors = []
     if halo:
         chunk_shift = 5
-        C = 1 << chunk_shift
-        ng = (layout.padded_len + C - 1) // C
-        needs = []
+        needs = [mats[r].read_chunks(chunk_shift) for r in range(P)]
         for r in range(P):
-            need = np.zeros(ng, dtype=np.uint8)
+            # the device-derived read set equals the one computed from the slab's CSC rows (a 2D block reads its whole row part)
             rr = slabs[r].rowval.astype(np.int64) - 1
-            need[rr >> chunk_shift] = 1
-            need[np.maximum(rr - (u - 1), 0) >> chunk_shift] = 1
-            need[np.minimum(rr + (u - 1), layout.padded_len - 1) >> chunk_shift] = 1
-            needs.append(need)
+            ref_need = np.zeros(len(needs[r]), dtype=np.uint8)
+            ref_need[(rr // u * u) >> chunk_shift] = 1
+            ref_need[(rr // u * u + u - 1) >> chunk_shift] = 1
+            assert np.array_equal(needs[r], ref_need)
         for r in range(P):
-            mask, nbr = vdist.halo_mask(slabs[r].rowval.astype(np.int64) - 1, layout, r, P, mats[r].n, chunk_shift, u - 1, _fake_allgather(needs))
+            mask, nbr = vdist.halo_mask(needs[r], layout, r, P, mats[r].n, chunk_shift, _fake_allgather(needs))
             _lib.check(Lh.vbc_peer_set_mask(peers[r], mask.ctypes.data_as(ctypes.c_void_p), len(mask), chunk_shift))
             _lib.check(Lh.vbc_peer_set_neighbors(peers[r], nbr))
             i0, i1 = ctypes.c_int64(), ctypes.c_int64()
