@@ -413,8 +413,9 @@ def run_ours(args, rank, world, local_rank):
         # NCCL's own log (the driver reads the communicator's rank count from it) must stay on, but off stdout: this
         # process prints exactly one JSON line there.  NCCL_DEBUG_FILE would hide it from the driver, so stdout is
         # pointed at stderr while NCCL initialises and speaks, and restored for the JSON line.
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):   # VERSION / WARN / unset: raise it to INFO for the init lines
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         sys.stdout.flush()
         saved_stdout = os.dup(1)
         os.dup2(2, 1)

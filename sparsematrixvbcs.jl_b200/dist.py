@@ -415,3 +415,67 @@ class PeerExchangeOperator:
             self.close()
         except Exception:
             pass
+
+
+class DistributedOperator:
+    """`vbc_dist_*`: the iterated adjoint multiply x <- alpha * A' x of a square operator over several GPUs driven by THIS
+    process (no torch.distributed): stripes split by the reference's memory cost model, one packed slab per device, the
+    exchange fused into the multiply (exchange="fused") or multiply + ncclAllGather (exchange="nccl", the comparator)."""
+
+    def __init__(self, A: SparseMatrixCSC, phi: SplitPartition, pi: SplitPartition = None, U=1, W=None, ngpus=1, devices=None, exchange="fused"):
+        import ctypes
+
+        from . import _lib
+        if A.m != A.n:
+            raise ValueError("the iterated row-partitioned multiply needs a square operator")
+        self._lib, self._h = _lib, ctypes.c_void_p()
+        ti = A.colptr.dtype
+        vt = _lib.VBC_F64 if A.nzval.dtype == np.dtype(np.float64) else _lib.VBC_F32
+        it = _lib.VBC_I64 if ti == np.dtype(np.int64) else _lib.VBC_I32
+        phi = phi.astype(ti)
+        pi = None if pi is None else pi.astype(ti)
+        W = int(np.diff(phi.spl).max()) if W is None else int(W)
+        dev = None if devices is None else (ctypes.c_int * ngpus)(*devices)
+        vp = lambda a: None if a is None else ctypes.c_void_p(a.ctypes.data)
+        _lib.check(_lib.lib().vbc_dist_create(ctypes.byref(self._h), int(ngpus), dev, vt, it, A.n, int(U), W, vp(A.colptr), vp(A.rowval), vp(A.nzval),
+                                             vp(None if pi is None else pi.spl), 0 if pi is None else len(pi), vp(phi.spl), len(phi),
+                                             _lib.EXCH_FUSED if exchange == "fused" else _lib.EXCH_NCCL))
+        self.n, self.P, self.Tv = A.n, int(ngpus), A.nzval.dtype
+        S = ctypes.c_int64()
+        b = (ctypes.c_int64 * (self.P + 1))()
+        c = (ctypes.c_int64 * self.P)()
+        inter = (ctypes.c_int64 * (2 * self.P))()
+        _lib.check(_lib.lib().vbc_dist_info(self._h, None, ctypes.byref(S), b, c, inter))
+        self.slice_len, self.stripe_bounds, self.cost_per_gpu = S.value, list(b), list(c)
+        self.interior = [(inter[2 * r], inter[2 * r + 1]) for r in range(self.P)]
+
+    def set_x(self, x):
+        import ctypes
+        x = np.ascontiguousarray(x, dtype=self.Tv)
+        assert len(x) == self.n
+        self._lib.check(self._lib.lib().vbc_dist_set_x(self._h, ctypes.c_void_p(x.ctypes.data)))
+
+    def iterate(self, iters, alpha=1.0):
+        """-> device milliseconds per iteration (maximum over the devices)"""
+        import ctypes
+        ms = ctypes.c_double()
+        self._lib.check(self._lib.lib().vbc_dist_spmv_iter(self._h, int(iters), float(alpha), ctypes.byref(ms)))
+        return ms.value
+
+    def x(self):
+        import ctypes
+        out = np.empty(self.n, dtype=self.Tv)
+        self._lib.check(self._lib.lib().vbc_dist_gather_x(self._h, ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            import ctypes
+            self._lib.lib().vbc_dist_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -187,3 +187,71 @@ def test_two_processes_cuda_ipc_halo_exchange():
     assert res["max_abs_diff_vs_allgather_path"] == 0.0
     assert res["max_rel_err_vs_scipy"] < 1e-12
     assert res["timed_out"] is False
+
+
+@pytest.mark.parametrize("kind", ["2d", "1d", "2d_f32_i32"])
+def test_single_process_multi_device_api(kind):
+    """vbc_dist_*: one process, P "devices" (the same GPU listed P times on a one-GPU box, distinct GPUs when the box has
+    them): cost-balanced split, slabs packed per device, fused exchange -- the iterate equals the host CSC iterate, for an
+    even and an odd number of iterations (graph + single launches), 1D and 2D, unequal slices."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    n, S = 24_000, 9
+    tv, ti = (np.float32, np.int32) if kind.endswith("i32") else (np.float64, np.int64)
+    A, pi, phi = synth.config_c2(n=n, S=S, dtype=tv, ti=ti)
+    # make the cost profile uneven: thin out the left third
+    keep = np.ones(A.nnz, dtype=bool)
+    cp = A.colptr.astype(np.int64) - 1
+    rng = np.random.default_rng(1)
+    for j in range(0, n // 3, 4):
+        b, e = cp[j], cp[j + 4]
+        if rng.random() < 0.7:
+            keep[b:e] = (A.rowval[b:e] - 1) // 4 == j // 4  # keep only the diagonal block of this stripe
+    counts = np.add.reduceat(keep.astype(np.int64), cp[:-1])
+    A = vb.SparseMatrixCSC(n, n, np.concatenate([[1], 1 + np.cumsum(counts)]).astype(ti), A.rowval[keep], A.nzval[keep])
+    Sg = A.to_scipy().astype(np.float64)
+    x0 = synth.vector(n, 2, dtype=tv)
+    tol = 1e-12 if tv == np.float64 else 2e-5
+    for P in (1, 2, 3):
+        devices = [r % max(ngpu, 1) for r in range(P)]
+        op = vdist.DistributedOperator(A, phi, None if kind == "1d" else pi, U=4, W=4, ngpus=P, devices=devices)
+        assert op.stripe_bounds[0] == 0 and op.stripe_bounds[-1] == len(phi) and all(np.diff(op.stripe_bounds) > 0)
+        if P > 1:
+            assert max(op.cost_per_gpu) < 1.25 * (sum(op.cost_per_gpu) / P)        # balanced by the memory model ...
+            assert op.stripe_bounds[1] > len(phi) // P                                # ... not by stripe count: the thin third is on rank 0
+            assert all(i1 > i0 for i0, i1 in op.interior)
+        op.set_x(x0)
+        ref = x0.astype(np.float64)
+        for iters in (4, 1, 3):
+            ms = op.iterate(iters, 0.05)
+            assert ms > 0
+            for _ in range(iters):
+                ref = 0.05 * (Sg.T @ ref)
+            x = op.x().astype(np.float64)
+            assert np.allclose(x, ref, rtol=tol * 10, atol=1e-300 if tv == np.float64 else 1e-12), (kind, P, iters)
+        op.close()
+
+
+def test_single_process_nccl_comparator():
+    """VBC_EXCH_NCCL: multiply + ncclAllGather through the dlopen'ed libnccl.  Needs two distinct GPUs; on a one-GPU box the
+    duplicate device must come back as a clean VBC_ENCCL error, not a crash."""
+    import torch
+    n = 16_000
+    A, pi, phi = synth.config_c2(n=n, S=7)
+    if torch.cuda.device_count() < 2:
+        with pytest.raises(_lib.VBCError) as ei:
+            vdist.DistributedOperator(A, phi, pi, U=4, W=4, ngpus=2, devices=[0, 0], exchange="nccl")
+        assert ei.value.code == _lib.VBC_ENCCL
+        return
+    Sg = A.to_scipy()
+    x0 = synth.vector(n, 2)
+    a = vdist.DistributedOperator(A, phi, pi, U=4, W=4, ngpus=2, exchange="nccl")
+    b = vdist.DistributedOperator(A, phi, pi, U=4, W=4, ngpus=2, exchange="fused")
+    a.set_x(x0); b.set_x(x0)
+    a.iterate(5, 0.05); b.iterate(5, 0.05)
+    ref = x0.copy()
+    for _ in range(5):
+        ref = 0.05 * (Sg.T @ ref)
+    assert np.array_equal(a.x(), b.x())
+    assert np.allclose(a.x(), ref, rtol=1e-11)
+    a.close(); b.close()
