@@ -144,9 +144,11 @@ int vbc_spmm(vbc_mat *A, int trans, int64_t k, double alpha, const void *X, int6
  * ("TrSpMV" there is the transposed multiply); BASELINE.json's north_star (d) asks for a
  * blocked, level-scheduled one.  Row block l of A' is stripe l; entries above the diagonal of A' are
  * ignored (BLAS trsv 'L'), the diagonal must be stored and nonzero.  vbc_trsv_analyse builds the level
- * schedule (also done lazily by the first solve) and reports the number of levels; the solve is one
- * cooperative persistent kernel that walks the row blocks in level order and waits on per-row-block
- * flags.  Stripes may be at most 8 columns wide (VBC_ELIMIT).  b and x have n entries; x != b. */
+ * schedule (also done lazily by the first solve), extracts the diagonal blocks and reports the number of levels;
+ * the solve is one cooperative persistent kernel that walks the row blocks in level order -- x itself carries the
+ * dependencies (it starts as a sentinel, a consumer polls the entries it needs), so there are no flags or epochs
+ * and a solve may be captured in a CUDA graph and replayed.  Stripes may be at most 32 columns wide (VBC_ELIMIT).
+ * b and x have n entries; x != b (VBC_EARG).  A zero diagonal entry is reported by the analysis (VBC_EARG). */
 int vbc_trsv_analyse(vbc_mat *A, int *nlevels);
 int vbc_trsv_levels(const vbc_mat *A, int *nlevels);
 int vbc_trsv_lower(vbc_mat *A, const void *b, void *x, int64_t len, int on_device);

@@ -772,3 +772,52 @@ def test_host_vector_multiply_replays_a_graph_for_repeated_pinned_buffers():
     y[:] = np.nan
     vb.mul_(y, B.T, x)
     assert np.array_equal(y, eager) and B.get_option(_lib.OPT_E2E_GRAPH) == 0
+
+
+def test_triangular_solve_graph_replay_wide_stripes_and_singular():
+    """a solve captured in a CUDA graph must stay correct when replayed (x carries the dependencies: no host-side
+    epoch); stripes up to 32 wide; a zero diagonal is an ArgumentError at analysis."""
+    import scipy.sparse as sp
+    import torch
+    from scipy.sparse.linalg import spsolve_triangular
+    rng = np.random.default_rng(5)
+    A, pi, phi = synth.config_c4_triangular(n=16_000, S=11)
+    B = vb.SparseMatrixVBC[4, 4](A, pi, phi)
+    T = sp.tril(A.to_scipy().T).tocsr()
+    bd = torch.from_numpy(rng.random(A.n)).cuda()
+    xd = torch.empty_like(bd)
+    vb.ldiv_lower_(xd, B.T, bd)  # analysis + warm-up outside capture
+    torch.cuda.synchronize()
+    side, g = torch.cuda.Stream(), torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        vb.ldiv_lower_(xd, B.T, bd)
+    for rep in range(3):
+        bd.copy_(torch.from_numpy(rng.random(A.n)))
+        xd.zero_()  # stale, finite x from an earlier solve must not satisfy any dependency
+        g.replay()
+        torch.cuda.synchronize()
+        xo = spsolve_triangular(T, bd.cpu().numpy(), lower=True)
+        assert np.max(np.abs(xd.cpu().numpy() - xo)) <= 1e-11 * max(1.0, np.max(np.abs(xo))), rep
+    B.sync()
+    # wide stripes (one lane per unknown of a row block)
+    for w in (12, 16, 32):
+        n = 640
+        S = sp.random(n, n, density=0.05, random_state=np.random.RandomState(w), format="csc")
+        S = sp.triu(S) + sp.identity(n) * 8.0   # A upper triangular <=> A' lower triangular
+        M = vb.SparseMatrixCSC.from_scipy(sp.csc_matrix(S))
+        Bw = vb.SparseMatrix1DVBC[w](M, vb.EquiChunker(w))
+        b = rng.random(n)
+        x = vb.ldiv_lower_(np.empty(n), Bw.T, b)
+        xo = spsolve_triangular(sp.tril(S.T).tocsr(), b, lower=True)
+        assert np.max(np.abs(x - xo)) <= 1e-11 * max(1.0, np.max(np.abs(xo))), w
+    # singular: a missing diagonal entry
+    S = sp.identity(16, format="lil") * 2.0
+    S[5, 5] = 0.0
+    S[2, 9] = 1.0
+    M = vb.SparseMatrixCSC.from_scipy(sp.csc_matrix(S))
+    Bs = vb.SparseMatrix1DVBC[4](M, vb.EquiChunker(4))
+    with pytest.raises(vb.ArgumentError):
+        vb.trsv_analyse(Bs.T)
+    with pytest.raises(vb.ArgumentError):
+        xb = np.ones(16)
+        vb.ldiv_lower_(xb, Bs.T, xb)  # in place is refused
