@@ -51,9 +51,13 @@ enum vbc_option {
     VBC_OPT_GRID_MULT = 3,  /* CTAs per SM for the persistent grid-stride launch: 0 = auto                   */
     VBC_OPT_PARITY_MODE = 4, /* 1: multiply straight from the canonical Ti arrays (pos/idx/ofs/spl) with the
                                   generic kernel instead of the compact device layout                         */
-    VBC_OPT_FWD_MODE = 5,    /* forward multiply: 0 = auto (owner-computes through a transposed unit index, built at first
-                                  use, for uniform 2D blocks; atomic scatter kernel otherwise), 1 = always the atomic
-                                  scatter kernel, 2 = the transposed index whenever the layout allows it              */
+    VBC_OPT_FWD_MODE = 5,    /* forward multiply y = A x (the reference's serial scatter, multiply_1DVBC.jl:9-83 / multiply_VBC.jl:3-87), made
+                              * owner-computes at the first forward multiply:
+                              *   0 = auto: uniform 2D blocks get a TRANSPOSED COPY of the values when device memory is plentiful (the
+                              *       forward multiply is then the adjoint kernel on that copy), else the transposed unit index; 1D and
+                              *       variable blocks use the atomic scatter kernel;
+                              *   1 = always the atomic scatter kernel;  2 = the transposed unit index (16 B per unit, no second copy of
+                              *       the values) whenever the layout allows it;  3 = the transposed copy, regardless of free memory    */
     VBC_OPT_SPMM_SIMT = 6,   /* Float64 adjoint SpMM: 0 = FP64 tensor (DMMA m8n8k4) tiles, 1 = the SIMT (DFMA) kernel            */
     VBC_OPT_E2E_PIPELINE = 7, /* host-vector adjoint multiplies: 1 (default) = x is uploaded in pieces on its own stream and each
                               * chunk of stripes starts as soon as the x rows it gathers from have arrived, while the y ranges of

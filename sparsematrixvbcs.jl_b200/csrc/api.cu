@@ -638,7 +638,8 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
     case VBC_OPT_E2E_UPLOAD_ELEMS:
         VBC_FAIL(VBC_EARG, "VBC_OPT_E2E_UPLOAD_ELEMS is read-only");
     case VBC_OPT_FWD_MODE:
-        if (value < 0 || value > 2) VBC_FAIL(VBC_EARG, "forward mode must be 0 (auto), 1 (atomic scatter) or 2 (transposed index whenever possible)");
+        if (value < 0 || value > 3) VBC_FAIL(VBC_EARG, "forward mode must be 0 (auto), 1 (atomic scatter), 2 (transposed unit index) or 3 (transposed copy)");
+        if ((int)value != A->opt_fwd_atomic && A->tindex) { DeviceGuard guard(A->device); cudaStreamSynchronize(A->stream); destroy_tindex(A->tindex); A->tindex = nullptr; } // rebuilt at the next forward multiply
         A->opt_fwd_atomic = (int)value;
         return VBC_OK;
     }

@@ -111,7 +111,7 @@ struct vbc_mat {
     int64_t e2e_upload = 0;
     vbc_trsv_plan *trsv = nullptr; // level schedule of the triangular solve (vbc_trsv_analyse)
     vbc::TIndex *tindex = nullptr; // transposed unit index of the owner-computes forward multiply (built at first use)
-    int opt_fwd_atomic = 0;        // 1: always use the atomic scatter kernel for the forward multiply
+    int opt_fwd_atomic = 0;        // VBC_OPT_FWD_MODE: 0 auto, 1 atomic scatter kernel, 2 transposed unit index, 3 transposed copy
     int opt_spmm_simt = 0;         // 1: Float64 adjoint SpMM on the SIMT (DFMA) kernel instead of the DMMA tiles
 };
 
@@ -164,6 +164,7 @@ int ensure_tindex(vbc_mat *A);
 int launch_fwdt(vbc_mat *A, double alpha, const void *x, double beta, void *y);
 void destroy_tindex(TIndex *t);
 int64_t tindex_bytes(const vbc_mat *A);
+int tindex_kind(const vbc_mat *A); // 0 none, 1 transposed unit index, 2 transposed copy
 // trsv.cu
 void destroy_trsv_plan(vbc_trsv_plan *p);
 int trsv_error_flag(const vbc_mat *A, int *flag);

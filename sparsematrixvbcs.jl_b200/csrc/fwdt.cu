@@ -77,6 +77,67 @@ __global__ void __launch_bounds__(128) k_t_fill(const StripeMeta *__restrict__ m
     }
 }
 
+// The atomic cursor leaves a key's units in arrival order; sorting them by stripe column (a handful per key) makes the
+// index -- and the summation order of the owner-computes forward multiply -- the same on every run.
+__global__ void __launch_bounds__(256) k_t_sort(const int *__restrict__ tptr, TRec *__restrict__ rec, const int nkeys)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    const int t0 = tptr[k], t1 = tptr[k + 1];
+    for (int i = t0 + 1; i < t1; i++) { // insertion sort
+        const TRec r = rec[i];
+        int j = i - 1;
+        while (j >= t0 && rec[j].col > r.col) { rec[j + 1] = rec[j]; j--; }
+        rec[j + 1] = r;
+    }
+}
+
+// Transposed copy of a matrix of uniform u0 x w0 blocks: row part k becomes "stripe" k (u columns wide: the part's rows)
+// holding its blocks transposed, w0 x u row-major, in ascending stripe-column order.  The forward multiply y = A x is then
+// the ADJOINT multiply of this copy -- the same streaming owner-computes kernel, at the same fraction of the HBM roofline
+// as mul!(y, B', x) -- at the price of a second copy of the values.
+template <typename Tv>
+__global__ void __launch_bounds__(256) k_t_meta(const int *__restrict__ tptr, const int nkeys, const int u0, const int w0, const long long m,
+                                                StripeMeta *__restrict__ meta2)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nkeys) return;
+    // every part before the last is u0 high, so the value offset is closed-form: blocks before * (w0 * u0)
+    StripeMeta s;
+    s.ofs = (long long)tptr[k] * w0 * u0;
+    if (k == nkeys && nkeys > 0) { // the last part may be shorter: its blocks are w0 x u_last
+        const long long u_last = m - (long long)(nkeys - 1) * u0;
+        s.ofs = (long long)tptr[k - 1] * w0 * u0 + (long long)(tptr[k] - tptr[k - 1]) * w0 * u_last;
+    }
+    s.pos = tptr[k];
+    const long long c = (long long)k * u0;
+    s.col = (int)(c < m ? c : m);
+    meta2[k] = s;
+}
+
+template <typename Tv>
+__global__ void __launch_bounds__(256) k_t_copy(const int *__restrict__ tptr, const TRec *__restrict__ rec, const Tv *__restrict__ val, const int nkeys,
+                                                const int u0, const int w0, const long long m, int *__restrict__ desc2, Tv *__restrict__ val2)
+{
+    // one warp per row part; lanes walk the elements of its transposed blocks, consecutive lanes -> consecutive outputs
+    const int k = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (k >= nkeys) return;
+    const int t0 = tptr[k], t1 = tptr[k + 1];
+    const long long i0 = (long long)k * u0;
+    const int u = (int)((m - i0) < u0 ? (m - i0) : u0);
+    const long long obase = (long long)t0 * w0 * u0;
+    const int per = w0 * u;
+    for (int t = t0; t < t1; t++) {
+        const TRec r = rec[t];
+        if (lane == 0) desc2[t] = r.col;
+        Tv *out = val2 + obase + (long long)(t - t0) * per;
+        for (int e = lane; e < per; e += 32) {
+            const int dj = e / u, di = e - dj * u; // transposed block: row dj (a column of A), column di (a row of the part)
+            out[e] = val[r.vofs + (long long)di * w0 + dj];
+        }
+    }
+}
+
 // ---- rows mode: SG lanes per destination row, units are w-wide row segments ---------------------
 template <typename Tv, int SG>
 __global__ void __launch_bounds__(256) k_fwdt_rows(const int *__restrict__ tptr, const TRec *__restrict__ rec, const Tv *__restrict__ val,
@@ -196,6 +257,7 @@ struct TIndex {
     TRec *d_rec = nullptr;
     int nkeys = 0;
     int mode = 0; // DESC_ROWS / DESC_BLOCKS
+    vbc_mat *At = nullptr; // transposed copy (uniform blocks): an internal handle whose adjoint multiply is this matrix' forward multiply
 };
 
 void destroy_tindex(TIndex *t)
@@ -203,6 +265,10 @@ void destroy_tindex(TIndex *t)
     if (!t) return;
     cudaFree(t->d_tptr);
     cudaFree(t->d_rec);
+    if (t->At) {
+        cudaFree(t->At->d_meta); cudaFree(t->At->d_desc); cudaFree(t->At->d_val);
+        delete t->At;
+    }
     delete t;
 }
 
@@ -241,9 +307,52 @@ static int build_tindex_mode(vbc_mat *A, TIndex *T)
     long long total = 0;
     if (rc == VBC_OK) rc = exclusive_scan<int>((const long long *)d_cnt, T->d_tptr, nkeys, 0, d_tmp, &total, st, &A->launches);
     if (rc == VBC_OK && L > 0) { k_t_fill<MODE><<<g, 128, 0, st>>>(A->d_meta, A->d_desc, L, A->u0, log2u, T->d_tptr, d_cur, T->d_rec); A->launches++; }
+    if (rc == VBC_OK && nkeys > 0) { k_t_sort<<<(unsigned)((nkeys + 255) / 256), 256, 0, st>>>(T->d_tptr, T->d_rec, (int)nkeys); A->launches++; }
     if (rc == VBC_OK && (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)) { set_error("transposed index kernels failed"); rc = VBC_ECUDA; }
     cudaFree(d_cnt); cudaFree(d_tmp); cudaFree(d_cur);
     return rc;
+}
+
+// uniform blocks: materialise the transposed copy from the index (opt_fwd_atomic 0 = when device memory is plentiful, 3 = always)
+template <typename Tv>
+static int build_transposed_copy(vbc_mat *A, TIndex *T)
+{
+    if (T->mode != DESC_BLOCKS || A->w_uniform <= 0) return VBC_OK;
+    const size_t need = sizeof(Tv) * ((size_t)A->nval + 64) + 4 * (size_t)A->ndesc + sizeof(StripeMeta) * ((size_t)T->nkeys + 1);
+    if (A->opt_fwd_atomic != 3) {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess || need * 4 > fr) { cudaGetLastError(); return VBC_OK; } // keep the second copy for when memory is plentiful
+    }
+    vbc_mat *At = new (std::nothrow) vbc_mat();
+    if (!At) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
+    At->vt = A->vt; At->it = A->it; At->ndim = 2; At->device = A->device;
+    At->m = A->n; At->n = A->m; At->K = A->L; At->L = T->nkeys; At->U = A->W; At->W = A->u0;
+    At->nidx = A->ndesc; At->nval = A->nval; At->ndesc = A->ndesc;
+    At->desc_mode = DESC_BLOCKS; At->u0 = A->w_uniform; At->w_uniform = A->u0;
+    At->sm_count = A->sm_count; At->stream = A->stream;
+    cudaError_t e = cudaMalloc(&At->d_meta, sizeof(StripeMeta) * ((size_t)T->nkeys + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&At->d_desc, sizeof(int) * (size_t)(A->ndesc > 0 ? A->ndesc : 1));
+    if (e == cudaSuccess) e = cudaMalloc(&At->d_val, sizeof(Tv) * ((size_t)A->nval + 64));
+    if (e == cudaSuccess) e = cudaMemsetAsync((char *)At->d_val + sizeof(Tv) * (size_t)A->nval, 0, sizeof(Tv) * 64, A->stream);
+    if (e == cudaSuccess) {
+        k_t_meta<Tv><<<(unsigned)((T->nkeys + 1 + 255) / 256), 256, 0, A->stream>>>(T->d_tptr, T->nkeys, A->u0, A->w_uniform, A->m, At->d_meta);
+        if (T->nkeys > 0) k_t_copy<Tv><<<(unsigned)(((long long)T->nkeys * 32 + 255) / 256), 256, 0, A->stream>>>(T->d_tptr, T->d_rec, (const Tv *)A->d_val, T->nkeys, A->u0, A->w_uniform, A->m, At->d_desc, (Tv *)At->d_val);
+        A->launches += 2;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(A->stream);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(At->d_meta); cudaFree(At->d_desc); cudaFree(At->d_val);
+        delete At;
+        if (A->opt_fwd_atomic == 3) VBC_FAIL(e == cudaErrorMemoryAllocation ? VBC_ENOMEM : VBC_ECUDA, "transposed copy: %s", cudaGetErrorString(e));
+        return VBC_OK; // auto mode: fall back to the index
+    }
+    T->At = At;
+    // the records are no longer needed: the copy's descriptors and meta carry the structure
+    cudaFree(T->d_rec);
+    T->d_rec = nullptr;
+    return VBC_OK;
 }
 
 // eligible: rows mode always; blocks mode when every stripe has one width that is a multiple of the 16-byte vector
@@ -263,17 +372,22 @@ int ensure_tindex(vbc_mat *A)
     if (A->tindex || !tindex_eligible(A)) return VBC_OK;
     TIndex *T = new (std::nothrow) TIndex();
     if (!T) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
-    const int rc = A->desc_mode == DESC_ROWS ? build_tindex_mode<DESC_ROWS>(A, T) : build_tindex_mode<DESC_BLOCKS>(A, T);
+    int rc = A->desc_mode == DESC_ROWS ? build_tindex_mode<DESC_ROWS>(A, T) : build_tindex_mode<DESC_BLOCKS>(A, T);
+    if (rc == VBC_OK && A->opt_fwd_atomic != 2) rc = A->vt == VBC_F64 ? build_transposed_copy<double>(A, T) : build_transposed_copy<float>(A, T);
     if (rc != VBC_OK) { destroy_tindex(T); return rc; }
     A->tindex = T;
     return VBC_OK;
 }
 
+// bytes one forward multiply reads besides the values: the copy's meta + descriptors, or the index
 int64_t tindex_bytes(const vbc_mat *A)
 {
     if (!A->tindex) return 0;
+    if (A->tindex->At) return (int64_t)sizeof(StripeMeta) * ((int64_t)A->tindex->nkeys + 1) + 4 * A->ndesc;
     return (int64_t)sizeof(TRec) * A->ndesc + 4 * ((int64_t)A->tindex->nkeys + 1);
 }
+
+int tindex_kind(const vbc_mat *A) { return !A->tindex ? 0 : (A->tindex->At ? 2 : 1); }
 
 template <typename Tv>
 static int launch_fwdt_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
@@ -303,6 +417,15 @@ static int launch_fwdt_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
 
 int launch_fwdt(vbc_mat *A, double alpha, const void *x, double beta, void *y)
 {
+    if (A->tindex->At) { // forward multiply of A = adjoint multiply of its transposed copy
+        vbc_mat *At = A->tindex->At;
+        At->stream = A->stream;
+        At->opt_adj_group = A->opt_fwd_group == 8 || A->opt_fwd_group == 32 ? A->opt_fwd_group : 0;
+        const int64_t before = At->launches;
+        const int rc = launch_spmv(At, 1, alpha, x, beta, y);
+        A->launches += At->launches - before;
+        return rc;
+    }
     return A->vt == VBC_F64 ? launch_fwdt_t<double>(A, alpha, (const double *)x, beta, (double *)y)
                             : launch_fwdt_t<float>(A, (float)alpha, (const float *)x, (float)beta, (float *)y);
 }

@@ -173,7 +173,7 @@ def test_wide_and_odd_widths_all_paths():
                 for g in (4, 8, 16, 32):
                     B2.set_option(_lib.OPT_ADJ_GROUP, g)
                     B2.set_option(_lib.OPT_FWD_GROUP, g if g in (8, 32) else 0)
-                    B2.set_option(_lib.OPT_FWD_MODE, 1 if g in (4, 8) else 2)
+                    B2.set_option(_lib.OPT_FWD_MODE, {4: 1, 8: 0, 16: 2, 32: 3}[g])  # atomic scatter / auto / transposed index / transposed copy
                     randx_check(A, B2, H2, rng)
 
 
