@@ -273,7 +273,10 @@ void vbc_peer_destroy(vbc_peer *P);
  * vbc_pack_csc, m == n), x lives in peer-mapped buffers and an iteration is one launch per device
  * (VBC_EXCH_FUSED: the exchange of the new x is fused into the multiply, see vbc_peer_*), or the plain multiply
  * followed by ncclAllGather (VBC_EXCH_NCCL: the unfused comparator; libnccl.so.2 is loaded at first use and its
- * failures are reported as VBC_ENCCL).  devices == NULL: devices 0..ngpus-1; the same device may appear twice. */
+ * failures are reported as VBC_ENCCL).  devices == NULL: devices 0..ngpus-1.  A device listed more than once is accepted
+ * for testing on a small box: kernels of ranks that share a device must not wait for one another (nothing guarantees
+ * they run at the same time), so such a handle launches every iteration without in-kernel flags and synchronises the
+ * ranks on the host between iterations. */
 typedef struct vbc_dist vbc_dist;
 enum vbc_exchange { VBC_EXCH_FUSED = 0, VBC_EXCH_NCCL = 1 };
 int vbc_dist_create(vbc_dist **out, int ngpus, const int *devices, int vt, int it, int64_t n, int U, int W,

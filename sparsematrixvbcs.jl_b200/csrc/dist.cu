@@ -33,6 +33,9 @@ struct vbc_dist {
     std::vector<cudaEvent_t> ev0, ev1;
     std::vector<cudaGraphExec_t> graph;
     int graph_iters = 0, graph_cur = -1;
+    bool lockstep = false;    // a device is listed more than once: its ranks' kernels may not wait for one another on the device
+                              // (nothing guarantees they run at the same time), so every iteration is launched without in-kernel
+                              // flags and the host synchronises all ranks between iterations
     double graph_alpha = 0.0;
     // NCCL comparator
     void *nccl_lib = nullptr;
@@ -181,6 +184,10 @@ int vbc_dist_create(vbc_dist **out, int ngpus, const int *devices, int vt, int i
         D->dev.push_back(d);
     }
     const int P = ngpus;
+    for (int r = 0; r < P; r++)
+        for (int q = 0; q < r; q++)
+            if (D->dev[(size_t)r] == D->dev[(size_t)q]) D->lockstep = true;
+    if (D->lockstep && exchange == VBC_EXCH_NCCL) { delete D; VBC_FAIL(VBC_ENCCL, "the NCCL exchange needs one distinct device per rank (a device is listed twice)"); }
     const int64_t tv = (int64_t)vt_size(vt), ti = (int64_t)it_size(it);
     // ---- split the stripes by cost; a rank boundary must also be a row-part boundary (the slices of x are whole row parts)
     stripe_costs(it, n, n, colptr, rowval, pi_spl, K, phi_spl, L, tv, D->cost);
@@ -428,6 +435,24 @@ int vbc_dist_spmv_iter(vbc_dist *D, int iters, double alpha, double *ms_per_iter
     const bool fused = D->exchange == VBC_EXCH_FUSED;
     // fused: an even number of iterations is captured per device into one graph and replayed (the x buffers alternate, so an
     // even count leaves every pointer where the capture found it); an odd remainder runs as a plain launch
+    if (fused && D->lockstep) { // ranks sharing a device: no kernel waits for another one; the host is the barrier
+        for (int r = 0; r < P; r++) { VBC_CUDA(cudaSetDevice(D->dev[(size_t)r])); VBC_CUDA(cudaEventRecord(D->ev0[(size_t)r], D->stream[(size_t)r])); }
+        for (int t = 0; t < iters; t++) {
+            for (int r = 0; r < P; r++) VBC_TRY(vbc_peer_spmv_step(D->peer[(size_t)r], D->mat[(size_t)r], alpha, (int64_t)r * D->S, 0));
+            for (int r = 0; r < P; r++) { VBC_CUDA(cudaSetDevice(D->dev[(size_t)r])); VBC_CUDA(cudaStreamSynchronize(D->stream[(size_t)r])); }
+        }
+        double worst = 0.0;
+        for (int r = 0; r < P; r++) {
+            VBC_CUDA(cudaSetDevice(D->dev[(size_t)r]));
+            VBC_CUDA(cudaEventRecord(D->ev1[(size_t)r], D->stream[(size_t)r]));
+            VBC_CUDA(cudaStreamSynchronize(D->stream[(size_t)r]));
+            float ms = 0.f;
+            VBC_CUDA(cudaEventElapsedTime(&ms, D->ev0[(size_t)r], D->ev1[(size_t)r]));
+            worst = std::max(worst, (double)ms);
+        }
+        if (ms_per_iter) *ms_per_iter = worst / iters;
+        return VBC_OK;
+    }
     const int git = fused ? (iters & ~1) : 0;
     int cur0 = 0;
     if (fused) VBC_TRY(vbc_peer_current(D->peer[0], &cur0));

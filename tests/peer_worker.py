@@ -38,9 +38,16 @@ def main():
     peer = vdist.PeerExchangeOperator(B, layout, rank, world, dev, alpha=alpha, halo=True)
     peer.set_x(x0)
     dist.barrier()
-    for _ in range(steps):
-        peer.step()
-    peer.finish()
+    lockstep = bool(os.environ.get("VBC_TEST_SHARE_GPU"))
+    if lockstep:  # the processes share one GPU: no kernel may wait for another one -> no in-kernel flags, the host is the barrier
+        for _ in range(steps):
+            peer.step(barrier=0)
+            torch.cuda.synchronize()
+            dist.barrier()
+    else:
+        for _ in range(steps):
+            peer.step()
+        peer.finish()
     torch.cuda.synchronize()
     timed_out = peer.timed_out()
     x_peer = peer.x_global()
@@ -66,7 +73,7 @@ def main():
         d = float(np.max(np.abs(x_peer - x_ag)))
         print(json.dumps({"ok": bool(d == 0.0 and err < 1e-12 and not timed_out), "max_abs_diff_vs_allgather_path": d,
                           "max_rel_err_vs_scipy": err, "timed_out": bool(timed_out), "interior": list(peer.interior),
-                          "neighbors": peer.neighbors, "sent_fraction": peer.sent_fraction, "wait_stats": stats}), flush=True)
+                          "neighbors": peer.neighbors, "sent_fraction": peer.sent_fraction, "wait_stats": stats, "lockstep": lockstep}), flush=True)
     dist.barrier()
     peer.close()
     dist.destroy_process_group()

@@ -1,7 +1,12 @@
 """GPU tests of the row-partitioned multiply with the x exchange fused into the kernel (csrc/peer.cu, k_spmv_adj_halo):
-sparsity-aware masks, neighbour-only flags, device-derived interior ranges and the in-kernel wait / signal -- first with
-several "ranks" driven by one process on one GPU (each on its own stream), then with two real PROCESSES exchanging
-CUDA IPC handles (both on cuda:0 when the box has one GPU), which is the path bench.py --gpus N uses.
+sparsity-aware masks, neighbour-only flags, device-derived interior ranges, peer stores and the in-kernel wait / signal.
+
+Kernels that wait for one another must never share a GPU (nothing guarantees they run at the same time), so:
+  * several "ranks" on ONE GPU run in lockstep -- every rank's step is launched without in-kernel flags (barrier = 0) and
+    the host synchronises between iterations; masks, interiors, staging and peer stores are exactly the product's;
+  * the in-kernel wait / signal code runs on one GPU as a single kernel whose neighbour flags were preset by the host;
+  * with >= 2 GPUs the same tests use one rank per device and the real flags (barrier = 3), and two real PROCESSES
+    exchange CUDA IPC handles -- the path bench.py --gpus N uses (which also carries its own exchange_parity check).
 
 Oracle: the iterate of the global operator, x_{t+1} = alpha * A' x_t, from scipy on the host CSC matrix and from the
 single-GPU kernel (bit-exact: every stripe runs the same body in both)."""
@@ -84,12 +89,11 @@ def _run_ranks_one_process(n, S, P, steps, alpha, shift_bounds, Tv=np.float64, h
     for r in range(P):
         _lib.check(Lh.vbc_set_stream(mats[r]._h, ctypes.c_void_p(streams[r].cuda_stream)))
     x_ref = x0.astype(np.float64)
-    for it in range(steps):  # interleaved issue: every rank's step t is enqueued before anybody's step t + 1
+    for it in range(steps):  # lockstep: all ranks share this GPU, so no kernel may wait for another one (barrier = 0)
         for r in range(P):
-            _lib.check(Lh.vbc_peer_spmv_step(peers[r], mats[r]._h, alpha, r * layout.S, 3))
+            _lib.check(Lh.vbc_peer_spmv_step(peers[r], mats[r]._h, alpha, r * layout.S, 0))
+        torch.cuda.synchronize()
         x_ref = alpha * (Sg.T @ x_ref)
-    for r in range(P):
-        _lib.check(Lh.vbc_peer_barrier(peers[r], ctypes.c_void_p(streams[r].cuda_stream), 2))
     torch.cuda.synchronize()
     outs = []
     for r in range(P):
@@ -102,9 +106,6 @@ def _run_ranks_one_process(n, S, P, steps, alpha, shift_bounds, Tv=np.float64, h
         out = np.empty(layout.padded_len, dtype=Tv)
         rt.cudaMemcpy(ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(p.value), ctypes.c_size_t(out.nbytes), 2)
         outs.append(out)
-        st = (ctypes.c_uint64 * 4)()
-        _lib.check(Lh.vbc_peer_wait_stats(peers[r], st, 0))
-        assert st[0] == steps
     for h in peers:
         Lh.vbc_peer_destroy(h)
     return layout, outs, x_ref, interiors, b
@@ -112,7 +113,7 @@ def _run_ranks_one_process(n, S, P, steps, alpha, shift_bounds, Tv=np.float64, h
 
 @pytest.mark.parametrize("P", [2, 3])
 def test_halo_exchange_ranks_on_one_gpu(P):
-    """Sparsity-aware exchange, neighbour flags, device-derived interior, in-kernel wait + signal."""
+    """Sparsity-aware exchange (masks from the packed slabs), device-derived interiors, staged peer stores."""
     n, S, steps = 24_000, 9, 5
     layout, outs, x_ref, interiors, b = _run_ranks_one_process(n, S, P, steps, 0.05, 7)
     tol = 1e-12
@@ -134,7 +135,7 @@ def test_halo_exchange_ranks_on_one_gpu(P):
         assert np.allclose(y_loc, (Sg.T @ x_ref)[c0:c1], rtol=1e-11, atol=1e-300), f"rank {r} holds a stale halo"
 
 
-def test_full_replication_in_kernel_flags_and_float32():
+def test_full_replication_and_float32():
     """No mask: every stripe is a boundary stripe (claimed runs, everything sent everywhere) -- a fused all-gather."""
     n, S, P, steps = 16_000, 7, 2, 4
     layout, outs, x_ref, _, _ = _run_ranks_one_process(n, S, P, steps, 0.05, 5, Tv=np.float32, halo=False)
@@ -163,23 +164,105 @@ def test_fused_step_refuses_stripes_wider_than_its_staging_row():
     Lh.vbc_peer_destroy(h)
 
 
-def _spawn(world, extra_env=None, args=()):
+def test_in_kernel_wait_and_signal_with_preset_flags():
+    """The flag code of the fused kernel on ONE GPU without any kernel waiting for another: rank 1 of 3; the host presets
+    the neighbours' flags in this rank's flag block (so every wait passes at once) and the 'peers' are scratch buffers of
+    this process -- the step must publish epoch + 1 into slot 1 of both neighbours' flag blocks and push the halo."""
     import torch
+    n, u, w, P, me = 24_000, 4, 4, 3, 1
+    L = n // w
+    b = (np.arange(P + 1) * L) // P
+    layout = vdist.PaddedLayout(b * w)
+    A, pi, phi = synth.config_c2(n=n, S=9)
+    Sg = A.to_scipy()
+    Ar, _, phir = synth.config_c2(n=n, S=9, stripes=(int(b[me]), int(b[me + 1])))
+    Ar = vdist.remap_rows_to_padded(Ar, layout, u)
+    B = vb.SparseMatrixVBC[u, w](Ar, vdist.padded_row_partition(layout, u, np.int64), phir)
+    Lh = _lib.lib()
+    h = ctypes.c_void_p()
+    _lib.check(Lh.vbc_peer_create(ctypes.byref(h), _lib.VBC_F64, layout.padded_len, me, P, 0, None))
+    scratch = [[torch.zeros(layout.padded_len, dtype=torch.float64, device="cuda") for _ in range(2)] + [torch.zeros(8, dtype=torch.int64, device="cuda")] for _ in range(P)]
+    ptrs = (ctypes.c_void_p * (P * 3))()
+    p = ctypes.c_void_p()
+    for r in range(P):
+        for k in range(3):
+            if r == me:
+                _lib.check(Lh.vbc_peer_buffer(h, k, ctypes.byref(p)))
+                ptrs[r * 3 + k] = p.value
+            else:
+                ptrs[r * 3 + k] = scratch[r][k].data_ptr()
+    _lib.check(Lh.vbc_peer_connect_local(h, ptrs))
+    # the read sets of the neighbours: what a banded slab reads = its own columns widened by the band
+    need_me = B.read_chunks(5)
+    needs = []
+    for r in range(P):
+        if r == me:
+            needs.append(need_me)
+        else:
+            Aq, _, phiq = synth.config_c2(n=n, S=9, stripes=(int(b[r]), int(b[r + 1])))
+            Aq = vdist.remap_rows_to_padded(Aq, layout, u)
+            Bq = vb.SparseMatrixVBC[u, w](Aq, vdist.padded_row_partition(layout, u, np.int64), phiq)
+            needs.append(Bq.read_chunks(5))
+            Bq.close()
+    mask, nbr = vdist.halo_mask(need_me, layout, me, P, B.n, 5, _fake_allgather(needs))
+    assert nbr == 0b101
+    _lib.check(Lh.vbc_peer_set_mask(h, mask.ctypes.data_as(ctypes.c_void_p), len(mask), 5))
+    _lib.check(Lh.vbc_peer_set_neighbors(h, nbr))
+    i0, i1 = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(Lh.vbc_peer_auto_interior(h, B._h, me * layout.S, ctypes.byref(i0), ctypes.byref(i1)))
+    assert 0 < i0.value < i1.value < B.L
+    # x into the own current buffer; the neighbours' flags preset far ahead
+    x0 = synth.vector(n, 3)
+    rt = ctypes.CDLL("libcudart.so")
+    _lib.check(Lh.vbc_peer_buffer(h, 0, ctypes.byref(p)))
+    xp = layout.scatter(x0)
+    rt.cudaMemcpy(ctypes.c_void_p(p.value), ctypes.c_void_p(xp.ctypes.data), ctypes.c_size_t(xp.nbytes), 1)
+    _lib.check(Lh.vbc_peer_buffer(h, 2, ctypes.byref(p)))
+    big = np.full(8, 1 << 40, dtype=np.int64)
+    rt.cudaMemcpy(ctypes.c_void_p(p.value), ctypes.c_void_p(big.ctypes.data), ctypes.c_size_t(64), 1)
+    y = 0.05 * (Sg.T @ x0)
+    c0 = int(b[me]) * w
+    for step in range(3):
+        _lib.check(Lh.vbc_peer_spmv_step(h, B._h, 0.05, me * layout.S, 3))
+        torch.cuda.synchronize()
+        for r in (0, 2):
+            assert int(scratch[r][2][me]) == step + 1, "the step was not published to the neighbour"
+        if step == 0:
+            # step 1 wrote buffer 1 of every destination: the halo pushed to a neighbour is this rank's y on the columns it reads
+            for r, dest in ((0, 2), (2, 1)):  # destination index i = (r - me) % P
+                got = scratch[r][1].cpu().numpy()
+                cols = np.flatnonzero((np.repeat(mask, 32)[: B.n] >> dest) & 1)
+                assert len(cols) > 0
+                assert np.allclose(got[me * layout.S + cols], y[c0 + cols], rtol=1e-12)
+                untouched = np.ones(layout.padded_len, dtype=bool)
+                untouched[me * layout.S + cols] = False
+                assert np.all(got[untouched] == 0.0)  # nothing else was sent
+    to = ctypes.c_int()
+    _lib.check(Lh.vbc_peer_status(h, ctypes.byref(to)))
+    assert to.value == 0
+    st = (ctypes.c_uint64 * 4)()
+    _lib.check(Lh.vbc_peer_wait_stats(h, st, 0))
+    assert st[0] == 3 and st[2] == 0  # three steps published, no wait had to spin
+    Lh.vbc_peer_destroy(h)
+
+
+def _spawn(world, extra_env=None, args=()):
     env = dict(os.environ)
     env.update(extra_env or {})
     env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
-    if torch.cuda.device_count() < world:
-        env["VBC_TEST_SHARE_GPU"] = "1"  # every process uses cuda:0 (CUDA IPC works between processes on one device)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29547", os.path.join(ROOT, "tests", "peer_worker.py"), *args]
     return subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
 
 
 def test_two_processes_cuda_ipc_halo_exchange():
-    """vbc_peer_connect with real IPC handles between two processes, the halo mode bench.py runs by default:
-    the distributed iterate equals the single-process one bit for bit on every rank's own slice, and equals the
-    all-gather path (RowPartitionedOperator over torch.distributed) exactly."""
-    r = _spawn(2)
+    """vbc_peer_connect with real IPC handles between two processes, the halo mode bench.py runs by default: the distributed
+    iterate equals the all-gather path (RowPartitionedOperator over torch.distributed) exactly and the host CSC iterate to
+    rounding.  Two GPUs: one rank per device, in-kernel flags.  One GPU: both processes share it, so the steps run in
+    lockstep (no in-kernel flags, a host barrier between iterations) -- CUDA IPC works between processes on one device."""
+    import torch
+    share = torch.cuda.device_count() < 2
+    r = _spawn(2, extra_env={"VBC_TEST_SHARE_GPU": "1"} if share else None)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
     res = json.loads(line)
@@ -187,13 +270,14 @@ def test_two_processes_cuda_ipc_halo_exchange():
     assert res["max_abs_diff_vs_allgather_path"] == 0.0
     assert res["max_rel_err_vs_scipy"] < 1e-12
     assert res["timed_out"] is False
+    assert res["lockstep"] == share
 
 
 @pytest.mark.parametrize("kind", ["2d", "1d", "2d_f32_i32"])
 def test_single_process_multi_device_api(kind):
-    """vbc_dist_*: one process, P "devices" (the same GPU listed P times on a one-GPU box, distinct GPUs when the box has
-    them): cost-balanced split, slabs packed per device, fused exchange -- the iterate equals the host CSC iterate, for an
-    even and an odd number of iterations (graph + single launches), 1D and 2D, unequal slices."""
+    """vbc_dist_*: one process, P ranks (distinct GPUs when the box has them -- in-kernel flags, one CUDA graph per device --
+    else the same GPU listed P times, which the library runs in lockstep): cost-balanced split, slabs packed per device,
+    fused exchange -- the iterate equals the host CSC iterate, for even and odd iteration counts, 1D and 2D, unequal slices."""
     import torch
     ngpu = torch.cuda.device_count()
     n, S = 24_000, 9
