@@ -16,6 +16,11 @@
 #   LinearAlgebra.mul!(y, B', x, α, β)    multiply_1DVBC.jl:85, multiply_VBC.jl:89
 #   Base.:*                               multiply_1DVBC.jl:182-183, multiply_VBC.jl:194-195
 #   TrSpMV!(y, A, x)                      TrSpMV.jl:1 -> TrSpMV!(y, ::CuCSC, x)
+#   model_*_memory (per-stripe bytes)     costs.jl:10, :140 -> memory_cost(::CuVBC), format_bytes(::CuVBC)
+# Added for device-resident use (no reference counterpart; the reference's vectors are host Arrays):
+#   CuVec{Tv}                             a device vector handle (raw CUdeviceptr + length), `mul!` methods on it enqueue only
+#   CuVBCDist                             the row-partitioned iteration over several GPUs, one process (vbc_dist_*)
+#   set_option! / get_option              kernel options (VBC_OPT_*)
 
 using LinearAlgebra
 using SparseArrays
@@ -209,4 +214,117 @@ function TrSpMV!(y::Vector{Tv}, A::CuCSC{Tv}, x::Vector{Tv}) where {Tv}
             A.handle, x, length(x), y, length(y), 0))
     end
     return y
+end
+
+
+# ---- device-resident vectors ---------------------------------------------------------------------------
+# The reference's `mul!` takes any StridedVector on the host (multiply_1DVBC.jl:9, :85).  For iterative use the vectors
+# should stay on the device: CuVec wraps a raw device pointer (from CUDA.jl's `pointer(::CuArray)`, or from cuda_malloc
+# below) and the `mul!` methods on it pass on_device = 1, i.e. they only enqueue on the matrix' stream -- call `sync(A)`.
+struct CuVec{Tv}
+    ptr::Ptr{Cvoid}     # device address on the matrix' device
+    len::Int
+end
+Base.length(v::CuVec) = v.len
+Base.eltype(::CuVec{Tv}) where {Tv} = Tv
+
+const libcudart = get(ENV, "LIBCUDART", "libcudart.so")
+function cuda_malloc(::Type{Tv}, n::Integer) where {Tv}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:cudaMalloc, libcudart), Cint, (Ref{Ptr{Cvoid}}, Csize_t), p, n * sizeof(Tv))
+    rc == 0 || throw(OutOfMemoryError())
+    return CuVec{Tv}(p[], n)
+end
+cuda_free(v::CuVec) = ccall((:cudaFree, libcudart), Cint, (Ptr{Cvoid},), v.ptr)
+function Base.copyto!(dst::CuVec{Tv}, src::Vector{Tv}) where {Tv}
+    length(src) == dst.len || throw(DimensionMismatch())
+    GC.@preserve src ccall((:cudaMemcpy, libcudart), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Cint), dst.ptr, src, sizeof(src), 1)
+    return dst
+end
+function Base.copyto!(dst::Vector{Tv}, src::CuVec{Tv}) where {Tv}
+    length(dst) == src.len || throw(DimensionMismatch())
+    GC.@preserve dst ccall((:cudaMemcpy, libcudart), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Cint), dst, src.ptr, sizeof(dst), 2)
+    return dst
+end
+
+function _cuvbc_mul!(y::CuVec{Tv}, A::CuVBC{U, W, Tv}, x::CuVec{Tv}, α::Number, β::Number, trans::Bool) where {U, W, Tv}
+    vbc_check(ccall((:vbc_spmv, libvbc), Cint,
+        (Ptr{Cvoid}, Cint, Cdouble, Ptr{Cvoid}, Int64, Cdouble, Ptr{Cvoid}, Int64, Cint),
+        A.handle, trans, Float64(α), x.ptr, x.len, Float64(β), y.ptr, y.len, 1))   # on_device = 1: enqueued, not awaited
+    return y
+end
+LinearAlgebra.mul!(y::CuVec, A::CuVBC, x::CuVec, α::Number = true, β::Number = false) = _cuvbc_mul!(y, A, x, α, β, false)
+LinearAlgebra.mul!(y::CuVec, adjA::Union{Adjoint{<:Any, <:CuVBC}, Transpose{<:Any, <:CuVBC}}, x::CuVec, α::Number = true, β::Number = false) =
+    _cuvbc_mul!(y, adjA.parent, x, α, β, true)
+sync(A::CuVBC) = vbc_check(ccall((:vbc_sync, libvbc), Cint, (Ptr{Cvoid},), A.handle))
+set_stream!(A::CuVBC, stream::Ptr{Cvoid}) = vbc_check(ccall((:vbc_set_stream, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), A.handle, stream))
+
+# ---- cost models and options ---------------------------------------------------------------------------
+# model_SparseMatrix1DVBC_memory / model_SparseMatrixVBC_memory evaluated per stripe on the packed matrix (costs.jl:10, :140):
+# the balance weight of the multi-GPU split.  Returns (cost per stripe, row term = K * sizeof(Ti) for 2D).
+function memory_cost(A::CuVBC)
+    cost = Vector{Int64}(undef, length(A.Φ))
+    row_term = Ref{Int64}(0)
+    vbc_check(ccall((:vbc_memory_cost, libvbc), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ref{Int64}), A.handle, cost, row_term))
+    return cost, row_term[]
+end
+# (reference accounting of bin/test_table.jl:78/:120, bytes one adjoint multiply reads, bytes one forward multiply reads)
+function format_bytes(A::CuVBC)
+    b = Vector{Int64}(undef, 3)
+    vbc_check(ccall((:vbc_format_bytes, libvbc), Cint, (Ptr{Cvoid}, Ptr{Int64}), A.handle, b))
+    return (reference = b[1], adjoint = b[2], forward = b[3])
+end
+const VBC_OPT_ADJ_GROUP, VBC_OPT_FWD_GROUP, VBC_OPT_GRID_MULT, VBC_OPT_PARITY_MODE = 1, 2, 3, 4
+const VBC_OPT_FWD_MODE, VBC_OPT_SPMM_SIMT, VBC_OPT_E2E_PIPELINE, VBC_OPT_E2E_UPLOAD_ELEMS, VBC_OPT_E2E_GRAPH = 5, 6, 7, 8, 9
+set_option!(A::CuVBC, opt::Integer, value::Integer) =
+    vbc_check(ccall((:vbc_set_option, libvbc), Cint, (Ptr{Cvoid}, Cint, Int64), A.handle, opt, value))
+function get_option(A::CuVBC, opt::Integer)
+    v = Ref{Int64}(0)
+    vbc_check(ccall((:vbc_get_option, libvbc), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}), A.handle, opt, v))
+    return v[]
+end
+launch_count(A::CuVBC) = (c = Ref{Int64}(0); vbc_check(ccall((:vbc_launch_count, libvbc), Cint, (Ptr{Cvoid}, Ref{Int64}), A.handle, c)); c[])
+
+# ---- multi-GPU: the row-partitioned iteration x <- α A' x over the GPUs of one box, driven by this process -----------------
+# (north_star (e).  The loop it scales is the @threads stripe loop of multiply_1DVBC.jl:169-177 / multiply_VBC.jl:182-189:
+# stripes are independent row blocks of A'; here contiguous ranges of them live on different GPUs, balanced by memory_cost.)
+const VBC_EXCH_FUSED, VBC_EXCH_NCCL = Cint(0), Cint(1)
+mutable struct CuVBCDist{Tv, Ti}
+    handle::Ptr{Cvoid}
+    n::Int
+    ngpus::Int
+    function CuVBCDist(A::SparseMatrixCSC{Tv, Ti}, Φ::SplitPartition{Ti}; Π::Union{Nothing, SplitPartition{Ti}} = nothing, U::Integer = 0, W::Integer,
+                       ngpus::Integer, devices::Union{Nothing, Vector{Cint}} = nothing, exchange::Cint = VBC_EXCH_FUSED) where {Tv, Ti}
+        size(A, 1) == size(A, 2) || throw(DimensionMismatch("the iterated operator must be square"))
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve A Φ Π devices begin
+            vbc_check(ccall((:vbc_dist_create, libvbc), Cint,
+                (Ref{Ptr{Cvoid}}, Cint, Ptr{Cint}, Cint, Cint, Int64, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint),
+                h, ngpus, devices === nothing ? C_NULL : pointer(devices), vbc_vt(Tv), vbc_it(Ti), size(A, 2), U, W, A.colptr, A.rowval, A.nzval,
+                Π === nothing ? C_NULL : pointer(Π.spl), Π === nothing ? 0 : length(Π), Φ.spl, length(Φ), exchange))
+        end
+        D = new{Tv, Ti}(h[], size(A, 2), ngpus)
+        finalizer(d -> (ccall((:vbc_dist_destroy, libvbc), Cvoid, (Ptr{Cvoid},), d.handle); d.handle = C_NULL), D)
+        return D
+    end
+end
+set_x!(D::CuVBCDist{Tv}, x::Vector{Tv}) where {Tv} =
+    (GC.@preserve x vbc_check(ccall((:vbc_dist_set_x, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), D.handle, x)); D)
+# `iters` iterations x <- α A' x, device-resident; returns the device milliseconds per iteration (maximum over the GPUs)
+function iterate!(D::CuVBCDist, iters::Integer; α::Number = 1.0)
+    ms = Ref{Cdouble}(0.0)
+    vbc_check(ccall((:vbc_dist_spmv_iter, libvbc), Cint, (Ptr{Cvoid}, Cint, Cdouble, Ref{Cdouble}), D.handle, iters, Float64(α), ms))
+    return ms[]
+end
+function gather_x(D::CuVBCDist{Tv}) where {Tv}
+    x = Vector{Tv}(undef, D.n)
+    GC.@preserve x vbc_check(ccall((:vbc_dist_gather_x, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), D.handle, x))
+    return x
+end
+# stripe ranges, padded slice length, bytes per GPU under the memory model, interior stripe range of every rank
+function partition_info(D::CuVBCDist)
+    S = Ref{Int64}(0)
+    bounds, cost, interior = Vector{Int64}(undef, D.ngpus + 1), Vector{Int64}(undef, D.ngpus), Vector{Int64}(undef, 2 * D.ngpus)
+    vbc_check(ccall((:vbc_dist_info, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ref{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}), D.handle, C_NULL, S, bounds, cost, interior))
+    return (slice_len = S[], stripe_bounds = bounds, cost_per_gpu = cost, interior = reshape(interior, 2, :))
 end
