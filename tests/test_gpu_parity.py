@@ -3,6 +3,8 @@
 Bar (BASELINE.json north_star): packed index arrays bit-exact; y within 1e-12 relative (Float64) /
 1e-5 (Float32), measured componentwise against |A||x| because summation order differs.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -821,3 +823,54 @@ def test_triangular_solve_graph_replay_wide_stripes_and_singular():
     with pytest.raises(vb.ArgumentError):
         xb = np.ones(16)
         vb.ldiv_lower_(xb, Bs.T, xb)  # in place is refused
+
+
+def test_benchmark_table_on_matrix_market_inputs(fixtures, tmp_path):
+    """the reference's benchmark table (bin/test_table.jl:27-129) over Matrix Market files -- two of the
+    SuiteSparse matrices the reference's own tests hold (test/matrices.jl:5-6), written as .mtx and read back through the
+    script's reader (MatrixDepot itself needs the network): every method row packs, multiplies `y = B'x` and passes the
+    script's `y ≈ z` check (test_table.jl:42/:84/:126); memory is the reference's format accounting."""
+    import json
+    import subprocess
+    import sys
+    import scipy.io
+    paths = []
+    for name in ("HB__west0132", "LPnetlib__lp_etamacro"):
+        pth = str(tmp_path / (name + ".mtx"))
+        scipy.io.mmwrite(pth, fixtures[name].to_scipy())
+        paths.append(pth)
+    out = str(tmp_path / "table.json")
+    env = dict(os.environ, TABLE_OUT=out, TABLE_CACHE_BYTES=str(2 << 20))
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "test_table.py")] + paths, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    table = json.load(open(out))
+    assert set(table) == {"HB__west0132.mtx", "LPnetlib__lp_etamacro.mtx"}
+    for name, rows in table.items():
+        methods = [row["method"] for row in rows]
+        assert methods[0].startswith("reference") and len(methods) == 1 + 5 + 7
+        assert all(row["runtime"] > 0 and row["memory"] > 0 for row in rows)
+        strict = next(row for row in rows if row["method"] == "strict")
+        minmem = next(row for row in rows if row["method"] == "min memory")
+        assert minmem["memory"] <= strict["memory"]  # the DP under the memory model cannot do worse than the strict chunker
+
+
+def test_device_layout_limits_answer_elimit():
+    """Limits the reference does not have must be refused with VBC_ELIMIT, not overflow: a stripe wider than the pack
+    kernel holds (32 columns) and dimensions beyond the compact layout's 32-bit fields (2^31)."""
+    import ctypes
+    A = sprand(20, 70, 0.3, np.random.default_rng(3))
+    phi = vb.SplitPartition(np.array([1, 34, 60, 71], dtype=np.int64))  # widths 33, 26, 11
+    with pytest.raises(_lib.VBCError) as ei:
+        vb.SparseMatrix1DVBC[40](A, phi)
+    assert ei.value.code == _lib.VBC_ELIMIT and "32" in str(ei.value)
+    with pytest.raises(AssertionError):  # the reference's own `@assert w <= W` (constructors_1DVBC.jl:46) still comes first
+        vb.SparseMatrix1DVBC[8](A, phi)
+    one = np.array([1], dtype=np.int64)
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+    rc = L.vbc_pack_csc(ctypes.byref(h), _lib.VBC_F64, _lib.VBC_I64, 1 << 31, 0, 0, 4, vp(one), vp(one), vp(one), None, 0, vp(one), 0, 0)
+    assert rc == _lib.VBC_ELIMIT and b"32-bit" in L.vbc_last_error() and not h.value
+    rc = L.vbc_upload(ctypes.byref(h), _lib.VBC_F64, _lib.VBC_I64, 1 << 31, 0, 0, 4, None, 0, vp(one), 0, vp(one), vp(one), vp(one), vp(one), 0)
+    assert rc == _lib.VBC_ELIMIT and not h.value

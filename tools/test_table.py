@@ -48,7 +48,8 @@ def run_matrix(name, A, out):
 
     mdl_blocks_1d = costs.model_SparseMatrix1DVBC_blocks()
     mdl_memory_1d = costs.model_SparseMatrix1DVBC_memory(np.float64, np.int64)
-    mdl_time_1d = costs.model_SparseMatrix1DVBC_TrSpMV_time(W_MAX, np.float64, np.int64, np.float64, exceed=True)
+    tkw = {"cache_bytes": int(os.environ["TABLE_CACHE_BYTES"]), "use_cache": False} if os.environ.get("TABLE_CACHE_BYTES") else {}
+    mdl_time_1d = costs.model_SparseMatrix1DVBC_TrSpMV_time(W_MAX, np.float64, np.int64, np.float64, exceed=True, **tkw)
     mdl_blocks_2d = costs.model_SparseMatrixVBC_blocks()
     mdl_memory_2d = costs.model_SparseMatrixVBC_memory(np.float64, np.int64)
     DP = vb.DynamicTotalChunker
@@ -101,7 +102,7 @@ def main():
         run_matrix("synthetic supernodal (natural blocks 1..6)", A, out)
         A, _, _ = synth.config_c2(n=int(os.environ.get("TABLE_N2", "400000")), S=41)
         run_matrix("synthetic FEM band (4x4 blocks)", A, out)
-    p = os.path.join(ROOT, "gpurun_out", "test_table.json")
+    p = os.environ.get("TABLE_OUT") or os.path.join(ROOT, "gpurun_out", "test_table.json")
     os.makedirs(os.path.dirname(p), exist_ok=True)
     json.dump(out, open(p, "w"), indent=1)
 
