@@ -269,6 +269,15 @@ def extra_configs(peak):
     Y = torch.empty(A.n, k, dtype=torch.float64, device="cuda")
     med, mn = timed_graph(lambda: vb.mul_(Y, B.T, X), 10)
     S = A.to_scipy()
+    # the same 1D matrix: adjoint and forward SpMV (a6 / a7 of SURVEY 8a)
+    out["C3m_1D_f64_w8_adjoint"] = adj_record(B, A, 30)
+    xf = synth.vector(A.n, 13)
+    xfd, yfd = torch.from_numpy(xf).cuda(), torch.empty(A.m, dtype=torch.float64, device="cuda")
+    vb.mul_(yfd, B, xfd)  # builds the transposed copy outside graph capture
+    fmed, fmn = timed_graph(lambda: vb.mul_(yfd, B, xfd), 30)
+    fnb = B.format_bytes()[2] + 8 * (A.m + A.n)
+    out["C3m_1D_f64_w8_forward"] = {"us": fmed * 1e6, "us_min": fmn * 1e6, "algorithmic_bytes": fnb, "GBps": fnb / fmed / 1e9, "frac_of_hbm_peak": fnb / fmed / 1e9 / peak,
+                                    "gflops": 2.0 * A.nnz / fmed / 1e9, "parity_err_over_bound_1e-12": bound_err(yfd.cpu().numpy(), S @ xf, abs(S) @ np.abs(xf), 1e-12)}
     Xh = X.cpu().numpy()
     err = bound_err(Y.cpu().numpy(), S.T @ Xh, abs(S).T @ np.abs(Xh), 1e-12)
     nb = B.format_bytes()[1] + 8 * k * (A.m + A.n)

@@ -641,6 +641,7 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
         if (value < 0 || value > 3) VBC_FAIL(VBC_EARG, "forward mode must be 0 (auto), 1 (atomic scatter), 2 (transposed unit index) or 3 (transposed copy)");
         if ((int)value != A->opt_fwd_atomic && A->tindex) { DeviceGuard guard(A->device); cudaStreamSynchronize(A->stream); destroy_tindex(A->tindex); A->tindex = nullptr; } // rebuilt at the next forward multiply
         A->opt_fwd_atomic = (int)value;
+        A->opt_fwd_no_copy = 0;
         return VBC_OK;
     }
     VBC_FAIL(VBC_EARG, "unknown option %d", option);

@@ -112,6 +112,7 @@ struct vbc_mat {
     vbc_trsv_plan *trsv = nullptr; // level schedule of the triangular solve (vbc_trsv_analyse)
     vbc::TIndex *tindex = nullptr; // transposed unit index of the owner-computes forward multiply (built at first use)
     int opt_fwd_atomic = 0;        // VBC_OPT_FWD_MODE: 0 auto, 1 atomic scatter kernel, 2 transposed unit index, 3 transposed copy
+    int opt_fwd_no_copy = 0;       // the transposed copy was tried and is not available (memory): do not retry at every multiply
     int opt_spmm_simt = 0;         // 1: Float64 adjoint SpMM on the SIMT (DFMA) kernel instead of the DMMA tiles
 };
 

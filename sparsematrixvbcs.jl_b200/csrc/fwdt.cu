@@ -184,6 +184,71 @@ __global__ void __launch_bounds__(256) k_fwdt_rows(const int *__restrict__ tptr,
     }
 }
 
+// ---- rows mode with the transposed copy: row i owns a contiguous run of its w0-wide segments (val2) and their first columns
+// (desc2).  A 16-byte vector never leaves a segment (w0 is a multiple of the vector), so lane v multiplies one vector of values
+// with one vector of x: a plain dot product per row, SG lanes per row, fully coalesced -- y[i] is stored once, no atomics.
+template <typename Tv, int SG>
+__global__ void __launch_bounds__(256) k_fwdc_rows(const StripeMeta *__restrict__ meta2, const int *__restrict__ desc2, const Tv *__restrict__ val2,
+                                                    const Tv *__restrict__ x, Tv *__restrict__ y, const int nrows, const int w0, const int log2vps,
+                                                    const Tv alpha, const Tv beta)
+{
+    constexpr int VE = 16 / (int)sizeof(Tv);
+    const int lane = threadIdx.x % SG;
+    unsigned gmask = 0xffffffffu;
+    if constexpr (SG < 32) gmask = ((1u << SG) - 1u) << (((threadIdx.x & 31) / SG) * SG);
+    const int ngroups = (int)((gridDim.x * blockDim.x) / SG);
+    const int vps = w0 / VE; // vectors per segment
+    for (int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) / SG); i < nrows; i += ngroups) {
+        const StripeMeta a = ld_meta(meta2 + i), b = ld_meta(meta2 + i + 1);
+        const int nvec = (int)((b.ofs - a.ofs) / VE);
+        const Tv *vp = val2 + a.ofs;
+        const int *dp = desc2 + a.pos;
+        Tv acc[VE];
+#pragma unroll
+        for (int e = 0; e < VE; e++) acc[e] = (Tv)0;
+        constexpr int UNR = 4;
+        for (int v = lane; v < nvec; v += UNR * SG) {
+            Tv vv[UNR][VE], xx[UNR][VE];
+            int col[UNR];
+#pragma unroll
+            for (int k = 0; k < UNR; k++) {
+                const int vk = v + k * SG;
+                const bool ok = vk < nvec;
+                const int seg = log2vps >= 0 ? (vk >> log2vps) : vk / vps;
+                col[k] = ok ? __ldg(dp + seg) + (vk - seg * vps) * VE : 0;
+                if (ok) {
+                    if constexpr (VE == 2) { const double2 q = __ldcs(reinterpret_cast<const double2 *>(vp + (long long)vk * VE)); vv[k][0] = (Tv)q.x; vv[k][1] = (Tv)q.y; }
+                    else { const float4 q = __ldcs(reinterpret_cast<const float4 *>(vp + (long long)vk * VE)); vv[k][0] = (Tv)q.x; vv[k][1] = (Tv)q.y; vv[k][2] = (Tv)q.z; vv[k][3] = (Tv)q.w; }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VE; e++) vv[k][e] = (Tv)0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < UNR; k++) {
+                const bool ok = v + k * SG < nvec;
+                if (ok && (col[k] % VE) == 0) { // aligned stripe start: one 16-byte x load
+                    if constexpr (VE == 2) { const double2 q = __ldg(reinterpret_cast<const double2 *>(x + col[k])); xx[k][0] = (Tv)q.x; xx[k][1] = (Tv)q.y; }
+                    else { const float4 q = __ldg(reinterpret_cast<const float4 *>(x + col[k])); xx[k][0] = (Tv)q.x; xx[k][1] = (Tv)q.y; xx[k][2] = (Tv)q.z; xx[k][3] = (Tv)q.w; }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VE; e++) xx[k][e] = ok ? __ldg(x + col[k] + e) : (Tv)0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < UNR; k++)
+#pragma unroll
+                for (int e = 0; e < VE; e++) acc[e] = fma(vv[k][e], xx[k][e], acc[e]);
+        }
+        Tv sum = (Tv)0;
+#pragma unroll
+        for (int e = 0; e < VE; e++) sum += acc[e];
+#pragma unroll
+        for (int d = 1; d < SG; d <<= 1) sum += __shfl_xor_sync(gmask, sum, d, SG);
+        if (lane == 0) y[i] = (beta == (Tv)0) ? alpha * sum : alpha * sum + beta * y[i];
+    }
+}
+
 // ---- blocks mode: one stripe width w0 and part height u0 for the whole matrix; SG = lanes per part ---
 // lane v of the group holds vector v of every block (row-in-block v / cpr, column-vector v % cpr).
 template <typename Tv, int SG>
@@ -317,7 +382,8 @@ static int build_tindex_mode(vbc_mat *A, TIndex *T)
 template <typename Tv>
 static int build_transposed_copy(vbc_mat *A, TIndex *T)
 {
-    if (T->mode != DESC_BLOCKS || A->w_uniform <= 0) return VBC_OK;
+    if (A->w_uniform <= 0) return VBC_OK; // the copy's blocks are w0 high: one stripe width for the whole matrix
+    const int uu = T->mode == DESC_BLOCKS ? A->u0 : 1; // rows of a unit: a u0-high block, or one stored row (1D / expanded rows)
     const size_t need = sizeof(Tv) * ((size_t)A->nval + 64) + 4 * (size_t)A->ndesc + sizeof(StripeMeta) * ((size_t)T->nkeys + 1);
     if (A->opt_fwd_atomic != 3) {
         size_t fr = 0, tot = 0;
@@ -326,17 +392,17 @@ static int build_transposed_copy(vbc_mat *A, TIndex *T)
     vbc_mat *At = new (std::nothrow) vbc_mat();
     if (!At) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
     At->vt = A->vt; At->it = A->it; At->ndim = 2; At->device = A->device;
-    At->m = A->n; At->n = A->m; At->K = A->L; At->L = T->nkeys; At->U = A->W; At->W = A->u0;
+    At->m = A->n; At->n = A->m; At->K = A->L; At->L = T->nkeys; At->U = A->W; At->W = uu;
     At->nidx = A->ndesc; At->nval = A->nval; At->ndesc = A->ndesc;
-    At->desc_mode = DESC_BLOCKS; At->u0 = A->w_uniform; At->w_uniform = A->u0;
+    At->desc_mode = DESC_BLOCKS; At->u0 = A->w_uniform; At->w_uniform = uu;
     At->sm_count = A->sm_count; At->stream = A->stream;
     cudaError_t e = cudaMalloc(&At->d_meta, sizeof(StripeMeta) * ((size_t)T->nkeys + 1));
     if (e == cudaSuccess) e = cudaMalloc(&At->d_desc, sizeof(int) * (size_t)(A->ndesc > 0 ? A->ndesc : 1));
     if (e == cudaSuccess) e = cudaMalloc(&At->d_val, sizeof(Tv) * ((size_t)A->nval + 64));
     if (e == cudaSuccess) e = cudaMemsetAsync((char *)At->d_val + sizeof(Tv) * (size_t)A->nval, 0, sizeof(Tv) * 64, A->stream);
     if (e == cudaSuccess) {
-        k_t_meta<Tv><<<(unsigned)((T->nkeys + 1 + 255) / 256), 256, 0, A->stream>>>(T->d_tptr, T->nkeys, A->u0, A->w_uniform, A->m, At->d_meta);
-        if (T->nkeys > 0) k_t_copy<Tv><<<(unsigned)(((long long)T->nkeys * 32 + 255) / 256), 256, 0, A->stream>>>(T->d_tptr, T->d_rec, (const Tv *)A->d_val, T->nkeys, A->u0, A->w_uniform, A->m, At->d_desc, (Tv *)At->d_val);
+        k_t_meta<Tv><<<(unsigned)((T->nkeys + 1 + 255) / 256), 256, 0, A->stream>>>(T->d_tptr, T->nkeys, uu, A->w_uniform, A->m, At->d_meta);
+        if (T->nkeys > 0) k_t_copy<Tv><<<(unsigned)(((long long)T->nkeys * 32 + 255) / 256), 256, 0, A->stream>>>(T->d_tptr, T->d_rec, (const Tv *)A->d_val, T->nkeys, uu, A->w_uniform, A->m, At->d_desc, (Tv *)At->d_val);
         A->launches += 2;
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(A->stream);
@@ -362,19 +428,20 @@ static int build_transposed_copy(vbc_mat *A, TIndex *T)
 static bool tindex_eligible(const vbc_mat *A)
 {
     if (A->L == 0 || A->m == 0 || A->opt_fwd_atomic == 1) return false;
-    if (A->desc_mode == DESC_ROWS) return A->opt_fwd_atomic == 2;
+    if (A->desc_mode == DESC_ROWS) return A->opt_fwd_atomic == 2 || A->w_uniform > 0; // one stripe width: the transposed copy is possible
     const int VE = 16 / (int)vt_size(A->vt);
     return A->w_uniform > 0 && (A->w_uniform % VE) == 0 && A->u0 * (A->w_uniform / VE) <= 32;
 }
 
 int ensure_tindex(vbc_mat *A)
 {
-    if (A->tindex || !tindex_eligible(A)) return VBC_OK;
+    if (A->tindex || A->opt_fwd_no_copy || !tindex_eligible(A)) return VBC_OK;
     TIndex *T = new (std::nothrow) TIndex();
     if (!T) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
     int rc = A->desc_mode == DESC_ROWS ? build_tindex_mode<DESC_ROWS>(A, T) : build_tindex_mode<DESC_BLOCKS>(A, T);
     if (rc == VBC_OK && A->opt_fwd_atomic != 2) rc = A->vt == VBC_F64 ? build_transposed_copy<double>(A, T) : build_transposed_copy<float>(A, T);
     if (rc != VBC_OK) { destroy_tindex(T); return rc; }
+    if (!T->At && A->desc_mode == DESC_ROWS && A->opt_fwd_atomic != 2) { destroy_tindex(T); A->opt_fwd_no_copy = 1; return VBC_OK; } // rows mode without the copy: atomics win over the index
     A->tindex = T;
     return VBC_OK;
 }
@@ -417,6 +484,25 @@ static int launch_fwdt_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
 
 int launch_fwdt(vbc_mat *A, double alpha, const void *x, double beta, void *y)
 {
+    if (A->tindex->At && A->tindex->mode == DESC_ROWS && (A->w_uniform % (16 / (int)vt_size(A->vt))) == 0) {
+        // rows mode: the copy is row-contiguous segments -> a dot product per row (k_fwdc_rows)
+        const vbc_mat *At = A->tindex->At;
+        const int VE = 16 / (int)vt_size(A->vt), vps = A->w_uniform / VE;
+        int64_t grid = (int64_t)A->sm_count * 8;
+        const double vec_per_row = At->L > 0 ? (double)At->nval / VE / (double)At->L : 1.0;
+        const int SG = vec_per_row >= 64 ? 16 : (vec_per_row >= 16 ? 8 : 4);
+        const int64_t need = (At->L * SG + 255) / 256;
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        const int l2 = ilog2x(vps);
+#define FWDC(Tv, SGv) k_fwdc_rows<Tv, SGv><<<(unsigned)grid, 256, 0, A->stream>>>(At->d_meta, At->d_desc, (const Tv *)At->d_val, (const Tv *)x, (Tv *)y, (int)At->L, A->w_uniform, l2, (Tv)alpha, (Tv)beta)
+        if (A->vt == VBC_F64) { if (SG == 16) FWDC(double, 16); else if (SG == 8) FWDC(double, 8); else FWDC(double, 4); }
+        else { if (SG == 16) FWDC(float, 16); else if (SG == 8) FWDC(float, 8); else FWDC(float, 4); }
+#undef FWDC
+        A->launches++;
+        VBC_CUDA(cudaGetLastError());
+        return VBC_OK;
+    }
     if (A->tindex->At) { // forward multiply of A = adjoint multiply of its transposed copy
         vbc_mat *At = A->tindex->At;
         At->stream = A->stream;

@@ -258,7 +258,7 @@ static inline unsigned nblk(int64_t n, int t);
 
 // Kernel-body class of a stripe: must mirror the per-stripe dispatch of k_spmv_adj / k_spmv_fwd (spmv.cu):
 // elements per load (from width and slab alignment) and vectors per row.
-__device__ __forceinline__ int stripe_class(const StripeMeta a, const StripeMeta b, const int VE)
+__device__ __forceinline__ int stripe_class(const StripeMeta a, const StripeMeta b, const int VE, const int rows_mode)
 {
     const int w = b.col - a.col;
     if (w <= 0) return 0;
@@ -266,18 +266,18 @@ __device__ __forceinline__ int stripe_class(const StripeMeta a, const StripeMeta
     if ((w % VE) == 0 && (a.ofs % VE) == 0) { epv_code = 0; cpr = w / VE; }
     else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0) { epv_code = 1; cpr = w / 2; }
     else { epv_code = 2; cpr = w; }
-    return 1 + epv_code * 64 + (cpr > 63 ? 63 : cpr);
+    return (1 + epv_code * 64 + (cpr > 62 ? 62 : cpr)) & 255;
 }
 
 // hist[0..255]: stripes per class; hist[256], hist[257]: min and max stripe width
-__global__ void k_class_hist(const StripeMeta *__restrict__ meta, int64_t L, int VE, unsigned *__restrict__ hist)
+__global__ void k_class_hist(const StripeMeta *__restrict__ meta, int64_t L, int VE, int rows_mode, unsigned *__restrict__ hist)
 {
     __shared__ unsigned sh[256];
     sh[threadIdx.x] = 0;
     __syncthreads();
     unsigned wmin = 0xffffffffu, wmax = 0;
     for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < L; l += (int64_t)gridDim.x * blockDim.x) {
-        atomicAdd(&sh[stripe_class(meta[l], meta[l + 1], VE) & 255], 1u);
+        atomicAdd(&sh[stripe_class(meta[l], meta[l + 1], VE, rows_mode) & 255], 1u);
         const unsigned w = (unsigned)(meta[l + 1].col - meta[l].col);
         wmin = w < wmin ? w : wmin;
         wmax = w > wmax ? w : wmax;
@@ -288,11 +288,11 @@ __global__ void k_class_hist(const StripeMeta *__restrict__ meta, int64_t L, int
 }
 
 // order[cursor[class]++] = l.  Stripes are visited in ascending blocks, so neighbours of one class stay close.
-__global__ void k_class_scatter(const StripeMeta *__restrict__ meta, int64_t L, int VE, unsigned *__restrict__ cursor, int *__restrict__ order)
+__global__ void k_class_scatter(const StripeMeta *__restrict__ meta, int64_t L, int VE, int rows_mode, unsigned *__restrict__ cursor, int *__restrict__ order)
 {
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= L) return;
-    const int c = stripe_class(meta[l], meta[l + 1], VE) & 255;
+    const int c = stripe_class(meta[l], meta[l + 1], VE, rows_mode) & 255;
     order[atomicAdd(&cursor[c], 1u)] = (int)l;
 }
 
@@ -314,7 +314,7 @@ static int build_class_order(vbc_mat *A)
     if (e == cudaSuccess) {
         int64_t g = (L + 255) / 256;
         if (g > 2048) g = 2048;
-        k_class_hist<<<(unsigned)g, 256, 0, st>>>(A->d_meta, L, VE, d_hist);
+        k_class_hist<<<(unsigned)g, 256, 0, st>>>(A->d_meta, L, VE, A->desc_mode == DESC_ROWS ? 1 : 0, d_hist);
         A->launches++;
         e = cudaMemcpyAsync(h, d_hist, sizeof(h), cudaMemcpyDeviceToHost, st);
     }
@@ -329,7 +329,7 @@ static int build_class_order(vbc_mat *A)
     e = cudaMalloc(&A->d_order, sizeof(int) * (size_t)L);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_hist, cur, sizeof(cur), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-        k_class_scatter<<<nblk(L, 256), 256, 0, st>>>(A->d_meta, L, VE, d_hist, A->d_order);
+        k_class_scatter<<<nblk(L, 256), 256, 0, st>>>(A->d_meta, L, VE, A->desc_mode == DESC_ROWS ? 1 : 0, d_hist, A->d_order);
         A->launches++;
         e = cudaStreamSynchronize(st);
     }

@@ -596,6 +596,9 @@ static int auto_group(const vbc_mat *A)
     // few stripes (C1: L = 1250): widen the groups until the grid has ~1 CTA of 256 threads per SM x 4, as long as
     // a stripe still has >= 2 vectors per lane (4.0 vs 7.1 us on C1 at 32 vs 8 lanes)
     while (G < 32 && (double)A->L * G < 148.0 * 4 * 256 && vec_per_stripe >= 4.0 * G) G *= 2;
+    // mixed widths (stripes regrouped by body class): the unaligned classes use one lane per column ELEMENT, and with 8 lanes
+    // a 5..7-wide stripe leaves lanes idle; 16 lanes hold two or three rows per step (C2v: 238 -> 214 us)
+    if (A->d_order != nullptr && G == 8) G = 16;
     return G;
 }
 
@@ -759,7 +762,7 @@ static int launch_spmv_t(vbc_mat *A, int trans, double alpha_d, const void *xv, 
     }
     if (A->opt_fwd_atomic != 1) { // owner-computes forward through the transposed unit index (fwdt.cu)
         VBC_TRY(ensure_tindex(A));
-        if (A->tindex && (A->opt_fwd_atomic == 2 || A->desc_mode == DESC_BLOCKS)) return launch_fwdt(A, alpha_d, xv, beta_d, yv);
+        if (A->tindex && (tindex_kind(A) == 2 || A->opt_fwd_atomic == 2 || A->desc_mode == DESC_BLOCKS)) return launch_fwdt(A, alpha_d, xv, beta_d, yv);
     }
     VBC_TRY(scale_y<Tv>(A, y, A->m, beta));
     if (A->L == 0 || A->nval == 0) return VBC_OK;

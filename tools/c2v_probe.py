@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""C2v (variable 2..8 blocks over the configs[1] matrix) adjoint multiply: time per group size; parity against scipy."""
+import json, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, ROOT)
+import vbc_b200 as vb
+from vbc_b200 import _lib, synth
+from bench import timed_graph
+A, _, _ = synth.config_c2()
+pv, fv = synth.variable_partition(A.m, 8, 3), synth.variable_partition(A.n, 8, 4)
+B = vb.SparseMatrixVBC[8, 8](A, pv, fv)
+x = synth.vector(A.m, 7)
+xd, yd = torch.from_numpy(x).cuda(), torch.empty(A.n, dtype=torch.float64, device="cuda")
+S = A.to_scipy()
+yref = S.T @ x
+out = {"lib": os.environ.get("VBC_LIBRARY", "product")}
+for g in (0, 8, 16, 32):
+    B.set_option(_lib.OPT_ADJ_GROUP, g)
+    med, mn = timed_graph(lambda: vb.mul_(yd, B.T, xd), 30)
+    err = float(np.max(np.abs(yd.cpu().numpy() - yref) / (abs(S).T @ np.abs(x))))
+    out[f"G{g}_us"] = round(med * 1e6, 1)
+    out[f"G{g}_err"] = err
+print(json.dumps(out))
