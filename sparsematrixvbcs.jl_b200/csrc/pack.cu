@@ -12,6 +12,8 @@
 //   (4) val is zero-filled and every stored nonzero is scattered to its slot, found by a
 //       binary search of its row (part) in the stripe's idx segment -- equivalent to the
 //       reference's in-order emission with `zero(Tv)` fill       [:66-87 / VBC :94-128]
+#include <algorithm>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -139,6 +141,90 @@ __global__ void __launch_bounds__(128) k_merge_stripes(const Ti *__restrict__ co
     if (!WRITE) {
         cnt[l] = units;
         nvals[l] = (DIM2 ? rows : units) * (long long)w;
+    }
+}
+
+// longest CSC segment of a stripe (entries of all its columns): sizes the shared-memory staging of the warp merge
+template <typename Ti>
+__global__ void __launch_bounds__(256) k_max_seglen(const Ti *__restrict__ colptr, const Ti *__restrict__ phi_spl, int64_t L, unsigned long long *__restrict__ out)
+{
+    unsigned long long mx = 0;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < L; l += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long len = (unsigned long long)((int64_t)colptr[(int64_t)phi_spl[l + 1] - 1] - (int64_t)colptr[(int64_t)phi_spl[l] - 1]);
+        mx = len > mx ? len : mx;
+    }
+    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, mx, d); mx = o > mx ? o : mx; }
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(out, mx);
+}
+
+// One WARP per stripe (the same merge, with memory-level parallelism): the stripe's CSC segment -- its columns are adjacent
+// in rowval -- is loaded coalesced and mapped to units (rows / row parts) by all lanes into shared memory; lane dj then owns
+// column dj's head, the next unit is a warp-wide minimum (REDUX), the lanes whose head equals it advance, and the sorted
+// distinct units collect in a second shared list from which the counts (2D: the heights, in parallel) or idx (coalesced
+// stores) are produced.  One thread per stripe walking global memory spent ~2 us per entry on two dependent loads.
+template <typename Ti, bool DIM2, bool WRITE>
+__global__ void __launch_bounds__(256) k_merge_stripes_warp(const Ti *__restrict__ colptr, const Ti *__restrict__ rowval,
+                                                            const Ti *__restrict__ phi_spl, int64_t L,
+                                                            const Ti *__restrict__ pi_spl, const int *__restrict__ asg,
+                                                            long long *__restrict__ cnt, long long *__restrict__ nvals,
+                                                            const Ti *__restrict__ pos, Ti *__restrict__ idx, const int cap, int *err)
+{
+    extern __shared__ int merge_smem[]; // per warp: units[cap], outs[cap]
+    const int lane = threadIdx.x & 31;
+    int *units = merge_smem + (size_t)(threadIdx.x >> 5) * 2 * cap, *outs = units + cap;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < L; l += nwarps) {
+        const int64_t j0 = (int64_t)phi_spl[l] - 1;
+        const int w = (int)((int64_t)phi_spl[l + 1] - 1 - j0);
+        if (w > WMAX) {
+            if (lane == 0) { atomicMax(err, PERR_WMAX); if (!WRITE) { cnt[l] = 0; nvals[l] = 0; } }
+            continue;
+        }
+        const int64_t b = (int64_t)colptr[j0] - 1;
+        // lane dj: [h, end) = column dj's entries, relative to the segment
+        int h = 0, end = 0;
+        if (lane < w) { h = (int)((int64_t)colptr[j0 + lane] - 1 - b); end = (int)((int64_t)colptr[j0 + lane + 1] - 1 - b); }
+        const int len = __shfl_sync(0xffffffffu, end, w > 0 ? w - 1 : 0);
+        for (int tb = 0; tb < len; tb += 32 * 8) { // eight independent row loads in flight per lane, then their (dependent) part lookups
+            long long r[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const int t = tb + k * 32 + lane; r[k] = t < len ? (long long)rowval[b + t] - 1 : -1; }
+            int uu[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) uu[k] = r[k] < 0 ? 0 : (DIM2 ? asg[r[k]] : (int)r[k]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const int t = tb + k * 32 + lane; if (t < len) units[t] = uu[k]; }
+        }
+        __syncwarp();
+        int n = 0;
+        if (w == 1 && !DIM2) { // :47-55 -- the column itself
+            n = len;
+            if (WRITE) { const int64_t out = (int64_t)pos[l] - 1; for (int t = lane; t < len; t += 32) idx[out + t] = (Ti)(units[t] + 1); }
+        } else {
+            const unsigned SENT = 0x7fffffffu;
+            unsigned key = h < end ? (unsigned)units[h] : SENT;
+            for (;;) {
+                const unsigned cur = __reduce_min_sync(0xffffffffu, key);
+                if (cur == SENT) break;
+                if (key == cur) { // advance this column past the current unit (2D: several rows of one part)
+                    do { h++; } while (h < end && (unsigned)units[h] == cur);
+                    key = h < end ? (unsigned)units[h] : SENT;
+                }
+                if (lane == 0) outs[n] = (int)cur;
+                n++;
+            }
+            __syncwarp();
+            if (WRITE) { const int64_t out = (int64_t)pos[l] - 1; for (int t = lane; t < n; t += 32) idx[out + t] = (Ti)(outs[t] + 1); }
+        }
+        if (!WRITE) {
+            long long rows = 0;
+            if (DIM2) {
+                for (int t = lane; t < n; t += 32) { const int u = (w == 1 && !DIM2) ? units[t] : outs[t]; rows += (long long)pi_spl[u + 1] - (long long)pi_spl[u]; }
+                for (int d = 16; d > 0; d >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, d);
+            }
+            if (lane == 0) { cnt[l] = n; nvals[l] = (DIM2 ? rows : (long long)n) * (long long)w; }
+        }
+        __syncwarp();
     }
 }
 
@@ -460,10 +546,37 @@ static int pack_t(vbc_mat *A, const Ti *colptr, const Ti *rowval, const Tv *nzva
         VBC_CUDA(cudaMalloc(&t.asg, sizeof(int) * (size_t)(m > 0 ? m : 1)));
         if (m > 0) { k_build_map<Ti><<<nblk(m, 256), 256, 0, st>>>(pi, K, m, t.asg); A->launches++; }
     }
-    // (1) count
+    // (1) count.  Warp-per-stripe merge staged in shared memory when the longest stripe segment fits (2 x cap ints per warp),
+    // else one thread per stripe straight from global memory.
+    int cap = 0;
     if (L > 0) {
-        if (d2) k_merge_stripes<Ti, true, false><<<nblk(L, 128), 128, 0, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, t.err);
-        else    k_merge_stripes<Ti, false, false><<<nblk(L, 128), 128, 0, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, t.err);
+        unsigned long long *d_mx = nullptr, h_mx = 0;
+        VBC_CUDA(cudaMalloc(&d_mx, sizeof(unsigned long long)));
+        cudaError_t ce = cudaMemsetAsync(d_mx, 0, sizeof(unsigned long long), st);
+        if (ce == cudaSuccess) { k_max_seglen<Ti><<<(unsigned)(nblk(L, 256) > 1024 ? 1024 : nblk(L, 256)), 256, 0, st>>>(colptr, phi, L, d_mx); A->launches++; ce = cudaMemcpyAsync(&h_mx, d_mx, sizeof(h_mx), cudaMemcpyDeviceToHost, st); }
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        cudaFree(d_mx);
+        if (ce != cudaSuccess) VBC_FAIL(VBC_ECUDA, "pack: %s", cudaGetErrorString(ce));
+        for (int c = 256; c <= 2048; c *= 2)
+            if (h_mx <= (unsigned long long)c) { cap = c; break; }
+    }
+    const size_t merge_smem_bytes = (size_t)8 * 2 * cap * sizeof(int);
+    if (cap > 0 && merge_smem_bytes > 48 * 1024) {
+        cudaError_t ce = d2 ? cudaFuncSetAttribute(k_merge_stripes_warp<Ti, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes)
+                            : cudaFuncSetAttribute(k_merge_stripes_warp<Ti, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes);
+        if (ce == cudaSuccess) ce = d2 ? cudaFuncSetAttribute(k_merge_stripes_warp<Ti, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes)
+                                        : cudaFuncSetAttribute(k_merge_stripes_warp<Ti, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes);
+        if (ce != cudaSuccess) { cudaGetLastError(); cap = 0; }
+    }
+    const unsigned warp_grid = (unsigned)std::min<int64_t>((L + 7) / 8 > 0 ? (L + 7) / 8 : 1, (int64_t)A->sm_count * 8);
+    if (L > 0) {
+        if (cap > 0) {
+            if (d2) k_merge_stripes_warp<Ti, true, false><<<warp_grid, 256, merge_smem_bytes, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, cap, t.err);
+            else    k_merge_stripes_warp<Ti, false, false><<<warp_grid, 256, merge_smem_bytes, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, cap, t.err);
+        } else {
+            if (d2) k_merge_stripes<Ti, true, false><<<nblk(L, 128), 128, 0, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, t.err);
+            else    k_merge_stripes<Ti, false, false><<<nblk(L, 128), 128, 0, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, t.err);
+        }
         A->launches++;
     }
     VBC_CUDA(cudaGetLastError());
@@ -486,8 +599,13 @@ static int pack_t(vbc_mat *A, const Ti *colptr, const Ti *rowval, const Tv *nzva
     VBC_CUDA(cudaMalloc(&A->d_val, sizeof(Tv) * ((size_t)nval + pad)));
     VBC_CUDA(cudaMemsetAsync(A->d_val, 0, sizeof(Tv) * ((size_t)nval + pad), st));
     if (L > 0) {
-        if (d2) k_merge_stripes<Ti, true, true><<<nblk(L, 128), 128, 0, st>>>(colptr, rowval, phi, L, pi, t.asg, nullptr, nullptr, (const Ti *)A->d_pos, (Ti *)A->d_idx, t.err);
-        else    k_merge_stripes<Ti, false, true><<<nblk(L, 128), 128, 0, st>>>(colptr, rowval, phi, L, pi, t.asg, nullptr, nullptr, (const Ti *)A->d_pos, (Ti *)A->d_idx, t.err);
+        if (cap > 0) {
+            if (d2) k_merge_stripes_warp<Ti, true, true><<<warp_grid, 256, merge_smem_bytes, st>>>(colptr, rowval, phi, L, pi, t.asg, nullptr, nullptr, (const Ti *)A->d_pos, (Ti *)A->d_idx, cap, t.err);
+            else    k_merge_stripes_warp<Ti, false, true><<<warp_grid, 256, merge_smem_bytes, st>>>(colptr, rowval, phi, L, pi, t.asg, nullptr, nullptr, (const Ti *)A->d_pos, (Ti *)A->d_idx, cap, t.err);
+        } else {
+            if (d2) k_merge_stripes<Ti, true, true><<<nblk(L, 128), 128, 0, st>>>(colptr, rowval, phi, L, pi, t.asg, nullptr, nullptr, (const Ti *)A->d_pos, (Ti *)A->d_idx, t.err);
+            else    k_merge_stripes<Ti, false, true><<<nblk(L, 128), 128, 0, st>>>(colptr, rowval, phi, L, pi, t.asg, nullptr, nullptr, (const Ti *)A->d_pos, (Ti *)A->d_idx, t.err);
+        }
         A->launches++;
     }
     VBC_CUDA(cudaGetLastError());
