@@ -683,6 +683,50 @@ def test_host_vector_pipeline_matches_plain_upload():
     assert B.get_option(_lib.OPT_E2E_UPLOAD_ELEMS) < 0.6 * m
 
 
+def test_spmm_row_stream_kernel_uniform_widths():
+    """The default Float64 adjoint SpMM of a matrix whose stripes all have width 4 or 8 (k_spmm_adj_stream): stripes with 0,
+    1, odd and many stored rows, empty leading / trailing stripes, units that end on and off a 16-row chunk, k below, at and
+    above one 32-column panel, alpha / beta, against scipy and against the FP64 tensor-tile kernel (option 2).  Parity of SpMM
+    is unpinned by the reference: the oracle is k independent products."""
+    import scipy.sparse as sp
+    import torch
+    rng = np.random.default_rng(77)
+    for w, L, m, dens in ((8, 37, 300, 0.02), (8, 700, 900, 0.04), (4, 1201, 500, 0.01), (8, 3000, 4000, 0.012), (4, 64, 40, 0.5)):
+        n = w * L
+        M = sp.random(m, n, density=dens, random_state=np.random.RandomState(int(rng.integers(1 << 30))), format="lil")
+        M[:, : 3 * w] = 0.0                      # empty stripes at the start,
+        M[:, n - 2 * w:] = 0.0                   # at the end,
+        M[:, 10 * w: 11 * w] = 0.0               # and inside
+        M[5, 12 * w] = 1.5                       # a stripe with exactly one stored row
+        A = vb.SparseMatrixCSC.from_scipy(sp.csc_matrix(M))
+        S = A.to_scipy()
+        absS = abs(S)
+        B = vb.SparseMatrix1DVBC[w](A, vb.pack_stripe(A, vb.EquiChunker(w)))
+        for k in (2, 32, 34, 64):
+            X = torch.rand(m, k, dtype=torch.float64, device="cuda")
+            Y0 = torch.rand(n, k, dtype=torch.float64, device="cuda")
+            want = S.T @ X.cpu().numpy()
+            bound = absS.T @ np.abs(X.cpu().numpy()) + 1.0
+            outs = []
+            for mode in (0, 2, 3, 4):
+                B.set_option(_lib.OPT_SPMM_SIMT, mode)
+                Y = torch.full((n, k), float("nan"), dtype=torch.float64, device="cuda")
+                vb.mul_(Y, B.T, X)
+                assert np.all(np.abs(Y.cpu().numpy() - want) <= 1e-12 * bound), (w, L, k, mode)
+                Yb = vb.mul_(Y0.clone(), B.T, X, 1.5, -0.25)
+                assert np.all(np.abs(Yb.cpu().numpy() - (1.5 * want - 0.25 * Y0.cpu().numpy())) <= 2e-12 * bound), (w, L, k, mode)
+                outs.append(Y)
+            for o in outs[1:]:
+                assert torch.allclose(outs[0], o, rtol=1e-12, atol=1e-13)
+        B.set_option(_lib.OPT_SPMM_SIMT, 0)
+        # a strided view (ldx > k) keeps the alignment the kernel needs; an odd k falls back to the tile kernel
+        Xw = torch.rand(m, 40, dtype=torch.float64, device="cuda")
+        Y = vb.mul_(torch.empty(n, 6, dtype=torch.float64, device="cuda"), B.T, Xw[:, 2:8])
+        assert np.allclose(Y.cpu().numpy(), S.T @ Xw[:, 2:8].cpu().numpy(), rtol=1e-11, atol=1e-12)
+        Y = vb.mul_(torch.empty(n, 5, dtype=torch.float64, device="cuda"), B.T, Xw[:, 1:6].contiguous())
+        assert np.allclose(Y.cpu().numpy(), S.T @ Xw[:, 1:6].cpu().numpy(), rtol=1e-11, atol=1e-12)
+
+
 def test_spmm_host_panels_with_leading_dimension_padding():
     """a host panel with ld > inner holds (outer-1)*ld + inner elements; the copies must not touch more."""
     rng = np.random.default_rng(8)
