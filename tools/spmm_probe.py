@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """configs[2] adjoint SpMM (1D-VBC, Float64, k = 32, n = 1M): the DMMA kernel against the SIMT kernel
-(PROBE_MODES = comma list of VBC_OPT_SPMM_SIMT values, first one is the reference: 0 row stream, 1 SIMT, 2 DMMA tiles; the round-1 variants
+(PROBE_MODES = comma list of VBC_OPT_SPMM_SIMT values, first one is the reference: 0 DMMA tiles, 1 SIMT; the round-1 variants
 with other X feeds were validated in round 2 -- profiles/r02_round2_checks.json -- and removed) -- results compared first,
 then CUDA-graph timing.  PROBE_BAND=1 swaps
 the strided rows for a contiguous band; PROBE_NCU=1 only launches each kernel twice (for an `ncu -k regex:k_spmm_adj`
@@ -29,8 +29,8 @@ def main():
     B = vb.SparseMatrix1DVBC[8](A, phi)
     X = torch.rand(A.m, k, dtype=torch.float64, device="cuda")
     out, ys = {}, {}
-    modes = {"0": (0, "auto"), "1": (1, "simt"), "2": (2, "dmma"), "3": (3, "tma"), "4": (4, "stream")}
-    picked = [modes[m] for m in os.environ.get("PROBE_MODES", "2,0,1").split(",")]
+    modes = {"0": (0, "dmma"), "1": (1, "simt")}
+    picked = [modes[m] for m in os.environ.get("PROBE_MODES", "0,1").split(",")]
     tag = "_".join(n for _, n in picked[1:])
     for mode, name in picked:
         B.set_option(_lib.OPT_SPMM_SIMT, mode)
