@@ -73,6 +73,8 @@ struct vbc_mat {
     int desc_mode = vbc::DESC_ROWS;
     int u0 = 1; // DESC_BLOCKS: uniform part height
     int w_uniform = 0; // >0 when every stripe has this width
+    int has_unaligned = 0; // some stripe has an odd width or starts on an odd element (Float64: the flat-slab adjoint bodies apply)
+    int opt_no_flat = 0;   // experiments: 1 = never use the flat-slab bodies
     // staging vectors for host-pointer multiplies
     void *d_x = nullptr, *d_y = nullptr;
     int64_t x_cap = 0, y_cap = 0;

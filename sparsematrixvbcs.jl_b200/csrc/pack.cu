@@ -13,6 +13,7 @@
 //       binary search of its row (part) in the stripe's idx segment -- equivalent to the
 //       reference's in-order emission with `zero(Tv)` fill       [:66-87 / VBC :94-128]
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "scan.cuh"
@@ -407,6 +408,9 @@ static int build_class_order(vbc_mat *A)
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { cudaFree(d_hist); VBC_FAIL(VBC_ECUDA, "class histogram: %s", cudaGetErrorString(e)); }
     if (h[256] == h[257] && h[257] > 0) A->w_uniform = (int)h[257];
+    A->has_unaligned = 0;
+    A->opt_no_flat = getenv("VBC_NO_FLAT") != nullptr; // experiments: per-element bodies for unaligned stripes, as before round 2
+    for (int c = 129; c < 192; c++) if (h[c]) A->has_unaligned = 1; // class codes 1 + 2 * 64 + cpr: one element per load
     int ncls = 0;
     unsigned run = 0, cur[256];
     for (int c = 0; c < 256; c++) { cur[c] = run; run += h[c]; if (h[c]) ncls++; }

@@ -20,15 +20,6 @@
 
 namespace vbc {
 
-// x index of stored row r of a stripe (any lane, no walk state)
-template <int MODE>
-__device__ __forceinline__ int row_xindex(const int *__restrict__ desc, const int pos0, const int r, const int u0, const int log2u)
-{
-    if (MODE == DESC_ROWS) return __ldg(desc + pos0 + r);
-    if (log2u >= 0) return __ldg(desc + pos0 + (r >> log2u)) + (r & (u0 - 1));
-    return __ldg(desc + pos0 + r / u0) + r % u0;
-}
-
 // Adjoint SpMM.  One warp per stripe; rows are taken RB at a time in a two-stage software pipeline: while
 // batch t is multiplied, batch t+1's X rows (RB independent coalesced loads per lane), its slab of val
 // (loaded coalesced, each value once per warp, parked in the other half of a shared-memory double buffer)

@@ -44,6 +44,9 @@ namespace vbc {
 #ifndef VBC_HALO_RUN_INLINE
 #define VBC_HALO_RUN_INLINE __forceinline__ // the boundary-run body of k_spmv_adj_halo: inlined (a call in that kernel slows its interior loop)
 #endif
+#ifndef VBC_FLAT_ALL
+#define VBC_FLAT_ALL 0    // 1: in the FLAT kernels every stripe (aligned ones too) takes the flat-slab body
+#endif
 #ifndef VBC_WIDE_LD
 #define VBC_WIDE_LD 0      // 1: 256-bit loads (sm_100+ LDG.256) for Float64 stripes whose width is a multiple of 4
 #endif
@@ -202,6 +205,79 @@ __device__ __forceinline__ void adj_stripe(const StripeMeta a, const StripeMeta 
     if (lane < cpr) store_y<Tv, EPV>(y, a.col + lane * EPV, acc, alpha, beta);
 }
 
+// Unaligned stripes (Float64: odd width, or a slab that starts on an odd element): the slab is read as what it is in
+// memory -- one contiguous array -- with ALIGNED 16-byte loads, whatever the row length.  S = per * floor(G / per) lanes
+// (per = w for odd w, w/2 for even w) read consecutive vectors; 2S elements are a whole number of rows, so the two elements
+// of a lane always fall on the same two columns (c0, c1) and on rows that advance by a fixed step.  The x values of the
+// stripe's rows are gathered ONCE per row into the group's shared-memory row (one descriptor and one x load per stored row
+// instead of one per element) and read back per element.  The element before the slab (odd start) and the one after it are
+// masked.  Lanes that share (c0, c1) are summed with the strided shuffle tree of the generic body; for odd w column j is
+// the sum of one lane's first and another lane's second accumulator (one more shuffle).
+// One 8-byte load per element with its own descriptor and x loads was 0.58 of the HBM peak on the C2v matrix.
+template <int G, int MODE, bool XC>
+__device__ __forceinline__ void adj_stripe_flat(const StripeMeta a, const StripeMeta b, const int w, const int R, const int lane, const unsigned gmask,
+                                                const int *__restrict__ desc, const double *__restrict__ val, const double *__restrict__ x,
+                                                double *__restrict__ y, const int u0, const int log2u, const double alpha, const double beta,
+                                                double *__restrict__ xs)
+{
+    const int n = (int)(b.ofs - a.ofs);
+    const int shift = (int)(a.ofs & 1);
+    const int odd = w & 1;
+    const int per = odd ? w : (w >> 1);
+    const int reps = small_div(G, per);
+    const int S = reps * per;             // active lanes
+    const int rstep = odd ? 2 * reps : reps; // rows per step (2S / w)
+    // this lane's two elements in step 0, relative to the slab: q0 (-1: the element before an odd-aligned slab), q0 + 1
+    const int q0 = 2 * lane - shift;
+    int ra, c0;
+    if (q0 < 0) { ra = -1; c0 = w - 1; } else { ra = small_div(q0, w); c0 = q0 - ra * w; }
+    int rb = small_div(q0 + 1, w);
+    const int c1 = q0 + 1 - rb * w;
+    const double2 *vp = reinterpret_cast<const double2 *>(val + (a.ofs - shift)) + lane;
+    double acc0 = 0.0, acc1 = 0.0;
+    constexpr int UNR = VBC_ADJ_UNR;
+    int p = lane < S ? q0 : n;
+    double2 v[UNR];
+    auto load_batch = [&]() {
+#pragma unroll
+        for (int k = 0; k < UNR; k++) {
+            v[k] = (p + k * 2 * S < n) ? ld_val(vp) : make_double2(0.0, 0.0);
+            vp += S;
+        }
+    };
+    load_batch(); // the first values are on their way while the descriptors and x values of the rows are fetched
+    for (int i = lane; i < R; i += G) xs[i] = ld_x<double, XC>(x + row_xindex<MODE>(desc, a.pos, i, u0, log2u));
+    __syncwarp(gmask);
+    while (p < n) {
+#pragma unroll
+        for (int k = 0; k < UNR; k++) {
+            const int pk = p + k * 2 * S;
+            const bool m0 = pk >= 0 && pk < n, m1 = pk + 1 < n;
+            const double x0 = m0 ? xs[ra + k * rstep] : 0.0, x1 = m1 ? xs[rb + k * rstep] : 0.0;
+            if (m0) acc0 = fma(v[k].x, x0, acc0);
+            if (m1) acc1 = fma(v[k].y, x1, acc1);
+        }
+        ra += UNR * rstep; rb += UNR * rstep;
+        p += UNR * 2 * S;
+        if (p < n) load_batch();
+    }
+    for (int d = per; d < G; d <<= 1) {
+        const double t0 = __shfl_down_sync(gmask, acc0, d, G), t1 = __shfl_down_sync(gmask, acc1, d, G);
+        if (lane + d < G) { acc0 += t0; acc1 += t1; }
+    }
+    double *yp = y + a.col;
+    if (odd) { // column c0 = this lane's first accumulator + the second accumulator of lane (lane + (w-1)/2) mod w
+        int src = lane + ((w - 1) >> 1);
+        if (src >= w) src -= w;
+        const double t = __shfl_sync(gmask, acc1, src, G);
+        if (lane < w) { const double s = acc0 + t; yp[c0] = (beta == 0.0) ? alpha * s : alpha * s + beta * yp[c0]; }
+    } else if (lane < per) {
+        yp[c0] = (beta == 0.0) ? alpha * acc0 : alpha * acc0 + beta * yp[c0];
+        yp[c1] = (beta == 0.0) ? alpha * acc1 : alpha * acc1 + beta * yp[c1];
+    }
+    __syncwarp(gmask); // the group's x row is rewritten by the next stripe
+}
+
 // wide stripes (more vectors per row than lanes): one lane per column, serial over rows
 template <typename Tv, int G, int MODE, bool XC>
 __device__ __noinline__ void adj_stripe_wide(const StripeMeta a, const StripeMeta b, const int w, const int lane,
@@ -234,14 +310,25 @@ __device__ __forceinline__ void adj_dispatch_cpr(const StripeMeta a, const Strip
 }
 
 // one stripe, body class chosen from its width and the alignment of its slab (the analogue of le_nest, util.jl:28-38)
-template <typename Tv, int G, int MODE, bool XC>
+constexpr int FLAT_XCAP_PER_LANE = 16; // shared-memory x row of a group in the FLAT kernels: 16 * G values (32 KB per CTA of 256 threads)
+
+template <typename Tv, int G, int MODE, bool XC, bool FLAT = false>
 __device__ __forceinline__ void adj_one_stripe(const StripeMeta a, const StripeMeta b, const int lane, const unsigned gmask,
                                                const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
-                                               Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta)
+                                               Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta, Tv *__restrict__ xs = nullptr)
 {
     constexpr int VE = 16 / (int)sizeof(Tv);
     const int w = b.col - a.col;
     if (w <= 0) return;
+    if constexpr (FLAT && sizeof(Tv) == 8) {
+        if (VBC_FLAT_ALL || (w & 1) || (a.ofs & 1)) {
+            const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
+            if (((w & 1) ? w : (w >> 1)) <= G && R <= FLAT_XCAP_PER_LANE * G) {
+                adj_stripe_flat<G, MODE, XC>(a, b, w, R, lane, gmask, desc, (const double *)val, (const double *)x, (double *)y, u0, log2u, (double)alpha, (double)beta, (double *)xs);
+                return;
+            }
+        }
+    }
 #if VBC_WIDE_LD
     if (sizeof(Tv) == 8 && (w % 4) == 0 && (a.ofs % 4) == 0)
         adj_dispatch_cpr<Tv, G, MODE, (sizeof(Tv) == 8 ? 4 : VE), XC>(a, b, w, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
@@ -258,16 +345,38 @@ __device__ __forceinline__ void adj_one_stripe(const StripeMeta a, const StripeM
 // stripes [lo, hi) dealt round-robin to the groups of the grid.  order == null: stripes in index order, next stripe's
 // meta prefetched.  order != null (mixed widths): position l holds stripe order[l], stripes of one body class are
 // adjacent, so a warp's groups agree.  (One loop for both, so the stripe bodies exist once in the kernel.)
-template <typename Tv, int G, int MODE>
+template <typename Tv, int G, int MODE, bool FLAT = false>
 __device__ __forceinline__ void adj_range(const StripeMeta *__restrict__ meta, const int *__restrict__ order, const int lo, const int hi,
                                           const int group, const int ngroups,
                                           const int *__restrict__ desc, const Tv *__restrict__ val, const Tv *__restrict__ x,
-                                          Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta)
+                                          Tv *__restrict__ y, const int u0, const int log2u, const Tv alpha, const Tv beta, Tv *__restrict__ xs = nullptr)
 {
     const int lane = threadIdx.x % G;
     const unsigned gmask = group_mask<G>();
     int l = lo + group;
     if (l >= hi) return;
+    if constexpr (FLAT) { // the kernels for matrices with unaligned stripes: meta prefetched in both modes (order mode: through the index fetched one stripe earlier)
+        StripeMeta na, nb;
+        int lsn = 0;
+        if (order == nullptr) { na = ld_meta(meta + l); nb = ld_meta(meta + l + 1); }
+        else {
+            const int ls = __ldg(order + l);
+            na = ld_meta(meta + ls); nb = ld_meta(meta + ls + 1);
+            if (l + ngroups < hi) lsn = __ldg(order + l + ngroups);
+        }
+        for (; l < hi; l += ngroups) {
+            const StripeMeta a = na, b = nb;
+            if (l + ngroups < hi) {
+                if (order == nullptr) { na = ld_meta(meta + l + ngroups); nb = ld_meta(meta + l + ngroups + 1); }
+                else {
+                    na = ld_meta(meta + lsn); nb = ld_meta(meta + lsn + 1);
+                    if (l + 2 * ngroups < hi) lsn = __ldg(order + l + 2 * ngroups);
+                }
+            }
+            adj_one_stripe<Tv, G, MODE, false, true>(a, b, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta, xs);
+        }
+        return;
+    }
     StripeMeta na, nb;
     if (order == nullptr) { na = ld_meta(meta + l); nb = ld_meta(meta + l + 1); }
     for (; l < hi; l += ngroups) {
@@ -290,6 +399,17 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
 {
     adj_range<Tv, G, MODE>(meta, order, 0, L, (int)((blockIdx.x * blockDim.x + threadIdx.x) / G), (int)((gridDim.x * blockDim.x) / G),
                            desc, val, x, y, u0, log2u, alpha, beta);
+}
+
+// the same loop for Float64 matrices that hold unaligned stripes: those take adj_stripe_flat, with one shared-memory x row per group
+template <int G, int MODE>
+__global__ void VBC_ADJ_BOUNDS k_spmv_adj_flat(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+                                               const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+                                               const int *__restrict__ order, const int L, const int u0, const int log2u, const double alpha, const double beta)
+{
+    __shared__ double xs_all[256 / G][FLAT_XCAP_PER_LANE * G];
+    adj_range<double, G, MODE, true>(meta, order, 0, L, (int)((blockIdx.x * blockDim.x + threadIdx.x) / G), (int)((gridDim.x * blockDim.x) / G),
+                                     desc, val, x, y, u0, log2u, alpha, beta, xs_all[threadIdx.x / G]);
 }
 
 // ---- adjoint with the x exchange of the row-partitioned iteration fused in (north_star (e)) -------------------------
@@ -616,6 +736,21 @@ static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
     const int64_t need = ((l1 - l0) * G + 255) / 256;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    if constexpr (sizeof(Tv) == 8 && G >= 8) {
+        if (A->has_unaligned && !A->opt_no_flat) { // odd widths / odd slab starts: the flat-slab bodies (one shared-memory x row per group)
+            int occf = 0;
+            VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occf, k_spmv_adj_flat<G, MODE>, 256, 0));
+            if (occf < 1) occf = 1;
+            if (A->opt_grid_mult > 0) occf = A->opt_grid_mult;
+            int64_t gridf = (int64_t)A->sm_count * occf;
+            if (gridf > need) gridf = need;
+            if (gridf < 1) gridf = 1;
+            k_spmv_adj_flat<G, MODE><<<(unsigned)gridf, 256, 0, A->stream>>>(A->d_meta + l0, A->d_desc, (const double *)A->d_val, (const double *)x, (double *)y, A->d_order, (int)(l1 - l0), A->u0, ilog2_exact(A->u0), (double)alpha, (double)beta);
+            A->launches++;
+            VBC_CUDA(cudaGetLastError());
+            return VBC_OK;
+        }
+    }
     k_spmv_adj<Tv, G, MODE><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta + l0, A->d_desc, (const Tv *)A->d_val, x, y, A->d_order, (int)(l1 - l0), A->u0, ilog2_exact(A->u0), alpha, beta);
     A->launches++;
     VBC_CUDA(cudaGetLastError());

@@ -32,6 +32,15 @@ template <int G> __device__ __forceinline__ unsigned group_mask()
     else return ((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G);
 }
 
+// x index of stored row r of a stripe (any lane, no walk state)
+template <int MODE>
+__device__ __forceinline__ int row_xindex(const int *__restrict__ desc, const int pos0, const int r, const int u0, const int log2u)
+{
+    if (MODE == DESC_ROWS) return __ldg(desc + pos0 + r);
+    if (log2u >= 0) return __ldg(desc + pos0 + (r >> log2u)) + (r & (u0 - 1));
+    return __ldg(desc + pos0 + r / u0) + r % u0;
+}
+
 // x-index stream of a stripe for one lane: row r0, then r0+rps, ...
 template <int MODE> struct RowWalk;
 template <> struct RowWalk<DESC_ROWS> {
