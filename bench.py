@@ -246,6 +246,16 @@ def extra_configs(peak):
     pv, fv = synth.variable_partition(A.m, 8, 3), synth.variable_partition(A.n, 8, 4)
     B = vb.SparseMatrixVBC[8, 8](A, pv, fv)
     out["C2v_2D_f64_variable_2to8_blocks"] = adj_record(B, A, 50)
+    # ... and its forward multiply (the rows-mode transposed copy of the variable blocks, built at the first call)
+    xv = synth.vector(A.n, 11)
+    xvd, yvd = torch.from_numpy(xv).cuda(), torch.empty(A.m, dtype=torch.float64, device="cuda")
+    vb.mul_(yvd, B, xvd)
+    med, mn = timed_graph(lambda: vb.mul_(yvd, B, xvd), 50)
+    Sv = A.to_scipy()
+    nb = B.format_bytes()[2] + 8 * (A.m + A.n)
+    out["C2v_forward_2D_f64_variable_2to8_blocks"] = {"us": med * 1e6, "us_min": mn * 1e6, "algorithmic_bytes": nb, "GBps": nb / med / 1e9, "frac_of_hbm_peak": nb / med / 1e9 / peak,
+                                                      "gflops": 2.0 * A.nnz / med / 1e9, "parity_err_over_bound_1e-12": bound_err(yvd.cpu().numpy(), Sv @ xv, abs(Sv) @ np.abs(xv), 1e-12)}
+    del Sv
     B.close()
     # forward multiply on the C2 matrix (the reference's serial scatter orientation, multiply_VBC.jl:3-87)
     from vbc_b200.partition import SplitPartition

@@ -145,6 +145,7 @@ struct DeviceGuard {
 // pack.cu
 int pack_from_device_csc(vbc_mat *A, const void *d_colptr, const void *d_rowval, const void *d_nzval);
 int finalize_layout(vbc_mat *A, const void *h_pi_spl /* host copy, may be null for 1D */);
+int build_class_order(vbc_mat *A); // stripes grouped by kernel-body class; sets w_uniform / has_unaligned
 int memory_cost_device(const vbc_mat *A, int64_t *h_cost, int64_t *row_term);
 // spmv.cu
 int launch_spmv(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y);

@@ -331,7 +331,7 @@ void destroy_tindex(TIndex *t)
     cudaFree(t->d_tptr);
     cudaFree(t->d_rec);
     if (t->At) {
-        cudaFree(t->At->d_meta); cudaFree(t->At->d_desc); cudaFree(t->At->d_val);
+        cudaFree(t->At->d_meta); cudaFree(t->At->d_desc); cudaFree(t->At->d_val); cudaFree(t->At->d_order);
         delete t->At;
     }
     delete t;
@@ -421,6 +421,163 @@ static int build_transposed_copy(vbc_mat *A, TIndex *T)
     return VBC_OK;
 }
 
+// ---- variable blocks (2D, parts of different heights): the transposed copy in ROWS mode ----------------------------------
+// Row part k becomes stripe k of the copy (u_k columns wide: the part's rows); each of its blocks, taken in ascending
+// stripe-column order, contributes w_l stored rows (one per column of A in that block) whose descriptor is the column index
+// and whose u_k values are that column of the block.  y = A x is then the adjoint multiply of the copy -- the owner-computes
+// streaming kernel with its flat-slab bodies for the odd widths, no atomics, fixed summation order -- instead of one
+// floating-point atomic per stored row (0.35 of the HBM peak on the C2v matrix).
+template <typename Ti>
+__global__ void __launch_bounds__(128) k_tb_count(const Ti *__restrict__ pos, const Ti *__restrict__ idx, const int L, unsigned long long *__restrict__ cnt)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    for (long long Q = (long long)pos[l] - 1; Q < (long long)pos[l + 1] - 1; Q++) atomicAdd(&cnt[(long long)idx[Q] - 1], 1ull);
+}
+
+template <typename Ti>
+__global__ void __launch_bounds__(128) k_tb_fill(const Ti *__restrict__ pos, const Ti *__restrict__ idx, const Ti *__restrict__ ofs, const Ti *__restrict__ phi,
+                                                  const int *__restrict__ brow, const int L, const int *__restrict__ tptr, unsigned *__restrict__ cursor,
+                                                  TRec *__restrict__ rec)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const int j0 = (int)((long long)phi[l] - 1), w = (int)((long long)phi[l + 1] - (long long)phi[l]);
+    if (w <= 0) return;
+    const long long v0 = (long long)ofs[l] - 1;
+    for (long long Q = (long long)pos[l] - 1; Q < (long long)pos[l + 1] - 1; Q++) {
+        const long long k = (long long)idx[Q] - 1;
+        TRec r;
+        r.vofs = v0 + (long long)brow[Q] * w;
+        r.col = j0;
+        r.w = w;
+        rec[tptr[k] + atomicAdd(&cursor[k], 1u)] = r;
+    }
+}
+
+// stored rows and values of every stripe of the copy
+template <typename Ti>
+__global__ void __launch_bounds__(256) k_tb_rows(const int *__restrict__ tptr, const TRec *__restrict__ rec, const Ti *__restrict__ pi, const int K,
+                                                  long long *__restrict__ rows, long long *__restrict__ vals)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    long long r = 0;
+    for (int t = tptr[k]; t < tptr[k + 1]; t++) r += rec[t].w;
+    rows[k] = r;
+    vals[k] = r * ((long long)pi[k + 1] - (long long)pi[k]);
+}
+
+template <typename Ti>
+__global__ void __launch_bounds__(256) k_tb_meta(const long long *__restrict__ ofs2, const int *__restrict__ pos2, const Ti *__restrict__ pi, const int K,
+                                                  StripeMeta *__restrict__ meta2)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > K) return;
+    StripeMeta s;
+    s.ofs = ofs2[k]; s.pos = pos2[k]; s.col = (int)((long long)pi[k] - 1);
+    meta2[k] = s;
+}
+
+template <typename Ti, typename Tv>
+__global__ void __launch_bounds__(256) k_tb_copy(const int *__restrict__ tptr, const TRec *__restrict__ rec, const Tv *__restrict__ val, const Ti *__restrict__ pi,
+                                                  const StripeMeta *__restrict__ meta2, const int K, int *__restrict__ desc2, Tv *__restrict__ val2)
+{
+    const int k = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (k >= K) return;
+    const int u = (int)((long long)pi[k + 1] - (long long)pi[k]);
+    const StripeMeta a = meta2[k];
+    int row = 0;
+    for (int t = tptr[k]; t < tptr[k + 1]; t++) {
+        const TRec r = rec[t];
+        for (int dj = lane; dj < r.w; dj += 32) desc2[a.pos + row + dj] = r.col + dj;
+        Tv *out = val2 + a.ofs + (long long)row * u;
+        const int per = r.w * u;
+        for (int e = lane; e < per; e += 32) {
+            const int dj = e / u, di = e - dj * u; // stored row dj of the copy (a column of A), column di (a row of the part)
+            out[e] = val[r.vofs + (long long)di * r.w + dj];
+        }
+        row += r.w;
+    }
+}
+
+template <typename Ti, typename Tv>
+static int build_transposed_blocks(vbc_mat *A, TIndex *T)
+{
+    const int L = (int)A->L, K = (int)A->K;
+    cudaStream_t st = A->stream;
+    const size_t need = sizeof(Tv) * ((size_t)A->nval + 64) + 4 * (size_t)A->nval + sizeof(StripeMeta) * ((size_t)K + 1);
+    if (A->opt_fwd_atomic != 3) {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess || need * 4 > fr) { cudaGetLastError(); return VBC_OK; }
+    }
+    T->nkeys = K; T->mode = DESC_ROWS;
+    struct Scratch {
+        unsigned long long *cnt = nullptr; long long *tmp = nullptr, *rows = nullptr, *vals = nullptr, *ofs2 = nullptr; unsigned *cur = nullptr; int *pos2 = nullptr;
+        ~Scratch() { cudaFree(cnt); cudaFree(tmp); cudaFree(rows); cudaFree(vals); cudaFree(ofs2); cudaFree(cur); cudaFree(pos2); }
+    } sc;
+    const size_t nk = (size_t)(K > 0 ? K : 1);
+    VBC_CUDA(cudaMalloc(&sc.cnt, 8 * nk));
+    VBC_CUDA(cudaMalloc(&sc.tmp, 8 * (size_t)scan_tmp_elems(K)));
+    VBC_CUDA(cudaMalloc(&sc.rows, 8 * nk));
+    VBC_CUDA(cudaMalloc(&sc.vals, 8 * nk));
+    VBC_CUDA(cudaMalloc(&sc.ofs2, 8 * (nk + 1)));
+    VBC_CUDA(cudaMalloc(&sc.cur, 4 * nk));
+    VBC_CUDA(cudaMalloc(&sc.pos2, 4 * (nk + 1)));
+    VBC_CUDA(cudaMalloc(&T->d_tptr, 4 * (nk + 1)));
+    VBC_CUDA(cudaMalloc(&T->d_rec, sizeof(TRec) * (size_t)(A->nidx > 0 ? A->nidx : 1)));
+    VBC_CUDA(cudaMemsetAsync(sc.cnt, 0, 8 * nk, st));
+    VBC_CUDA(cudaMemsetAsync(sc.cur, 0, 4 * nk, st));
+    const Ti *pos = (const Ti *)A->d_pos, *idx = (const Ti *)A->d_idx, *ofs = (const Ti *)A->d_ofs, *phi = (const Ti *)A->d_phi_spl, *pi = (const Ti *)A->d_pi_spl;
+    const unsigned g = (unsigned)((L + 127) / 128 > 0 ? (L + 127) / 128 : 1);
+    long long total = 0, nrows = 0, nvals = 0;
+    if (L > 0) { k_tb_count<Ti><<<g, 128, 0, st>>>(pos, idx, L, sc.cnt); A->launches++; }
+    VBC_TRY(exclusive_scan<int>((const long long *)sc.cnt, T->d_tptr, K, 0, sc.tmp, &total, st, &A->launches));
+    if (L > 0) { k_tb_fill<Ti><<<g, 128, 0, st>>>(pos, idx, ofs, phi, A->d_brow, L, T->d_tptr, sc.cur, T->d_rec); A->launches++; }
+    if (K > 0) {
+        k_t_sort<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(T->d_tptr, T->d_rec, K);
+        k_tb_rows<Ti><<<(unsigned)((K + 255) / 256), 256, 0, st>>>(T->d_tptr, T->d_rec, pi, K, sc.rows, sc.vals);
+        A->launches += 2;
+    }
+    VBC_CUDA(cudaGetLastError());
+    VBC_TRY(exclusive_scan<int>(sc.rows, sc.pos2, K, 0, sc.tmp, &nrows, st, &A->launches));
+    VBC_TRY(exclusive_scan<long long>(sc.vals, sc.ofs2, K, 0, sc.tmp, &nvals, st, &A->launches));
+    if (nrows >= (1LL << 31)) return VBC_OK; // 32-bit descriptor space: keep the scatter kernel
+    vbc_mat *At = new (std::nothrow) vbc_mat();
+    if (!At) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
+    At->vt = A->vt; At->it = A->it; At->ndim = 2; At->device = A->device;
+    At->m = A->n; At->n = A->m; At->K = A->L; At->L = K; At->U = A->W; At->W = A->U;
+    At->nidx = nrows; At->nval = nvals; At->ndesc = nrows;
+    At->desc_mode = DESC_ROWS; At->u0 = 1;
+    At->sm_count = A->sm_count; At->stream = st;
+    cudaError_t e = cudaMalloc(&At->d_meta, sizeof(StripeMeta) * ((size_t)K + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&At->d_desc, sizeof(int) * (size_t)(nrows > 0 ? nrows : 1));
+    if (e == cudaSuccess) e = cudaMalloc(&At->d_val, sizeof(Tv) * ((size_t)nvals + 64));
+    if (e == cudaSuccess) e = cudaMemsetAsync((char *)At->d_val + sizeof(Tv) * (size_t)nvals, 0, sizeof(Tv) * 64, st);
+    int rc = VBC_OK;
+    if (e == cudaSuccess) {
+        k_tb_meta<Ti><<<(unsigned)((K + 1 + 255) / 256), 256, 0, st>>>(sc.ofs2, sc.pos2, pi, K, At->d_meta);
+        if (K > 0) k_tb_copy<Ti, Tv><<<(unsigned)(((long long)K * 32 + 255) / 256), 256, 0, st>>>(T->d_tptr, T->d_rec, (const Tv *)A->d_val, pi, At->d_meta, K, At->d_desc, (Tv *)At->d_val);
+        A->launches += 2;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) rc = build_class_order(At);
+    }
+    if (e != cudaSuccess || rc != VBC_OK) {
+        cudaGetLastError();
+        cudaFree(At->d_meta); cudaFree(At->d_desc); cudaFree(At->d_val); cudaFree(At->d_order);
+        delete At;
+        if (A->opt_fwd_atomic == 3) VBC_FAIL(e == cudaErrorMemoryAllocation ? VBC_ENOMEM : VBC_ECUDA, "transposed copy: %s", cudaGetErrorString(e));
+        return VBC_OK;
+    }
+    A->launches += At->launches;
+    At->launches = 0;
+    T->At = At;
+    cudaFree(T->d_rec);
+    T->d_rec = nullptr;
+    return VBC_OK;
+}
+
 // eligible: rows mode always; blocks mode when every stripe has one width that is a multiple of the 16-byte vector
 // (opt_fwd_atomic: 0 = auto, 1 = never, 2 = whenever possible).  Measured (profiles/r01_tuning.md): the index wins
 // for uniform 2D blocks (113 vs 127 us on configs[1]) and loses to 32-lane atomics in rows mode (116 vs 110 us
@@ -428,7 +585,7 @@ static int build_transposed_copy(vbc_mat *A, TIndex *T)
 static bool tindex_eligible(const vbc_mat *A)
 {
     if (A->L == 0 || A->m == 0 || A->opt_fwd_atomic == 1) return false;
-    if (A->desc_mode == DESC_ROWS) return A->opt_fwd_atomic == 2 || A->w_uniform > 0; // one stripe width: the transposed copy is possible
+    if (A->desc_mode == DESC_ROWS) return A->opt_fwd_atomic == 2 || A->w_uniform > 0 || A->ndim == 2; // one stripe width, or variable 2D blocks: a transposed copy is possible
     const int VE = 16 / (int)vt_size(A->vt);
     return A->w_uniform > 0 && (A->w_uniform % VE) == 0 && A->u0 * (A->w_uniform / VE) <= 32;
 }
@@ -438,8 +595,14 @@ int ensure_tindex(vbc_mat *A)
     if (A->tindex || A->opt_fwd_no_copy || !tindex_eligible(A)) return VBC_OK;
     TIndex *T = new (std::nothrow) TIndex();
     if (!T) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
-    int rc = A->desc_mode == DESC_ROWS ? build_tindex_mode<DESC_ROWS>(A, T) : build_tindex_mode<DESC_BLOCKS>(A, T);
-    if (rc == VBC_OK && A->opt_fwd_atomic != 2) rc = A->vt == VBC_F64 ? build_transposed_copy<double>(A, T) : build_transposed_copy<float>(A, T);
+    int rc;
+    if (A->ndim == 2 && A->desc_mode == DESC_ROWS && A->opt_fwd_atomic != 2 && A->w_uniform <= 0) { // variable blocks: the copy is built from the canonical block arrays
+        if (A->it == VBC_I64) rc = A->vt == VBC_F64 ? build_transposed_blocks<int64_t, double>(A, T) : build_transposed_blocks<int64_t, float>(A, T);
+        else rc = A->vt == VBC_F64 ? build_transposed_blocks<int32_t, double>(A, T) : build_transposed_blocks<int32_t, float>(A, T);
+    } else {
+        rc = A->desc_mode == DESC_ROWS ? build_tindex_mode<DESC_ROWS>(A, T) : build_tindex_mode<DESC_BLOCKS>(A, T);
+        if (rc == VBC_OK && A->opt_fwd_atomic != 2) rc = A->vt == VBC_F64 ? build_transposed_copy<double>(A, T) : build_transposed_copy<float>(A, T);
+    }
     if (rc != VBC_OK) { destroy_tindex(T); return rc; }
     if (!T->At && A->desc_mode == DESC_ROWS && A->opt_fwd_atomic != 2) { destroy_tindex(T); A->opt_fwd_no_copy = 1; return VBC_OK; } // rows mode without the copy: atomics win over the index
     A->tindex = T;
@@ -450,7 +613,7 @@ int ensure_tindex(vbc_mat *A)
 int64_t tindex_bytes(const vbc_mat *A)
 {
     if (!A->tindex) return 0;
-    if (A->tindex->At) return (int64_t)sizeof(StripeMeta) * ((int64_t)A->tindex->nkeys + 1) + 4 * A->ndesc;
+    if (A->tindex->At) return (int64_t)sizeof(StripeMeta) * ((int64_t)A->tindex->nkeys + 1) + 4 * A->tindex->At->ndesc;
     return (int64_t)sizeof(TRec) * A->ndesc + 4 * ((int64_t)A->tindex->nkeys + 1);
 }
 
@@ -484,7 +647,7 @@ static int launch_fwdt_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
 
 int launch_fwdt(vbc_mat *A, double alpha, const void *x, double beta, void *y)
 {
-    if (A->tindex->At && A->tindex->mode == DESC_ROWS && (A->w_uniform % (16 / (int)vt_size(A->vt))) == 0) {
+    if (A->tindex->At && A->tindex->mode == DESC_ROWS && A->w_uniform > 0 && (A->w_uniform % (16 / (int)vt_size(A->vt))) == 0) {
         // rows mode: the copy is row-contiguous segments -> a dot product per row (k_fwdc_rows)
         const vbc_mat *At = A->tindex->At;
         const int VE = 16 / (int)vt_size(A->vt), vps = A->w_uniform / VE;

@@ -385,7 +385,7 @@ __global__ void k_class_scatter(const StripeMeta *__restrict__ meta, int64_t L, 
 
 // Group the stripes by kernel-body class when the matrix mixes several (variable widths): a warp then runs
 // one body instead of serialising up to four.
-static int build_class_order(vbc_mat *A)
+int build_class_order(vbc_mat *A)
 {
     const int64_t L = A->L;
     A->nclasses = 1;

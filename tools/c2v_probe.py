@@ -23,3 +23,18 @@ for g in (0, 8, 16, 32):
     out[f"G{g}_us"] = round(med * 1e6, 1)
     out[f"G{g}_err"] = err
 print(json.dumps(out))
+# forward multiply y = B x: auto mode (variable blocks: the rows-mode transposed copy), the atomic scatter kernel, the unit index
+xn = synth.vector(A.n, 9)
+xnd, ymd = torch.from_numpy(xn).cuda(), torch.empty(A.m, dtype=torch.float64, device="cuda")
+fref = S @ xn
+fb = abs(S) @ np.abs(xn)
+fwd = {}
+for mode, name in ((0, "auto"), (1, "atomic"), (2, "unit_index")):
+    B.set_option(_lib.OPT_FWD_MODE, mode)
+    B.set_option(_lib.OPT_FWD_GROUP, 0)
+    vb.mul_(ymd, B, xnd)
+    med, mn = timed_graph(lambda: vb.mul_(ymd, B, xnd), 30)
+    fwd[f"fwd_{name}_us"] = round(med * 1e6, 1)
+    fwd[f"fwd_{name}_err"] = float(np.max(np.abs(ymd.cpu().numpy() - fref) / fb))
+fwd["fwd_bytes"] = B.format_bytes()[2] + 8 * (A.n + A.m)
+print(json.dumps(fwd))
