@@ -176,6 +176,10 @@ __global__ void __launch_bounds__(256) k_trsv_lower(const StripeMeta *__restrict
                 for (int k = 0; k < TB; k++) acc = fma(v[k], (xi[k] >= 0 && !Sentinel<Tv>::is(xv[k])) ? xv[k] : (Tv)0, acc);
             }
         }
+        // The lanes leave the poll loop one by one.  Without an explicit reconvergence here ptxas reaches the first shuffle with
+        // the warp still split and takes its divergent-warp path (BRA.DIV): 1.5 us per level on the dependency chain of the
+        // Float64 solve (2.71 -> 1.2 us per level; the Float32 build happened to reconverge by itself).
+        __syncwarp();
         for (int d = w; d < 32; d <<= 1) {
             const Tv tsum = __shfl_down_sync(0xffffffffu, acc, d);
             if (lane + d < 32) acc += tsum;
