@@ -168,8 +168,11 @@ __global__ void __launch_bounds__(256) k_merge_stripes_warp(const Ti *__restrict
                                                             const Ti *__restrict__ phi_spl, int64_t L,
                                                             const Ti *__restrict__ pi_spl, const int *__restrict__ asg,
                                                             long long *__restrict__ cnt, long long *__restrict__ nvals,
-                                                            const Ti *__restrict__ pos, Ti *__restrict__ idx, const int cap, int *err)
+                                                            const Ti *__restrict__ pos, Ti *__restrict__ idx, const int cap, int *err,
+                                                            int *__restrict__ keep = nullptr)
 {
+    // keep (count pass only): the merged units of stripe l are parked at keep[b, b + n), b = the stripe's first CSC entry (n <= its
+    // entries, so stripes never overlap); the write pass is then a plain copy (k_copy_units) instead of a second merge
     extern __shared__ int merge_smem[]; // per warp: units[cap], outs[cap]
     const int lane = threadIdx.x & 31;
     int *units = merge_smem + (size_t)(threadIdx.x >> 5) * 2 * cap, *outs = units + cap;
@@ -224,8 +227,23 @@ __global__ void __launch_bounds__(256) k_merge_stripes_warp(const Ti *__restrict
                 for (int d = 16; d > 0; d >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, d);
             }
             if (lane == 0) { cnt[l] = n; nvals[l] = (DIM2 ? rows : (long long)n) * (long long)w; }
+            if (keep != nullptr) { const int *src = (w == 1 && !DIM2) ? units : outs; for (int t = lane; t < n; t += 32) keep[b + t] = src[t]; }
         }
         __syncwarp();
+    }
+}
+
+// idx[pos[l] - 1 + t] = keep[first CSC entry of stripe l + t] + 1: the write pass when the count pass kept its merged units
+template <typename Ti>
+__global__ void __launch_bounds__(256) k_copy_units(const Ti *__restrict__ colptr, const Ti *__restrict__ phi_spl, int64_t L, const Ti *__restrict__ pos,
+                                                    const int *__restrict__ keep, Ti *__restrict__ idx)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < L; l += nwarps) {
+        const int64_t b = (int64_t)colptr[(int64_t)phi_spl[l] - 1] - 1, out = (int64_t)pos[l] - 1;
+        const int n = (int)((int64_t)pos[l + 1] - 1 - out);
+        for (int t = lane; t < n; t += 32) idx[out + t] = (Ti)(keep[b + t] + 1);
     }
 }
 
@@ -518,9 +536,9 @@ static int pack_t(vbc_mat *A, const Ti *colptr, const Ti *rowval, const Tv *nzva
     const Ti *phi = (const Ti *)A->d_phi_spl, *pi = (const Ti *)A->d_pi_spl;
 
     struct Tmp {
-        int *err = nullptr, *asg = nullptr, *c2s = nullptr;
+        int *err = nullptr, *asg = nullptr, *c2s = nullptr, *keep = nullptr;
         long long *cnt = nullptr, *nv = nullptr, *scan = nullptr;
-        ~Tmp() { cudaFree(err); cudaFree(asg); cudaFree(c2s); cudaFree(cnt); cudaFree(nv); cudaFree(scan); }
+        ~Tmp() { cudaFree(err); cudaFree(asg); cudaFree(c2s); cudaFree(keep); cudaFree(cnt); cudaFree(nv); cudaFree(scan); }
     } t;
     VBC_CUDA(cudaMalloc(&t.err, sizeof(int)));
     VBC_CUDA(cudaMemsetAsync(t.err, 0, sizeof(int), st));
@@ -528,12 +546,14 @@ static int pack_t(vbc_mat *A, const Ti *colptr, const Ti *rowval, const Tv *nzva
     k_check_spl<Ti><<<nblk(L + 1, 256), 256, 0, st>>>(phi, L, n, A->W, PERR_W, t.err); A->launches++;
     if (d2) { k_check_spl<Ti><<<nblk(K + 1, 256), 256, 0, st>>>(pi, K, m, A->U, PERR_U, t.err); A->launches++; }
     int herr = 0;
+    int64_t nnz_in = 0; // entries of the input CSC
     VBC_CUDA(cudaMemcpyAsync(&herr, t.err, sizeof(int), cudaMemcpyDeviceToHost, st));
     VBC_CUDA(cudaStreamSynchronize(st));
     if (herr == 0 && n > 0) { // CSC arrays (the partitions are valid, so the kernels below index them safely)
         int64_t nnz_h = 0;
         { Ti last; VBC_CUDA(cudaMemcpy(&last, colptr + n, sizeof(Ti), cudaMemcpyDeviceToHost)); nnz_h = (int64_t)last - 1; }
         if (nnz_h < 0) VBC_FAIL(VBC_EARG, "ArgumentError: colptr[end] < 1");
+        nnz_in = nnz_h;
         k_check_csc<Ti><<<nblk(n * 8, 256), 256, 0, st>>>(colptr, rowval, n, m, nnz_h, t.err); A->launches++;
         VBC_CUDA(cudaMemcpyAsync(&herr, t.err, sizeof(int), cudaMemcpyDeviceToHost, st));
         VBC_CUDA(cudaStreamSynchronize(st));
@@ -575,8 +595,10 @@ static int pack_t(vbc_mat *A, const Ti *colptr, const Ti *rowval, const Tv *nzva
     const unsigned warp_grid = (unsigned)std::min<int64_t>((L + 7) / 8 > 0 ? (L + 7) / 8 : 1, (int64_t)A->sm_count * 8);
     if (L > 0) {
         if (cap > 0) {
-            if (d2) k_merge_stripes_warp<Ti, true, false><<<warp_grid, 256, merge_smem_bytes, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, cap, t.err);
-            else    k_merge_stripes_warp<Ti, false, false><<<warp_grid, 256, merge_smem_bytes, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, cap, t.err);
+            // scratch for the merged units (4 bytes per CSC entry, freed with the other temporaries); without it the write pass merges again
+            if (nnz_in > 0 && cudaMalloc(&t.keep, sizeof(int) * (size_t)nnz_in) != cudaSuccess) { cudaGetLastError(); t.keep = nullptr; }
+            if (d2) k_merge_stripes_warp<Ti, true, false><<<warp_grid, 256, merge_smem_bytes, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, cap, t.err, t.keep);
+            else    k_merge_stripes_warp<Ti, false, false><<<warp_grid, 256, merge_smem_bytes, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, cap, t.err, t.keep);
         } else {
             if (d2) k_merge_stripes<Ti, true, false><<<nblk(L, 128), 128, 0, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, t.err);
             else    k_merge_stripes<Ti, false, false><<<nblk(L, 128), 128, 0, st>>>(colptr, rowval, phi, L, pi, t.asg, t.cnt, t.nv, nullptr, nullptr, t.err);
@@ -603,7 +625,9 @@ static int pack_t(vbc_mat *A, const Ti *colptr, const Ti *rowval, const Tv *nzva
     VBC_CUDA(cudaMalloc(&A->d_val, sizeof(Tv) * ((size_t)nval + pad)));
     VBC_CUDA(cudaMemsetAsync(A->d_val, 0, sizeof(Tv) * ((size_t)nval + pad), st));
     if (L > 0) {
-        if (cap > 0) {
+        if (cap > 0 && t.keep != nullptr) {
+            k_copy_units<Ti><<<warp_grid, 256, 0, st>>>(colptr, phi, L, (const Ti *)A->d_pos, t.keep, (Ti *)A->d_idx);
+        } else if (cap > 0) {
             if (d2) k_merge_stripes_warp<Ti, true, true><<<warp_grid, 256, merge_smem_bytes, st>>>(colptr, rowval, phi, L, pi, t.asg, nullptr, nullptr, (const Ti *)A->d_pos, (Ti *)A->d_idx, cap, t.err);
             else    k_merge_stripes_warp<Ti, false, true><<<warp_grid, 256, merge_smem_bytes, st>>>(colptr, rowval, phi, L, pi, t.asg, nullptr, nullptr, (const Ti *)A->d_pos, (Ti *)A->d_idx, cap, t.err);
         } else {
