@@ -15,6 +15,8 @@
 // flop/byte ratio grows with k (k = 32, Float64: 3.3 flop/B) -- DFMA throughput and the L2 gathers of X
 // rows bound it, not HBM.  Column-major panels (Julia's layout) are transposed into row-major staging
 // buffers on the device and back.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "walk.cuh"
 
@@ -211,6 +213,91 @@ __global__ void __launch_bounds__(256, VBC_DMMA_MINB) k_spmm_adj_dmma(const Stri
     }
 }
 
+// The same tiles with the X rows loaded the way the memory system wants them and handed to the fragment layout by shuffles.
+// In k_spmm_adj_dmma the four lanes of a quad (the contraction slots) read four DIFFERENT gathered rows, so the coalescer
+// serves every 32-byte sector on its own: 8 L1 wavefronts per fragment load, 10 per stored row, and the L1 data pipe (90 %
+// busy) bounds the kernel.  Here lane 8t' + g' loads 16 bytes of row t' -- eight adjacent lanes cover one 128-byte line, a
+// warp-wide LDG.128 is four full lines -- and the fragment lane 4g + t fetches its four values from loader lane 8t + g with
+// eight SHFL (the val tile stays on per-lane loads: routing it the same way cost 12 us).  The columns of the four N-tiles are permuted to make that a pure lane permutation: tile 0 / 1 = even / odd
+// columns of 0..15, tile 2 / 3 = even / odd columns of 16..31; a lane's accumulators are then columns 4t..4t+3 and
+// 16+4t..19+4t of output row g, stored as four 16-byte vectors.  Needs 16-byte aligned panels with even k and leading
+// dimensions (else the kernel above runs).
+template <int MODE>
+__global__ void __launch_bounds__(256, VBC_DMMA_MINB) k_spmm_adj_dmma_v(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
+                                                          const double *__restrict__ val, const double *__restrict__ X, const long long ldx,
+                                                          double *__restrict__ Y, const long long ldy, const int L, const int k,
+                                                          const int u0, const int log2u, const double alpha, const double beta)
+{
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int lt = lane >> 3, lg = lane & 7; // loader role: row lt of a k-step, columns 2*lg, 2*lg + 1 of both 16-column halves
+    const int src = 8 * t + g;               // the loader lane that holds this lane's fragment values
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); l < L; l += nwarps) {
+        const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
+        const int w = b.col - a.col;
+        if (w <= 0) continue;
+        const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
+        for (int kb = 0; kb < k; kb += 32) {
+            const int c0 = kb + 2 * lg, c1 = c0 + 16;
+            const bool ok0 = c0 < k, ok1 = c1 < k; // k is even: a 16-byte vector never straddles the panel's edge
+            for (int wb = 0; wb < w; wb += 8) {
+                double c[4][2];
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) { c[nt][0] = 0.0; c[nt][1] = 0.0; }
+                const bool arow = wb + g < w;
+                const double *vp = val + a.ofs + (long long)t * w + wb + g;
+                int xi_next = lt < R ? row_xindex<MODE>(desc, a.pos, lt, u0, log2u) : -1;
+                constexpr int KS = VBC_DMMA_KS;
+                // (a second register set that is loaded while this one is multiplied was tried: 317 us -- spills at the register
+                // budget of 3 CTAs per SM, and the wait for one set also waits for the loads of the other: they share scoreboards)
+                for (int r = 0; r < R; r += 4 * KS) {
+                    int xi[KS];
+                    xi[0] = xi_next;
+#pragma unroll
+                    for (int q = 1; q < KS; q++) xi[q] = (r + 4 * q + lt < R) ? row_xindex<MODE>(desc, a.pos, r + 4 * q + lt, u0, log2u) : -1;
+                    xi_next = (r + 4 * KS + lt < R) ? row_xindex<MODE>(desc, a.pos, r + 4 * KS + lt, u0, log2u) : -1;
+                    double av[KS];
+                    double2 x0[KS], x1[KS];
+#pragma unroll
+                    for (int q = 0; q < KS; q++) av[q] = (arow && r + 4 * q + t < R) ? __ldcs(vp + 4 * q * (long long)w) : 0.0;
+                    vp += 4 * KS * (long long)w;
+#pragma unroll
+                    for (int q = 0; q < KS; q++) {
+                        const double *xp = X + (long long)(xi[q] >= 0 ? xi[q] : 0) * ldx;
+                        x0[q] = (xi[q] >= 0 && ok0) ? __ldg(reinterpret_cast<const double2 *>(xp + c0)) : make_double2(0.0, 0.0);
+                        x1[q] = (xi[q] >= 0 && ok1) ? __ldg(reinterpret_cast<const double2 *>(xp + c1)) : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int q = 0; q < KS; q++) {
+                        const double b0 = __shfl_sync(0xffffffffu, x0[q].x, src), b1 = __shfl_sync(0xffffffffu, x0[q].y, src);
+                        const double b2 = __shfl_sync(0xffffffffu, x1[q].x, src), b3 = __shfl_sync(0xffffffffu, x1[q].y, src);
+                        dmma_m8n8k4(c[0], av[q], b0);
+                        dmma_m8n8k4(c[1], av[q], b1);
+                        dmma_m8n8k4(c[2], av[q], b2);
+                        dmma_m8n8k4(c[3], av[q], b3);
+                    }
+                }
+                if (arow) { // accumulator (nt, e) is column 4t + 2e + (nt & 1) of half nt >> 1
+                    double *yp = Y + (long long)(a.col + wb + g) * ldy + kb + 4 * t;
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int col = kb + 16 * hf + 4 * t + 2 * e;
+                            if (col < k) {
+                                double2 *p2 = reinterpret_cast<double2 *>(yp + 16 * hf + 2 * e);
+                                double2 o = make_double2(alpha * c[2 * hf][e], alpha * c[2 * hf + 1][e]);
+                                if (beta != 0.0) { const double2 old = *p2; o.x += beta * old.x; o.y += beta * old.y; }
+                                *p2 = o;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <typename Tv, int MODE, int WB, int KT>
 __global__ void __launch_bounds__(256) k_spmm_fwd(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                    const Tv *__restrict__ val, const Tv *__restrict__ X, const long long ldx,
@@ -307,7 +394,10 @@ static int launch_spmm_mode(vbc_mat *A, int trans, int k, Tv alpha, const Tv *X,
                 int64_t g2 = (int64_t)A->sm_count * 8;
                 if (g2 > need) g2 = need;
                 if (g2 < 1) g2 = 1;
-                k_spmm_adj_dmma<MODE><<<(unsigned)g2, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const double *)A->d_val, (const double *)X, ldx,
+                const bool vec = (k % 2) == 0 && (ldx % 2) == 0 && (ldy % 2) == 0 && ((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 16) == 0 && !getenv("VBC_SPMM_NOVEC");
+                if (vec) k_spmm_adj_dmma_v<MODE><<<(unsigned)g2, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const double *)A->d_val, (const double *)X, ldx,
+                                                                          (double *)Y, ldy, L, k, A->u0, log2u, (double)alpha, (double)beta);
+                else k_spmm_adj_dmma<MODE><<<(unsigned)g2, 256, 0, A->stream>>>(A->d_meta, A->d_desc, (const double *)A->d_val, (const double *)X, ldx,
                                                                           (double *)Y, ldy, L, k, A->u0, log2u, (double)alpha, (double)beta);
                 A->launches++;
                 VBC_CUDA(cudaGetLastError());
