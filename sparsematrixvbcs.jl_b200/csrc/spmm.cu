@@ -15,6 +15,8 @@
 // flop/byte ratio grows with k (k = 32, Float64: 3.3 flop/B) -- DFMA throughput and the L2 gathers of X
 // rows bound it, not HBM.  Column-major panels (Julia's layout) are transposed into row-major staging
 // buffers on the device and back.
+#include <cuda.h>
+#include <limits.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -298,6 +300,224 @@ __global__ void __launch_bounds__(256, VBC_DMMA_MINB) k_spmm_adj_dmma_v(const St
     }
 }
 
+// ---- Adjoint SpMM fed by TMA row gathers (Float64, rows mode, uniform stripe width 8, panels of <= 32 right-hand sides) -------------
+// Same row-stream decomposition as k_spmm_adj_stream, same FP64 tensor tiles as k_spmm_adj_dmma, but the gathered X rows never
+// pass through the load/store unit as per-lane requests (the L1 data pipe is what bounds both of those kernels):
+//   * one `cp.async.bulk.tensor.2d ... tile::gather4` fetches four arbitrary rows of X (row indices straight from desc) as a
+//     [4][16] Float64 tile; the tensor map is encoded with a {16, 1} box and SWIZZLE_128B, so that an 8-row x 128-byte atom
+//     holds rows r = 0..7 with their 16-byte chunks XORed by r;
+//   * a k-step of the m8n8k4 tile takes rows {0, 3, 4, 7} or {1, 2, 5, 6} of the atom: the four lanes of a quad (contraction
+//     slots t = 0..3) then read chunks whose XOR patterns differ in bits 1-2 -- every B-fragment LDS.64 is conflict-free
+//     (2 wavefronts for 256 bytes; the same fragment costs 8 when loaded from global memory);
+//   * the 8 x 8 values of the chunk's val rows arrive by one 1-D bulk copy on the same mbarrier (A fragments: 2-way conflicts).
+// Every warp runs its own ring of S stages (8 rows each) with one mbarrier per stage: no CTA-wide synchronisation at all.
+__device__ __forceinline__ void mbar_init(const unsigned bar, const unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(const unsigned bar, const unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(const unsigned bar, const unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_gather4(const unsigned dst, const CUtensorMap *tm, const int c0, const int r0, const int r1, const int r2, const int r3, const unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void bulk_copy_g2s(const unsigned dst, const void *src, const unsigned bytes, const unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+#ifndef VBC_TMA_S
+#define VBC_TMA_S 4
+#endif
+#ifndef VBC_TMA_MINB
+#define VBC_TMA_MINB 2
+#endif
+constexpr int TMA_S = VBC_TMA_S;                           // stages per warp
+constexpr int TMA_CR = 8;                                  // rows per stage
+constexpr int TMA_STAGE_X = 2048, TMA_STAGE_V = 512;       // bytes per stage: two swizzle atoms of X, 8 x 8 values
+constexpr int TMA_WARP_BYTES = TMA_S * (TMA_STAGE_X + TMA_STAGE_V);
+constexpr int TMA_SMEM_BYTES = 8 * TMA_WARP_BYTES + 8 * TMA_S * 8 + 8 * (TMA_S + 2) * 16 + 1024; // + mbarriers + chunk queue + alignment slack
+
+template <bool FULL>
+__global__ void __launch_bounds__(256, VBC_TMA_MINB) k_spmm_adj_tma(const __grid_constant__ CUtensorMap tmX, const StripeMeta *__restrict__ meta,
+                                                         const int *__restrict__ desc, const double *__restrict__ val, double *__restrict__ Y,
+                                                         const long long ldy, const int L, const int nunits, const double ratio, const int k,
+                                                         const int kb, const double alpha, const double beta)
+{
+    constexpr int S = TMA_S, CR = TMA_CR, W = 8;
+    constexpr int DEAD = INT_MIN;
+    extern __shared__ unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int wq = (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5); // the warp's index as a value known to be warp-uniform
+    const int nwarps = (int)gridDim.x * 8, wid = (int)blockIdx.x * 8 + wq;
+    const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
+    const unsigned xs = smem0 + (unsigned)wq * (S * TMA_STAGE_X);                        // [S][2 atoms][8 rows][128 B]
+    const unsigned vsm = smem0 + 8u * S * TMA_STAGE_X + (unsigned)wq * (S * TMA_STAGE_V); // [S][8 rows][8 values]
+    const unsigned bars = smem0 + 8u * S * (TMA_STAGE_X + TMA_STAGE_V) + (unsigned)wq * (S * 8);
+    const unsigned queue = smem0 + 8u * S * (TMA_STAGE_X + TMA_STAGE_V) + 8u * S * 8 + (unsigned)wq * ((S + 2) * 16); // chunk descriptors {unit, first row, rows, -}
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < S; s++) mbar_init(bars + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    if (wid >= nunits) return;
+
+    auto unit_lo = [&](const int u) { return u >= nunits ? L : min(L, (int)((double)u * ratio)); };
+    // ---- chunk generator (as in k_spmm_adj_stream): every unit yields ceil(rows / 8) chunks, at least one
+    int gu = wid, gP, gE, gnP = 0, gnE = 0;
+    bool gfresh = true;
+    gP = __ldg(&meta[unit_lo(gu)].pos); gE = __ldg(&meta[unit_lo(gu + 1)].pos);
+    if (gu + nwarps < nunits) { gnP = __ldg(&meta[unit_lo(gu + nwarps)].pos); gnE = __ldg(&meta[unit_lo(gu + nwarps + 1)].pos); }
+    int cu, cP, cn;
+    auto gen = [&]() {
+        if (gP >= gE && !gfresh) {
+            gu += nwarps; gP = gnP; gE = gnE; gfresh = true;
+            if (gu + nwarps < nunits) { gnP = __ldg(&meta[unit_lo(gu + nwarps)].pos); gnE = __ldg(&meta[unit_lo(gu + nwarps + 1)].pos); }
+        }
+        if (gu < nunits) { cu = gu; cP = gP; cn = min(CR, gE - gP); gP += CR; gfresh = false; }
+        else { cu = -1; cP = 0; cn = 0; }
+    };
+    auto put_desc = [&](const int slot) { // chunk descriptor -> queue[slot] (every lane writes the same words)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(queue + 16u * (unsigned)slot), "r"(cu), "r"(cP), "r"(cn), "r"(0) : "memory");
+    };
+    auto get_desc = [&](const int slot, int &u, int &P, int &n) {
+        int z;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u), "=r"(P), "=r"(n), "=r"(z) : "r"(queue + 16u * (unsigned)slot) : "memory");
+    };
+    auto load_idx = [&](const int P, const int n) { return lane < n ? __ldcs(desc + P + lane) : 0; };
+    // requests of one chunk, all from ONE elected lane with operands the compiler knows to be warp-uniform: every row index is
+    // extracted with a warp reduction (REDUX writes a uniform register), so UTMALDG / UBLKCP take their operands without the
+    // ELECT / R2UR / branch waterfall that per-lane values need (12 instructions per request in the first version of this kernel)
+    auto issue = [&](const int u, const int P, const int n, const int idx, const int stage) {
+        int r[CR];
+#pragma unroll
+        for (int j = 0; j < CR; j++) r[j] = __reduce_add_sync(0xffffffffu, lane == j ? idx : 0);
+        if (u < 0) return;
+        const unsigned bar = bars + 8u * (unsigned)stage, dst = xs + (unsigned)stage * TMA_STAGE_X;
+        if (elect_one()) {
+            mbar_expect_tx(bar, (unsigned)(TMA_STAGE_X + n * W * 8));
+            if (n > 0) bulk_copy_g2s(vsm + (unsigned)stage * TMA_STAGE_V, val + (long long)P * W, (unsigned)(n * W * 8), bar);
+            tma_gather4(dst, &tmX, kb, r[0], r[1], r[2], r[3], bar);
+            tma_gather4(dst + 512u, &tmX, kb, r[4], r[5], r[6], r[7], bar);
+            tma_gather4(dst + 1024u, &tmX, kb + 16, r[0], r[1], r[2], r[3], bar);
+            tma_gather4(dst + 1536u, &tmX, kb + 16, r[4], r[5], r[6], r[7], bar);
+        }
+    };
+
+    // ---- prologue: chunks 0..S described (queue of S + 2 slots), 0..S-2 requested; A = the chunk whose requests go out next
+    // (S-1 ahead of the one being multiplied), B = the one after it: row indices are fetched two iterations before they are used
+    int idxA = 0, uA = -1, PA = 0, nA = 0, idxB = 0, uB = -1, PB = 0, nB = 0;
+#pragma unroll
+    for (int q = 0; q <= S; q++) {
+        gen(); put_desc(q);
+        const int idx = load_idx(cP, cn);
+        if (q < S - 1) issue(cu, cP, cn, idx, q);
+        else if (q == S - 1) { idxA = idx; uA = cu; PA = cP; nA = cn; }
+        else { idxB = idx; uB = cu; PB = cP; nB = cn; }
+    }
+    __syncwarp();
+
+    // ---- consumer state (stripe ends of the unit in `segs`, one per lane)
+    int cur_u = -1, l = 0, l0 = 0, ulast = 0, seg_end = DEAD, segs = 0;
+    int nlo = unit_lo(wid), nlast = unit_lo(wid + 1);
+    int nsegs = lane < nlast - nlo ? __ldg(&meta[nlo + 1 + lane].pos) : 0;
+    double c[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) c[nt][0] = c[nt][1] = 0.0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const int col = kb + nt * 8 + 2 * t;
+            if (FULL || col < k) {
+                double2 *yp = reinterpret_cast<double2 *>(Y + ((long long)l * W + g) * ldy + col);
+                double2 o = make_double2(alpha * c[nt][0], alpha * c[nt][1]);
+                if (beta != 0.0) { const double2 old = *yp; o.x += beta * old.x; o.y += beta * old.y; }
+                *yp = o;
+            }
+            c[nt][0] = c[nt][1] = 0.0;
+        }
+    };
+    // this lane's rows in the two k-steps of a chunk and the swizzled byte offsets of its B-fragment elements (n-tiles 0 / 1; 2 and 3: + 1024)
+    const int r_ks0 = 2 * t + (t & 1), r_ks1 = 2 * t + 1 - (t & 1); // {0, 3, 4, 7} and {1, 2, 5, 6}
+    const unsigned xo0 = (unsigned)(r_ks0 * 128 + ((((g >> 1) ^ r_ks0) & 7) << 4) + (g & 1) * 8);
+    const unsigned xo1 = (unsigned)(r_ks1 * 128 + ((((g >> 1) ^ r_ks1) & 7) << 4) + (g & 1) * 8);
+    const unsigned vo0 = (unsigned)(r_ks0 * 64 + g * 8), vo1 = (unsigned)(r_ks1 * 64 + g * 8);
+
+    int stage = 0, rslot = 0;
+    unsigned parity = 0;
+    for (;;) {
+        int u0c, P0c, n0c;
+        get_desc(rslot, u0c, P0c, n0c);
+        // the stage multiplied in the previous iteration is free: chunk (S-1 ahead)'s requests go there
+        issue(uA, PA, nA, idxA, stage == 0 ? S - 1 : stage - 1);
+        idxA = idxB; uA = uB; PA = PB; nA = nB;
+        // describe the chunk S + 1 ahead (into the slot read one iteration ago) and fetch its row indices
+        gen(); put_desc(rslot == 0 ? S + 1 : rslot - 1);
+        uB = cu; PB = cP; nB = cn;
+        idxB = load_idx(cP, cn);
+        if (u0c != cur_u) {
+            if (seg_end != DEAD) { while (l < ulast) { flush(); l++; } }
+            if (u0c < 0) return;
+            cur_u = u0c; l = l0 = nlo; ulast = nlast; segs = nsegs;
+            nlo = unit_lo(cur_u + nwarps); nlast = unit_lo(cur_u + nwarps + 1);
+            nsegs = lane < nlast - nlo ? __ldg(&meta[nlo + 1 + lane].pos) : 0;
+            seg_end = __shfl_sync(0xffffffffu, segs, 0);
+        }
+        const unsigned bar = bars + 8u * (unsigned)stage;
+        for (unsigned spins = 0; !mbar_try_wait(bar, parity); spins++)
+            if (spins > (1u << 24)) __trap(); // a request that never completes must not hang the GPU (try_wait itself blocks for a while)
+        const unsigned xb = xs + (unsigned)stage * TMA_STAGE_X, vb = vsm + (unsigned)stage * TMA_STAGE_V;
+        double a0, a1, b0[4], b1[4];
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a0) : "r"(vb + vo0) : "memory");
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a1) : "r"(vb + vo1) : "memory");
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const unsigned ofs = (nt >> 1) * 1024u;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b0[nt]) : "r"(xb + ofs + ((nt & 1) ? (xo0 ^ 64u) : xo0)) : "memory");
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b1[nt]) : "r"(xb + ofs + ((nt & 1) ? (xo1 ^ 64u) : xo1)) : "memory");
+        }
+        if (seg_end > P0c + CR) { // all eight rows belong to the open stripe
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], a0, b0[nt]);
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], a1, b1[nt]);
+        } else {
+            int lo = P0c;
+            while (seg_end != DEAD) {
+                const int hi = min(seg_end, P0c + CR);
+                if (hi > lo) { // rows [lo, hi) of the chunk belong to stripe l: everything else is masked on both operands
+                    const bool m0 = P0c + r_ks0 >= lo && P0c + r_ks0 < hi, m1 = P0c + r_ks1 >= lo && P0c + r_ks1 < hi;
+                    const double am0 = m0 ? a0 : 0.0, am1 = m1 ? a1 : 0.0;
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], am0, m0 ? b0[nt] : 0.0);
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], am1, m1 ? b1[nt] : 0.0);
+                }
+                if (seg_end > P0c + CR) break; // the stripe continues in the next chunk
+                flush(); l++;
+                seg_end = l == ulast ? DEAD : __shfl_sync(0xffffffffu, segs, l - l0);
+                lo = hi;
+            }
+        }
+        __syncwarp(); // every lane has read the stage before the next iteration overwrites it
+        stage = stage == S - 1 ? 0 : stage + 1;
+        if (stage == 0) parity ^= 1u;
+        rslot = rslot == S + 1 ? 0 : rslot + 1;
+    }
+}
+
+
 template <typename Tv, int MODE, int WB, int KT>
 __global__ void __launch_bounds__(256) k_spmm_fwd(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
                                                    const Tv *__restrict__ val, const Tv *__restrict__ X, const long long ldx,
@@ -390,6 +610,52 @@ static int launch_spmm_mode(vbc_mat *A, int trans, int k, Tv alpha, const Tv *X,
     if (trans) {
         if (L == 0) return VBC_OK;
         if constexpr (sizeof(Tv) == 8) {
+            // one stripe width 8 over the whole matrix, rows mode, 16-byte aligned even-k panels: the TMA-fed kernel applies
+            const int Wu = A->w_uniform;
+            const bool streamable = MODE == DESC_ROWS && Wu == 8 && A->nval == A->ndesc * Wu && A->n == (int64_t)L * Wu &&
+                                    (k % 2) == 0 && (ldx % 2) == 0 && (ldy % 2) == 0 && ldx < (1ll << 28) && ((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 16) == 0;
+            if (A->opt_spmm_simt == 3 && streamable && Wu == 8) { // TMA-fed tensor tiles
+                typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                             const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+                static EncodeFn encode = nullptr;
+                static bool attr_set = false;
+                if (!encode) {
+                    cudaDriverEntryPointQueryResult qres;
+                    void *fn = nullptr;
+                    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) VBC_FAIL(VBC_ECUDA, "cuTensorMapEncodeTiled is not available");
+                    encode = (EncodeFn)fn;
+                }
+                if (!attr_set) {
+                    VBC_CUDA(cudaFuncSetAttribute(k_spmm_adj_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+                    VBC_CUDA(cudaFuncSetAttribute(k_spmm_adj_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+                    attr_set = true;
+                }
+                CUtensorMap tm;
+                const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)A->m}, gstr[1] = {(cuuint64_t)ldx * 8};
+                const cuuint32_t box[2] = {16, 1}, estr[2] = {1, 1};
+                const CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<Tv *>(X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (cr != CUDA_SUCCESS) VBC_FAIL(VBC_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+                int64_t g2 = (int64_t)A->sm_count * VBC_TMA_MINB;
+                const int64_t nw = g2 * 8;
+                const double avg_rows = (double)A->ndesc / (double)L;
+                int64_t U0 = (int64_t)(384.0 / (avg_rows > 1.0 ? avg_rows : 1.0) + 0.5);
+                if (U0 < 1) U0 = 1;
+                if (U0 > 24) U0 = 24;
+                int64_t q = (L + nw * U0 / 2) / (nw * U0);
+                if (q < 1) q = 1;
+                while ((double)L / (double)(nw * q) > 30.0) q++;
+                int64_t nunits = nw * q;
+                if (nunits > L) { nunits = L; g2 = (nunits + 7) / 8; }
+                const double ratio = (double)L / (double)nunits;
+                for (int kb = 0; kb < k; kb += 32) {
+                    if (k - kb >= 32) k_spmm_adj_tma<true><<<(unsigned)g2, 256, TMA_SMEM_BYTES, A->stream>>>(tm, A->d_meta, A->d_desc, (const double *)A->d_val, (double *)Y, ldy, L, (int)nunits, ratio, k, kb, (double)alpha, (double)beta);
+                    else k_spmm_adj_tma<false><<<(unsigned)g2, 256, TMA_SMEM_BYTES, A->stream>>>(tm, A->d_meta, A->d_desc, (const double *)A->d_val, (double *)Y, ldy, L, (int)nunits, ratio, k, kb, (double)alpha, (double)beta);
+                    A->launches++;
+                }
+                VBC_CUDA(cudaGetLastError());
+                return VBC_OK;
+            }
             if (A->opt_spmm_simt != 1) { // Float64: tensor (DMMA) tiles
                 int64_t g2 = (int64_t)A->sm_count * 8;
                 if (g2 > need) g2 = need;
