@@ -767,7 +767,27 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    if world > 1:
+        bind_to_gpu_cpus(local_rank)  # N = 1 keeps every core: the cpu_baseline leg uses them all
     run_ours(args, rank, world, local_rank)
+
+
+def bind_to_gpu_cpus(local_rank):
+    """Pin this rank to the CPU cores NVML reports as local to its GPU (before any pinned host buffer is allocated: first touch
+    then places the e2e leg's host vectors on the GPU's own NUMA node, so that N ranks do not share one memory controller for
+    their PCIe copies).  Best effort: any failure leaves the affinity alone."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

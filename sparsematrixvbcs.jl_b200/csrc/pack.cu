@@ -428,7 +428,7 @@ int build_class_order(vbc_mat *A)
     if (h[256] == h[257] && h[257] > 0) A->w_uniform = (int)h[257];
     A->has_unaligned = 0;
     A->opt_no_flat = getenv("VBC_NO_FLAT") != nullptr; // experiments: per-element bodies for unaligned stripes, as before round 2
-    for (int c = 129; c < 192; c++) if (h[c]) A->has_unaligned = 1; // class codes 1 + 2 * 64 + cpr: one element per load
+    for (int c = 65; c < 192; c++) if (h[c]) A->has_unaligned = 1; // class codes 1 + epv_code * 64 + cpr with epv_code 1, 2: stripes that are not 16-byte aligned
     int ncls = 0;
     unsigned run = 0, cur[256];
     for (int c = 0; c < 256; c++) { cur[c] = run; run += h[c]; if (h[c]) ncls++; }

@@ -278,6 +278,84 @@ __device__ __forceinline__ void adj_stripe_flat(const StripeMeta a, const Stripe
     __syncwarp(gmask); // the group's x row is rewritten by the next stripe
 }
 
+// The same for Float32 (four elements per 16-byte vector): a stripe is unaligned when its width or its start is not a multiple
+// of four.  per = w / gcd(w, 4) lanes make a period (4 * per elements = 4 / gcd whole rows), every lane keeps four accumulators
+// with fixed columns; after the strided shuffle tree the period's 4 * per partial sums go through the group's shared-memory row
+// (free once the loop is done) and lane j adds the 4 / gcd of them that belong to column j.
+template <int G, int MODE, bool XC>
+__device__ __forceinline__ void adj_stripe_flat4(const StripeMeta a, const StripeMeta b, const int w, const int R, const int lane, const unsigned gmask,
+                                                 const int *__restrict__ desc, const float *__restrict__ val, const float *__restrict__ x,
+                                                 float *__restrict__ y, const int u0, const int log2u, const float alpha, const float beta,
+                                                 float *__restrict__ xs)
+{
+    const int n = (int)(b.ofs - a.ofs);
+    const int shift = (int)(a.ofs & 3);
+    const int lg = (w & 3) == 0 ? 2 : ((w & 1) == 0 ? 1 : 0); // log2 gcd(w, 4)
+    const int per = w >> lg;
+    const int reps = small_div(G, per);
+    const int S = reps * per;            // active lanes
+    const int m = 4 >> lg;               // rows per period = partial sums per column
+    const int rstep = reps * m;          // rows per step (4S / w)
+    const int q0 = 4 * lane - shift;     // this lane's first element in step 0, relative to the slab (negative: before the slab)
+    int r[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) r[e] = q0 + e < 0 ? -small_div(w - 1 - (q0 + e), w) : small_div(q0 + e, w); // floor((q0 + e) / w): up to three elements precede the slab
+    const float4 *vp = reinterpret_cast<const float4 *>(val + (a.ofs - shift)) + lane;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int UNR = VBC_ADJ_UNR;
+    int p = lane < S ? q0 : n;
+    float4 v[UNR];
+    auto load_batch = [&]() {
+#pragma unroll
+        for (int k = 0; k < UNR; k++) {
+            v[k] = (p + k * 4 * S < n) ? ld_val(vp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vp += S;
+        }
+    };
+    load_batch();
+    for (int i = lane; i < R; i += G) xs[i] = ld_x<float, XC>(x + row_xindex<MODE>(desc, a.pos, i, u0, log2u));
+    __syncwarp(gmask);
+    while (p < n) {
+#pragma unroll
+        for (int k = 0; k < UNR; k++) {
+            const int pk = p + k * 4 * S;
+            const float ve[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const bool ok = pk + e >= 0 && pk + e < n;
+                const float xv = ok ? xs[r[e] + k * rstep] : 0.f;
+                if (ok) acc[e] = fmaf(ve[e], xv, acc[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) r[e] += UNR * rstep;
+        p += UNR * 4 * S;
+        if (p < n) load_batch();
+    }
+    __syncwarp(gmask);
+    for (int d = per; d < G; d <<= 1) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float t = __shfl_down_sync(gmask, acc[e], d, G);
+            if (lane + d < G) acc[e] += t;
+        }
+    }
+    if (lane < per) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) xs[4 * lane + e] = acc[e]; // partial sum of period element u = 4 * lane + e, column (u - shift) mod w
+    }
+    __syncwarp(gmask);
+    float *yp = y + a.col;
+    for (int j = lane; j < w; j += G) {
+        int u = j + shift;
+        u -= small_div(u, w) * w;
+        float sum = 0.f;
+        for (int t = 0; t < m; t++) sum += xs[u + t * w];
+        yp[j] = (beta == 0.f) ? alpha * sum : alpha * sum + beta * yp[j];
+    }
+    __syncwarp(gmask); // the group's row is rewritten by the next stripe
+}
+
 // wide stripes (more vectors per row than lanes): one lane per column, serial over rows
 template <typename Tv, int G, int MODE, bool XC>
 __device__ __noinline__ void adj_stripe_wide(const StripeMeta a, const StripeMeta b, const int w, const int lane,
@@ -320,6 +398,16 @@ __device__ __forceinline__ void adj_one_stripe(const StripeMeta a, const StripeM
     constexpr int VE = 16 / (int)sizeof(Tv);
     const int w = b.col - a.col;
     if (w <= 0) return;
+    if constexpr (FLAT && sizeof(Tv) == 4) {
+        if ((w & 3) || (a.ofs & 3)) {
+            const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
+            const int per = (w & 3) == 0 ? (w >> 2) : ((w & 1) == 0 ? (w >> 1) : w);
+            if (per <= G && R <= FLAT_XCAP_PER_LANE * G) {
+                adj_stripe_flat4<G, MODE, XC>(a, b, w, R, lane, gmask, desc, (const float *)val, (const float *)x, (float *)y, u0, log2u, (float)alpha, (float)beta, (float *)xs);
+                return;
+            }
+        }
+    }
     if constexpr (FLAT && sizeof(Tv) == 8) {
         if (VBC_FLAT_ALL || (w & 1) || (a.ofs & 1)) {
             const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
@@ -401,15 +489,15 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj(const StripeMeta *__restrict__ meta, c
                            desc, val, x, y, u0, log2u, alpha, beta);
 }
 
-// the same loop for Float64 matrices that hold unaligned stripes: those take adj_stripe_flat, with one shared-memory x row per group
-template <int G, int MODE>
+// the same loop for matrices that hold unaligned stripes: those take adj_stripe_flat / adj_stripe_flat4, with one shared-memory x row per group
+template <typename Tv, int G, int MODE>
 __global__ void VBC_ADJ_BOUNDS k_spmv_adj_flat(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
-                                               const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
-                                               const int *__restrict__ order, const int L, const int u0, const int log2u, const double alpha, const double beta)
+                                               const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ y,
+                                               const int *__restrict__ order, const int L, const int u0, const int log2u, const Tv alpha, const Tv beta)
 {
-    __shared__ double xs_all[256 / G][FLAT_XCAP_PER_LANE * G];
-    adj_range<double, G, MODE, true>(meta, order, 0, L, (int)((blockIdx.x * blockDim.x + threadIdx.x) / G), (int)((gridDim.x * blockDim.x) / G),
-                                     desc, val, x, y, u0, log2u, alpha, beta, xs_all[threadIdx.x / G]);
+    __shared__ Tv xs_all[256 / G][FLAT_XCAP_PER_LANE * G];
+    adj_range<Tv, G, MODE, true>(meta, order, 0, L, (int)((blockIdx.x * blockDim.x + threadIdx.x) / G), (int)((gridDim.x * blockDim.x) / G),
+                                 desc, val, x, y, u0, log2u, alpha, beta, xs_all[threadIdx.x / G]);
 }
 
 // ---- adjoint with the x exchange of the row-partitioned iteration fused in (north_star (e)) -------------------------
@@ -736,16 +824,16 @@ static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
     const int64_t need = ((l1 - l0) * G + 255) / 256;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    if constexpr (sizeof(Tv) == 8 && G >= 8) {
-        if (A->has_unaligned && !A->opt_no_flat) { // odd widths / odd slab starts: the flat-slab bodies (one shared-memory x row per group)
+    if constexpr (G >= 8) {
+        if (A->has_unaligned && !A->opt_no_flat) { // stripes that are not 16-byte aligned: the flat-slab bodies (one shared-memory x row per group)
             int occf = 0;
-            VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occf, k_spmv_adj_flat<G, MODE>, 256, 0));
+            VBC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occf, k_spmv_adj_flat<Tv, G, MODE>, 256, 0));
             if (occf < 1) occf = 1;
             if (A->opt_grid_mult > 0) occf = A->opt_grid_mult;
             int64_t gridf = (int64_t)A->sm_count * occf;
             if (gridf > need) gridf = need;
             if (gridf < 1) gridf = 1;
-            k_spmv_adj_flat<G, MODE><<<(unsigned)gridf, 256, 0, A->stream>>>(A->d_meta + l0, A->d_desc, (const double *)A->d_val, (const double *)x, (double *)y, A->d_order, (int)(l1 - l0), A->u0, ilog2_exact(A->u0), (double)alpha, (double)beta);
+            k_spmv_adj_flat<Tv, G, MODE><<<(unsigned)gridf, 256, 0, A->stream>>>(A->d_meta + l0, A->d_desc, (const Tv *)A->d_val, x, y, A->d_order, (int)(l1 - l0), A->u0, ilog2_exact(A->u0), alpha, beta);
             A->launches++;
             VBC_CUDA(cudaGetLastError());
             return VBC_OK;
