@@ -1,8 +1,8 @@
-// spmm_variants.cuh -- two adjoint-SpMM kernels that were built, validated on the GPU (bit-level agreement with the shipped
-// kernel to 1e-15 relative, tests of commit "SpMM experiments") and measured in round 2, and that LOST to the shipped
-// k_spmm_adj_dmma on configs[2] (290 / 292 us against 275 us): see profiles/r02_spmm_attempts.md for the ncu numbers and what
-// each one is bound by.  Kept as a record; NOT compiled into libvbc.so.  To revive one, paste the kernel and its launch block
-// back into csrc/spmm.cu (the launch block goes in front of the DMMA launch in launch_spmm_mode) and include <cuda.h>, <limits.h>.
+// spmm_variants.cuh -- adjoint-SpMM kernels that were built, validated on the GPU (agreement with the shipped kernel to 1e-15
+// relative, tests of commit "SpMM experiments") and measured in round 2, and that LOST to the shipped kernels on configs[2]:
+// the row-stream DFMA kernel (292 us) and the FIRST version of the TMA gather4-fed DMMA kernel (290 us; its second version,
+// with the row indices passed through REDUX into uniform registers, is in csrc/spmm.cu as k_spmm_adj_tma: 238 us).  See
+// profiles/r02_spmm_attempts.md for the ncu numbers and what each one is bound by.  Kept as a record; NOT compiled.
 #if 0
 // ===================================================== kernels ======================================================
 // Adjoint SpMM as a row STREAM (Float64, rows mode, one stripe width W for the whole matrix, a panel of <= 32 right-hand
