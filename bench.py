@@ -292,7 +292,7 @@ def extra_configs(peak):
     err = bound_err(Y.cpu().numpy(), S.T @ Xh, abs(S).T @ np.abs(Xh), 1e-12)
     nb = B.format_bytes()[1] + 8 * k * (A.m + A.n)
     out["C3_SpMM_1D_f64_k32"] = {"us": med * 1e6, "us_min": mn * 1e6, "algorithmic_bytes": nb, "GBps": nb / med / 1e9, "frac_of_hbm_peak": nb / med / 1e9 / peak,
-                                 "tflops": 2.0 * A.nnz * k / med / 1e12, "kernel": "k_spmm_adj_dmma_v (FP64 mma.sync m8n8k4 tiles; X rows loaded as full lines, fragments by lane permutation)", "parity_err_over_bound_1e-12": err,
+                                 "tflops": 2.0 * A.nnz * k / med / 1e12, "kernel": "k_spmm_adj_tma (FP64 mma.sync m8n8k4 tiles fed by TMA tile::gather4 row gathers)", "parity_err_over_bound_1e-12": err,
                                  "parity": "unpinned by the reference (SURVEY.md R3); checked against k independent CSC products"}
     B.close()
     del A, S, X, Y, Xh

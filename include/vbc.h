@@ -58,9 +58,10 @@ enum vbc_option {
                               *       variable blocks use the atomic scatter kernel;
                               *   1 = always the atomic scatter kernel;  2 = the transposed unit index (16 B per unit, no second copy of
                               *       the values) whenever the layout allows it;  3 = the transposed copy, regardless of free memory    */
-    VBC_OPT_SPMM_SIMT = 6,   /* Float64 adjoint SpMM: 0 = FP64 tensor (DMMA m8n8k4) tiles fed by per-lane loads, 1 = the SIMT (DFMA)
-                              * kernel, 3 = the same tiles fed by TMA row gathers (cp.async.bulk.tensor tile::gather4; needs one stripe
-                              * width 8, rows mode and 16-byte aligned panels with even k / leading dimensions, else behaves as 0) */
+    VBC_OPT_SPMM_SIMT = 6,   /* Float64 adjoint SpMM: 0 = auto: FP64 tensor (DMMA m8n8k4) tiles, fed by TMA row gathers
+                              * (cp.async.bulk.tensor tile::gather4) when every stripe is 8 wide, the matrix is in rows mode and
+                              * the panels are 16-byte aligned with even k and leading dimensions, else by per-lane loads;
+                              * 1 = the SIMT (DFMA) kernel; 2 = always per-lane loads; 3 = same as 0                             */
     VBC_OPT_E2E_PIPELINE = 7, /* host-vector adjoint multiplies: 1 (default) = x is uploaded in pieces on its own stream and each
                               * chunk of stripes starts as soon as the x rows it gathers from have arrived, while the y ranges of
                               * finished chunks are already on their way back (pays when the matrix is banded; any matrix stays

@@ -625,7 +625,7 @@ int vbc_set_option(vbc_mat *A, int option, int64_t value)
         A->opt_parity = value ? 1 : 0;
         return VBC_OK;
     case VBC_OPT_SPMM_SIMT:
-        if (value < 0 || value > 3) VBC_FAIL(VBC_EARG, "SpMM kernel must be 0 (FP64 tensor tiles), 1 (SIMT) or 3 (TMA-fed tiles)");
+        if (value < 0 || value > 3) VBC_FAIL(VBC_EARG, "SpMM kernel must be 0 (auto), 1 (SIMT), 2 (tensor tiles fed by per-lane loads) or 3 (TMA-fed tensor tiles)");
         A->opt_spmm_simt = (int)value;
         return VBC_OK;
     case VBC_OPT_E2E_PIPELINE:

@@ -345,7 +345,7 @@ constexpr int TMA_S = VBC_TMA_S;                           // stages per warp
 constexpr int TMA_CR = 8;                                  // rows per stage
 constexpr int TMA_STAGE_X = 2048, TMA_STAGE_V = 512;       // bytes per stage: two swizzle atoms of X, 8 x 8 values
 constexpr int TMA_WARP_BYTES = TMA_S * (TMA_STAGE_X + TMA_STAGE_V);
-constexpr int TMA_SMEM_BYTES = 8 * TMA_WARP_BYTES + 8 * TMA_S * 8 + 8 * (TMA_S + 2) * 16 + 1024; // + mbarriers + chunk queue + alignment slack
+constexpr int TMA_SMEM_BYTES = 8 * TMA_WARP_BYTES + 8 * TMA_S * 8 + 1024; // + mbarriers + alignment slack
 
 template <bool FULL>
 __global__ void __launch_bounds__(256, VBC_TMA_MINB) k_spmm_adj_tma(const __grid_constant__ CUtensorMap tmX, const StripeMeta *__restrict__ meta,
@@ -354,16 +354,14 @@ __global__ void __launch_bounds__(256, VBC_TMA_MINB) k_spmm_adj_tma(const __grid
                                                          const int kb, const double alpha, const double beta)
 {
     constexpr int S = TMA_S, CR = TMA_CR, W = 8;
-    constexpr int DEAD = INT_MIN;
     extern __shared__ unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int wq = (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5); // the warp's index as a value known to be warp-uniform
     const int nwarps = (int)gridDim.x * 8, wid = (int)blockIdx.x * 8 + wq;
     const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
-    const unsigned xs = smem0 + (unsigned)wq * (S * TMA_STAGE_X);                        // [S][2 atoms][8 rows][128 B]
+    const unsigned xs = smem0 + (unsigned)wq * (S * TMA_STAGE_X);                        // [S][2 column halves][8 rows][128 B], 128-byte swizzle
     const unsigned vsm = smem0 + 8u * S * TMA_STAGE_X + (unsigned)wq * (S * TMA_STAGE_V); // [S][8 rows][8 values]
     const unsigned bars = smem0 + 8u * S * (TMA_STAGE_X + TMA_STAGE_V) + (unsigned)wq * (S * 8);
-    const unsigned queue = smem0 + 8u * S * (TMA_STAGE_X + TMA_STAGE_V) + 8u * S * 8 + (unsigned)wq * ((S + 2) * 16); // chunk descriptors {unit, first row, rows, -}
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < S; s++) mbar_init(bars + 8 * s, 1);
@@ -373,150 +371,121 @@ __global__ void __launch_bounds__(256, VBC_TMA_MINB) k_spmm_adj_tma(const __grid
     __syncwarp();
     if (wid >= nunits) return;
 
+    // Units of <= 32 adjacent stripes are dealt round-robin (all warps work in one sliding window of X: L2 reuse of the gathered
+    // rows); a unit is a flat run of stored rows [P, E), taken in chunks of 8 rows = one stage.  The requests of chunk c + S - 1 go
+    // out while chunk c is multiplied; the pipeline drains at the end of a unit (a few per warp) and the next unit's bounds and
+    // stripe ends are fetched while this one runs.
     auto unit_lo = [&](const int u) { return u >= nunits ? L : min(L, (int)((double)u * ratio)); };
-    // ---- chunk generator (as in k_spmm_adj_stream): every unit yields ceil(rows / 8) chunks, at least one
-    int gu = wid, gP, gE, gnP = 0, gnE = 0;
-    bool gfresh = true;
-    gP = __ldg(&meta[unit_lo(gu)].pos); gE = __ldg(&meta[unit_lo(gu + 1)].pos);
-    if (gu + nwarps < nunits) { gnP = __ldg(&meta[unit_lo(gu + nwarps)].pos); gnE = __ldg(&meta[unit_lo(gu + nwarps + 1)].pos); }
-    int cu, cP, cn;
-    auto gen = [&]() {
-        if (gP >= gE && !gfresh) {
-            gu += nwarps; gP = gnP; gE = gnE; gfresh = true;
-            if (gu + nwarps < nunits) { gnP = __ldg(&meta[unit_lo(gu + nwarps)].pos); gnE = __ldg(&meta[unit_lo(gu + nwarps + 1)].pos); }
-        }
-        if (gu < nunits) { cu = gu; cP = gP; cn = min(CR, gE - gP); gP += CR; gfresh = false; }
-        else { cu = -1; cP = 0; cn = 0; }
-    };
-    auto put_desc = [&](const int slot) { // chunk descriptor -> queue[slot] (every lane writes the same words)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(queue + 16u * (unsigned)slot), "r"(cu), "r"(cP), "r"(cn), "r"(0) : "memory");
-    };
-    auto get_desc = [&](const int slot, int &u, int &P, int &n) {
-        int z;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u), "=r"(P), "=r"(n), "=r"(z) : "r"(queue + 16u * (unsigned)slot) : "memory");
-    };
-    auto load_idx = [&](const int P, const int n) { return lane < n ? __ldcs(desc + P + lane) : 0; };
-    // requests of one chunk, all from ONE elected lane with operands the compiler knows to be warp-uniform: every row index is
-    // extracted with a warp reduction (REDUX writes a uniform register), so UTMALDG / UBLKCP take their operands without the
-    // ELECT / R2UR / branch waterfall that per-lane values need (12 instructions per request in the first version of this kernel)
-    auto issue = [&](const int u, const int P, const int n, const int idx, const int stage) {
-        int r[CR];
-#pragma unroll
-        for (int j = 0; j < CR; j++) r[j] = __reduce_add_sync(0xffffffffu, lane == j ? idx : 0);
-        if (u < 0) return;
-        const unsigned bar = bars + 8u * (unsigned)stage, dst = xs + (unsigned)stage * TMA_STAGE_X;
-        if (elect_one()) {
-            mbar_expect_tx(bar, (unsigned)(TMA_STAGE_X + n * W * 8));
-            if (n > 0) bulk_copy_g2s(vsm + (unsigned)stage * TMA_STAGE_V, val + (long long)P * W, (unsigned)(n * W * 8), bar);
-            tma_gather4(dst, &tmX, kb, r[0], r[1], r[2], r[3], bar);
-            tma_gather4(dst + 512u, &tmX, kb, r[4], r[5], r[6], r[7], bar);
-            tma_gather4(dst + 1024u, &tmX, kb + 16, r[0], r[1], r[2], r[3], bar);
-            tma_gather4(dst + 1536u, &tmX, kb + 16, r[4], r[5], r[6], r[7], bar);
-        }
-    };
+    int u = wid;
+    int l0n = unit_lo(u), l1n = unit_lo(u + 1);
+    int Pn = __ldg(&meta[l0n].pos), En = __ldg(&meta[l1n].pos);
+    int segsn = lane < l1n - l0n ? __ldg(&meta[l0n + 1 + lane].pos) : 0;
 
-    // ---- prologue: chunks 0..S described (queue of S + 2 slots), 0..S-2 requested; A = the chunk whose requests go out next
-    // (S-1 ahead of the one being multiplied), B = the one after it: row indices are fetched two iterations before they are used
-    int idxA = 0, uA = -1, PA = 0, nA = 0, idxB = 0, uB = -1, PB = 0, nB = 0;
-#pragma unroll
-    for (int q = 0; q <= S; q++) {
-        gen(); put_desc(q);
-        const int idx = load_idx(cP, cn);
-        if (q < S - 1) issue(cu, cP, cn, idx, q);
-        else if (q == S - 1) { idxA = idx; uA = cu; PA = cP; nA = cn; }
-        else { idxB = idx; uB = cu; PB = cP; nB = cn; }
-    }
-    __syncwarp();
-
-    // ---- consumer state (stripe ends of the unit in `segs`, one per lane)
-    int cur_u = -1, l = 0, l0 = 0, ulast = 0, seg_end = DEAD, segs = 0;
-    int nlo = unit_lo(wid), nlast = unit_lo(wid + 1);
-    int nsegs = lane < nlast - nlo ? __ldg(&meta[nlo + 1 + lane].pos) : 0;
     double c[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; nt++) c[nt][0] = c[nt][1] = 0.0;
-    auto flush = [&]() {
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-            const int col = kb + nt * 8 + 2 * t;
-            if (FULL || col < k) {
-                double2 *yp = reinterpret_cast<double2 *>(Y + ((long long)l * W + g) * ldy + col);
-                double2 o = make_double2(alpha * c[nt][0], alpha * c[nt][1]);
-                if (beta != 0.0) { const double2 old = *yp; o.x += beta * old.x; o.y += beta * old.y; }
-                *yp = o;
-            }
-            c[nt][0] = c[nt][1] = 0.0;
-        }
-    };
     // this lane's rows in the two k-steps of a chunk and the swizzled byte offsets of its B-fragment elements (n-tiles 0 / 1; 2 and 3: + 1024)
     const int r_ks0 = 2 * t + (t & 1), r_ks1 = 2 * t + 1 - (t & 1); // {0, 3, 4, 7} and {1, 2, 5, 6}
     const unsigned xo0 = (unsigned)(r_ks0 * 128 + ((((g >> 1) ^ r_ks0) & 7) << 4) + (g & 1) * 8);
     const unsigned xo1 = (unsigned)(r_ks1 * 128 + ((((g >> 1) ^ r_ks1) & 7) << 4) + (g & 1) * 8);
     const unsigned vo0 = (unsigned)(r_ks0 * 64 + g * 8), vo1 = (unsigned)(r_ks1 * 64 + g * 8);
-
-    int stage = 0, rslot = 0;
+    int stage = 0, istage = 0; // stage multiplied next / stage filled next (both advance once per chunk, in the same order)
     unsigned parity = 0;
-    for (;;) {
-        int u0c, P0c, n0c;
-        get_desc(rslot, u0c, P0c, n0c);
-        // the stage multiplied in the previous iteration is free: chunk (S-1 ahead)'s requests go there
-        issue(uA, PA, nA, idxA, stage == 0 ? S - 1 : stage - 1);
-        idxA = idxB; uA = uB; PA = PB; nA = nB;
-        // describe the chunk S + 1 ahead (into the slot read one iteration ago) and fetch its row indices
-        gen(); put_desc(rslot == 0 ? S + 1 : rslot - 1);
-        uB = cu; PB = cP; nB = cn;
-        idxB = load_idx(cP, cn);
-        if (u0c != cur_u) {
-            if (seg_end != DEAD) { while (l < ulast) { flush(); l++; } }
-            if (u0c < 0) return;
-            cur_u = u0c; l = l0 = nlo; ulast = nlast; segs = nsegs;
-            nlo = unit_lo(cur_u + nwarps); nlast = unit_lo(cur_u + nwarps + 1);
-            nsegs = lane < nlast - nlo ? __ldg(&meta[nlo + 1 + lane].pos) : 0;
-            seg_end = __shfl_sync(0xffffffffu, segs, 0);
+
+    for (; u < nunits; u += nwarps) {
+        const int l0 = l0n, l1 = l1n, P = Pn, E = En, segs = segsn;
+        if (u + nwarps < nunits) {
+            l0n = unit_lo(u + nwarps); l1n = unit_lo(u + nwarps + 1);
+            Pn = __ldg(&meta[l0n].pos); En = __ldg(&meta[l1n].pos);
+            segsn = lane < l1n - l0n ? __ldg(&meta[l0n + 1 + lane].pos) : 0;
         }
-        const unsigned bar = bars + 8u * (unsigned)stage;
-        for (unsigned spins = 0; !mbar_try_wait(bar, parity); spins++)
-            if (spins > (1u << 24)) __trap(); // a request that never completes must not hang the GPU (try_wait itself blocks for a while)
-        const unsigned xb = xs + (unsigned)stage * TMA_STAGE_X, vb = vsm + (unsigned)stage * TMA_STAGE_V;
-        double a0, a1, b0[4], b1[4];
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a0) : "r"(vb + vo0) : "memory");
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a1) : "r"(vb + vo1) : "memory");
+        const int nch = (E - P + CR - 1) / CR;
+        auto ldidx = [&](const int ci) { const int row = P + CR * ci + lane; return (lane < CR && row < E) ? __ldcs(desc + row) : 0; };
+        // requests of chunk ci, all from ONE elected lane with operands the compiler knows to be warp-uniform: every row index is
+        // extracted with a warp reduction (REDUX writes a uniform register), so UTMALDG / UBLKCP take their operands without the
+        // ELECT / R2UR / branch waterfall that per-lane values need
+        auto issue = [&](const int ci, const int idx) {
+            if (ci >= nch) return;
+            int r[CR];
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-            const unsigned ofs = (nt >> 1) * 1024u;
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b0[nt]) : "r"(xb + ofs + ((nt & 1) ? (xo0 ^ 64u) : xo0)) : "memory");
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b1[nt]) : "r"(xb + ofs + ((nt & 1) ? (xo1 ^ 64u) : xo1)) : "memory");
-        }
-        if (seg_end > P0c + CR) { // all eight rows belong to the open stripe
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], a0, b0[nt]);
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], a1, b1[nt]);
-        } else {
-            int lo = P0c;
-            while (seg_end != DEAD) {
-                const int hi = min(seg_end, P0c + CR);
-                if (hi > lo) { // rows [lo, hi) of the chunk belong to stripe l: everything else is masked on both operands
-                    const bool m0 = P0c + r_ks0 >= lo && P0c + r_ks0 < hi, m1 = P0c + r_ks1 >= lo && P0c + r_ks1 < hi;
-                    const double am0 = m0 ? a0 : 0.0, am1 = m1 ? a1 : 0.0;
-#pragma unroll
-                    for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], am0, m0 ? b0[nt] : 0.0);
-#pragma unroll
-                    for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], am1, m1 ? b1[nt] : 0.0);
-                }
-                if (seg_end > P0c + CR) break; // the stripe continues in the next chunk
-                flush(); l++;
-                seg_end = l == ulast ? DEAD : __shfl_sync(0xffffffffu, segs, l - l0);
-                lo = hi;
+            for (int j = 0; j < CR; j++) r[j] = __reduce_add_sync(0xffffffffu, lane == j ? idx : 0);
+            const int n = min(CR, E - P - CR * ci);
+            const unsigned bar = bars + 8u * (unsigned)istage, dst = xs + (unsigned)istage * TMA_STAGE_X;
+            if (elect_one()) {
+                mbar_expect_tx(bar, (unsigned)(TMA_STAGE_X + n * W * 8));
+                bulk_copy_g2s(vsm + (unsigned)istage * TMA_STAGE_V, val + (long long)(P + CR * ci) * W, (unsigned)(n * W * 8), bar);
+                tma_gather4(dst, &tmX, kb, r[0], r[1], r[2], r[3], bar);
+                tma_gather4(dst + 512u, &tmX, kb, r[4], r[5], r[6], r[7], bar);
+                tma_gather4(dst + 1024u, &tmX, kb + 16, r[0], r[1], r[2], r[3], bar);
+                tma_gather4(dst + 1536u, &tmX, kb + 16, r[4], r[5], r[6], r[7], bar);
             }
+            istage = istage == S - 1 ? 0 : istage + 1;
+        };
+        auto flush = [&](const int l) { // stripe l is complete: Y[l*8 + g, panel] <- alpha * c + beta * Y
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const int col = kb + nt * 8 + 2 * t;
+                if (FULL || col < k) {
+                    double2 *yp = reinterpret_cast<double2 *>(Y + ((long long)l * W + g) * ldy + col);
+                    double2 o = make_double2(alpha * c[nt][0], alpha * c[nt][1]);
+                    if (beta != 0.0) { const double2 old = *yp; o.x += beta * old.x; o.y += beta * old.y; }
+                    *yp = o;
+                }
+                c[nt][0] = c[nt][1] = 0.0;
+            }
+        };
+#pragma unroll
+        for (int ci = 0; ci < S - 1; ci++) issue(ci, ldidx(ci));
+        int idxA = ldidx(S - 1), idxB = ldidx(S); // row indices are fetched two chunks before their requests go out
+        int l = l0, seg_end = __shfl_sync(0xffffffffu, segs, 0);
+        for (int ci = 0; ci < nch; ci++) {
+            issue(ci + S - 1, idxA); // into the stage multiplied in the previous iteration
+            idxA = idxB; idxB = ldidx(ci + S + 1);
+            const unsigned bar = bars + 8u * (unsigned)stage;
+            for (unsigned spins = 0; !mbar_try_wait(bar, parity); spins++)
+                if (spins > (1u << 24)) __trap(); // a request that never completes must not hang the GPU
+            const unsigned xb = xs + (unsigned)stage * TMA_STAGE_X, vb = vsm + (unsigned)stage * TMA_STAGE_V;
+            double a0, a1, b0[4], b1[4];
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a0) : "r"(vb + vo0) : "memory");
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a1) : "r"(vb + vo1) : "memory");
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const unsigned ofs = (nt >> 1) * 1024u;
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b0[nt]) : "r"(xb + ofs + ((nt & 1) ? (xo0 ^ 64u) : xo0)) : "memory");
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b1[nt]) : "r"(xb + ofs + ((nt & 1) ? (xo1 ^ 64u) : xo1)) : "memory");
+            }
+            const int Pc = P + CR * ci;
+            if (seg_end > Pc + CR) { // all eight rows belong to the open stripe
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], a0, b0[nt]);
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], a1, b1[nt]);
+            } else {
+                int lo = Pc;
+                for (;;) {
+                    const int hi = min(seg_end, Pc + CR);
+                    if (hi > lo) { // rows [lo, hi) of the chunk belong to stripe l: everything else is masked on both operands
+                        const bool m0 = Pc + r_ks0 >= lo && Pc + r_ks0 < hi, m1 = Pc + r_ks1 >= lo && Pc + r_ks1 < hi;
+                        const double am0 = m0 ? a0 : 0.0, am1 = m1 ? a1 : 0.0;
+#pragma unroll
+                        for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], am0, m0 ? b0[nt] : 0.0);
+#pragma unroll
+                        for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(c[nt], am1, m1 ? b1[nt] : 0.0);
+                    }
+                    if (seg_end > Pc + CR) break; // the stripe continues in the next chunk
+                    flush(l); l++;
+                    if (l == l1) break;
+                    seg_end = __shfl_sync(0xffffffffu, segs, l - l0);
+                    lo = hi;
+                }
+            }
+            __syncwarp(); // every lane has read the stage before the next iteration overwrites it
+            stage = stage == S - 1 ? 0 : stage + 1;
+            if (stage == 0) parity ^= 1u;
         }
-        __syncwarp(); // every lane has read the stage before the next iteration overwrites it
-        stage = stage == S - 1 ? 0 : stage + 1;
-        if (stage == 0) parity ^= 1u;
-        rslot = rslot == S + 1 ? 0 : rslot + 1;
+        while (l < l1) { flush(l); l++; } // stripes without stored rows at the end of the unit (or a unit without rows)
     }
 }
-
 
 template <typename Tv, int MODE, int WB, int KT>
 __global__ void __launch_bounds__(256) k_spmm_fwd(const StripeMeta *__restrict__ meta, const int *__restrict__ desc,
@@ -614,32 +583,39 @@ static int launch_spmm_mode(vbc_mat *A, int trans, int k, Tv alpha, const Tv *X,
             const int Wu = A->w_uniform;
             const bool streamable = MODE == DESC_ROWS && Wu == 8 && A->nval == A->ndesc * Wu && A->n == (int64_t)L * Wu &&
                                     (k % 2) == 0 && (ldx % 2) == 0 && (ldy % 2) == 0 && ldx < (1ll << 28) && ((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 16) == 0;
-            if (A->opt_spmm_simt == 3 && streamable && Wu == 8) { // TMA-fed tensor tiles
+            if ((A->opt_spmm_simt == 0 || A->opt_spmm_simt == 3) && streamable && Wu == 8) { // TMA-fed tensor tiles
                 typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                              const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
                 static EncodeFn encode = nullptr;
-                static bool attr_set = false;
-                if (!encode) {
+                static int tma_state_dev[64] = {}; // per device (the shared-memory attribute belongs to its context): 0 untried, 1 ready, -1 unavailable
+                int &tma_state = tma_state_dev[A->device & 63];
+                if (tma_state == 0) {
                     cudaDriverEntryPointQueryResult qres;
                     void *fn = nullptr;
-                    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) VBC_FAIL(VBC_ECUDA, "cuTensorMapEncodeTiled is not available");
-                    encode = (EncodeFn)fn;
-                }
-                if (!attr_set) {
-                    VBC_CUDA(cudaFuncSetAttribute(k_spmm_adj_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
-                    VBC_CUDA(cudaFuncSetAttribute(k_spmm_adj_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
-                    attr_set = true;
+                    tma_state = 1;
+                    if (!encode) {
+                        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) tma_state = -1;
+                        else encode = (EncodeFn)fn;
+                    }
+                    if (tma_state == 1 && (cudaFuncSetAttribute(k_spmm_adj_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES) != cudaSuccess ||
+                                           cudaFuncSetAttribute(k_spmm_adj_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES) != cudaSuccess)) tma_state = -1;
+                    if (tma_state < 0) cudaGetLastError();
                 }
                 CUtensorMap tm;
-                const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)A->m}, gstr[1] = {(cuuint64_t)ldx * 8};
-                const cuuint32_t box[2] = {16, 1}, estr[2] = {1, 1};
-                const CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<Tv *>(X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (cr != CUDA_SUCCESS) VBC_FAIL(VBC_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+                bool tma_ok = tma_state == 1;
+                if (tma_ok) {
+                    const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)A->m}, gstr[1] = {(cuuint64_t)ldx * 8};
+                    const cuuint32_t box[2] = {16, 1}, estr[2] = {1, 1};
+                    tma_ok = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<Tv *>(X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                }
+                if (tma_ok) { // (not available: the per-lane-load tiles below run instead)
                 int64_t g2 = (int64_t)A->sm_count * VBC_TMA_MINB;
                 const int64_t nw = g2 * 8;
                 const double avg_rows = (double)A->ndesc / (double)L;
-                int64_t U0 = (int64_t)(384.0 / (avg_rows > 1.0 ? avg_rows : 1.0) + 0.5);
+                static int unit_rows = -1;
+                if (unit_rows < 0) { const char *e = getenv("VBC_TMA_UNIT_ROWS"); unit_rows = e ? atoi(e) : 288; if (unit_rows < 8) unit_rows = 8; }
+                int64_t U0 = (int64_t)((double)unit_rows / (avg_rows > 1.0 ? avg_rows : 1.0) + 0.5); // stripes per unit: the pipeline drains once per unit
                 if (U0 < 1) U0 = 1;
                 if (U0 > 24) U0 = 24;
                 int64_t q = (L + nw * U0 / 2) / (nw * U0);
@@ -655,6 +631,7 @@ static int launch_spmm_mode(vbc_mat *A, int trans, int k, Tv alpha, const Tv *X,
                 }
                 VBC_CUDA(cudaGetLastError());
                 return VBC_OK;
+                }
             }
             if (A->opt_spmm_simt != 1) { // Float64: tensor (DMMA) tiles
                 int64_t g2 = (int64_t)A->sm_count * 8;

@@ -742,7 +742,7 @@ def test_spmm_uniform_widths_ragged_stripes():
             want = S.T @ X.cpu().numpy()
             bound = absS.T @ np.abs(X.cpu().numpy()) + 1.0
             outs = []
-            for mode in (0, 1, 3):  # tensor tiles, SIMT, TMA-fed tiles (width 8 only; otherwise the same as 0)
+            for mode in (0, 1, 2):  # auto (TMA-fed tensor tiles for width 8), SIMT, tensor tiles fed by per-lane loads
                 B.set_option(_lib.OPT_SPMM_SIMT, mode)
                 Y = torch.full((n, k), float("nan"), dtype=torch.float64, device="cuda")
                 vb.mul_(Y, B.T, X)

@@ -29,8 +29,8 @@ def main():
     B = vb.SparseMatrix1DVBC[8](A, phi)
     X = torch.rand(A.m, k, dtype=torch.float64, device="cuda")
     out, ys = {}, {}
-    modes = {"0": (0, "dmma"), "1": (1, "simt"), "3": (3, "tma")}
-    picked = [modes[m] for m in os.environ.get("PROBE_MODES", "0,1").split(",")]
+    modes = {"0": (0, "auto"), "1": (1, "simt"), "2": (2, "dmma"), "3": (3, "tma")}
+    picked = [modes[m] for m in os.environ.get("PROBE_MODES", "2,3,1").split(",")]
     tag = "_".join(n for _, n in picked[1:])
     for mode, name in picked:
         B.set_option(_lib.OPT_SPMM_SIMT, mode)
