@@ -270,7 +270,19 @@ def extra_configs(peak):
     out["C2_forward_2D_f64"] = {"us": med * 1e6, "us_min": mn * 1e6, "algorithmic_bytes": nb, "GBps": nb / med / 1e9, "frac_of_hbm_peak": nb / med / 1e9 / peak,
                                 "gflops": 2.0 * A.nnz / med / 1e9, "parity_err_over_bound_1e-12": bound_err(yd.cpu().numpy(), S @ x, abs(S) @ np.abs(x), 1e-12)}
     B.close()
-    del A, S
+    # the same matrix stored in Float32 / Int32, applied to Float64 vectors (the reference converts values and x to eltype(y): vbc_spmv_mixed)
+    A32 = A.astype(np.float32, np.int32)
+    B32 = vb.SparseMatrixVBC[4, 4](A32, pi.astype(np.int32), phi.astype(np.int32))
+    S32 = A32.to_scipy().astype(np.float64)
+    xm = synth.vector(A.m, 15)
+    xmd, ymd = torch.from_numpy(xm).cuda(), torch.empty(A.n, dtype=torch.float64, device="cuda")
+    vb.mul_(ymd, B32.T, xmd)
+    med, mn = timed_graph(lambda: vb.mul_(ymd, B32.T, xmd), 50)
+    nb = B32.format_bytes()[1] + 8 * (A.m + A.n)
+    out["C2_mixed_f32_matrix_f64_vectors_adjoint"] = {"us": med * 1e6, "us_min": mn * 1e6, "algorithmic_bytes": nb, "GBps": nb / med / 1e9, "frac_of_hbm_peak": nb / med / 1e9 / peak,
+                                                      "gflops": 2.0 * A.nnz / med / 1e9, "parity_err_over_bound_1e-12": bound_err(ymd.cpu().numpy(), S32.T @ xm, abs(S32).T @ np.abs(xm), 1e-12)}
+    B32.close()
+    del A, S, A32, S32
     # C3: 1D-VBC SpMM, k = 32, n = 1M, W = 8, 50 rows per stripe (parity unpinned by the reference: its matrix `*` cannot run)
     K, L, k = 1_000_000, 125_000, 32
     A, _, phi = synth.banded_blocks(K, L, 1, 8, np.arange(-25, 25) * 37)

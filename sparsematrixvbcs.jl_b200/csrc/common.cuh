@@ -169,6 +169,7 @@ int launch_fwdt(vbc_mat *A, double alpha, const void *x, double beta, void *y);
 void destroy_tindex(TIndex *t);
 int64_t tindex_bytes(const vbc_mat *A);
 int tindex_kind(const vbc_mat *A); // 0 none, 1 transposed unit index, 2 transposed copy
+vbc_mat *tindex_copy(const vbc_mat *A); // the transposed copy (forward multiply = adjoint multiply of it), or null
 // trsv.cu
 void destroy_trsv_plan(vbc_trsv_plan *p);
 int trsv_error_flag(const vbc_mat *A, int *flag);

@@ -618,6 +618,7 @@ int64_t tindex_bytes(const vbc_mat *A)
 }
 
 int tindex_kind(const vbc_mat *A) { return !A->tindex ? 0 : (A->tindex->At ? 2 : 1); }
+vbc_mat *tindex_copy(const vbc_mat *A) { return A->tindex ? A->tindex->At : nullptr; }
 
 template <typename Tv>
 static int launch_fwdt_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
