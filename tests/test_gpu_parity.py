@@ -683,6 +683,34 @@ def test_host_vector_pipeline_matches_plain_upload():
     assert B.get_option(_lib.OPT_E2E_UPLOAD_ELEMS) < 0.6 * m
 
 
+def test_flat_slab_bodies_short_long_and_oversized_stripes():
+    """Unaligned stripes (odd widths, odd / non-multiple-of-four slab starts) with 0 ... 700 stored rows: short ones, ones that
+    need several batches, and ones whose x row does not fit the group's shared-memory row (16 * G values) and fall back to the
+    per-element bodies inside the same kernel -- every group size, Float64 and Float32, 1D and variable 2D, against the oracle."""
+    rng = np.random.default_rng(2024)
+    for tv in (np.float64, np.float32):
+        for m, dens in ((700, 0.95), (700, 0.3), (333, 0.04)):
+            for w in (3, 5, 6, 7):
+                n = 7 * w + 2  # the last stripe is narrower: its slab starts wherever the others end
+                A = sprand(m, n, dens, rng).astype(tv)
+                phi = vb.pack_stripe(A, vb.EquiChunker(w))
+                H = oracle.pack_1d(A.m, A.n, A.colptr, A.rowval, A.nzval, phi.spl, w)
+                B = vb.SparseMatrix1DVBC[w](A, phi)
+                for g in (8, 16, 32):
+                    B.set_option(_lib.OPT_ADJ_GROUP, g)
+                    randx_check(A, B, H, rng)
+                B.close()
+        A = sprand(300, 211, 0.4, rng).astype(tv)
+        pv, fv = synth.variable_partition(A.m, 8, 5), synth.variable_partition(A.n, 8, 6)
+        H2 = oracle.pack_2d(A.m, A.n, A.colptr, A.rowval, A.nzval, pv.spl, fv.spl, 8, 8)
+        B2 = vb.SparseMatrixVBC[8, 8](A, pv, fv)
+        for g in (8, 16, 32):
+            B2.set_option(_lib.OPT_ADJ_GROUP, g)
+            B2.set_option(_lib.OPT_FWD_GROUP, g if g != 16 else 0)
+            randx_check(A, B2, H2, rng)
+        B2.close()
+
+
 def test_forward_variable_blocks_through_transposed_copy():
     """2D blocks with iid heights and widths (2..8): the forward multiply in auto mode (0) and with the copy forced (3) runs the
     adjoint kernel on a rows-mode transposed copy built from the canonical block arrays -- against the oracle, scipy and the
