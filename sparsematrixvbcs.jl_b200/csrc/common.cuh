@@ -69,6 +69,7 @@ struct vbc_mat {
     int *d_brow = nullptr;             // 2D only: first (stripe-relative) expanded row of each block
     int *d_order = nullptr;            // stripes grouped by kernel body class (null: all stripes share one class)
     int nclasses = 1;
+    int64_t n_long = 0;                // LONG stripes (dense column groups): the last n_long entries of d_order, multiplied by one CTA each
     int64_t ndesc = 0;
     int desc_mode = vbc::DESC_ROWS;
     int u0 = 1; // DESC_BLOCKS: uniform part height

@@ -363,10 +363,11 @@ static inline unsigned nblk(int64_t n, int t);
 
 // Kernel-body class of a stripe: must mirror the per-stripe dispatch of k_spmv_adj / k_spmv_fwd (spmv.cu):
 // elements per load (from width and slab alignment) and vectors per row.
-__device__ __forceinline__ int stripe_class(const StripeMeta a, const StripeMeta b, const int VE, const int rows_mode)
+__device__ __forceinline__ int stripe_class(const StripeMeta a, const StripeMeta b, const int VE, const int rows_mode, const long long long_vals)
 {
     const int w = b.col - a.col;
     if (w <= 0) return 0;
+    if (b.ofs - a.ofs > long_vals) return 255; // a LONG stripe (a dense column group): last in the order, multiplied by one CTA each (k_spmv_adj_long)
     int epv_code, cpr;
     if ((w % VE) == 0 && (a.ofs % VE) == 0) { epv_code = 0; cpr = w / VE; }
     else if (VE == 4 && (w % 2) == 0 && (a.ofs % 2) == 0) { epv_code = 1; cpr = w / 2; }
@@ -375,14 +376,14 @@ __device__ __forceinline__ int stripe_class(const StripeMeta a, const StripeMeta
 }
 
 // hist[0..255]: stripes per class; hist[256], hist[257]: min and max stripe width
-__global__ void k_class_hist(const StripeMeta *__restrict__ meta, int64_t L, int VE, int rows_mode, unsigned *__restrict__ hist)
+__global__ void k_class_hist(const StripeMeta *__restrict__ meta, int64_t L, int VE, int rows_mode, long long long_vals, unsigned *__restrict__ hist)
 {
     __shared__ unsigned sh[256];
     sh[threadIdx.x] = 0;
     __syncthreads();
     unsigned wmin = 0xffffffffu, wmax = 0;
     for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < L; l += (int64_t)gridDim.x * blockDim.x) {
-        atomicAdd(&sh[stripe_class(meta[l], meta[l + 1], VE, rows_mode) & 255], 1u);
+        atomicAdd(&sh[stripe_class(meta[l], meta[l + 1], VE, rows_mode, long_vals) & 255], 1u);
         const unsigned w = (unsigned)(meta[l + 1].col - meta[l].col);
         wmin = w < wmin ? w : wmin;
         wmax = w > wmax ? w : wmax;
@@ -393,11 +394,11 @@ __global__ void k_class_hist(const StripeMeta *__restrict__ meta, int64_t L, int
 }
 
 // order[cursor[class]++] = l.  Stripes are visited in ascending blocks, so neighbours of one class stay close.
-__global__ void k_class_scatter(const StripeMeta *__restrict__ meta, int64_t L, int VE, int rows_mode, unsigned *__restrict__ cursor, int *__restrict__ order)
+__global__ void k_class_scatter(const StripeMeta *__restrict__ meta, int64_t L, int VE, int rows_mode, long long long_vals, unsigned *__restrict__ cursor, int *__restrict__ order)
 {
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= L) return;
-    const int c = stripe_class(meta[l], meta[l + 1], VE, rows_mode) & 255;
+    const int c = stripe_class(meta[l], meta[l + 1], VE, rows_mode, long_vals) & 255;
     order[atomicAdd(&cursor[c], 1u)] = (int)l;
 }
 
@@ -408,7 +409,13 @@ int build_class_order(vbc_mat *A)
     const int64_t L = A->L;
     A->nclasses = 1;
     A->w_uniform = 0;
+    A->n_long = 0;
     if (L < 1) return VBC_OK;
+    // a stripe is LONG when it holds more than 2 K values and more than 16 times the average: one group of lanes would
+    // still be streaming it long after every other stripe is done (dense column groups; dense ROWS in the transposed copy)
+    long long long_vals = 16 * (A->nval / L + 1);
+    if (long_vals < 2048) long_vals = 2048;
+    { const char *e = getenv("VBC_LONG_STRIPE_VALUES"); if (e && atoll(e) > 0) long_vals = atoll(e); }
     cudaStream_t st = A->stream;
     const int VE = 16 / (int)vt_size(A->vt);
     unsigned *d_hist = nullptr;
@@ -419,7 +426,7 @@ int build_class_order(vbc_mat *A)
     if (e == cudaSuccess) {
         int64_t g = (L + 255) / 256;
         if (g > 2048) g = 2048;
-        k_class_hist<<<(unsigned)g, 256, 0, st>>>(A->d_meta, L, VE, A->desc_mode == DESC_ROWS ? 1 : 0, d_hist);
+        k_class_hist<<<(unsigned)g, 256, 0, st>>>(A->d_meta, L, VE, A->desc_mode == DESC_ROWS ? 1 : 0, long_vals, d_hist);
         A->launches++;
         e = cudaMemcpyAsync(h, d_hist, sizeof(h), cudaMemcpyDeviceToHost, st);
     }
@@ -431,13 +438,14 @@ int build_class_order(vbc_mat *A)
     for (int c = 65; c < 192; c++) if (h[c]) A->has_unaligned = 1; // class codes 1 + epv_code * 64 + cpr with epv_code 1, 2: stripes that are not 16-byte aligned
     int ncls = 0;
     unsigned run = 0, cur[256];
-    for (int c = 0; c < 256; c++) { cur[c] = run; run += h[c]; if (h[c]) ncls++; }
-    A->nclasses = ncls;
-    if (ncls <= 1) { cudaFree(d_hist); return VBC_OK; }
+    for (int c = 0; c < 256; c++) { cur[c] = run; run += h[c]; if (h[c] && c != 255) ncls++; }
+    A->nclasses = ncls > 0 ? ncls : 1;
+    A->n_long = (int64_t)h[255];
+    if (ncls <= 1 && A->n_long == 0) { cudaFree(d_hist); return VBC_OK; }
     e = cudaMalloc(&A->d_order, sizeof(int) * (size_t)L);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_hist, cur, sizeof(cur), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-        k_class_scatter<<<nblk(L, 256), 256, 0, st>>>(A->d_meta, L, VE, A->desc_mode == DESC_ROWS ? 1 : 0, d_hist, A->d_order);
+        k_class_scatter<<<nblk(L, 256), 256, 0, st>>>(A->d_meta, L, VE, A->desc_mode == DESC_ROWS ? 1 : 0, long_vals, d_hist, A->d_order);
         A->launches++;
         e = cudaStreamSynchronize(st);
     }

@@ -500,6 +500,49 @@ __global__ void VBC_ADJ_BOUNDS k_spmv_adj_flat(const StripeMeta *__restrict__ me
                                  desc, val, x, y, u0, log2u, alpha, beta, xs_all[threadIdx.x / G]);
 }
 
+// LONG stripes (pack.cu, build_class_order: more than 2 K values and more than 16 times the average stripe -- a dense column
+// group, or a dense row of A in the transposed copy): one CTA per stripe instead of one group of lanes.  T = 256 - 256 % w
+// threads read consecutive values of the slab (coalesced); T is a multiple of w, so a thread keeps one column and walks rows
+// r0, r0 + T/w, ...; the per-thread sums of a column are added up in shared memory in a fixed order (deterministic).
+template <typename Tv, int MODE>
+__global__ void __launch_bounds__(256) k_spmv_adj_long(const StripeMeta *__restrict__ meta, const int *__restrict__ stripes, const int *__restrict__ desc,
+                                                        const Tv *__restrict__ val, const Tv *__restrict__ x, Tv *__restrict__ y,
+                                                        const int u0, const int log2u, const Tv alpha, const Tv beta)
+{
+    __shared__ Tv part[256];
+    const int l = __ldg(stripes + blockIdx.x);
+    const StripeMeta a = ld_meta(meta + l), b = ld_meta(meta + l + 1);
+    const int w = b.col - a.col;
+    if (w <= 0 || w > 256) return; // (wider than a CTA: cannot be a packed stripe; uploaded ones stay with the generic kernel's result)
+    const int R = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
+    const int T = 256 - 256 % w, rstep = T / w;
+    const int tid = (int)threadIdx.x, c = tid % w;
+    Tv acc = (Tv)0;
+    if (tid < T) {
+        const Tv *vp = val + a.ofs + tid;
+        constexpr int UNR = 8; // independent row-steps in flight per thread
+        for (int r = tid / w; r < R; r += UNR * rstep) {
+            Tv v[UNR], xv[UNR];
+            int xi[UNR];
+#pragma unroll
+            for (int k = 0; k < UNR; k++) { const bool ok = r + k * rstep < R; v[k] = ok ? __ldcs(vp + (long long)k * T) : (Tv)0; xi[k] = ok ? row_xindex<MODE>(desc, a.pos, r + k * rstep, u0, log2u) : -1; }
+#pragma unroll
+            for (int k = 0; k < UNR; k++) xv[k] = xi[k] >= 0 ? __ldg(x + xi[k]) : (Tv)0;
+#pragma unroll
+            for (int k = 0; k < UNR; k++) acc = fma(v[k], xv[k], acc);
+            vp += (long long)UNR * T;
+        }
+    }
+    part[tid] = acc;
+    __syncthreads();
+    if (tid < w) {
+        Tv s = (Tv)0;
+        for (int t = tid; t < T; t += w) s += part[t];
+        Tv *yp = y + a.col + c;
+        *yp = (beta == (Tv)0) ? alpha * s : alpha * s + beta * *yp;
+    }
+}
+
 // ---- adjoint with the x exchange of the row-partitioned iteration fused in (north_star (e)) -------------------------
 // One launch per iteration x_{t+1} <- alpha * A' x_t on this rank's stripes.
 //   boundary stripes (for a banded operator the few thousand at both ends of the slab) read x entries that the neighbours
@@ -806,7 +849,9 @@ static int auto_group(const vbc_mat *A)
     while (G < 32 && (double)A->L * G < 148.0 * 4 * 256 && vec_per_stripe >= 4.0 * G) G *= 2;
     // mixed widths (stripes regrouped by body class): the unaligned classes use one lane per column ELEMENT, and with 8 lanes
     // a 5..7-wide stripe leaves lanes idle; 16 lanes hold two or three rows per step (C2v: 238 -> 214 us)
-    if (A->d_order != nullptr && G == 8) G = 16;
+    if (A->d_order != nullptr && A->nclasses > 1 && G == 8) G = 16;
+    // unaligned stripes: the flat-slab bodies need at least 8 lanes (natural 1..6-wide blocks, 1 KB stripes: 32 -> 23.5 us)
+    if (A->has_unaligned && !A->opt_no_flat && G == 4) G = 8;
     return G;
 }
 
@@ -820,7 +865,15 @@ static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
     int64_t grid = (int64_t)A->sm_count * occ;
     // a stripe range [l0, l1) is launched by offsetting meta: its entries are absolute (value offset, descriptor, column)
     const bool ranged = A->range_l0 >= 0 && A->d_order == nullptr;
-    const int64_t l0 = ranged ? A->range_l0 : 0, l1 = ranged ? A->range_l1 : A->L;
+    const int64_t n_long = A->d_order != nullptr ? A->n_long : 0; // the last n_long entries of the order: one CTA each, below
+    const int64_t l0 = ranged ? A->range_l0 : 0, l1 = (ranged ? A->range_l1 : A->L) - n_long;
+    auto launch_long = [&]() -> int {
+        if (n_long == 0) return VBC_OK;
+        k_spmv_adj_long<Tv, MODE><<<(unsigned)n_long, 256, 0, A->stream>>>(A->d_meta, A->d_order + (A->L - n_long), A->d_desc, (const Tv *)A->d_val, x, y, A->u0, ilog2_exact(A->u0), alpha, beta);
+        A->launches++;
+        VBC_CUDA(cudaGetLastError());
+        return VBC_OK;
+    };
     const int64_t need = ((l1 - l0) * G + 255) / 256;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
@@ -836,13 +889,15 @@ static int launch_adj_t(vbc_mat *A, Tv alpha, const Tv *x, Tv beta, Tv *y)
             k_spmv_adj_flat<Tv, G, MODE><<<(unsigned)gridf, 256, 0, A->stream>>>(A->d_meta + l0, A->d_desc, (const Tv *)A->d_val, x, y, A->d_order, (int)(l1 - l0), A->u0, ilog2_exact(A->u0), alpha, beta);
             A->launches++;
             VBC_CUDA(cudaGetLastError());
-            return VBC_OK;
+            return launch_long();
         }
     }
-    k_spmv_adj<Tv, G, MODE><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta + l0, A->d_desc, (const Tv *)A->d_val, x, y, A->d_order, (int)(l1 - l0), A->u0, ilog2_exact(A->u0), alpha, beta);
-    A->launches++;
+    if (l1 > l0) {
+        k_spmv_adj<Tv, G, MODE><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta + l0, A->d_desc, (const Tv *)A->d_val, x, y, A->d_order, (int)(l1 - l0), A->u0, ilog2_exact(A->u0), alpha, beta);
+        A->launches++;
+    }
     VBC_CUDA(cudaGetLastError());
-    return VBC_OK;
+    return launch_long();
 }
 
 // the fused multiply + exchange: same persistent grid as the plain kernel

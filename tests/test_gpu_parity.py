@@ -711,6 +711,37 @@ def test_flat_slab_bodies_short_long_and_oversized_stripes():
         B2.close()
 
 
+def test_long_stripes_take_the_cta_per_stripe_kernel():
+    """A dense column group among sparse ones (adjoint) and a dense row (forward through the transposed copy: a dense row of A
+    is a long stripe of the copy): stripes with more than 2 K values and more than 16 times the average are multiplied by one
+    CTA each (k_spmv_adj_long).  1D and 2D, uniform and variable blocks, both value types, alpha / beta, against scipy."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(99)
+    m = n = 24_000
+    M = sp.random(m, n, density=2.0 / n, random_state=np.random.RandomState(3), format="lil")
+    M[:, 4000:4004] = rng.random((m, 4))     # a dense column group: 96 000 values in one stripe
+    M[9001, :] = rng.random(n)               # a dense row
+    S = sp.csc_matrix(M)
+    for tv, tol in ((np.float64, 1e-12), (np.float32, 2e-5)):
+        A = vb.SparseMatrixCSC.from_scipy(S).astype(tv)
+        Sd = A.to_scipy().astype(np.float64)
+        absS = abs(Sd)
+        pv, fv = synth.variable_partition(A.m, 8, 3), synth.variable_partition(A.n, 8, 4)
+        mats = [vb.SparseMatrix1DVBC[4](A, vb.pack_stripe(A, vb.EquiChunker(4))),
+                vb.SparseMatrixVBC[4, 4](A, vb.pack_stripe(A.transpose(), vb.EquiChunker(4)), vb.pack_stripe(A, vb.EquiChunker(4))),
+                vb.SparseMatrixVBC[8, 8](A, pv, fv)]
+        for B in mats:
+            x, y0 = synth.vector(A.m, 3, dtype=tv), synth.vector(A.n, 4, dtype=tv)
+            y = vb.mul_(y0.copy(), B.T, x, 1.5, -0.5)
+            want = 1.5 * (Sd.T @ x.astype(np.float64)) - 0.5 * y0
+            assert np.all(np.abs(y - want) <= 8 * tol * (absS.T @ np.abs(x.astype(np.float64)) + np.abs(y0))), "adjoint"
+            xf, yf0 = synth.vector(A.n, 5, dtype=tv), synth.vector(A.m, 6, dtype=tv)
+            yf = vb.mul_(yf0.copy(), B, xf, 1.5, -0.5)
+            wantf = 1.5 * (Sd @ xf.astype(np.float64)) - 0.5 * yf0
+            assert np.all(np.abs(yf - wantf) <= 8 * tol * (absS @ np.abs(xf.astype(np.float64)) + np.abs(yf0))), "forward"
+            B.close()
+
+
 def test_forward_variable_blocks_through_transposed_copy():
     """2D blocks with iid heights and widths (2..8): the forward multiply in auto mode (0) and with the copy forced (3) runs the
     adjoint kernel on a rows-mode transposed copy built from the canonical block arrays -- against the oracle, scipy and the
