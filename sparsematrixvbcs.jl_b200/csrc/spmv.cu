@@ -690,28 +690,48 @@ __device__ __forceinline__ void fwd_stripe(const StripeMeta a, const StripeMeta 
     const int vstride = rps * w;
     RowWalk<MODE> walk;
     walk.init(desc, a.pos, r0, rps, u0, log2u);
-    for (int rb = 0; rb < R; rb += rps) { // group-uniform trip count: every lane joins the shuffles
-        const bool ok = active && (rb + r0 < R);
-        Tv p = (Tv)0;
-        int xi = 0;
-        if (ok) {
-            Tv v[EPV];
-            Ld<Tv, EPV>::s(vp, v);
-            xi = walk.next();
+    // batches of UNR row-steps (group-uniform trip count: every lane joins the shuffles): all loads of a batch are issued before
+    // the first product, then the per-row sums are reduced and scattered -- one load in flight per lane left this kernel
+    // waiting for memory between any two atomics
+    constexpr int UNR = 4;
+    for (int rb = 0; rb < R; rb += UNR * rps) {
+        Tv v[UNR][EPV], p[UNR];
+        int xi[UNR];
+        bool ok[UNR];
 #pragma unroll
-            for (int e = 0; e < EPV; e++) p = fma(v[e], xs[e], p);
+        for (int k = 0; k < UNR; k++) {
+            ok[k] = active && (rb + k * rps + r0 < R);
+            if (ok[k]) Ld<Tv, EPV>::s(vp, v[k]);
+            else {
+#pragma unroll
+                for (int e = 0; e < EPV; e++) v[k][e] = (Tv)0;
+            }
+            vp += vstride;
         }
-        vp += vstride;
-        if constexpr (CPR > 0) {
 #pragma unroll
-            for (int d = 1; d < CPR; d <<= 1) p += __shfl_xor_sync(gmask, p, d, G);
-        } else {
-            for (int d = 1; d < cpr; d <<= 1) {
-                const Tv t = __shfl_down_sync(gmask, p, d, G);
-                if (c + d < cpr) p += t;
+        for (int k = 0; k < UNR; k++) xi[k] = walk.next_if(ok[k]);
+#pragma unroll
+        for (int k = 0; k < UNR; k++) {
+            p[k] = (Tv)0;
+#pragma unroll
+            for (int e = 0; e < EPV; e++) p[k] = fma(v[k][e], xs[e], p[k]);
+        }
+        __syncwarp(gmask);
+#pragma unroll
+        for (int k = 0; k < UNR; k++) {
+            if constexpr (CPR > 0) {
+#pragma unroll
+                for (int d = 1; d < CPR; d <<= 1) p[k] += __shfl_xor_sync(gmask, p[k], d, G);
+            } else {
+                for (int d = 1; d < cpr; d <<= 1) {
+                    const Tv t = __shfl_down_sync(gmask, p[k], d, G);
+                    if (c + d < cpr) p[k] += t;
+                }
             }
         }
-        if (ok && c == 0) atomicAdd(y + xi, alpha * p); // y[idx[Q]] += ...  (multiply_1DVBC.jl:34)
+#pragma unroll
+        for (int k = 0; k < UNR; k++)
+            if (ok[k] && c == 0) atomicAdd(y + xi[k], alpha * p[k]); // y[idx[Q]] += ...  (multiply_1DVBC.jl:34)
     }
 }
 
