@@ -513,22 +513,33 @@ __global__ void __launch_bounds__(256) k_spmm_fwd(const StripeMeta *__restrict__
                 RowWalk<MODE> walk;
                 walk.init(desc, a.pos, 0, 1, u0, log2u);
                 const Tv *vp = val + a.ofs + wb;
-                for (int r = 0; r < R; r++) {
-                    const int xi = walk.next();
-                    Tv p[KT];
+                constexpr int RU = (WB * KT <= 16) ? 2 : 1; // stored rows whose values are loaded before the first product
+                for (int r = 0; r < R; r += RU) {
+                    int xi[RU];
+                    Tv v[RU][WB];
 #pragma unroll
-                    for (int t = 0; t < KT; t++) p[t] = (Tv)0;
+                    for (int q = 0; q < RU; q++) {
+                        xi[q] = walk.next_if(r + q < R);
 #pragma unroll
-                    for (int dj = 0; dj < WB; dj++) {
-                        const Tv v = (wb + dj < w) ? __ldg(vp + dj) : (Tv)0;
-#pragma unroll
-                        for (int t = 0; t < KT; t++) p[t] = fma(v, xs[dj][t], p[t]);
+                        for (int dj = 0; dj < WB; dj++) v[q][dj] = (r + q < R && wb + dj < w) ? __ldg(vp + dj) : (Tv)0;
+                        vp += w;
                     }
-                    vp += w;
 #pragma unroll
-                    for (int t = 0; t < KT; t++) {
-                        const int c = kb + t * 32 + lane;
-                        if (c < k) atomicAdd(Y + (long long)xi * ldy + c, alpha * p[t]);
+                    for (int q = 0; q < RU; q++) {
+                        Tv p[KT];
+#pragma unroll
+                        for (int t = 0; t < KT; t++) p[t] = (Tv)0;
+#pragma unroll
+                        for (int dj = 0; dj < WB; dj++)
+#pragma unroll
+                            for (int t = 0; t < KT; t++) p[t] = fma(v[q][dj], xs[dj][t], p[t]);
+                        if (r + q < R) {
+#pragma unroll
+                            for (int t = 0; t < KT; t++) {
+                                const int c = kb + t * 32 + lane;
+                                if (c < k) atomicAdd(Y + (long long)xi[q] * ldy + c, alpha * p[t]);
+                            }
+                        }
                     }
                 }
             }
