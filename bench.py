@@ -737,6 +737,8 @@ def run_ours(args, rank, world, local_rank):
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        if world > 1:
+            os.dup2(2, 1)  # NCCL also speaks while the communicator is destroyed: keep that off stdout too
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
