@@ -30,7 +30,12 @@ extern "C" {
 typedef struct vbc_mat vbc_mat; /* device-resident 1D-VBC or 2D-VBC matrix ("CuVBC")            */
 typedef struct vbc_csc vbc_csc; /* device-resident CSC matrix (comparator for TrSpMV!)           */
 
-enum vbc_dtype { VBC_F32 = 0, VBC_F64 = 1 };
+/* Element types.  The integer types (the reference's methods are generic over Tv, and test/runtests.jl:15-16 runs Bool and Int32
+ * matrices) are packed, uploaded, downloaded and multiplied (vbc_spmv, vbc_csc_trspmv) with Julia's wrapping arithmetic, exact in
+ * any summation order; alpha and beta must then be integers of the type (else VBC_EARG, the InexactError of `convert(eltype(y), α)`).
+ * Bool is widened to Int32 by the host layers.  SpMM, the triangular solve, the mixed-type multiply and the multi-GPU entry points
+ * are floating-point only (VBC_EARG). */
+enum vbc_dtype { VBC_F32 = 0, VBC_F64 = 1, VBC_INT32 = 2, VBC_INT64 = 3 };
 enum vbc_itype { VBC_I32 = 0, VBC_I64 = 1 };
 
 enum vbc_status {

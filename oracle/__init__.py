@@ -78,7 +78,7 @@ def set_static_schedule(on: bool):
     lib().vbc_oracle_set_static_schedule(ctypes.c_int(1 if on else 0))
 
 
-_TV = {np.dtype(np.float64): "f64", np.dtype(np.float32): "f32"}
+_TV = {np.dtype(np.float64): "f64", np.dtype(np.float32): "f32", np.dtype(np.int32): "s32", np.dtype(np.int64): "s64"}
 _TI = {np.dtype(np.int64): "i64", np.dtype(np.int32): "i32"}
 
 

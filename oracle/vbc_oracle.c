@@ -82,6 +82,40 @@ static void vbc_oracle_apply_schedule(void)
 #undef TI
 #undef FN
 
+/* Integer element types (test/runtests.jl:15-16 packs and multiplies Bool and Int32 matrices).  Julia's Int32 / Int64
+ * arithmetic wraps; unsigned C arithmetic is the same bits without undefined behaviour. */
+#define TV uint32_t
+#define TI int64_t
+#define FN(name) CAT3(name, s32, i64)
+#include "vbc_oracle_body.inc"
+#undef TV
+#undef TI
+#undef FN
+
+#define TV uint32_t
+#define TI int32_t
+#define FN(name) CAT3(name, s32, i32)
+#include "vbc_oracle_body.inc"
+#undef TV
+#undef TI
+#undef FN
+
+#define TV uint64_t
+#define TI int64_t
+#define FN(name) CAT3(name, s64, i64)
+#include "vbc_oracle_body.inc"
+#undef TV
+#undef TI
+#undef FN
+
+#define TV uint64_t
+#define TI int32_t
+#define FN(name) CAT3(name, s64, i32)
+#include "vbc_oracle_body.inc"
+#undef TV
+#undef TI
+#undef FN
+
 int vbc_oracle_max_threads(void)
 {
 #ifdef _OPENMP

@@ -12,7 +12,7 @@ from ._lib import ArgumentError, DimensionMismatch, VBCError, LIB_PATH  # noqa: 
 from . import partition  # noqa: F401
 from .partition import (AlternatingPacker, DynamicTotalChunker, EquiChunker, OverlapChunker, RandomChunker, SparseMatrixCSC,  # noqa: F401
                         SplitPartition, StrictChunker, pack_plaid, pack_stripe, permutedims)
-from .matrix import (Adjoint, CuSparseMatrixCSC, CuVBC1D, CuVBC2D, SparseMatrix1DVBC,  # noqa: F401
+from .matrix import (Adjoint, CuSparseMatrixCSC, CuVBC1D, CuVBC2D, InexactError, SparseMatrix1DVBC,  # noqa: F401
                      SparseMatrixVBC, TrSpMV_, adjoint, ldiv_lower_, mul_, size, trsv_analyse)
 from . import costs, solvers, synth  # noqa: F401
 from .costs import (model_SparseMatrix1DVBC_blocks, model_SparseMatrix1DVBC_memory,  # noqa: F401
@@ -24,7 +24,7 @@ __all__ = [
     "mul_", "TrSpMV_", "adjoint", "size", "ldiv_lower_", "trsv_analyse",
     "SparseMatrixCSC", "SplitPartition", "EquiChunker", "StrictChunker", "RandomChunker",
     "AlternatingPacker", "DynamicTotalChunker", "OverlapChunker", "permutedims", "pack_stripe", "pack_plaid",
-    "DimensionMismatch", "ArgumentError", "VBCError", "synth", "costs", "solvers",
+    "DimensionMismatch", "ArgumentError", "InexactError", "VBCError", "synth", "costs", "solvers",
     "model_SparseMatrix1DVBC_blocks", "model_SparseMatrix1DVBC_memory", "model_SparseMatrix1DVBC_TrSpMV_time",
     "model_SparseMatrixVBC_blocks", "model_SparseMatrixVBC_memory", "model_SparseMatrixVBC_TrSpMV_time", "total_value",
 ]

@@ -9,7 +9,7 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 # VBC_LIBRARY: another build of the same library (kernel-variant experiments, tools/build_variants.sh); default = the in-tree one
 LIB_PATH = os.environ.get("VBC_LIBRARY") or os.path.join(_DIR, "libvbc.so")
 
-VBC_F32, VBC_F64 = 0, 1
+VBC_F32, VBC_F64, VBC_INT32, VBC_INT64 = 0, 1, 2, 3
 VBC_I32, VBC_I64 = 0, 1
 VBC_OK, VBC_EDIM, VBC_EARG, VBC_ELIMIT, VBC_ECUDA, VBC_ENCCL, VBC_ENOMEM = range(7)
 OPT_ADJ_GROUP, OPT_FWD_GROUP, OPT_GRID_MULT, OPT_PARITY_MODE, OPT_FWD_MODE, OPT_SPMM_SIMT, OPT_E2E_PIPELINE, OPT_E2E_UPLOAD_ELEMS, OPT_E2E_GRAPH = 1, 2, 3, 4, 5, 6, 7, 8, 9

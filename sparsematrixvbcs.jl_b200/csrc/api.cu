@@ -20,7 +20,7 @@ const char *get_error() { return g_err; }
 
 static int check_types(int vt, int it)
 {
-    if (vt != VBC_F32 && vt != VBC_F64) VBC_FAIL(VBC_EARG, "vt must be VBC_F32 or VBC_F64, got %d", vt);
+    if (!vt_is_valid(vt)) VBC_FAIL(VBC_EARG, "vt must be VBC_F32, VBC_F64, VBC_INT32 or VBC_INT64, got %d", vt);
     if (it != VBC_I32 && it != VBC_I64) VBC_FAIL(VBC_EARG, "it must be VBC_I32 or VBC_I64, got %d", it);
     return VBC_OK;
 }
@@ -442,7 +442,7 @@ extern "C" int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int6
     const size_t tv = vt_size(A->vt);
     VBC_TRY(ensure_vec(&A->d_x, &A->x_cap, xlen, tv));
     VBC_TRY(ensure_vec(&A->d_y, &A->y_cap, ylen, tv));
-    const bool chunkable = trans && !A->opt_parity && A->d_order == nullptr;
+    const bool chunkable = trans && !A->opt_parity && A->d_order == nullptr && vt_is_float(A->vt);
     // adjoint with a large y: launch the stripes in chunks and copy each finished y range back on a second stream
     // while the next chunk computes (the D2H copy is as long as the whole kernel)
     if (chunkable && A->nchunks == 0) {
@@ -497,7 +497,8 @@ extern "C" int vbc_spmv(vbc_mat *A, int trans, double alpha, const void *x, int6
 extern "C" int vbc_spmv_mixed(vbc_mat *A, int trans, double alpha, const void *x, int64_t xlen, double beta, void *y, int64_t ylen, int vec_vt, int on_device)
 {
     if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
-    if (vec_vt != VBC_F32 && vec_vt != VBC_F64) VBC_FAIL(VBC_EARG, "vector type must be VBC_F32 or VBC_F64");
+    if (vec_vt == A->vt && vt_is_valid(vec_vt)) return vbc_spmv(A, trans, alpha, x, xlen, beta, y, ylen, on_device);
+    if (!vt_is_float(A->vt) || !vt_is_float(vec_vt)) VBC_FAIL(VBC_EARG, "ArgumentError: the mixed-type multiply pairs a Float32 matrix with Float64 vectors; integer element types multiply vectors of their own type");
     if (vec_vt == A->vt) return vbc_spmv(A, trans, alpha, x, xlen, beta, y, ylen, on_device);
     if (vec_vt == VBC_F32) VBC_FAIL(VBC_EARG, "ArgumentError: Float64 values with Float32 vectors (narrowing) is not offered");
     const int64_t need_x = trans ? A->m : A->n, need_y = trans ? A->n : A->m;

@@ -34,7 +34,9 @@ const char *get_error();
         return (code);                                                                          \
     } while (0)
 
-static inline size_t vt_size(int vt) { return vt == VBC_F64 ? 8 : 4; }
+static inline size_t vt_size(int vt) { return (vt == VBC_F64 || vt == VBC_INT64) ? 8 : 4; }
+static inline bool vt_is_float(int vt) { return vt == VBC_F32 || vt == VBC_F64; }
+static inline bool vt_is_valid(int vt) { return vt == VBC_F32 || vt == VBC_F64 || vt == VBC_INT32 || vt == VBC_INT64; }
 static inline size_t it_size(int it) { return it == VBC_I64 ? 8 : 4; }
 
 // ---- device layout --------------------------------------------------------------------------
@@ -162,6 +164,8 @@ struct HaloLaunch { // one step of the row-partitioned iteration (peer.cu -> spm
     int *timed_out;
 };
 int launch_spmv_adj_halo(vbc_mat *A, double alpha, const void *d_x, const HaloLaunch *hl);
+// inttypes.cu (Int32 / Int64 element types, wrapping arithmetic)
+int launch_spmv_int(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y);
 // mixed.cu
 int launch_spmv_mixed(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y);
 // fwdt.cu

@@ -4,7 +4,17 @@
 // gather x[rowval[q]], and finish with a shuffle reduction (CSR-vector shape).
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace vbc {
+
+// a * b + c: one FMA for the floating-point types; the integer element types are computed on the unsigned type of their width
+// (Julia's wrapping arithmetic without signed-overflow undefined behaviour)
+template <typename T> __device__ __forceinline__ T mad_any(const T a, const T b, const T c)
+{
+    if constexpr (std::is_floating_point<T>::value) return fma(a, b, c);
+    else return a * b + c;
+}
 
 template <typename Tv, typename Ti, int G>
 __global__ void __launch_bounds__(256) k_csc_trspmv(const Ti *__restrict__ colptr, const Ti *__restrict__ rowval,
@@ -25,9 +35,9 @@ __global__ void __launch_bounds__(256) k_csc_trspmv(const Ti *__restrict__ colpt
 #pragma unroll
             for (int k = 0; k < 4; k++) { v[k] = __ldcs(nzval + q + k * G); r[k] = __ldcs(rowval + q + k * G); }
 #pragma unroll
-            for (int k = 0; k < 4; k++) tmp = fma(v[k], __ldg(x + (int64_t)r[k] - 1), tmp);
+            for (int k = 0; k < 4; k++) tmp = mad_any(v[k], __ldg(x + (int64_t)r[k] - 1), tmp);
         }
-        for (; q < e; q += G) tmp = fma(__ldcs(nzval + q), __ldg(x + (int64_t)__ldcs(rowval + q) - 1), tmp);
+        for (; q < e; q += G) tmp = mad_any(__ldcs(nzval + q), __ldg(x + (int64_t)__ldcs(rowval + q) - 1), tmp);
 #pragma unroll
         for (int d = 1; d < G; d <<= 1) tmp += __shfl_xor_sync(gmask, tmp, d, G);
         if (lane == 0) y[i] = tmp; // TrSpMV.jl:16  (plain store, no alpha/beta)
@@ -60,10 +70,19 @@ static int launch_t(vbc_csc *A, const void *x, void *y)
     return launch_g<Tv, Ti, 2>(A, (const Tv *)x, (Tv *)y);
 }
 
+template <typename Ti> static int launch_ti(vbc_csc *A, const void *d_x, void *d_y)
+{
+    switch (A->vt) {
+    case VBC_F64: return launch_t<double, Ti>(A, d_x, d_y);
+    case VBC_F32: return launch_t<float, Ti>(A, d_x, d_y);
+    case VBC_INT64: return launch_t<unsigned long long, Ti>(A, d_x, d_y);
+    default: return launch_t<unsigned, Ti>(A, d_x, d_y);
+    }
+}
+
 int launch_csc_trspmv(vbc_csc *A, const void *d_x, void *d_y)
 {
-    if (A->it == VBC_I64) return A->vt == VBC_F64 ? launch_t<double, int64_t>(A, d_x, d_y) : launch_t<float, int64_t>(A, d_x, d_y);
-    return A->vt == VBC_F64 ? launch_t<double, int32_t>(A, d_x, d_y) : launch_t<float, int32_t>(A, d_x, d_y);
+    return A->it == VBC_I64 ? launch_ti<int64_t>(A, d_x, d_y) : launch_ti<int32_t>(A, d_x, d_y);
 }
 
 } // namespace vbc

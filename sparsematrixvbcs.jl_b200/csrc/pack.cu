@@ -674,10 +674,10 @@ static int pack_t(vbc_mat *A, const Ti *colptr, const Ti *rowval, const Tv *nzva
 int pack_from_device_csc(vbc_mat *A, const void *c, const void *r, const void *v)
 {
     if (A->it == VBC_I64) {
-        if (A->vt == VBC_F64) return pack_t<int64_t, double>(A, (const int64_t *)c, (const int64_t *)r, (const double *)v);
+        if (vt_size(A->vt) == 8) return pack_t<int64_t, double>(A, (const int64_t *)c, (const int64_t *)r, (const double *)v);
         return pack_t<int64_t, float>(A, (const int64_t *)c, (const int64_t *)r, (const float *)v);
     }
-    if (A->vt == VBC_F64) return pack_t<int32_t, double>(A, (const int32_t *)c, (const int32_t *)r, (const double *)v);
+    if (vt_size(A->vt) == 8) return pack_t<int32_t, double>(A, (const int32_t *)c, (const int32_t *)r, (const double *)v);
     return pack_t<int32_t, float>(A, (const int32_t *)c, (const int32_t *)r, (const float *)v);
 }
 

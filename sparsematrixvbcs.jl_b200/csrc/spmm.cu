@@ -733,6 +733,7 @@ static int spmm_t(vbc_mat *A, int trans, int64_t k, double alpha_d, const Tv *X,
 int launch_spmm(vbc_mat *A, int trans, int64_t k, double alpha, const void *X, int64_t ldx, double beta, void *Y, int64_t ldy, int layout)
 {
     if (A->opt_parity) VBC_FAIL(VBC_EARG, "spmm needs the compact layout (parity mode is on)");
+    if (!vt_is_float(A->vt)) VBC_FAIL(VBC_EARG, "ArgumentError: spmm is offered for Float32 / Float64 matrices");
     return A->vt == VBC_F64 ? spmm_t<double>(A, trans, k, alpha, (const double *)X, ldx, beta, (double *)Y, ldy, layout)
                             : spmm_t<float>(A, trans, k, alpha, (const float *)X, ldx, beta, (float *)Y, ldy, layout);
 }

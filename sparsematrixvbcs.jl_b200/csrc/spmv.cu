@@ -1091,12 +1091,14 @@ int launch_spmv_adj_halo(vbc_mat *A, double alpha, const void *d_x, const HaloLa
     for (int r = 0; r < VBC_MAX_PEERS; r++) h.flags[r] = r < hl->nranks ? hl->flags[r] : nullptr;
     h.ctl = hl->ctl;
     h.timed_out = hl->timed_out;
+    if (!vt_is_float(A->vt)) VBC_FAIL(VBC_EARG, "ArgumentError: the fused multiply + exchange is offered for Float32 / Float64 matrices");
     if (A->vt == VBC_F64) return launch_halo_any<double>(A, alpha, (const double *)d_x, h);
     return launch_halo_any<float>(A, (float)alpha, (const float *)d_x, h);
 }
 
 int launch_spmv(vbc_mat *A, int trans, double alpha, const void *d_x, double beta, void *d_y)
 {
+    if (!vt_is_float(A->vt)) return launch_spmv_int(A, trans, alpha, d_x, beta, d_y);
     return A->vt == VBC_F64 ? launch_spmv_t<double>(A, trans, alpha, d_x, beta, d_y) : launch_spmv_t<float>(A, trans, alpha, d_x, beta, d_y);
 }
 

@@ -286,6 +286,7 @@ int vbc_trsv_analyse(vbc_mat *A, int *nlevels)
     if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
     if (A->m != A->n) VBC_FAIL(VBC_EDIM, "DimensionMismatch: triangular solve needs a square matrix, got %lld x %lld", (long long)A->m, (long long)A->n);
     if (A->opt_parity) VBC_FAIL(VBC_EARG, "triangular solve needs the compact layout (parity mode is on)");
+    if (!vt_is_float(A->vt)) VBC_FAIL(VBC_EARG, "ArgumentError: the triangular solve is offered for Float32 / Float64 matrices");
     DeviceGuard guard(A->device);
     if (!guard.ok) VBC_FAIL(VBC_ECUDA, "cudaSetDevice(%d) failed", A->device);
     const int64_t L = A->L, n = A->n;
@@ -345,6 +346,7 @@ int vbc_trsv_lower(vbc_mat *A, const void *b, void *x, int64_t len, int on_devic
     if (!A) VBC_FAIL(VBC_EARG, "matrix handle is NULL");
     if (A->m != A->n || len != A->n) VBC_FAIL(VBC_EDIM, "DimensionMismatch: triangular solve with a %lld x %lld matrix and vectors of length %lld", (long long)A->m, (long long)A->n, (long long)len);
     if (A->opt_parity) VBC_FAIL(VBC_EARG, "triangular solve needs the compact layout (parity mode is on)");
+    if (!vt_is_float(A->vt)) VBC_FAIL(VBC_EARG, "ArgumentError: the triangular solve is offered for Float32 / Float64 matrices");
     if (!A->trsv) VBC_TRY(vbc_trsv_analyse(A, nullptr));
     if (len == 0) return VBC_OK;
     if (!b || !x) VBC_FAIL(VBC_EARG, "NULL vector");

@@ -28,10 +28,12 @@ using ChainPartitioners
 
 const libvbc = get(ENV, "LIBVBC", "libvbc.so")
 
-const VBC_F32, VBC_F64 = Cint(0), Cint(1)
+const VBC_F32, VBC_F64, VBC_INT32, VBC_INT64 = Cint(0), Cint(1), Cint(2), Cint(3)
 const VBC_I32, VBC_I64 = Cint(0), Cint(1)
 vbc_vt(::Type{Float32}) = VBC_F32
 vbc_vt(::Type{Float64}) = VBC_F64
+vbc_vt(::Type{Int32}) = VBC_INT32   # integer element types (test/runtests.jl:16): wrapping arithmetic on the device, exact
+vbc_vt(::Type{Int64}) = VBC_INT64
 vbc_it(::Type{Int32}) = VBC_I32
 vbc_it(::Type{Int64}) = VBC_I64
 
@@ -142,6 +144,18 @@ function _cuvbc_mul!(y::StridedVector{Tv}, A::CuVBC{U, W, Tv}, x::StridedVector{
     end
     return y
 end
+
+# Bool matrices (test/runtests.jl:15) live on the device widened to Int32: `CuVBC{W}(A::SparseMatrixCSC{Bool}, Φ)` packs
+# `SparseMatrixCSC{Int32}(A)`; Bool vectors are widened for the call and the Int32 result is converted back, which throws the
+# same InexactError Julia raises when a sum above 1 is stored into a Bool vector.
+function _cuvbc_mul!(y::StridedVector{Bool}, A::CuVBC{U, W, Int32}, x::StridedVector{Bool}, α::Number, β::Number, trans::Bool) where {U, W}
+    yw = convert(Vector{Int32}, y)
+    _cuvbc_mul!(yw, A, convert(Vector{Int32}, x), α, β, trans)
+    y .= yw                                                     # InexactError: Bool(2)
+    return y
+end
+CuVBC{W}(A::SparseMatrixCSC{Bool, Ti}, Φ::SplitPartition{Ti}; kw...) where {W, Ti} = CuVBC{W}(SparseMatrixCSC{Int32, Ti}(A), Φ; kw...)
+CuVBC{U, W}(A::SparseMatrixCSC{Bool, Ti}, Π::SplitPartition{Ti}, Φ::SplitPartition{Ti}; kw...) where {U, W, Ti} = CuVBC{U, W}(SparseMatrixCSC{Int32, Ti}(A), Π, Φ; kw...)
 
 # eltype(y) wider than the stored values: the reference converts values and x to eltype(y) before multiplying
 # (multiply_1DVBC.jl:23/27/34, :102) -> Float64 accumulation over a Float32 matrix (csrc/mixed.cu)

@@ -29,7 +29,29 @@ from . import _lib
 from ._lib import ArgumentError, DimensionMismatch, check
 from .partition import SparseMatrixCSC, SplitPartition, pack_plaid, pack_stripe
 
-_VT = {np.dtype(np.float32): _lib.VBC_F32, np.dtype(np.float64): _lib.VBC_F64}
+# Float32 / Float64 run the tuned kernels; Int32 / Int64 (test/runtests.jl:16) the exact wrapping-arithmetic kernels of
+# csrc/inttypes.cu.  Bool (test/runtests.jl:15) is stored widened to Int32 on the device and narrowed at this boundary.
+_VT = {np.dtype(np.float32): _lib.VBC_F32, np.dtype(np.float64): _lib.VBC_F64,
+       np.dtype(np.int32): _lib.VBC_INT32, np.dtype(np.int64): _lib.VBC_INT64}
+_BOOL = np.dtype(np.bool_)
+_I32 = np.dtype(np.int32)
+
+
+class InexactError(ValueError):
+    """Julia's InexactError: an integer result that does not fit the element type (a Bool sum above 1)."""
+
+
+def _torch_dtype(tv):
+    import torch
+    return {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+            np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}[np.dtype(tv)]
+
+
+def _widen_bool(A):
+    """Bool matrix -> (Int32 matrix, True); anything else -> (A, False)."""
+    if A.nzval.dtype == _BOOL:
+        return SparseMatrixCSC(A.m, A.n, A.colptr, A.rowval, A.nzval.astype(np.int32)), True
+    return A, False
 _IT = {np.dtype(np.int32): _lib.VBC_I32, np.dtype(np.int64): _lib.VBC_I64}
 _VT_INV = {v: k for k, v in _VT.items()}
 _IT_INV = {v: k for k, v in _IT.items()}
@@ -54,7 +76,7 @@ def _vec_args(handle_dtype, v, name):
     """-> (pointer, length, on_device, keepalive)"""
     if _is_torch(v):
         import torch
-        want = torch.float64 if handle_dtype == np.dtype(np.float64) else torch.float32
+        want = _torch_dtype(handle_dtype)
         if v.dtype != want or v.dim() != 1 or not v.is_contiguous():
             raise TypeError(f"{name} must be a contiguous 1-D {want} tensor")
         if not v.is_cuda:
@@ -117,6 +139,7 @@ class _CuVBC:
         self.m, self.n, self.K, self.L = m.value, n.value, K.value, Ls.value
         self.U, self.W = U.value, W.value
         self.Tv, self.Ti = _VT_INV[vt.value], _IT_INV[it.value]
+        self.eltype = _BOOL if getattr(self, "_bool", False) else self.Tv  # eltype(A) of the host matrix (Bool is held as Int32)
         nidx, nval = ctypes.c_int64(), ctypes.c_int64()
         check(L.vbc_sizes(self._h, nidx, nval))
         self.nidx, self.nval = nidx.value, nval.value
@@ -141,6 +164,8 @@ class _CuVBC:
         idx = np.empty(self.nidx, dtype=self.Ti)
         val = np.empty(self.nval, dtype=self.Tv)
         check(_lib.lib().vbc_download(self._h, _vp(pos), _vp(idx), _vp(ofs), _vp(val)))
+        if getattr(self, "_bool", False):
+            val = val.astype(np.bool_)
         return dict(pos=pos, idx=idx, ofs=ofs, val=val)
 
     def format_bytes(self):
@@ -194,7 +219,7 @@ class _CuVBC:
 def _colptr_types(A: SparseMatrixCSC):
     tv, ti = A.nzval.dtype, A.colptr.dtype
     if tv not in _VT:
-        raise TypeError(f"CuVBC supports Tv in (Float32, Float64); got {tv} -- convert with A.astype(...)")
+        raise TypeError(f"CuVBC supports Tv in (Float32, Float64, Int32, Int64, Bool); got {tv} -- convert with A.astype(...)")
     return _VT[tv], _IT[ti]
 
 
@@ -228,6 +253,7 @@ class SparseMatrix1DVBC(_CuVBC, metaclass=_ParamMeta):
             raise TypeError("the default partitioner (DynamicTotalChunker, constructors_1DVBC.jl:1-2) lives in "
                             "ChainPartitioners, which is not vendored: pass Φ or a chunker from .partition")
         phi = method_or_phi if isinstance(method_or_phi, SplitPartition) else pack_stripe(A, method_or_phi)
+        A, self._bool = _widen_bool(A)
         vt, it = _colptr_types(A)
         phi = phi.astype(A.colptr.dtype)
         self.Phi = phi
@@ -248,6 +274,9 @@ class SparseMatrix1DVBC(_CuVBC, metaclass=_ParamMeta):
         _CuVBC.__init__(self)
         ti, tv = np.dtype(pos.dtype), np.dtype(val.dtype)
         arrs = [np.ascontiguousarray(a, dtype=ti) for a in (phi_spl, pos, idx, ofs)]
+        self._bool = tv == _BOOL
+        if self._bool:
+            val, tv = np.asarray(val).astype(np.int32), _I32
         val = np.ascontiguousarray(val)
         self.Phi = SplitPartition(arrs[0])
         check(_lib.lib().vbc_upload(ctypes.byref(self._h), _VT[tv], _IT[ti], m, n, 0, W, None, 0, _vp(arrs[0]),
@@ -277,6 +306,7 @@ class SparseMatrixVBC(_CuVBC, metaclass=_ParamMeta):
             pi = pi_or_method
         else:
             pi, phi = pack_plaid(A, pi_or_method)
+        A, self._bool = _widen_bool(A)
         vt, it = _colptr_types(A)
         pi, phi = pi.astype(A.colptr.dtype), phi.astype(A.colptr.dtype)
         self.Pi, self.Phi = pi, phi
@@ -295,6 +325,9 @@ class SparseMatrixVBC(_CuVBC, metaclass=_ParamMeta):
         _CuVBC.__init__(self)
         ti, tv = np.dtype(pos.dtype), np.dtype(val.dtype)
         arrs = [np.ascontiguousarray(a, dtype=ti) for a in (pi_spl, phi_spl, pos, idx, ofs)]
+        self._bool = tv == _BOOL
+        if self._bool:
+            val, tv = np.asarray(val).astype(np.int32), _I32
         val = np.ascontiguousarray(val)
         self.Pi, self.Phi = SplitPartition(arrs[0]), SplitPartition(arrs[1])
         check(_lib.lib().vbc_upload(ctypes.byref(self._h), _VT[tv], _IT[ti], m, n, U, W, _vp(arrs[0]), len(arrs[0]) - 1,
@@ -307,7 +340,7 @@ class SparseMatrixVBC(_CuVBC, metaclass=_ParamMeta):
 def _from_device_csc(cls, U, W, m, n, colptr, rowval, nzval, pi_spl, phi_spl, device):
     import torch
     it = {torch.int32: _lib.VBC_I32, torch.int64: _lib.VBC_I64}[colptr.dtype]
-    vt = {torch.float32: _lib.VBC_F32, torch.float64: _lib.VBC_F64}[nzval.dtype]
+    vt = {torch.float32: _lib.VBC_F32, torch.float64: _lib.VBC_F64, torch.int32: _lib.VBC_INT32, torch.int64: _lib.VBC_INT64}[nzval.dtype]
     tens = [colptr, rowval, nzval, phi_spl] + ([pi_spl] if pi_spl is not None else [])
     for t in tens:
         if not (t.is_cuda and t.is_contiguous()):
@@ -345,7 +378,7 @@ def _panel_args(handle_dtype, v, name):
     1 = column-major (Fortran order, what a Julia Matrix is)."""
     if _is_torch(v):
         import torch
-        want = torch.float64 if handle_dtype == np.dtype(np.float64) else torch.float32
+        want = _torch_dtype(handle_dtype)
         if v.dtype != want or v.dim() != 2 or not v.is_cuda:
             raise TypeError(f"{name} must be a 2-D {want} CUDA tensor")
         rows, k = v.shape
@@ -394,6 +427,15 @@ def mul_(y, A, x, alpha=True, beta=False):
         raise TypeError("mul_ expects a SparseMatrix1DVBC / SparseMatrixVBC or its adjoint")
     if getattr(x, "ndim", 1) == 2:
         return _mul_panel(y, B, trans, x, alpha, beta)
+    if getattr(B, "_bool", False) and not _is_torch(y) and np.asarray(y).dtype == _BOOL:
+        # Bool matrix, Bool vectors (test/runtests.jl:15, :27-53): computed in Int32 on the device; a result outside {0, 1} is the
+        # InexactError Julia raises when it stores an Int sum into a Bool vector
+        yi = np.asarray(y).astype(np.int32)
+        mul_(yi, A, np.ascontiguousarray(np.asarray(x), dtype=np.int32), int(alpha), int(beta))
+        if yi.size and (yi.min() < 0 or yi.max() > 1):
+            raise InexactError(f"Bool({int(yi.max() if yi.max() > 1 else yi.min())})")
+        y[...] = yi.astype(np.bool_)
+        return y
     if B.Tv == np.dtype(np.float32) and _is_f64(y):
         # eltype(y) wider than Tv: values and x are converted to eltype(y) before multiplying
         # (multiply_1DVBC.jl:23/27, :102) -- Float64 accumulation over the Float32 matrix
@@ -467,6 +509,7 @@ class CuSparseMatrixCSC:
 
     def __init__(self, A: SparseMatrixCSC, device=0):
         self._h = ctypes.c_void_p()
+        A, self._bool = _widen_bool(A)
         vt, it = _colptr_types(A)
         self.m, self.n, self.Tv = A.m, A.n, A.nzval.dtype
         self._stream_set = None
@@ -496,6 +539,13 @@ def TrSpMV_(y, A, x):
     if isinstance(A, SparseMatrixCSC):
         own = A = CuSparseMatrixCSC(A)
     try:
+        if A._bool and not _is_torch(y) and np.asarray(y).dtype == _BOOL:
+            yi = np.zeros(len(y), dtype=np.int32)
+            TrSpMV_(yi, A, np.ascontiguousarray(np.asarray(x), dtype=np.int32))
+            if yi.size and (yi.min() < 0 or yi.max() > 1):
+                raise InexactError(f"Bool({int(yi.max() if yi.max() > 1 else yi.min())})")
+            y[...] = yi.astype(np.bool_)
+            return y
         xp, xlen, xdev, _kx = _vec_args(A.Tv, x, "x")
         yp, ylen, ydev, _ky = _vec_args(A.Tv, y, "y")
         if xdev != ydev:

@@ -64,6 +64,23 @@ def sprand(m, n, density, rng, kind="f64"):
     return vb.SparseMatrixCSC.from_scipy(sp.csc_matrix(np.where(mask, vals, 0.0)))
 
 
+def sprand_typed(m, n, density, rng, dtype, ti=np.int64):
+    """sprand(Bool, m, n, p) / sprand(Int32, m, n, p) of runtests.jl:15-16 with the element type kept: Bool entries are true,
+    integer entries span the whole range of the type (so products and sums wrap)."""
+    import vbc_b200 as vb
+    dtype = np.dtype(dtype)
+    mask = rng.random((m, n)) < density
+    cols, rows = np.nonzero(mask.T)  # column-major order: rows ascend inside a column
+    colptr = np.concatenate([[1], 1 + np.cumsum(mask.sum(axis=0))]).astype(ti)
+    if dtype == np.bool_:
+        vals = np.ones(len(rows), dtype=np.bool_)
+    else:
+        info = np.iinfo(dtype)
+        vals = rng.integers(info.min, info.max, size=len(rows), dtype=dtype, endpoint=True)
+        vals[vals == 0] = 1
+    return vb.SparseMatrixCSC(m, n, colptr, (rows + 1).astype(ti), vals)
+
+
 @pytest.fixture(scope="session")
 def fixtures():
     return load_fixtures()

@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 import vbc_b200 as vb
-from conftest import SIZES, sprand
+from conftest import SIZES, sprand, sprand_typed
 from vbc_b200 import _lib, synth
 
 pytestmark = pytest.mark.gpu
@@ -1011,3 +1011,111 @@ def test_device_layout_limits_answer_elimit():
     assert rc == _lib.VBC_ELIMIT and b"32-bit" in L.vbc_last_error() and not h.value
     rc = L.vbc_upload(ctypes.byref(h), _lib.VBC_F64, _lib.VBC_I64, 1 << 31, 0, 0, 4, None, 0, vp(one), 0, vp(one), vp(one), vp(one), vp(one), 0)
     assert rc == _lib.VBC_ELIMIT and not h.value
+
+
+def _dense_of(A):
+    D = np.zeros((A.m, A.n), dtype=A.nzval.dtype)
+    for j in range(A.n):
+        for q in range(A.colptr[j] - 1, A.colptr[j + 1] - 1):
+            D[A.rowval[q] - 1, j] = A.nzval[q]
+    return D
+
+
+@pytest.mark.parametrize("ti", [np.int64, np.int32])
+@pytest.mark.parametrize("tv", [np.int32, np.int64])
+def test_integer_element_types_exact_with_wrapping(tv, ti):
+    """runtests.jl:16 with the element type kept (Int32; Int64 is Julia's default Int): pack bit-exact against the oracle's integer
+    instantiation, every multiply exactly equal to Julia's wrapping arithmetic (numpy's modular integer matmul) in both directions,
+    1D and 2D, uniform and variable blocks, narrow and wide stripes, host arrays and device tensors, alpha / beta included."""
+    import torch
+    rng = np.random.default_rng(1616)
+    info = np.iinfo(tv)
+    tdt = torch.int32 if tv == np.int32 else torch.int64
+    cases = [(m, n, 4, 4, "rand") for m in (1, 3, 8, 17) for n in (1, 4, 9, 16)]
+    cases += [(64, 48, 4, 4, "strict"), (66, 50, 4, 4, "strict"), (90, 75, 8, 12, "rand"), (300, 211, 5, 3, "rand")]
+    for m, n, U, W, how in cases:
+        A = sprand_typed(m, n, 0.3, rng, tv, ti)
+        D = _dense_of(A)
+        ch = (lambda w, s: vb.StrictChunker(w)) if how == "strict" else (lambda w, s: vb.RandomChunker(w, seed=s))
+        phi = vb.pack_stripe(A, ch(W, m + n))
+        pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(ch(U, m), ch(W, n)))
+        H1 = oracle.pack_1d(m, n, A.colptr, A.rowval, A.nzval, phi.spl, W)
+        H2 = oracle.pack_2d(m, n, A.colptr, A.rowval, A.nzval, pi.spl, phi2.spl, U, W)
+        B1 = vb.SparseMatrix1DVBC[W](A, phi)
+        B2 = vb.SparseMatrixVBC[U, W](A, pi, phi2)
+        assert B1.Tv == np.dtype(tv) and B2.Tv == np.dtype(tv)
+        for B, H in ((B1, H1), (B2, H2)):
+            assert_packed_equal(B, H)
+            with np.errstate(over="ignore"):
+                for trans in (False, True):
+                    xlen, ylen = (m, n) if trans else (n, m)
+                    Dop = D.T if trans else D
+                    x = rng.integers(info.min, info.max, size=xlen, dtype=tv, endpoint=True)
+                    y0 = rng.integers(info.min, info.max, size=ylen, dtype=tv, endpoint=True)
+                    op = B.T if trans else B
+                    y = vb.mul_(y0.copy(), op, x)
+                    assert np.array_equal(y, Dop @ x), (m, n, trans, "product")
+                    assert np.array_equal(y, oracle.mul(H, x, trans=trans)), (m, n, trans, "oracle")
+                    y = vb.mul_(y0.copy(), op, x, 3, -2)
+                    assert np.array_equal(y, np.asarray(3, dtype=tv) * (Dop @ x) + np.asarray(-2, dtype=tv) * y0), (m, n, trans, "alpha, beta")
+                    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y0.copy()).cuda()
+                    assert xd.dtype == tdt
+                    vb.mul_(yd, op, xd, True, True)
+                    torch.cuda.synchronize()
+                    assert np.array_equal(yd.cpu().numpy(), Dop @ x + y0), (m, n, trans, "device tensors, beta = 1")
+                    assert np.array_equal((op @ x), Dop @ x)
+                xt = rng.integers(info.min, info.max, size=m, dtype=tv, endpoint=True)
+                assert np.array_equal(vb.TrSpMV_(np.empty(n, dtype=tv), A, xt), D.T @ xt)
+    # scalars that are not integers of the element type: the InexactError of convert(eltype(y), alpha)
+    with pytest.raises(vb.ArgumentError, match="InexactError"):
+        vb.mul_(np.zeros(m, dtype=tv), B1, np.zeros(n, dtype=tv), 0.5, 0)
+    # floating-point-only entry points refuse integer matrices instead of reinterpreting their bits
+    with pytest.raises(vb.ArgumentError):
+        vb.mul_(np.zeros((m, 2), dtype=tv), B1, np.zeros((n, 2), dtype=tv))
+    Asq = sprand_typed(12, 12, 0.3, rng, tv, ti)
+    with pytest.raises(vb.ArgumentError):
+        vb.trsv_analyse(vb.SparseMatrix1DVBC[4](Asq, vb.pack_stripe(Asq, vb.StrictChunker(4))))
+
+
+def test_bool_matrices_onehot_like_runtests_jl():
+    """runtests.jl:15 (`sprand(Bool, m, n, 0.2)`) over the whole size grid with Bool vectors: one-hot products in both directions equal
+    the matrix' columns / rows (:29-53, :63-87); val downloads as Bool; a sum above 1 is an InexactError as in Julia."""
+    rng = np.random.default_rng(15)
+    for m in SIZES:
+        for n in SIZES:
+            A = sprand_typed(m, n, 0.2, rng, np.bool_)
+            D = _dense_of(A)
+            A32 = vb.SparseMatrixCSC(m, n, A.colptr, A.rowval, A.nzval.astype(np.int32))
+            phi = vb.pack_stripe(A, vb.StrictChunker(4))
+            pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(vb.StrictChunker(4), vb.StrictChunker(4)))
+            H1 = oracle.pack_1d(m, n, A32.colptr, A32.rowval, A32.nzval, phi.spl, 4)
+            H2 = oracle.pack_2d(m, n, A32.colptr, A32.rowval, A32.nzval, pi.spl, phi2.spl, 4, 4)
+            for B, H in ((vb.SparseMatrix1DVBC[4](A, phi), H1), (vb.SparseMatrixVBC[4, 4](A, pi, phi2), H2)):
+                assert B.eltype == np.dtype(np.bool_)
+                d = B.download()
+                assert d["val"].dtype == np.bool_ and np.array_equal(d["val"], H.val.astype(np.bool_))
+                for f in ("pos", "idx", "ofs"):
+                    assert np.array_equal(d[f], getattr(H, f)), f
+                x = np.zeros(n, dtype=np.bool_)
+                y = np.empty(m, dtype=np.bool_)
+                for j in range(n):
+                    x[j] = True
+                    y.fill(True)
+                    vb.mul_(y, B, x, True, False)
+                    assert y.dtype == np.bool_ and np.array_equal(y, D[:, j]), f"forward col {j + 1}"
+                    x[j] = False
+                x = np.zeros(m, dtype=np.bool_)
+                y = np.empty(n, dtype=np.bool_)
+                for i in range(m):
+                    x[i] = True
+                    y.fill(True)
+                    vb.mul_(y, B.T, x, True, False)
+                    assert np.array_equal(y, D[i, :]), f"adjoint row {i + 1}"
+                    x[i] = False
+    A = sprand_typed(9, 9, 0.9, rng, np.bool_)
+    B = vb.SparseMatrix1DVBC[4](A, vb.pack_stripe(A, vb.StrictChunker(4)))
+    with pytest.raises(vb.InexactError):
+        vb.mul_(np.zeros(9, dtype=np.bool_), B, np.ones(9, dtype=np.bool_))
+    xt = np.zeros(9, dtype=np.bool_)
+    xt[2] = True
+    assert np.array_equal(vb.TrSpMV_(np.empty(9, dtype=np.bool_), A, xt), _dense_of(A)[2, :])

@@ -16,7 +16,7 @@ import pytest
 
 import oracle
 import vbc_b200 as vb
-from conftest import ROOT, SIZES, sprand
+from conftest import ROOT, SIZES, sprand, sprand_typed
 
 KA = json.load(open(os.path.join(ROOT, "tests", "golden", "known_answers.json")))
 FIXTURE_NAMES = [k for k in KA if not k.startswith("_") and k != "appendix_a"]
@@ -117,6 +117,42 @@ def test_size_grid_onehot(kind):
                 onehot_check(A, oracle.pack_1d(m, n, A.colptr, A.rowval, A.nzval, phi.spl, 4))
             for _, pi, phi in partitions_2d(A):
                 onehot_check(A, oracle.pack_2d(m, n, A.colptr, A.rowval, A.nzval, pi.spl, phi.spl, 4, 4))
+
+
+@pytest.mark.parametrize("tv", [np.int32, np.int64])
+@pytest.mark.parametrize("ti", [np.int64, np.int32])
+def test_integer_element_types_wrap_like_julia(tv, ti):
+    """runtests.jl:16 (`sprand(Int32, ...)`) with the element type kept: the oracle's integer instantiations pack the same arrays as
+    the floating-point ones and multiply with wrapping arithmetic (checked against numpy's modular integer arithmetic)."""
+    rng = np.random.default_rng(16)
+    info = np.iinfo(tv)
+    for m, n in [(1, 1), (5, 9), (17, 16), (40, 33)]:
+        A = sprand_typed(m, n, 0.3, rng, tv, ti)
+        D = np.zeros((m, n), dtype=tv)
+        for j in range(n):
+            for q in range(A.colptr[j] - 1, A.colptr[j + 1] - 1):
+                D[A.rowval[q] - 1, j] = A.nzval[q]
+        Af = vb.SparseMatrixCSC(m, n, A.colptr, A.rowval, np.arange(1, A.nnz + 1, dtype=np.float64))
+        phi = vb.pack_stripe(A, vb.RandomChunker(4, seed=m + n))
+        pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(vb.RandomChunker(4, seed=m), vb.RandomChunker(4, seed=n)))
+        H1 = oracle.pack_1d(m, n, A.colptr, A.rowval, A.nzval, phi.spl, 4)
+        H2 = oracle.pack_2d(m, n, A.colptr, A.rowval, A.nzval, pi.spl, phi2.spl, 4, 4)
+        F1 = oracle.pack_1d(m, n, Af.colptr, Af.rowval, Af.nzval, phi.spl, 4)
+        F2 = oracle.pack_2d(m, n, Af.colptr, Af.rowval, Af.nzval, pi.spl, phi2.spl, 4, 4)
+        for H, F in ((H1, F1), (H2, F2)):
+            assert H.val.dtype == np.dtype(tv)
+            for f in ("pos", "idx", "ofs"):
+                assert np.array_equal(getattr(H, f), getattr(F, f)), f
+            # the value slots hold the nonzeros in the same places (F carries the nonzero's ordinal)
+            slot = F.val.astype(np.int64)
+            assert np.array_equal(H.val[slot > 0], A.nzval[slot[slot > 0] - 1]) and not H.val[slot == 0].any()
+            with np.errstate(over="ignore"):
+                x = rng.integers(info.min, info.max, size=n, dtype=tv, endpoint=True)
+                assert np.array_equal(oracle.mul(H, x), D @ x)
+                xt = rng.integers(info.min, info.max, size=m, dtype=tv, endpoint=True)
+                assert np.array_equal(oracle.mul(H, xt, trans=True), D.T @ xt)
+                assert np.array_equal(oracle.csc_trspmv(m, n, A.colptr, A.rowval, A.nzval, xt), D.T @ xt)
+                assert np.array_equal(oracle.csc_spmv(m, n, A.colptr, A.rowval, A.nzval, x), D @ x)
 
 
 @pytest.mark.parametrize("tv,ti,tol", [(np.float64, np.int64, 1e-12), (np.float64, np.int32, 1e-12),
