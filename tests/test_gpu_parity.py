@@ -1038,7 +1038,7 @@ def test_integer_element_types_exact_with_wrapping(tv, ti):
         D = _dense_of(A)
         ch = (lambda w, s: vb.StrictChunker(w)) if how == "strict" else (lambda w, s: vb.RandomChunker(w, seed=s))
         phi = vb.pack_stripe(A, ch(W, m + n))
-        pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(ch(U, m), ch(W, n)))
+        pi, phi2 = vb.pack_plaid(A, vb.AlternatingPacker(ch(W, n), ch(U, m)))  # columns first
         H1 = oracle.pack_1d(m, n, A.colptr, A.rowval, A.nzval, phi.spl, W)
         H2 = oracle.pack_2d(m, n, A.colptr, A.rowval, A.nzval, pi.spl, phi2.spl, U, W)
         B1 = vb.SparseMatrix1DVBC[W](A, phi)
@@ -1074,7 +1074,7 @@ def test_integer_element_types_exact_with_wrapping(tv, ti):
         vb.mul_(np.zeros((m, 2), dtype=tv), B1, np.zeros((n, 2), dtype=tv))
     Asq = sprand_typed(12, 12, 0.3, rng, tv, ti)
     with pytest.raises(vb.ArgumentError):
-        vb.trsv_analyse(vb.SparseMatrix1DVBC[4](Asq, vb.pack_stripe(Asq, vb.StrictChunker(4))))
+        vb.trsv_analyse(vb.SparseMatrix1DVBC[4](Asq, vb.pack_stripe(Asq, vb.StrictChunker(4))).T)
 
 
 def test_bool_matrices_onehot_like_runtests_jl():
