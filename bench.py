@@ -282,7 +282,20 @@ def extra_configs(peak):
     out["C2_mixed_f32_matrix_f64_vectors_adjoint"] = {"us": med * 1e6, "us_min": mn * 1e6, "algorithmic_bytes": nb, "GBps": nb / med / 1e9, "frac_of_hbm_peak": nb / med / 1e9 / peak,
                                                       "gflops": 2.0 * A.nnz / med / 1e9, "parity_err_over_bound_1e-12": bound_err(ymd.cpu().numpy(), S32.T @ xm, abs(S32).T @ np.abs(xm), 1e-12)}
     B32.close()
-    del A, S, A32, S32
+    # the same matrix with Int32 elements (test/runtests.jl:16): wrapping arithmetic, exact -- a semantics path (csrc/inttypes.cu), timed for the record
+    Ai = vb.SparseMatrixCSC(A.m, A.n, A32.colptr, A32.rowval, (A.nzval * 65536.0 - 32768.0).astype(np.int32))
+    Bi = vb.SparseMatrixVBC[4, 4](Ai, pi.astype(np.int32), phi.astype(np.int32))
+    xi = (synth.vector(A.m, 17) * 65536.0 - 32768.0).astype(np.int32)
+    xid, yid = torch.from_numpy(xi).cuda(), torch.empty(A.n, dtype=torch.int32, device="cuda")
+    vb.mul_(yid, Bi.T, xid)
+    med, mn = timed_graph(lambda: vb.mul_(yid, Bi.T, xid), 20)
+    Si = Ai.to_scipy().astype(np.int64)
+    exact = bool(np.array_equal(yid.cpu().numpy(), (Si.T @ xi.astype(np.int64)).astype(np.int32)))  # int64 sums (no overflow at these magnitudes) wrapped to Int32
+    nb = Bi.format_bytes()[1] + 4 * (A.m + A.n)
+    out["C2_int32_elements_adjoint"] = {"us": med * 1e6, "us_min": mn * 1e6, "algorithmic_bytes": nb, "GBps": nb / med / 1e9, "frac_of_hbm_peak": nb / med / 1e9 / peak,
+                                        "exact_vs_wrapped_int64_product": exact, "note": "Int32 sums overflow and wrap as in Julia; kernel k_int_adj, not tuned"}
+    Bi.close()
+    del A, S, A32, S32, Ai, Si
     # C3: 1D-VBC SpMM, k = 32, n = 1M, W = 8, 50 rows per stripe (parity unpinned by the reference: its matrix `*` cannot run)
     K, L, k = 1_000_000, 125_000, 32
     A, _, phi = synth.banded_blocks(K, L, 1, 8, np.arange(-25, 25) * 37)
