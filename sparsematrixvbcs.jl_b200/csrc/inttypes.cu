@@ -6,7 +6,8 @@
 // reference's bits, so the forward multiply may scatter with integer atomics and stay exact.  All arithmetic here is done on
 // the unsigned type of the same width (same bits as two's-complement wrapping, no signed-overflow undefined behaviour).
 // The kernels read the compact layout of spmv.cu (StripeMeta + desc); pack.cu moves values as bits and needs no integer
-// instantiation of its own (the 4- and 8-byte ones serve).  A semantics path: one group of 8 lanes per stripe, scalar loads.
+// instantiation of its own (the 4- and 8-byte ones serve).  The adjoint has the lane mapping and 16-byte loads of the floating-point
+// kernels (8 lanes per stripe); the forward multiply is a plain scatter.
 #include "walk.cuh"
 #include <limits>
 
@@ -22,13 +23,82 @@ template <int MODE> __device__ __forceinline__ int int_x_index(const int *__rest
     else return __ldg(desc + pos0 + r / u0) + r % u0;
 }
 
+// EPV elements of a stripe's slab in one 16- / 8- / 4-byte load (streaming: every value is read once)
+template <typename T, int EPV> __device__ __forceinline__ void ld_vec(const T *p, T (&v)[EPV])
+{
+    if constexpr (sizeof(T) * EPV == 16) {
+        const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(p));
+        if constexpr (sizeof(T) == 4) { v[0] = (T)q.x; v[1] = (T)q.y; v[2] = (T)q.z; v[3] = (T)q.w; }
+        else { v[0] = (T)(((unsigned long long)q.y << 32) | q.x); v[1] = (T)(((unsigned long long)q.w << 32) | q.z); }
+    } else if constexpr (sizeof(T) * EPV == 8 && sizeof(T) == 4) {
+        const uint2 q = __ldcs(reinterpret_cast<const uint2 *>(p));
+        v[0] = (T)q.x; v[1] = (T)q.y;
+    } else {
+        static_assert(EPV == 1, "vector shapes: 4 x 4 B, 2 x 4 B, 2 x 8 B, or one element");
+        v[0] = __ldcs(p);
+    }
+}
+
 // y[j + c] = alpha * sum_r val[ofs + r w + c] * x[i_r] (+ beta y[j + c])      multiply_1DVBC.jl:98-118, multiply_VBC.jl:99-135
-// w <= IG: lane -> (row r0 = lane / w, column c = lane % w), IG / w rows per step, the lanes of one column summed by shuffles;
-// wider stripes: one lane per column, IG columns per pass.
+// The lane mapping of the floating-point adjoint kernels (spmv.cu, mixed.cu): the IG lanes of a group read consecutive EPV-element
+// vectors of the stripe's slab, lane v holds column-vector v mod cpr and rows r0, r0 + rps, ...; the loads of four row-steps are issued
+// before the first product; the lanes that share a column-vector are summed with the strided shuffle tree (any order is exact here).
+template <typename T, int MODE, int EPV>
+__device__ __forceinline__ void int_adj_stripe(const StripeMeta a, const int w, const int R, const int lane, const unsigned gmask,
+                                               const int *__restrict__ desc, const T *__restrict__ val, const T *__restrict__ x,
+                                               T *__restrict__ y, const int u0, const int log2u, const T alpha, const T beta)
+{
+    const int cpr = w / EPV, rps = small_div(IG, cpr), r0 = small_div(lane, cpr), c = lane - r0 * cpr;
+    const bool active = lane < rps * cpr;
+    T acc[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; e++) acc[e] = (T)0;
+    const T *vp = val + a.ofs + (long long)r0 * w + c * EPV;
+    const int vstride = rps * w;
+    RowWalk<MODE> walk;
+    walk.init(desc, a.pos, r0, rps, u0, log2u);
+    constexpr int UNR = 4;
+    for (int r = active ? r0 : R; r < R; r += UNR * rps) {
+        T v[UNR][EPV];
+        int xi[UNR];
+        T xv[UNR];
+        bool ok[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; k++) {
+            ok[k] = r + k * rps < R;
+#pragma unroll
+            for (int e = 0; e < EPV; e++) v[k][e] = (T)0;
+            if (ok[k]) ld_vec<T, EPV>(vp, v[k]);
+            vp += vstride;
+        }
+#pragma unroll
+        for (int k = 0; k < UNR; k++) xi[k] = walk.next_if(ok[k]);
+#pragma unroll
+        for (int k = 0; k < UNR; k++) xv[k] = ok[k] ? __ldg(x + xi[k]) : (T)0;
+#pragma unroll
+        for (int k = 0; k < UNR; k++)
+#pragma unroll
+            for (int e = 0; e < EPV; e++) acc[e] += v[k][e] * xv[k];
+    }
+    __syncwarp(gmask);
+    for (int d = cpr; d < IG; d <<= 1)
+#pragma unroll
+        for (int e = 0; e < EPV; e++) {
+            const T t = __shfl_down_sync(gmask, acc[e], d, IG);
+            if (lane + d < IG) acc[e] += t;
+        }
+    if (lane < cpr) {
+        T *yp = y + a.col + lane * EPV;
+#pragma unroll
+        for (int e = 0; e < EPV; e++) yp[e] = (beta == (T)0) ? alpha * acc[e] : alpha * acc[e] + beta * yp[e];
+    }
+}
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) k_int_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc, const T *__restrict__ val,
-                                                 const T *__restrict__ x, T *__restrict__ y, const int L, const int u0, const T alpha, const T beta)
+                                                 const T *__restrict__ x, T *__restrict__ y, const int L, const int u0, const int log2u, const T alpha, const T beta)
 {
+    constexpr int VE = 16 / (int)sizeof(T); // elements per 16-byte vector
     const int lane = threadIdx.x % IG;
     const unsigned gmask = ((1u << IG) - 1u) << (((threadIdx.x & 31) / IG) * IG);
     const long long groups = (long long)gridDim.x * (blockDim.x / IG);
@@ -37,23 +107,11 @@ __global__ void __launch_bounds__(256) k_int_adj(const StripeMeta *__restrict__ 
         const int w = b.col - a.col;
         if (w <= 0) continue; // uniform over the group
         const int rows = (MODE == DESC_ROWS) ? (b.pos - a.pos) : (int)((b.ofs - a.ofs) / w);
-        const T *vbase = val + a.ofs;
-        if (w <= IG) {
-            const int rps = IG / w, r0 = lane / w, c = lane - r0 * w;
-            T acc = (T)0;
-            if (r0 < rps)
-                for (int r = r0; r < rows; r += rps) acc += vbase[(long long)r * w + c] * __ldg(x + int_x_index<MODE>(desc, a.pos, r, u0));
-            __syncwarp(gmask);
-            T total = acc;
-            for (int k = 1; k < rps; k++) { // lane c < w collects the partial sums of lanes c + k w
-                const T t = __shfl_down_sync(gmask, acc, k * w, IG);
-                if (lane < w) total += t;
-            }
-            if (lane < w) {
-                T *yp = y + a.col + lane;
-                *yp = (beta == (T)0) ? alpha * total : alpha * total + beta * *yp;
-            }
-        } else {
+        if (w % VE == 0 && a.ofs % VE == 0 && w / VE <= IG) int_adj_stripe<T, MODE, VE>(a, w, rows, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+        else if (VE == 4 && (w & 1) == 0 && (a.ofs & 1) == 0 && (w >> 1) <= IG) int_adj_stripe<T, MODE, (VE == 4 ? 2 : 1)>(a, w, rows, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+        else if (w <= IG) int_adj_stripe<T, MODE, 1>(a, w, rows, lane, gmask, desc, val, x, y, u0, log2u, alpha, beta);
+        else { // wider than the group: one lane per column, IG columns per pass
+            const T *vbase = val + a.ofs;
             for (int c = lane; c < w; c += IG) {
                 T acc = (T)0;
                 for (int r = 0; r < rows; r++) acc += vbase[(long long)r * w + c] * __ldg(x + int_x_index<MODE>(desc, a.pos, r, u0));
@@ -105,12 +163,14 @@ int launch_int_t(vbc_mat *A, int trans, T alpha, const T *x, T beta, T *y)
         k_int_scale<T><<<(unsigned)g, 256, 0, A->stream>>>(y, ylen, beta);
         A->launches++;
     }
+    int log2u = -1;
+    if (A->u0 > 0 && !(A->u0 & (A->u0 - 1))) { log2u = 0; while ((1 << log2u) < A->u0) log2u++; }
     if (A->L > 0 && grid > 0) {
         const bool rows = A->desc_mode == DESC_ROWS;
         const T *val = (const T *)A->d_val;
         if (trans) {
-            if (rows) k_int_adj<T, DESC_ROWS><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, val, x, y, (int)A->L, A->u0, alpha, beta);
-            else k_int_adj<T, DESC_BLOCKS><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, val, x, y, (int)A->L, A->u0, alpha, beta);
+            if (rows) k_int_adj<T, DESC_ROWS><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, val, x, y, (int)A->L, A->u0, log2u, alpha, beta);
+            else k_int_adj<T, DESC_BLOCKS><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, val, x, y, (int)A->L, A->u0, log2u, alpha, beta);
         } else {
             if (rows) k_int_fwd<T, DESC_ROWS><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, val, x, y, (int)A->L, A->u0, alpha);
             else k_int_fwd<T, DESC_BLOCKS><<<(unsigned)grid, 256, 0, A->stream>>>(A->d_meta, A->d_desc, val, x, y, (int)A->L, A->u0, alpha);
