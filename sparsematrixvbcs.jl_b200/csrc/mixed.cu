@@ -82,7 +82,7 @@ __device__ __forceinline__ void mixed_adj_stripe(const StripeMeta a, const int w
 }
 
 template <typename Tm, typename Tu, int MODE>
-__global__ void __launch_bounds__(256) k_mixed_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc, const Tm *__restrict__ val,
+__global__ void __launch_bounds__(256, 4) k_mixed_adj(const StripeMeta *__restrict__ meta, const int *__restrict__ desc, const Tm *__restrict__ val,
                                                    const Tu *__restrict__ x, Tu *__restrict__ y, const int L, const int u0, const int log2u,
                                                    const Tu alpha, const Tu beta)
 {
