@@ -294,6 +294,12 @@ def extra_configs(peak):
     nb = Bi.format_bytes()[1] + 4 * (A.m + A.n)
     out["C2_int32_elements_adjoint"] = {"us": med * 1e6, "us_min": mn * 1e6, "algorithmic_bytes": nb, "GBps": nb / med / 1e9, "frac_of_hbm_peak": nb / med / 1e9 / peak,
                                         "exact_vs_wrapped_int64_product": exact, "note": "Int32 sums overflow and wrap as in Julia; kernel k_int_adj (16-byte loads, 8 lanes per stripe)"}
+    xf = (synth.vector(A.n, 19) * 65536.0 - 32768.0).astype(np.int32)
+    xfd, yfd = torch.from_numpy(xf).cuda(), torch.empty(A.m, dtype=torch.int32, device="cuda")
+    vb.mul_(yfd, Bi, xfd)  # builds the transposed copy outside graph capture
+    fmed, _ = timed_graph(lambda: vb.mul_(yfd, Bi, xfd), 20)
+    out["C2_int32_elements_adjoint"]["forward_us"] = fmed * 1e6
+    out["C2_int32_elements_adjoint"]["forward_exact"] = bool(np.array_equal(yfd.cpu().numpy(), (Si @ xf.astype(np.int64)).astype(np.int32)))
     Bi.close()
     del A, S, A32, S32, Ai, Si
     # C3: 1D-VBC SpMM, k = 32, n = 1M, W = 8, 50 rows per stripe (parity unpinned by the reference: its matrix `*` cannot run)

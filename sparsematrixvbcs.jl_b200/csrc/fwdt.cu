@@ -597,11 +597,12 @@ int ensure_tindex(vbc_mat *A)
     if (!T) VBC_FAIL(VBC_ENOMEM, "host allocation failed");
     int rc;
     if (A->ndim == 2 && A->desc_mode == DESC_ROWS && A->opt_fwd_atomic != 2 && A->w_uniform <= 0) { // variable blocks: the copy is built from the canonical block arrays
-        if (A->it == VBC_I64) rc = A->vt == VBC_F64 ? build_transposed_blocks<int64_t, double>(A, T) : build_transposed_blocks<int64_t, float>(A, T);
-        else rc = A->vt == VBC_F64 ? build_transposed_blocks<int32_t, double>(A, T) : build_transposed_blocks<int32_t, float>(A, T);
+        // the copies move values as bits: the 8- and 4-byte instantiations also serve the integer element types
+        if (A->it == VBC_I64) rc = vt_size(A->vt) == 8 ? build_transposed_blocks<int64_t, double>(A, T) : build_transposed_blocks<int64_t, float>(A, T);
+        else rc = vt_size(A->vt) == 8 ? build_transposed_blocks<int32_t, double>(A, T) : build_transposed_blocks<int32_t, float>(A, T);
     } else {
         rc = A->desc_mode == DESC_ROWS ? build_tindex_mode<DESC_ROWS>(A, T) : build_tindex_mode<DESC_BLOCKS>(A, T);
-        if (rc == VBC_OK && A->opt_fwd_atomic != 2) rc = A->vt == VBC_F64 ? build_transposed_copy<double>(A, T) : build_transposed_copy<float>(A, T);
+        if (rc == VBC_OK && A->opt_fwd_atomic != 2) rc = vt_size(A->vt) == 8 ? build_transposed_copy<double>(A, T) : build_transposed_copy<float>(A, T);
     }
     if (rc != VBC_OK) { destroy_tindex(T); return rc; }
     if (!T->At && A->desc_mode == DESC_ROWS && A->opt_fwd_atomic != 2) { destroy_tindex(T); A->opt_fwd_no_copy = 1; return VBC_OK; } // rows mode without the copy: atomics win over the index

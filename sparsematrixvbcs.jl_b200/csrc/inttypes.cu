@@ -152,6 +152,11 @@ template <typename T> __global__ void __launch_bounds__(256) k_int_scale(T *__re
 template <typename T>
 int launch_int_t(vbc_mat *A, int trans, T alpha, const T *x, T beta, T *y)
 {
+    if (!trans) { // forward through the transposed copy when the matrix has one (the adjoint kernel on it, no atomics), like mixed.cu
+        VBC_TRY(ensure_tindex(A));
+        vbc_mat *At = tindex_copy(A);
+        if (At != nullptr) { At->stream = A->stream; const int64_t before = At->launches; const int rc = launch_int_t<T>(At, 1, alpha, x, beta, y); A->launches += At->launches - before; return rc; }
+    }
     const int64_t ylen = trans ? A->n : A->m;
     const int per_block = 256 / IG;
     int64_t grid = (A->L + per_block - 1) / per_block;
