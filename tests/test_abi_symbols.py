@@ -63,6 +63,34 @@ def test_argument_errors_without_gpu():
         vb.SparseMatrix1DVBC[4.0]  # "W must be an Int"  SparseMatrixVBCs.jl:49
 
 
+def test_element_type_enumerants_and_host_type_rules():
+    """include/vbc.h's vbc_dtype values are the ones the Python and Julia bindings pass; an unknown element type is refused
+    before any CUDA call; Bool is widened to Int32 at the host boundary; other element types are a TypeError, not a reinterpretation."""
+    import re
+    import numpy as np
+    from vbc_b200 import matrix
+    hdr = open(os.path.join(ROOT, "include", "vbc.h")).read()
+    m = re.search(r"enum vbc_dtype \{([^}]*)\}", hdr)
+    vals = {k.strip(): int(v) for k, v in (kv.split("=") for kv in m.group(1).split(","))}
+    assert vals == {"VBC_F32": _lib.VBC_F32, "VBC_F64": _lib.VBC_F64, "VBC_INT32": _lib.VBC_INT32, "VBC_INT64": _lib.VBC_INT64}
+    jl = open(os.path.join(ROOT, "sparsematrixvbcs.jl_b200", "julia", "CuVBC.jl")).read()
+    assert "const VBC_F32, VBC_F64, VBC_INT32, VBC_INT64 = Cint(0), Cint(1), Cint(2), Cint(3)" in jl
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    one = np.array([1], dtype=np.int64)
+    p = ctypes.c_void_p(one.ctypes.data)
+    rc = L.vbc_pack_csc(ctypes.byref(h), 7, _lib.VBC_I64, 0, 0, 0, 4, p, p, p, None, 0, p, 0, 0)
+    assert rc == _lib.VBC_EARG and b"vt must be" in L.vbc_last_error() and not h.value
+    A = vb.SparseMatrixCSC(2, 2, np.array([1, 2, 3]), np.array([1, 2]), np.array([True, True]))
+    W, was_bool = matrix._widen_bool(A)
+    assert was_bool and W.nzval.dtype == np.int32 and W.nzval.tolist() == [1, 1] and W.colptr is not None
+    assert matrix._widen_bool(W) == (W, False)
+    assert matrix._colptr_types(W) == (_lib.VBC_INT32, _lib.VBC_I64)
+    with pytest.raises(TypeError, match="Int32, Int64, Bool"):
+        matrix._colptr_types(vb.SparseMatrixCSC(2, 2, np.array([1, 2, 3]), np.array([1, 2]), np.array([1, 1], dtype=np.int8)))
+    assert issubclass(vb.InexactError, ValueError)
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(ROOT, "does_not_exist", "libvbc.so"))
