@@ -20,6 +20,8 @@
 # Added for device-resident use (no reference counterpart; the reference's vectors are host Arrays):
 #   CuVec{Tv}                             a device vector handle (raw CUdeviceptr + length), `mul!` methods on it enqueue only
 #   CuVBCDist                             the row-partitioned iteration over several GPUs, one process (vbc_dist_*)
+#   CuVBCPeer                             the same iteration with one Julia process per GPU (vbc_peer_*; handles exchanged by the caller's transport)
+#   CuVBC{U,W}(m, n, ::CuVec...)          pack from a CSC matrix that is already on the device (vbc_pack_csc_dev)
 #   set_option! / get_option              kernel options (VBC_OPT_*)
 
 using LinearAlgebra
@@ -342,3 +344,106 @@ function partition_info(D::CuVBCDist)
     vbc_check(ccall((:vbc_dist_info, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ref{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}), D.handle, C_NULL, S, bounds, cost, interior))
     return (slice_len = S[], stripe_bounds = bounds, cost_per_gpu = cost, interior = reshape(interior, 2, :))
 end
+
+# ---- multi-GPU, one Julia process per GPU (e.g. under MPI.jl): the vbc_peer_* front end of the same fused kernel ---------
+# Each rank packs its own stripes (`CuVBC{U, W}(A_slab, Π, Φ_slab; device)`), creates a CuVBCPeer, the ranks exchange the IPC
+# handles with whatever transport they have (`MPI.Allgather(handles(P), comm)`), connect, and iterate.  `allgather` below is
+# that transport: a function `Vector{UInt8} -> Vector{UInt8}` returning the concatenation over ranks in rank order.
+const VBC_IPC_HANDLE_BYTES, VBC_PEER_HANDLES = 64, 3
+mutable struct CuVBCPeer{Tv}
+    handle::Ptr{Cvoid}
+    rank::Int
+    nranks::Int
+    xlen::Int
+    my_handles::Vector{UInt8}
+    function CuVBCPeer{Tv}(xlen::Integer, rank::Integer, nranks::Integer; device::Integer = rank) where {Tv}
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        hs = zeros(UInt8, VBC_IPC_HANDLE_BYTES * VBC_PEER_HANDLES)
+        GC.@preserve hs vbc_check(ccall((:vbc_peer_create, libvbc), Cint, (Ref{Ptr{Cvoid}}, Cint, Int64, Cint, Cint, Cint, Ptr{Cvoid}),
+                                        h, vbc_vt(Tv), xlen, rank, nranks, device, hs))
+        P = new{Tv}(h[], rank, nranks, xlen, hs)
+        finalizer(p -> (ccall((:vbc_peer_destroy, libvbc), Cvoid, (Ptr{Cvoid},), p.handle); p.handle = C_NULL), P)
+        return P
+    end
+end
+handles(P::CuVBCPeer) = P.my_handles
+function connect!(P::CuVBCPeer, allgather::Function)
+    all = allgather(P.my_handles)
+    length(all) == P.nranks * length(P.my_handles) || throw(ArgumentError("allgather must return the handles of all $(P.nranks) ranks"))
+    GC.@preserve all vbc_check(ccall((:vbc_peer_connect, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), P.handle, all))
+    return P
+end
+# device pointer of x buffer k (0 or 1) as a CuVec, and which of the two holds the current x
+function buffer(P::CuVBCPeer{Tv}, k::Integer) where {Tv}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    vbc_check(ccall((:vbc_peer_buffer, libvbc), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), P.handle, k, p))
+    return CuVec{Tv}(p[], P.xlen)
+end
+current(P::CuVBCPeer) = (c = Ref{Cint}(0); vbc_check(ccall((:vbc_peer_current, libvbc), Cint, (Ptr{Cvoid}, Ref{Cint}), P.handle, c)); Int(c[]))
+# sparsity-aware replication: mask[c >> chunk_shift] has bit i set when destination (rank + i) % nranks reads that chunk of this
+# rank's columns (`read_chunks` of the other ranks' matrices, gathered by the caller); neighbours = bit set of the ranks to synchronise with
+set_mask!(P::CuVBCPeer, mask::Vector{UInt8}, chunk_shift::Integer) =
+    (GC.@preserve mask vbc_check(ccall((:vbc_peer_set_mask, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint), P.handle, mask, length(mask), chunk_shift)); P)
+set_neighbors!(P::CuVBCPeer, mask::Integer) = (vbc_check(ccall((:vbc_peer_set_neighbors, libvbc), Cint, (Ptr{Cvoid}, Cuint), P.handle, mask)); P)
+function auto_interior!(P::CuVBCPeer, A::CuVBC, y_offset::Integer)
+    i0, i1 = Ref{Int64}(0), Ref{Int64}(0)
+    vbc_check(ccall((:vbc_peer_auto_interior, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{Int64}, Ref{Int64}), P.handle, A.handle, y_offset, i0, i1))
+    return (i0[], i1[])
+end
+function read_chunks(A::CuVBC, chunk_shift::Integer)
+    n = (A.m + (1 << chunk_shift) - 1) >> chunk_shift
+    need = zeros(UInt8, max(n, 1))
+    GC.@preserve need vbc_check(ccall((:vbc_read_chunks, libvbc), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt8}, Int64), A.handle, chunk_shift, need, length(need)))
+    return need[1:n]
+end
+# one iteration x_next[y_offset .+ (1:size(A, 2))] = α A' x_cur on this rank's stripes, stored on every rank that reads it: ONE kernel launch
+# on A's stream, the exchange fused in (barrier: 1 signal | 2 wait | 3 both).  Nothing is awaited on the host.
+step!(P::CuVBCPeer, A::CuVBC, y_offset::Integer; α::Number = 1.0, barrier::Integer = 3) =
+    (vbc_check(ccall((:vbc_peer_spmv_step, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Int64, Cint), P.handle, A.handle, Float64(α), y_offset, barrier)); P)
+barrier!(P::CuVBCPeer, stream::Ptr{Cvoid} = C_NULL; mode::Integer = 3) =
+    (vbc_check(ccall((:vbc_peer_barrier, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), P.handle, stream, mode)); P)
+function status(P::CuVBCPeer)   # true when no in-kernel flag wait has timed out (call after `sync(A)`)
+    t = Ref{Cint}(0)
+    vbc_check(ccall((:vbc_peer_status, libvbc), Cint, (Ptr{Cvoid}, Ref{Cint}), P.handle, t))
+    return t[] == 0
+end
+function wait_stats(P::CuVBCPeer; reset::Bool = false)
+    s = zeros(UInt64, 4)
+    GC.@preserve s vbc_check(ccall((:vbc_peer_wait_stats, libvbc), Cint, (Ptr{Cvoid}, Ptr{UInt64}, Cint), P.handle, s, reset))
+    return (steps = s[1], wait_ns = s[2], waits_that_spun = s[3], longest_wait_ns = s[4])
+end
+
+# ---- the rest of the surface -------------------------------------------------------------------------------------------------
+version() = Int(ccall((:vbc_version, libvbc), Cint, ()))
+device_count() = (c = Ref{Cint}(0); vbc_check(ccall((:vbc_device_count, libvbc), Cint, (Ref{Cint},), c)); Int(c[]))
+# (m, n, K, L, U, W, ndim, vt, it) as the device holds them
+function shape(A::CuVBC)
+    m, n, K, L = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    U, W, nd, vt, it = Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0)
+    vbc_check(ccall((:vbc_shape, libvbc), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Cint}, Ref{Cint}, Ref{Cint}, Ref{Cint}, Ref{Cint}),
+                    A.handle, m, n, K, L, U, W, nd, vt, it))
+    return (m = m[], n = n[], K = K[], L = L[], U = Int(U[]), W = Int(W[]), ndim = Int(nd[]), vt = vt[], it = it[])
+end
+# level schedule of the triangular solve (extension): built once, reused by every `ldiv_lower!`
+trsv_analyse!(A::CuVBC) = (l = Ref{Cint}(0); vbc_check(ccall((:vbc_trsv_analyse, libvbc), Cint, (Ptr{Cvoid}, Ref{Cint}), A.handle, l)); Int(l[]))
+trsv_levels(A::CuVBC) = (l = Ref{Cint}(0); vbc_check(ccall((:vbc_trsv_levels, libvbc), Cint, (Ptr{Cvoid}, Ref{Cint}), A.handle, l)); Int(l[]))
+set_stream!(A::CuCSC, stream::Ptr{Cvoid}) = vbc_check(ccall((:vbc_csc_set_stream, libvbc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), A.handle, stream))
+# pack from a CSC matrix that already lives on the device (colptr / rowval / Φ.spl / Π.spl as CuVec{Ti}, nzval as CuVec{Tv}); the host
+# copies of the partitions are kept for `A.Π` / `A.Φ`
+function CuVBC{U, W}(m::Integer, n::Integer, colptr::CuVec{Ti}, rowval::CuVec{Ti}, nzval::CuVec{Tv}, Π::Union{Nothing, SplitPartition{Ti}}, dΠ::Union{Nothing, CuVec{Ti}},
+                     Φ::SplitPartition{Ti}, dΦ::CuVec{Ti}; device::Integer = 0) where {U, W, Tv, Ti}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    vbc_check(ccall((:vbc_pack_csc_dev, libvbc), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint),
+        h, vbc_vt(Tv), vbc_it(Ti), m, n, U, W, colptr.ptr, rowval.ptr, nzval.ptr,
+        dΠ === nothing ? C_NULL : dΠ.ptr, Π === nothing ? 0 : length(Π), dΦ.ptr, length(Φ), device))
+    return CuVBC{U, W, Tv, Ti}(h[], m, n, Π, Φ)
+end
+set_interior!(P::CuVBCPeer, i0::Integer, i1::Integer) = (vbc_check(ccall((:vbc_peer_set_interior, libvbc), Cint, (Ptr{Cvoid}, Int64, Int64), P.handle, i0, i1)); P)
+function get_interior(P::CuVBCPeer)
+    i0, i1 = Ref{Int64}(0), Ref{Int64}(0)
+    vbc_check(ccall((:vbc_peer_get_interior, libvbc), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), P.handle, i0, i1))
+    return (i0[], i1[])
+end
+# Not bound on purpose: vbc_dp_chunk / vbc_overlap_chunk (ChainPartitioners does this work on the Julia side), vbc_gen_banded_csc /
+# vbc_gen_free (the benchmark's device-side matrix generator), vbc_peer_connect_local (ranks sharing one process: vbc_dist_* does that).
