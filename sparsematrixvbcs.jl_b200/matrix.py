@@ -340,7 +340,10 @@ class SparseMatrixVBC(_CuVBC, metaclass=_ParamMeta):
 def _from_device_csc(cls, U, W, m, n, colptr, rowval, nzval, pi_spl, phi_spl, device):
     import torch
     it = {torch.int32: _lib.VBC_I32, torch.int64: _lib.VBC_I64}[colptr.dtype]
-    vt = {torch.float32: _lib.VBC_F32, torch.float64: _lib.VBC_F64, torch.int32: _lib.VBC_INT32, torch.int64: _lib.VBC_INT64}[nzval.dtype]
+    vts = {torch.float32: _lib.VBC_F32, torch.float64: _lib.VBC_F64, torch.int32: _lib.VBC_INT32, torch.int64: _lib.VBC_INT64}
+    if nzval.dtype not in vts:
+        raise TypeError(f"from_device_csc supports nzval in (float32, float64, int32, int64); got {nzval.dtype} (widen Bool with nzval.int())")
+    vt = vts[nzval.dtype]
     tens = [colptr, rowval, nzval, phi_spl] + ([pi_spl] if pi_spl is not None else [])
     for t in tens:
         if not (t.is_cuda and t.is_contiguous()):
